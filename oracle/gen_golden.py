@@ -1,0 +1,134 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference  (TEST INFRASTRUCTURE ONLY).
+
+Run in the build container (needs /root/reference):   python oracle/gen_golden.py
+
+Each fixture stores, for a seeded case, everything needed to replay it without the reference:
+  x                      input values as float32 (bf16 cases: bf16-representable values)
+  s{step}_..._pre/post   codebook buffers (embed, embed_avg, cluster_size) before / after each step
+  s{step}_quantize/_indices/_loss   the reference outputs of that forward
+The reference runs on CPU with torch's fp32 kernels (Codebook.forward upcasts, vqp.py:692).
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from ref_loader import load_reference  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def f32(t):
+    return t.detach().float().cpu().numpy().astype(np.float32)
+
+
+def codebooks_of(module):
+    """Distinct Codebook objects in forward order."""
+    ref = sys.modules["vector_quantize_pytorch.vector_quantize_pytorch"]
+    seen, out = set(), []
+    for m in module.modules():
+        if isinstance(m, ref.Codebook) and id(m) not in seen:
+            seen.add(id(m))
+            out.append(m)
+    return out
+
+
+def snap(module, tag, store):
+    for i, cb in enumerate(codebooks_of(module)):
+        store[f"{tag}_cb{i}_embed"] = f32(cb.embed[0])
+        store[f"{tag}_cb{i}_embed_avg"] = f32(cb.embed_avg[0])
+        store[f"{tag}_cb{i}_cluster_size"] = f32(cb.cluster_size[0])
+
+
+def randomize_codebooks(module, gen, scale=1.0, cosine=False):
+    """Replace the degenerate kaiming init (|c| ~ 5e-3) by a seeded randn codebook."""
+    for cb in codebooks_of(module):
+        e = torch.randn(cb.embed.shape, generator=gen) * scale
+        if cosine:
+            e = torch.nn.functional.normalize(e, dim=-1)
+        cb.embed.data.copy_(e)
+        cb.embed_avg.data.copy_(e)
+
+
+def run_case(name, build, x_shape, dtype, steps, meta, randomize=True, scale=1.0, clustered=False):
+    ref = load_reference()
+    torch.manual_seed(1234)
+    gen = torch.Generator().manual_seed(4321)
+    module = build(ref)
+    cosine = bool(meta.get("use_cosine_sim", False))
+    if randomize:
+        randomize_codebooks(module, gen, scale, cosine)
+    store = {}
+    tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+    for step, mode in enumerate(steps):
+        x = torch.randn(*x_shape, generator=gen)
+        if clustered:
+            cb0 = codebooks_of(module)[0].embed[0]
+            pick = torch.randint(0, cb0.shape[0], x_shape[:-1], generator=gen)
+            if x_shape[-1] == cb0.shape[-1]:
+                x = cb0[pick] + 0.3 * x
+        x = x.to(tdtype)
+        module.train(mode == "train")
+        if step == 0:  # later steps: pre(step) == post(step-1)
+            snap(module, "s0_pre", store)
+        with torch.no_grad():
+            out = module(x)
+        store[f"s{step}_x"] = f32(x)
+        store[f"s{step}_quantize"] = f32(out[0])
+        store[f"s{step}_indices"] = out[1].cpu().numpy().astype(np.int64)
+        store[f"s{step}_loss"] = f32(out[2])
+        snap(module, f"s{step}_post", store)
+    meta = dict(meta, name=name, dtype=dtype, steps=list(steps), x_shape=list(x_shape),
+                torch=torch.__version__, n_codebooks=len(codebooks_of(module)))
+    store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    os.makedirs(OUT, exist_ok=True)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **store)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def main():
+    T, E = "train", "eval"
+    # --- VectorQuantize (vqp.py:802) ---
+    run_case("vq_euclid_fp32", lambda r: r.VectorQuantize(dim=64, codebook_size=96), (2, 80, 64), "fp32",
+             [T, T, E], dict(kind="vq", dim=64, codebook_size=96))
+    run_case("vq_euclid_bf16", lambda r: r.VectorQuantize(dim=64, codebook_size=96), (2, 80, 64), "bf16",
+             [T, T, E], dict(kind="vq", dim=64, codebook_size=96))
+    run_case("vq_cosine_fp32", lambda r: r.VectorQuantize(dim=64, codebook_size=96, use_cosine_sim=True),
+             (2, 80, 64), "fp32", [T, T, E], dict(kind="vq", dim=64, codebook_size=96, use_cosine_sim=True))
+    run_case("vq_cosine_bf16", lambda r: r.VectorQuantize(dim=64, codebook_size=96, use_cosine_sim=True),
+             (2, 80, 64), "bf16", [T, T, E], dict(kind="vq", dim=64, codebook_size=96, use_cosine_sim=True))
+    # default (kaiming) init: the tie-heavy regime of SURVEY §7.2
+    run_case("vq_euclid_fp32_coldinit", lambda r: r.VectorQuantize(dim=64, codebook_size=96), (1, 128, 64), "fp32",
+             [T, T], dict(kind="vq", dim=64, codebook_size=96), randomize=False)
+    # README example shape, BASELINE config 1 (README.md:17-29) with a smaller batch
+    run_case("vq_readme_fp32", lambda r: r.VectorQuantize(dim=256, codebook_size=512, decay=0.8, commitment_weight=1.),
+             (1, 128, 256), "fp32", [T], dict(kind="vq", dim=256, codebook_size=512))
+    run_case("vq_decay_cw_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=40, decay=0.95, commitment_weight=0.25, eps=1e-3),
+             (3, 50, 32), "fp32", [T, T], dict(kind="vq", dim=32, codebook_size=40, decay=0.95, commitment_weight=0.25, eps=1e-3))
+    # --- ResidualVQ (rvq.py:166) ---
+    for dtype in ("fp32", "bf16"):
+        run_case(f"rvq_shared_{dtype}", lambda r: r.ResidualVQ(dim=32, num_quantizers=4, codebook_size=64, shared_codebook=True),
+                 (2, 64, 32), dtype, [T, T, E], dict(kind="rvq", dim=32, codebook_size=64, num_quantizers=4, shared_codebook=True),
+                 clustered=True)
+        run_case(f"rvq_separate_{dtype}", lambda r: r.ResidualVQ(dim=32, num_quantizers=4, codebook_size=64),
+                 (2, 64, 32), dtype, [T, T, E], dict(kind="rvq", dim=32, codebook_size=64, num_quantizers=4, shared_codebook=False),
+                 clustered=True)
+    run_case("rvq_cosine_fp32", lambda r: r.ResidualVQ(dim=32, num_quantizers=3, codebook_size=64, use_cosine_sim=True),
+             (2, 64, 32), "fp32", [T, E], dict(kind="rvq", dim=32, codebook_size=64, num_quantizers=3, shared_codebook=False,
+                                                use_cosine_sim=True))
+    # --- GroupedResidualVQ (rvq.py:634) ---
+    run_case("grvq_fp32", lambda r: r.GroupedResidualVQ(dim=64, groups=2, num_quantizers=3, codebook_size=48),
+             (2, 48, 64), "fp32", [T, T, E], dict(kind="grvq", dim=64, groups=2, codebook_size=48, num_quantizers=3,
+                                                  shared_codebook=False))
+    run_case("grvq_shared_bf16", lambda r: r.GroupedResidualVQ(dim=64, groups=2, num_quantizers=3, codebook_size=48, shared_codebook=True),
+             (2, 48, 64), "bf16", [T, T], dict(kind="grvq", dim=64, groups=2, codebook_size=48, num_quantizers=3,
+                                               shared_codebook=True))
+
+
+if __name__ == "__main__":
+    main()

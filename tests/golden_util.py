@@ -1,0 +1,68 @@
+"""Helpers to replay tests/golden/*.npz (written by oracle/gen_golden.py from the real reference)."""
+import glob
+import json
+import os
+
+import numpy as np
+
+from oracle import vq_oracle as O
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+class Golden:
+    def __init__(self, name):
+        self.z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.meta = json.loads(bytes(self.z["meta"]).decode())
+        self.name = name
+
+    def __getitem__(self, k):
+        return self.z[k]
+
+    @property
+    def cfg(self):
+        m = self.meta
+        dim = m["dim"] // m.get("groups", 1)
+        return O.VQConfig(dim=dim, codebook_size=m["codebook_size"], use_cosine_sim=m.get("use_cosine_sim", False),
+                          decay=m.get("decay", 0.8), eps=m.get("eps", 1e-5),
+                          commitment_weight=m.get("commitment_weight", 1.0))
+
+    def state(self, tag, i):
+        return O.CodebookState(self.z[f"{tag}_cb{i}_embed"].copy(), self.z[f"{tag}_cb{i}_embed_avg"].copy(),
+                               self.z[f"{tag}_cb{i}_cluster_size"].copy())
+
+    def states(self, tag):
+        """Codebook states arranged as the oracle entry points expect them."""
+        m = self.meta
+        n = m["n_codebooks"]
+        flat = [self.state(tag, i) for i in range(n)]
+        if m["kind"] == "vq":
+            return flat[0]
+        Q = m["num_quantizers"]
+        if m["kind"] == "rvq":
+            return [flat[0]] * Q if m["shared_codebook"] else flat
+        G = m["groups"]
+        if m["shared_codebook"]:
+            return [[flat[g]] * Q for g in range(G)]
+        return [flat[g * Q:(g + 1) * Q] for g in range(G)]
+
+    def flat_states(self, states):
+        m = self.meta
+        if m["kind"] == "vq":
+            return [states]
+        if m["kind"] == "rvq":
+            return [states[0]] if m["shared_codebook"] else list(states)
+        out = []
+        for g in states:
+            out += [g[0]] if m["shared_codebook"] else list(g)
+        return out
+
+
+def near_tie_rows(x, embed, cosine, tol=2e-6):
+    """Rows whose two best float64 scores are within fp32 rounding noise of each other."""
+    _, gap = O.top2_gap_f64(x, embed, cosine)
+    return gap < tol

@@ -1,0 +1,76 @@
+"""The numpy oracle must reproduce every golden fixture generated from the real reference.
+
+Bar: indices identical except on rows the reference itself resolves inside fp32 rounding noise
+(float64 top-2 gap < 2e-6 relative; counted and bounded); values within 1e-5 (fp32) / one bf16 ulp.
+"""
+import numpy as np
+import pytest
+
+from golden_util import Golden, golden_names, near_tie_rows
+from oracle import vq_oracle as O
+
+
+def run_oracle(g, step, states, faithful=False):
+    m, cfg = g.meta, g.cfg
+    x = g[f"s{step}_x"]
+    training = m["steps"][step] == "train"
+    if m["kind"] == "vq":
+        q, ind, loss, loss32 = O.vq_forward(x, m["dtype"], states, cfg, training=training, faithful=faithful)
+    elif m["kind"] == "rvq":
+        q, ind, loss, loss32 = O.rvq_forward(x, m["dtype"], states, cfg, shared_codebook=m["shared_codebook"],
+                                              training=training, faithful=faithful)
+    else:
+        q, ind, loss, loss32 = O.grouped_rvq_forward(x, m["dtype"], states, cfg, shared_codebook=m["shared_codebook"],
+                                                      training=training, faithful=faithful)
+    return q, ind, loss, loss32
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("faithful", [False, True])
+def test_oracle_matches_reference(name, faithful):
+    g = Golden(name)
+    m = g.meta
+    states = g.states("s0_pre")
+    vtol = 1e-5 if m["dtype"] == "fp32" else 8e-3
+    for step in range(len(m["steps"])):
+        q, ind, loss, _ = run_oracle(g, step, states, faithful)
+        ref_ind = g[f"s{step}_indices"]
+        mism = ind != ref_ind
+        if m["kind"] == "vq" and mism.any():
+            # every disagreement must be a reference-internal near tie
+            pre = g.state("s0_pre", 0) if step == 0 else g.state(f"s{step - 1}_post", 0)
+            x = O.cast_like(g[f"s{step}_x"], m["dtype"]).reshape(-1, m["dim"])
+            if m.get("use_cosine_sim"):
+                x = O.l2norm(x, m["dtype"])
+            tie = near_tie_rows(x, pre.embed, m.get("use_cosine_sim", False)).reshape(mism.shape)
+            assert not (mism & ~tie).any(), f"{name} step {step}: non-tie index mismatch"
+        if "coldinit" not in name:
+            assert mism.sum() == 0, f"{name} step {step}: {mism.sum()} index mismatches"
+        else:
+            assert mism.mean() < 0.02
+            # make the later comparisons meaningful: continue from the reference's state
+            states = g.states(f"s{step}_post")
+            continue
+        np.testing.assert_allclose(q, g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss, g[f"s{step}_loss"], rtol=1e-5 if m["dtype"] == "fp32" else 8e-3, atol=1e-7)
+        for i, st in enumerate(g.flat_states(states)):
+            ref = g.state(f"s{step}_post", i)
+            np.testing.assert_allclose(st.cluster_size, ref.cluster_size, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(st.embed_avg, ref.embed_avg, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(st.embed, ref.embed, rtol=1e-5, atol=1e-5)
+
+
+def test_bf16_round_matches_torch():
+    import torch
+    a = np.random.default_rng(0).standard_normal(100000).astype(np.float32) * 37.0
+    ref = torch.from_numpy(a).bfloat16().float().numpy()
+    assert np.array_equal(O.bf16_round(a), ref)
+
+
+def test_decode_invariant():
+    """tests/test_readme.py:74-103 of the reference: sum of gathered codes == quantized_out."""
+    g = Golden("rvq_separate_fp32")
+    states = g.states("s0_pre")
+    q, ind, _, _ = O.rvq_forward(g["s0_x"], "fp32", states, g.cfg, training=False)
+    out = O.rvq_output_from_indices([s.embed for s in states], ind)
+    np.testing.assert_allclose(out, q, atol=1e-5)
