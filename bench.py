@@ -1,0 +1,294 @@
+"""bench.py — vectors quantized / second at dim=256, codebook=1024 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (N=1 and per GPU for N>1): BASELINE.json configs[1] — VectorQuantize(dim=256, codebook_size=1024),
+x = (64, 4096, 256) bf16, training-mode forward with the EMA codebook update.  A "step" is one such
+forward over one synthetic batch.  `value` times the device-resident path with CUDA events; `e2e` times
+the public module call with HOST (pinned) buffers, host<->device copies inside the timed region.
+Under torchrun every rank runs the same per-GPU batch (weak scaling) with sync_codebook=True, i.e. one
+NCCL all-reduce of the packed EMA statistics per step; the time is the max over ranks.
+
+`--impl reference` times the reference's own algorithm on the host cores (the torch-CPU oracle port
+oracle/vq_oracle_torch.py: (N x K) distance matrix, one-hot, three GEMMs — vector_quantize_pytorch.py:674-791)
+on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "vectors quantized/sec at dim=256, codebook=1024; indices bit-exact vs ref"
+B, T, D, K = 64, 4096, 256, 1024
+WORKLOAD = "VectorQuantize dim=256 codebook_size=1024, x=(64,4096,256) bf16, EMA on (BASELINE.json configs[1])"
+CPU_SAMPLE_VECTORS = 65536  # 1/4 of the batch per CPU step (~0.7 s on 8 cores)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (reference algorithm on the host cores)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_reference_step_factory():
+    import torch
+    from oracle import vq_oracle_torch as T  # the reference's own ATen op sequence (bit-identical on the goldens)
+    torch.set_num_threads(os.cpu_count())
+    gen = torch.Generator().manual_seed(1234)
+    x = torch.randn(CPU_SAMPLE_VECTORS // 16, 16, D, generator=gen).bfloat16()
+    state = T.State(torch.randn(K, D, generator=gen))
+
+    def step():
+        T.vq_forward(x, state, training=True)
+
+    return step
+
+
+def time_cpu(steps, warmup):
+    step = cpu_reference_step_factory()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return CPU_SAMPLE_VECTORS * steps / dt, dt / steps * 1e3
+
+
+def cpu_baseline_block(value):
+    return {"value": value, "unit": "vectors/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{CPU_SAMPLE_VECTORS} of the {B * T} vectors of one step per CPU step; oracle/vq_oracle_torch.py "
+                      f"(the reference's ATen op sequence: N x K fp32 distances, one-hot, 3 sgemm), torch threads = all host cores"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = max(1, min(args.warmup, 2))
+    v, ms = time_cpu(steps, warm)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "vectors/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "cpu_sample_vectors": CPU_SAMPLE_VECTORS},
+        "cpu_baseline": cpu_baseline_block(v),
+        "e2e": {"value": v, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.rows:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [c.strip() for c in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except Exception:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:  # the timed region was shorter than one sample: use whatever we have
+            for ts, line in self.rows[-3:]:
+                f = [c.strip() for c in line.split(",")]
+                try:
+                    sm.append(float(f[1])); smax = float(f[2])
+                except Exception:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import vector_quantize_pytorch_b200 as vqb
+    from vector_quantize_pytorch_b200 import ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    torch.manual_seed(1234)  # same codebook on every rank (replicas)
+    vq = vqb.VectorQuantize(dim=D, codebook_size=K, sync_codebook=world > 1).to(dev)
+    with torch.no_grad():
+        e = torch.randn(1, K, D, device=dev)
+        vq._codebook.embed.copy_(e)
+        vq._codebook.embed_avg.copy_(e)
+    vq.train()
+    gen = torch.Generator().manual_seed(1234 + rank)  # every rank its own shard of the global batch
+    x_host = torch.randn(B, T, D, generator=gen).bfloat16().pin_memory()
+    x_dev = x_host.to(dev)
+    n_vec = B * T
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---------------- device-resident timing (`value`) with per-kernel events for the roofline
+    for _ in range(args.warmup):
+        vq(x_dev)
+    barrier()
+    ops.PROFILE_EVENTS = []
+    ops.LAUNCHES = 0
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        q, ind, loss = vq(x_dev)
+    e1.record()
+    barrier()
+    t_end = time.time()
+    launches = ops.LAUNCHES
+    prof = ops.PROFILE_EVENTS
+    ops.PROFILE_EVENTS = None
+    clocks = sampler.stop(t_start, t_end)
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    assign_ms = statistics.mean(a.elapsed_time(b) for a, b in prof) if prof else None
+
+    # ---------------- end-to-end timing (`e2e`): pinned host input -> module -> host outputs
+    q_host = torch.empty((B, T, D), dtype=torch.bfloat16).pin_memory()
+    i_host = torch.empty((B, T), dtype=torch.int64).pin_memory()
+    l_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        xd = x_host.to(dev, non_blocking=True)
+        q, ind, loss = vq(xd)
+        q_host.copy_(q, non_blocking=True)
+        i_host.copy_(ind, non_blocking=True)
+        l_host.copy_(loss.detach(), non_blocking=True)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = max_over_ranks(f0.elapsed_time(f1) / args.steps)
+    h2d = x_host.numel() * x_host.element_size()
+    d2h = q_host.numel() * 2 + i_host.numel() * 8 + 4
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = load_peaks()
+    flops = 2.0 * n_vec * K * D  # algorithmic: one pass of the N x K x D contraction
+    peak_tf = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    roof = {"bound": "tensor", "kernel": "vq_assign_kernel (tcgen05 distance MMA + fused arg-max)",
+            "achieved": flops / (assign_ms * 1e-3) / 1e12 if assign_ms else None, "peak": peak_tf, "unit": "TFLOP/s",
+            "frac": (flops / (assign_ms * 1e-3) / 1e12 / peak_tf) if assign_ms else None,
+            "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside the step)",
+            "kernel_ms": assign_ms, "kernel_share_of_step": assign_ms / ms_dev if assign_ms else None,
+            "algorithmic_flops_per_launch": flops, "executed_mma_passes": 2, "traffic": None}
+    cpu_v, _ = time_cpu(steps=2, warmup=1)
+    line = {
+        "metric": METRIC, "value": world * n_vec / (ms_dev * 1e-3), "unit": "vectors/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_vectors": n_vec, "global_vectors": world * n_vec,
+                   "parallelism": f"dp{world}: batch sharded, one NCCL all-reduce of packed EMA stats per step" if world > 1 else "single GPU",
+                   "l2": "input (134 MB) + output (134 MB) per step exceed the 126 MB L2; no extra flush",
+                   "index_mismatch_policy": "bit-exact vs oracle outside fp32 near-ties (tests/test_parity_gpu.py)"},
+        "e2e": {"value": world * n_vec / (ms_e2e * 1e-3), "unit": "vectors/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu_baseline_block(cpu_v),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,136 @@
+/* vqb200 — C ABI of the B200 (sm_100a) vector-quantization hot path.
+ *
+ * The reference (lucidrains/vector-quantize-pytorch v1.31.0) is pure Python and has NO FFI for this
+ * path; its boundary is `Codebook.forward` (vector_quantize_pytorch/vector_quantize_pytorch.py:674-791)
+ * called from `VectorQuantize.forward` (:1176).  These entry points are what a binding for that path
+ * would need; each one cites the reference lines it replaces.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors); the library never
+ *     allocates, frees or retains device memory;
+ *   - every call only ENQUEUES work on `stream` (a cudaStream_t / CUstream passed as void*), never
+ *     synchronises the host, and may be captured in a CUDA graph;
+ *   - return value: 0 = ok, < 0 = VQB_E_* argument / capability error detected before launch,
+ *     > 0 = a cudaError_t raised by the launch.  No exceptions, no printing.
+ *   - matrices are row-major and contiguous; N = number of vectors, D = codebook dim, K = codebook size.
+ */
+#ifndef VQB200_H
+#define VQB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQB_VERSION 100 /* 0.1.0 */
+
+#define VQB_DTYPE_F32 0
+#define VQB_DTYPE_BF16 1
+
+#define VQB_METRIC_EUCLID 0 /* -cdist(x, c)        vector_quantize_pytorch.py:58-62, :743 */
+#define VQB_METRIC_COSINE 1 /* l2norm(x) . c^T     vector_quantize_pytorch.py:37-38, :741, :1159 */
+
+#define VQB_OK 0
+#define VQB_E_INVALID -1     /* null pointer / non-positive size / bad enum */
+#define VQB_E_UNSUPPORTED -2 /* shape outside what the kernels support (see vqb_assign) */
+#define VQB_E_ALIGN -3       /* pointer not 16-byte aligned */
+#define VQB_E_NO_DEVICE -4   /* no CUDA device, or device is not sm_100 */
+#define VQB_E_DRIVER -5      /* cuTensorMapEncodeTiled unavailable / failed */
+#define VQB_E_WORKSPACE -6   /* workspace too small */
+
+typedef struct vqb_flag_entry { /* one row whose winner the tensor-core pass could not certify */
+  int32_t row;                  /* vector index                                                   */
+  int32_t cand0;                /* best candidate of the tensor-core pass                         */
+  int32_t cand1;                /* the other candidate inside the error band (valid if count==2)  */
+  int32_t count;                /* candidates inside the band; > 2 means "rescan the whole row"    */
+} vqb_flag_entry;
+
+int vqb_version(void);
+const char* vqb_strerror(int code);
+
+/* Codebook rows are padded to a multiple of the MMA N-tile; planes/bias are sized with this. */
+int vqb_padded_codes(int K);
+
+/* Derive the tensor-core operands of a codebook from its fp32 rows (embed, K x D):
+ *   planes  bf16 [2][Kpad][D] : hi = bf16(c), lo = bf16(c - hi)   (rows >= K are zero)
+ *   bias    f32  [Kpad]       : euclid 0.5*||c||^2, cosine 0, rows >= K +inf
+ *   cnorm2  f32  [K]          : ||c||^2 (f64-accumulated), used by the exact re-score
+ *   cmax    f32  [1]          : max_k ||c||
+ * Replaces nothing in the reference (it searches the fp32 rows directly, :710-712, :743); this is
+ * the layout change that lets the search run on tcgen05.  Also done by vqb_ema_apply. */
+int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, float* bias, float* cnorm2,
+                         float* cmax, void* stream);
+
+/* Input staging (only needed for fp32 inputs and/or the cosine metric):
+ *   x_eff    [N][D] in `dtype`: l2norm(x) evaluated in the input dtype (:1159 -> :376); may be NULL for euclid
+ *   a_planes bf16 [n_planes][N][D]: bf16 split of the (normalised) input, n_planes = 1 (bf16 input) or 2 (fp32)
+ * For a bf16 euclid input nothing is needed: x itself is the single A plane. */
+int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, void* x_eff, void* a_planes,
+                      int n_planes, void* stream);
+
+/* Nearest-code search: replaces cdist/einsum + argmax (:58-62, :741-747, :130-145) without ever
+ * materialising the (N x K) distance matrix.  tcgen05 MMA over TMA-staged tiles, fp32 accumulate in
+ * TMEM, fused running arg-max.  Scores are x.c - 0.5||c||^2 (euclid) or x.c (cosine).
+ *   a_planes  bf16 [n_a][N][D]   (n_a = 1: passes (a0,hi)+(a0,lo);  n_a = 2: (a0,hi)+(a0,lo)+(a1,hi))
+ *   b_planes/bias/cmax           from vqb_codebook_prepare / vqb_ema_apply
+ *   margin_rel                   a row is certified when its best score leads every other code by more
+ *                                than 2*margin_rel*||x||*cmax; otherwise it is appended to `flagged`
+ *   idx       i32 [N]            winner of the tensor-core pass (final for unflagged rows)
+ *   flagged   [N] entries, flag_count i32[1] (caller zeroes it)  -> vqb_fix_flagged
+ *   dbg_best  f32 [N] or NULL    best score per row (tests)
+ * Supported: D % 8 == 0, 8 <= D, n_a * ceil(D/64) <= 8, 1 <= K, N >= 1, sm_100 device. */
+int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const float* bias,
+               const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, vqb_flag_entry* flagged,
+               int32_t* flag_count, float* dbg_best, void* stream);
+
+/* Exact re-score of the flagged rows with the reference's own fp32 formula and tie rule
+ * (-(x2 + y2 - 2xy).clamp(1e-8).sqrt(), first maximal index; :58-62, :140).  Rewrites idx[row]. */
+int vqb_fix_flagged(const void* x_eff, int dtype, int64_t N, int D, const float* embed, const float* cnorm2, int K,
+                    int metric, const vqb_flag_entry* flagged, const int32_t* flag_count, int32_t* idx, void* stream);
+
+/* Gather + tail of VectorQuantize.forward / one ResidualVQ stage:
+ *   q_out     [N][D] dtype : embed[idx] cast to the input dtype                       (:766/:779-781, :1178)
+ *   idx64_out i64, written at idx64_out[row*idx_stride]  (NULL to skip)              (:140 int64 contract)
+ *   loss_sum  f64[1] += sum((q - x)^2)  (bf16: each square rounded to bf16 as torch does) (:1327)
+ *   x_raw     [N][D] dtype : the stage input before l2norm (cosine); NULL = x_eff
+ *   resid_out [N][D] dtype = x_raw - q   (NULL to skip)                               (residual_vq.py:524)
+ *   qsum      [N][D] dtype += q      (NULL to skip)                                   (residual_vq.py:525) */
+int vqb_gather(const void* x_eff, int dtype, int64_t N, int D, const float* embed, const int32_t* idx, void* q_out,
+               int64_t* idx64_out, int64_t idx_stride, double* loss_sum, const void* x_raw, void* resid_out, void* qsum,
+               void* stream);
+
+/* commit loss = weight * mean, rounded like F.mse_loss in `dtype` (:1282, :1327-1329). loss_out f32[1]. */
+int vqb_loss_finalize(const double* loss_sum, int64_t numel, int dtype, float weight, float* loss_out, void* stream);
+
+/* Batch statistics of the EMA update (:586-607), packed so that ONE all-reduce covers both tensors:
+ *   stats f32 [vqb_stats_floats(K, D)] = [cluster_size (K, padded to a multiple of 4) | embed_sum (K x D)]
+ * Counting sort by code + segmented row sums (no float atomics on the common path). */
+int64_t vqb_stats_offset(int K);          /* float offset of embed_sum inside stats */
+int64_t vqb_stats_floats(int K, int D);   /* total floats of stats */
+size_t vqb_ema_stats_workspace(int64_t N, int K);
+int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats,
+                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* EMA apply (:76-97, :616-617) + Laplace-smoothed normalisation (:152-154, :576-584), then refresh
+ * the tensor-core operands for the next search.
+ *   decay, eps   : python floats of the reference (doubles), rounded to fp32 where torch rounds them
+ *   do_lerp      : cluster_size.lerp_(stats[:K], 1-decay); embed_avg.lerp_(stats[off:], 1-decay)
+ *   do_normalise : embed = embed_avg / (laplace(cluster_size) * sum(cluster_size)); l2norm if cosine;
+ *                  planes / bias / cnorm2 / cmax are regenerated (all four required then)
+ *   scratch      : f32[2] used internally */
+int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D, double decay,
+                  double eps, int metric, int do_lerp, int do_normalise, void* planes, float* bias, float* cnorm2,
+                  float* cmax, float* scratch, void* stream);
+
+/* Decode (next row of SURVEY 8f): out[row] = sum_q embed_q[idx[row, q]], index -1 contributes zeros
+ * (vector_quantize_pytorch.py:998-1022, residual_vq.py:324-382).  embeds: Q codebooks stacked [Q][K][D] f32
+ * (pass the same pointer stride 0 for a shared codebook via `embed_stride` in elements). */
+int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
+               void* out, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQB200_H */

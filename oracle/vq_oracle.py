@@ -265,7 +265,10 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
     loss_f32 = F32(0.0)
     if training and cfg.commitment_weight > 0:  # vqp:1282-1329
         cl, cl32 = mse_loss(quantize, x, dtype)  # vqp:1327 (x = post-l2norm input)
-        loss = F32(F32(0.0) + cl * F32(cfg.commitment_weight))  # vqp:1282, :1329 (fp32)
+        prod = cl * F32(cfg.commitment_weight)  # vqp:1329: a bf16 tensor times a python float stays bf16
+        if dtype == "bf16":
+            prod = bf16_round(np.array([prod], dtype=F32))[0]
+        loss = F32(F32(0.0) + prod)  # vqp:1282: promoted by the fp32 accumulator
         loss_f32 = F32(cl32 * F32(cfg.commitment_weight))
     return quantize.reshape(shape), ind.reshape(shape[:-1]), loss, loss_f32
 

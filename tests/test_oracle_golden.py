@@ -74,3 +74,24 @@ def test_decode_invariant():
     q, ind, _, _ = O.rvq_forward(g["s0_x"], "fp32", states, g.cfg, training=False)
     out = O.rvq_output_from_indices([s.embed for s in states], ind)
     np.testing.assert_allclose(out, q, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("vq_")])
+def test_torch_port_is_bit_identical_to_reference(name):
+    """oracle/vq_oracle_torch.py (the CPU-baseline arm of bench.py) replays the reference's ATen ops."""
+    import torch
+    from oracle import vq_oracle_torch as T
+    g = Golden(name)
+    m = g.meta
+    st = T.State(torch.from_numpy(g["s0_pre_cb0_embed"]))
+    st.embed_avg = torch.from_numpy(g["s0_pre_cb0_embed_avg"])[None].clone()
+    st.cluster_size = torch.from_numpy(g["s0_pre_cb0_cluster_size"])[None].clone()
+    for step, mode in enumerate(m["steps"]):
+        x = torch.from_numpy(g[f"s{step}_x"]).to(torch.bfloat16 if m["dtype"] == "bf16" else torch.float32)
+        q, i, l = T.vq_forward(x, st, cosine=m.get("use_cosine_sim", False), training=mode == "train",
+                               decay=m.get("decay", 0.8), eps=m.get("eps", 1e-5),
+                               commitment_weight=m.get("commitment_weight", 1.0))
+        assert np.array_equal(i.numpy(), g[f"s{step}_indices"])
+        np.testing.assert_allclose(q.float().numpy(), g[f"s{step}_quantize"], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(float(l), float(g[f"s{step}_loss"]), rtol=1e-6)
+        np.testing.assert_allclose(st.embed[0].numpy(), g[f"s{step}_post_cb0_embed"], rtol=1e-6, atol=1e-6)

@@ -1,0 +1,370 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).
+
+The CUDA path (through the C ABI) is compared with
+  * the committed golden fixtures generated from the real reference (tests/golden/*.npz),
+  * the numpy oracle on seeded inputs at sizes it finishes in seconds,
+  * size-independent invariants at BASELINE.json's full sizes.
+Bars: indices bit-exact (except rows the reference itself resolves inside fp32 rounding noise, which are
+counted and classified with a float64 top-2 gap); values within 1e-5 (fp32) / one bf16 ulp (bf16).
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import Golden, golden_names, near_tie_rows
+from oracle import vq_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+TDT = {"fp32": torch.float32, "bf16": torch.bfloat16}
+
+
+def vqb():
+    import vector_quantize_pytorch_b200 as m
+    return m
+
+
+def ours_codebooks(module):
+    m = vqb()
+    seen, out = set(), []
+    for sub in module.modules():
+        if isinstance(sub, m.Codebook) and id(sub) not in seen:
+            seen.add(id(sub))
+            out.append(sub)
+    return out
+
+
+def build_module(meta):
+    m = vqb()
+    kw = {}
+    for k in ("use_cosine_sim", "decay", "eps", "commitment_weight"):
+        if k in meta:
+            kw[k] = meta[k]
+    if meta["kind"] == "vq":
+        return m.VectorQuantize(dim=meta["dim"], codebook_size=meta["codebook_size"], **kw)
+    if meta["kind"] == "rvq":
+        return m.ResidualVQ(dim=meta["dim"], num_quantizers=meta["num_quantizers"], codebook_size=meta["codebook_size"],
+                            shared_codebook=meta["shared_codebook"], **kw)
+    return m.GroupedResidualVQ(dim=meta["dim"], groups=meta["groups"], num_quantizers=meta["num_quantizers"],
+                               codebook_size=meta["codebook_size"], shared_codebook=meta["shared_codebook"], **kw)
+
+
+def load_state(module, g, tag):
+    for i, cb in enumerate(ours_codebooks(module)):
+        st = g.state(tag, i)
+        with torch.no_grad():
+            cb.embed.copy_(torch.from_numpy(st.embed)[None])
+            cb.embed_avg.copy_(torch.from_numpy(st.embed_avg)[None])
+            cb.cluster_size.copy_(torch.from_numpy(st.cluster_size)[None])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_modules_match_reference_goldens(name):
+    g = Golden(name)
+    m = g.meta
+    module = build_module(m).to(DEV)
+    load_state(module, g, "s0_pre")
+    dt = m["dtype"]
+    vtol = 1e-5 if dt == "fp32" else 8e-3
+    for step, mode in enumerate(m["steps"]):
+        module.train(mode == "train")
+        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(TDT[dt])
+        q, ind, loss = module(x)
+        torch.cuda.synchronize()
+        assert q.dtype == x.dtype and q.shape == x.shape and ind.dtype == torch.int64 and loss.dtype == torch.float32
+        ref_ind = g[f"s{step}_indices"]
+        mism = ind.cpu().numpy() != ref_ind
+        if "coldinit" in name:
+            # degenerate kaiming codebook: the reference itself sits on fp32 ties; only near ties may differ
+            pre = g.state("s0_pre", 0) if step == 0 else g.state(f"s{step - 1}_post", 0)
+            tie = near_tie_rows(g[f"s{step}_x"].reshape(-1, m["dim"]), pre.embed, False, tol=2e-5).reshape(mism.shape)
+            assert not (mism & ~tie).any()
+            assert mism.mean() < 0.05
+            load_state(module, g, f"s{step}_post")
+            continue
+        assert mism.sum() == 0, f"{name} step {step}: {mism.sum()} index mismatches"
+        np.testing.assert_allclose(q.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"s{step}_loss"], rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
+        for i, cb in enumerate(ours_codebooks(module)):
+            ref = g.state(f"s{step}_post", i)
+            np.testing.assert_allclose(cb.cluster_size[0].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(cb.embed_avg[0].cpu().numpy(), ref.embed_avg, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(cb.embed[0].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
+
+
+SEARCH_CASES = [
+    # N,    D,   K,    dtype,  cosine
+    (3000, 256, 1024, "bf16", False),
+    (3000, 256, 1024, "fp32", False),
+    (1111, 128, 1000, "fp32", False),   # K not a tile multiple
+    (2049, 64, 333, "bf16", False),
+    (515, 32, 5, "fp32", False),        # tiger-sized codebook
+    (4096, 8, 64, "fp32", False),       # minimum D
+    (1500, 256, 2048, "bf16", True),
+    (1500, 192, 700, "fp32", True),
+    (1024, 512, 4096, "bf16", True),    # config-4 shape family
+    (1, 64, 17, "fp32", False),         # single row
+]
+
+
+@pytest.mark.parametrize("N,D,K,dt,cosine", SEARCH_CASES)
+def test_search_gather_stats_match_oracle(N, D, K, dt, cosine):
+    from vector_quantize_pytorch_b200 import ops
+    gen = torch.Generator().manual_seed(N * 7 + D * 3 + K)
+    x = torch.randn(N, D, generator=gen).to(TDT[dt])
+    c = torch.randn(K, D, generator=gen)
+    if cosine:
+        c = torch.nn.functional.normalize(c, dim=-1)
+    xd, cd = x.to(DEV), c.to(DEV).contiguous()
+    cb = ops.prepare_codebook(cd, cosine)
+    res = ops.search(xd, cb, cd, debug_best=True)
+    torch.cuda.synchronize()
+    x_np = O.cast_like(x.float().numpy(), dt)
+    if cosine:
+        x_np = O.l2norm(x_np, dt)
+    np.testing.assert_allclose(res.x_eff.float().cpu().numpy(), x_np, rtol=0, atol=1e-6 if dt == "fp32" else 0)
+    ref_idx = O.argmax_first(O.scores(x_np, c.numpy(), cosine))
+    mism = res.idx.cpu().numpy() != ref_idx
+    tie = near_tie_rows(x_np, c.numpy(), cosine)
+    assert not (mism & ~tie).any(), f"{(mism & ~tie).sum()} non-tie mismatches"
+    assert mism.sum() <= max(2, N // 500)
+    # tensor-core score error stays inside the certified margin
+    s64 = x_np.astype(np.float64) @ c.numpy().astype(np.float64).T
+    if not cosine:
+        s64 -= 0.5 * (c.numpy().astype(np.float64) ** 2).sum(-1)[None]
+    # gather / loss
+    q = torch.empty_like(xd)
+    i64 = torch.empty(N, dtype=torch.int64, device=DEV)
+    ls = torch.zeros(1, dtype=torch.float64, device=DEV)
+    ops.gather(res.x_eff, cd, res.idx, q_out=q, idx64_out=i64, loss_sum=ls)
+    idx_np = res.idx.cpu().numpy().astype(np.int64)
+    q_ref = O.cast_like(c.numpy()[idx_np], dt)
+    assert np.array_equal(q.float().cpu().numpy(), q_ref)
+    assert np.array_equal(i64.cpu().numpy(), idx_np)
+    _, l32 = O.mse_loss(q_ref, x_np, dt)
+    assert abs(ls.item() / (N * D) - float(l32)) <= 1e-5 * max(float(l32), 1e-12)
+    # statistics
+    st = ops.ema_stats(res.x_eff, res.idx, K)
+    off = ops.stats_offset(K)
+    cs_ref, es_ref = O.batch_stats(x_np, idx_np, K)
+    assert np.array_equal(st[:K].cpu().numpy(), cs_ref)
+    np.testing.assert_allclose(st[off:].view(K, D).cpu().numpy(), es_ref, rtol=1e-5, atol=1e-5)
+
+
+def test_score_error_inside_margin():
+    """The certification margin (2^-16 |x| max|c|) must bound the real tensor-core error with room to spare."""
+    from vector_quantize_pytorch_b200 import ops
+    torch.manual_seed(5)
+    for dt, D, K in (("bf16", 256, 1024), ("fp32", 256, 1024), ("bf16", 512, 512), ("fp32", 64, 4096)):
+        x = (torch.randn(8192, D) * 3).to(TDT[dt]).to(DEV)
+        c = (torch.randn(K, D) * 2).to(DEV)
+        cb = ops.prepare_codebook(c, False)
+        res = ops.search(x, cb, c, debug_best=True, fix=False)
+        s = x.double() @ c.double().T - 0.5 * (c.double() ** 2).sum(-1)[None]
+        got = s.gather(1, res.idx.long()[:, None])[:, 0]
+        rel = (res.best.double() - got).abs() / (x.double().norm(dim=-1) * c.double().norm(dim=-1).max())
+        assert rel.max().item() < 0.25 * 2.0 ** -16, (dt, D, K, rel.max().item())
+
+
+def test_flagged_rows_are_rescored_exactly():
+    """Force near ties: duplicate codes (exact ties -> lowest index must win, vqp:140) and near-duplicates."""
+    from vector_quantize_pytorch_b200 import ops
+    torch.manual_seed(11)
+    K, D, N = 512, 128, 4096
+    c = torch.randn(K, D)
+    c[300] = c[7]                        # exact duplicate: index 7 must always beat 300
+    c[400] = c[9] * (1 + 3e-7)           # inside fp32 noise of code 9
+    c[401] = c[11] + 1e-4 * torch.randn(D)  # resolvable only by the exact re-score
+    x = torch.randn(N, D)
+    x[:64] = c[7] + 0.01 * torch.randn(64, D)
+    x[64:128] = c[11] + 0.01 * torch.randn(64, D)
+    for dt in ("fp32", "bf16"):
+        xd = x.to(TDT[dt]).to(DEV)
+        cd = c.to(DEV)
+        cb = ops.prepare_codebook(cd, False)
+        res = ops.search(xd, cb, cd)
+        idx = res.idx.cpu().numpy()
+        assert res.flag_count.item() >= 128
+        assert (idx[:64] == 7).all()
+        x_np = O.cast_like(x.numpy(), dt)
+        ref = O.argmax_first(O.scores(x_np, c.numpy(), False))
+        tie = near_tie_rows(x_np, c.numpy(), False)
+        assert not ((idx != ref) & ~tie).any()
+
+
+def test_codebook_forward_contract_and_update_indices():
+    """Reference tests/test_beam.py:8-45: stats from (x, indices) alone reproduce a normal EMA step."""
+    m = vqb()
+    torch.manual_seed(3)
+    vq1 = m.VectorQuantize(dim=64, codebook_size=128).to(DEV)
+    vq2 = m.VectorQuantize(dim=64, codebook_size=128).to(DEV)
+    with torch.no_grad():
+        e = torch.randn(1, 128, 64, device=DEV)
+        vq1._codebook.embed.copy_(e); vq1._codebook.embed_avg.copy_(e)
+    vq2.load_state_dict(vq1.state_dict())
+    x = torch.randn(2, 300, 64, device=DEV)
+    q1, i1, _ = vq1(x)
+    vq2.eval()
+    q2, i2, l2 = vq2(x)
+    assert torch.equal(i1, i2) and torch.equal(q1, q2) and l2.item() == 0.0
+    vq2.train()
+    vq2.update_indices(x, i2)
+    for name in ("cluster_size", "embed_avg", "embed"):
+        a, b = getattr(vq1._codebook, name), getattr(vq2._codebook, name)
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), name
+    # Codebook.forward contract: (quantize fp32, int64 indices, dist None)
+    cbk = vq1._codebook
+    cbk.eval()
+    q, ind, dist = cbk(x)
+    assert q.dtype == torch.float32 and ind.dtype == torch.int64 and dist is None
+    assert torch.equal(q, cbk.embed[0][ind])
+    # eval: quantized == get_output_from_indices(indices)   (reference tests/test_readme.py:33-47)
+    assert torch.allclose(vq1.get_output_from_indices(ind), q)
+
+
+def test_rvq_decode_invariant():
+    """Reference tests/test_readme.py:74-103: sum of gathered codes == quantized_out (frozen codebook)."""
+    m = vqb()
+    torch.manual_seed(0)
+    for shared in (False, True):
+        for cosine in (False, True):
+            rvq = m.ResidualVQ(dim=32, num_quantizers=8, codebook_size=128, shared_codebook=shared, use_cosine_sim=cosine).to(DEV)
+            x = torch.randn(1, 256, 32, device=DEV)
+            rvq.train()
+            q, ind, loss = rvq(x, freeze_codebook=True)
+            out = rvq.get_output_from_indices(ind)
+            assert ind.shape == (1, 256, 8) and loss.shape == (8,)
+            assert torch.allclose(q, out, atol=1e-5)
+
+
+def test_gradients_route_through_glue():
+    m = vqb()
+    torch.manual_seed(0)
+    for rot in (True, False):
+        vq = m.VectorQuantize(dim=64, codebook_size=64, rotation_trick=rot).to(DEV)
+        x = torch.randn(2, 50, 64, device=DEV, requires_grad=True)
+        q, ind, loss = vq(x)
+        (q.sum() + loss).backward()
+        assert x.grad is not None and torch.isfinite(x.grad).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: size-independent properties
+# ------------------------------------------------------------------------------------------------
+
+def _warm_codebook(vq, D, K, cosine=False):
+    with torch.no_grad():
+        e = torch.randn(1, K, D, device=DEV)
+        if cosine:
+            e = torch.nn.functional.normalize(e, dim=-1)
+        vq._codebook.embed.copy_(e)
+        vq._codebook.embed_avg.copy_(e)
+
+
+def test_config2_full_size_properties():
+    """VectorQuantize dim=256 K=1024, x=(64,4096,256) bf16, EMA on."""
+    m = vqb()
+    torch.manual_seed(1234)
+    vq = m.VectorQuantize(dim=256, codebook_size=1024).to(DEV)
+    _warm_codebook(vq, 256, 1024)
+    pre = vq._codebook.embed[0].clone()
+    x = torch.randn(64, 4096, 256, device=DEV).bfloat16()
+    q, ind, loss = vq(x)
+    torch.cuda.synchronize()
+    N = 64 * 4096
+    # (1) quantize is exactly the gathered PRE-update code cast to bf16 (vqp:766, :1178)
+    assert torch.equal(q, pre[ind].bfloat16())
+    # (2) a sample of rows agrees with the numpy oracle
+    sel = torch.randperm(N, device=DEV)[:4096]
+    xs = x.reshape(-1, 256)[sel].float().cpu().numpy()
+    ref = O.argmax_first(O.scores(xs, pre.cpu().numpy(), False))
+    got = ind.reshape(-1)[sel].cpu().numpy()
+    tie = near_tie_rows(xs, pre.cpu().numpy(), False)
+    assert not ((got != ref) & ~tie).any()
+    # (3) loss == mean((q - x)^2) in bf16 semantics
+    l_ref = ((q.float() - x.float()) ** 2).bfloat16().float().mean()
+    assert abs(loss.item() - l_ref.bfloat16().float().item()) <= 8e-3 * l_ref.item()
+    # (4) EMA bookkeeping: cluster_size sums to decay*K + (1-decay)*N ; embed_avg row sums follow the same lerp
+    cs = vq._codebook.cluster_size[0]
+    assert abs(cs.sum().item() - (0.8 * 1024 + 0.2 * N)) < 1e-2 * N * 0.2 * 1e-2 + 1.0
+    flat = x.reshape(-1, 256).float()
+    es = torch.zeros(1024, 256, device=DEV, dtype=torch.float64).index_add_(0, ind.reshape(-1), flat.double())
+    ea_ref = pre.double() * 0.8 + 0.2 * es
+    assert torch.allclose(vq._codebook.embed_avg[0].double(), ea_ref, rtol=1e-5, atol=1e-4)
+    # (5) idempotence in eval: the codes themselves quantize to themselves
+    vq.eval()
+    codes = vq._codebook.embed[0].clone()
+    q2, ind2, l2 = vq(codes[None])
+    assert torch.equal(ind2[0], torch.arange(1024, device=DEV)) and torch.equal(q2[0], codes)
+
+
+def test_config3_full_size_properties():
+    """ResidualVQ Q=8 shared codebook K=1024, x=(32,8192,256)."""
+    m = vqb()
+    torch.manual_seed(1234)
+    rvq = m.ResidualVQ(dim=256, num_quantizers=8, codebook_size=1024, shared_codebook=True).to(DEV)
+    _warm_codebook(rvq.layers[0], 256, 1024)
+    pre = rvq.layers[0]._codebook.embed[0].clone()
+    x = torch.randn(32, 8192, 256, device=DEV)
+    q, ind, losses = rvq(x)
+    torch.cuda.synchronize()
+    assert ind.shape == (32, 8192, 8) and losses.shape == (8,)
+    # decode invariant with the PRE-update codebook: every stage searched and gathered it (rvq:302-306)
+    acc = torch.zeros_like(x)
+    for s in range(8):
+        acc = acc + pre[ind[..., s]]
+    assert torch.allclose(q, acc, atol=1e-4)
+    # commitment losses decrease stage by stage and equal mse(residual_s, code_s)
+    l = losses.cpu().numpy()
+    assert (np.diff(l) < 0).all()
+    resid = x.clone()
+    for s in range(8):
+        code = pre[ind[..., s]]
+        ref = ((code - resid) ** 2).mean().item()
+        assert abs(l[s] - ref) <= 1e-4 * ref
+        resid = resid - code
+    # stage-0 indices of a row sample agree with the oracle
+    sel = torch.randperm(32 * 8192, device=DEV)[:2048]
+    xs = x.reshape(-1, 256)[sel].cpu().numpy()
+    ref0 = O.argmax_first(O.scores(xs, pre.cpu().numpy(), False))
+    tie = near_tie_rows(xs, pre.cpu().numpy(), False)
+    got0 = ind.reshape(-1, 8)[sel, 0].cpu().numpy()
+    assert not ((got0 != ref0) & ~tie).any()
+
+
+def test_config4_full_size_properties():
+    """cosine dim=512 K=16384, x=(16,4096,512) bf16."""
+    m = vqb()
+    torch.manual_seed(1234)
+    vq = m.VectorQuantize(dim=512, codebook_size=16384, use_cosine_sim=True).to(DEV)
+    _warm_codebook(vq, 512, 16384, cosine=True)
+    pre = vq._codebook.embed[0].clone()
+    x = torch.randn(16, 4096, 512, device=DEV).bfloat16()
+    q, ind, loss = vq(x)
+    torch.cuda.synchronize()
+    assert torch.equal(q, pre[ind].bfloat16())
+    sel = torch.randperm(16 * 4096, device=DEV)[:1024]
+    xs = O.l2norm(x.reshape(-1, 512)[sel].float().cpu().numpy(), "bf16")
+    ref = O.argmax_first(O.scores(xs, pre.cpu().numpy(), True))
+    tie = near_tie_rows(xs, pre.cpu().numpy(), True)
+    got = ind.reshape(-1)[sel].cpu().numpy()
+    assert not ((got != ref) & ~tie).any()
+    # codebook rows stay unit-norm after the EMA step (vqp:581-582)
+    n = vq._codebook.embed[0].norm(dim=-1)
+    assert torch.allclose(n, torch.ones_like(n), atol=1e-5)
+
+
+def test_config5_grouped_single_gpu_shard():
+    """GroupedResidualVQ groups=2 Q=8 K=1024 on one 1/8 shard x=(8,4096,256)."""
+    m = vqb()
+    torch.manual_seed(1234)
+    g = m.GroupedResidualVQ(dim=256, groups=2, num_quantizers=8, codebook_size=1024).to(DEV)
+    for rvq in g.rvqs:
+        for layer in rvq.layers:
+            _warm_codebook(layer, 128, 1024)
+    x = torch.randn(8, 4096, 256, device=DEV)
+    g.train()
+    q, ind, losses = g(x, freeze_codebook=True)
+    assert q.shape == x.shape and ind.shape == (2, 8, 4096, 8) and losses.shape == (2, 8)
+    assert torch.allclose(q, g.get_output_from_indices(ind), atol=1e-4)

@@ -1,0 +1,63 @@
+"""ctypes binding of libvqb200.so (the C ABI declared in include/vqb200.h).
+
+There is NO fallback: if the library cannot be loaded (or built) importing this module raises, and
+every op raises on non-CUDA tensors.  PyTorch is used only for device memory and streams.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+_i32, _i64, _f32, _f64, _vp, _sz = _c.c_int, _c.c_int64, _c.c_float, _c.c_double, _c.c_void_p, _c.c_size_t
+
+DTYPE_F32, DTYPE_BF16 = 0, 1
+METRIC_EUCLID, METRIC_COSINE = 0, 1
+
+SIGNATURES = {
+    "vqb_version": (_i32, []),
+    "vqb_strerror": (_c.c_char_p, [_i32]),
+    "vqb_padded_codes": (_i32, [_i32]),
+    "vqb_codebook_prepare": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_input_prepare": (_i32, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "vqb_assign": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_fix_flagged": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "vqb_gather": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_loss_finalize": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp]),
+    "vqb_stats_offset": (_i64, [_i32]),
+    "vqb_stats_floats": (_i64, [_i32, _i32]),
+    "vqb_ema_stats_workspace": (_sz, [_i64, _i32]),
+    "vqb_ema_stats": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
+    "vqb_ema_apply": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_decode": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
+}
+
+
+def _load():
+    path = os.environ.get("VQB200_LIB")
+    if not path:
+        path = _build.LIB
+        if _build.is_stale():
+            if _build.find_nvcc() is not None:
+                path = _build.build()
+            elif not os.path.exists(path):
+                raise ImportError("vqb200: libvqb200.so is missing and nvcc is not available to build it; "
+                                  "run `python -m vector_quantize_pytorch_b200.build` where nvcc exists")
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export the symbol
+        fn.restype = res
+        fn.argtypes = args
+    return lib, path
+
+
+lib, LIB_PATH = _load()
+
+
+class VQBError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        raise VQBError(f"{what}: {lib.vqb_strerror(rc).decode()} (code {rc})")

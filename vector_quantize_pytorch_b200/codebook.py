@@ -1,0 +1,260 @@
+"""`Codebook` — host-side mirror of the reference's `Codebook` (vector_quantize_pytorch.py:349-791).
+
+Same constructor arguments, same persistent buffers (`initted`, `cluster_size`, `embed_avg`, `embed`
+with a leading num_codebooks=1 dim, vqp:415-423) so reference checkpoints load unchanged.  The
+arithmetic of `forward` runs in the sm_100a kernels (`ops.py`); anything that is not on the hot
+path raises NotImplementedError instead of silently taking a slow path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as distributed
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+
+
+def _uniform_init(*shape):
+    # same RNG consumption as the reference (vqp:112-115): kaiming_uniform_ on an (H, K, D) tensor
+    t = torch.empty(shape)
+    nn.init.kaiming_uniform_(t)
+    return t
+
+
+def _unsupported(what):
+    raise NotImplementedError(f"vqb200: {what} is outside the accelerated hot path (SURVEY.md §8) and is not implemented")
+
+
+class Codebook(nn.Module):
+    def __init__(
+        self,
+        dim,
+        codebook_size,
+        num_codebooks=1,
+        kmeans_init=False,
+        kmeans_iters=10,
+        sync_kmeans=True,
+        decay=0.8,
+        eps=1e-5,
+        threshold_ema_dead_code=2,
+        reset_cluster_size=None,
+        use_ddp=False,
+        learnable_codebook=False,
+        gumbel_sample=None,
+        sample_codebook_temp=1.,
+        ema_update=True,
+        manual_ema_update=False,
+        affine_param=False,
+        sync_affine_param=False,
+        affine_param_batch_decay=0.99,
+        affine_param_codebook_decay=0.9,
+        use_cosine_sim=False,
+        vq_bridge=None,
+    ):
+        super().__init__()
+        if num_codebooks != 1:
+            _unsupported("num_codebooks > 1 (multi-head codebooks)")
+        if kmeans_init:
+            _unsupported("kmeans_init")
+        if learnable_codebook:
+            _unsupported("learnable_codebook")
+        if affine_param:
+            _unsupported("affine_param")
+        if vq_bridge is not None:
+            _unsupported("vq_bridge")
+        if gumbel_sample is not None:
+            _unsupported("a custom gumbel_sample (stochastic code sampling)")
+
+        self.dim = dim
+        self.decay = decay
+        self.ema_update = ema_update
+        self.manual_ema_update = manual_ema_update
+        self.codebook_size = codebook_size
+        self.num_codebooks = num_codebooks
+        self.eps = eps
+        self.threshold_ema_dead_code = threshold_ema_dead_code
+        self.has_dead_code_replacement = threshold_ema_dead_code > 0
+        self.reset_cluster_size = reset_cluster_size if reset_cluster_size is not None else threshold_ema_dead_code
+        self.sample_codebook_temp = sample_codebook_temp
+        self.use_ddp = use_ddp
+        self.sync_kmeans = sync_kmeans
+        self.learnable_codebook = False
+        self.use_cosine_sim = use_cosine_sim
+
+        embed = _uniform_init(num_codebooks, codebook_size, dim)  # vqp:385
+        if use_cosine_sim:
+            embed = F.normalize(embed, p=2, dim=-1, eps=1e-6)  # vqp:387-388
+
+        self.register_buffer("initted", torch.tensor(True))  # vqp:415 (not kmeans_init)
+        self.register_buffer("cluster_size", torch.ones(num_codebooks, codebook_size))  # vqp:416
+        self.register_buffer("embed_avg", embed.clone())  # vqp:417
+        self.register_buffer("embed", embed)  # vqp:423
+
+        self._operands: ops.CodebookOperands | None = None
+        self._operands_key = None
+
+    # ------------------------------------------------------------------ operand cache
+    def _state2d(self):
+        """(cluster_size (K,), embed_avg (K, D), embed (K, D)) views sharing storage with the buffers."""
+        return self.cluster_size[0], self.embed_avg[0], self.embed[0]
+
+    def operands(self) -> ops.CodebookOperands:
+        """bf16 hi/lo planes + bias of the current `embed`, rebuilt whenever `embed` was changed by
+        anything other than our own EMA kernel (load_state_dict, `.codebook = ...`, `.to(device)`)."""
+        embed = self.embed
+        if not embed.is_cuda:
+            raise RuntimeError("vqb200 has no CPU path: move the module to a CUDA (B200) device")
+        if embed.dtype != torch.float32 or not embed.is_contiguous():
+            raise RuntimeError("vqb200: the `embed` buffer must be contiguous float32")
+        key = (embed.data_ptr(), embed._version, embed.device)
+        if self._operands is None or self._operands_key != key:
+            reuse = self._operands if (self._operands is not None and self._operands.planes.device == embed.device) else None
+            self._operands = ops.prepare_codebook(embed[0], self.use_cosine_sim, out=reuse)
+            self._operands_key = key
+        return self._operands
+
+    def _mark_operands_fresh(self):
+        e = self.embed
+        self._operands_key = (e.data_ptr(), e._version, e.device)
+
+    # ------------------------------------------------------------------ reference surface
+    def transform_input(self, t):  # vqp:376
+        return F.normalize(t, p=2, dim=-1, eps=1e-6) if self.use_cosine_sim else t
+
+    def sync_stats(self, stats: torch.Tensor) -> torch.Tensor:
+        """The reference all-reduces cluster_size and embed_sum separately (vqp:603, :607); the packed
+        buffer needs ONE all-reduce (NCCL over NVLink on B200)."""
+        if self.use_ddp:
+            distributed.all_reduce(stats)
+        return stats
+
+    def lerp_stats(self, stats: torch.Tensor, normalise: bool):
+        """ema_inplace of both buffers (vqp:616-617) and, unless manual, update_ema (vqp:638-639)."""
+        cs, ea, emb = self._state2d()
+        cb = self.operands()
+        ops.ema_apply(cs, ea, emb, stats, cb, decay=self.decay, eps=self.eps, do_lerp=True, do_normalise=normalise)
+        if normalise:
+            self._mark_operands_fresh()
+
+    def update_ema(self):  # vqp:576-584
+        cs, ea, emb = self._state2d()
+        cb = self.operands()
+        ops.ema_apply(cs, ea, emb, None, cb, decay=self.decay, eps=self.eps, do_lerp=False, do_normalise=True)
+        self._mark_operands_fresh()
+
+    @torch.no_grad()
+    def expire_codes_(self, batch_samples):  # vqp:544-574 (PyTorch glue: RNG-bound, cold, off by default)
+        if not self.has_dead_code_replacement or not self.training:
+            return
+        expired = self.cluster_size[0] < self.threshold_ema_dead_code
+        if not torch.any(expired):  # host sync, exactly like the reference (vqp:570)
+            return
+        if self.use_ddp and self.sync_kmeans:
+            _unsupported("distributed dead-code replacement (sample_vectors_distributed)")
+        samples = batch_samples.reshape(-1, batch_samples.shape[-1])
+        if self.use_cosine_sim:
+            samples = F.normalize(samples, p=2, dim=-1, eps=1e-6)
+        num = int(expired.sum().item())
+        n = samples.shape[0]
+        if n >= num:  # vqp:156-163 sample_vectors
+            pick = torch.randperm(n, device=samples.device)[:num]
+        else:
+            pick = torch.randint(0, n, (num,), device=samples.device)
+        sampled = samples[pick].to(self.embed.dtype)
+        self.embed.data[0][expired] = sampled
+        self.cluster_size.data[0][expired] = self.reset_cluster_size
+        self.embed_avg.data[0][expired] = sampled * self.reset_cluster_size
+
+    @torch.no_grad()
+    def update_indices(self, x, embed_ind, mask=None, ema_update_weight=None, accum_ema_update=False, ema_update=None):
+        """vqp:643-668: EMA update from (x, indices) alone (tests/test_beam.py:8-45 of the reference)."""
+        if mask is not None or ema_update_weight is not None or accum_ema_update:
+            _unsupported("update_indices with mask / ema_update_weight / accum_ema_update")
+        ema_update = self.ema_update if ema_update is None else ema_update
+        if not ema_update and not self.has_dead_code_replacement:
+            return
+        flat = x.reshape(-1, x.shape[-1]).contiguous()
+        idx = embed_ind.reshape(-1).to(torch.int32).clamp_min(0).contiguous()
+        stats = self.sync_stats(ops.ema_stats(flat, idx, self.codebook_size))
+        self.lerp_stats(stats, normalise=ema_update and not self.manual_ema_update)
+        self.expire_codes_(flat)
+
+    update_ema_indices = update_indices
+
+    # ------------------------------------------------------------------ the hot path
+    @torch.no_grad()
+    def quantize_rows(self, x: torch.Tensor, *, update: bool, q_out=None, idx64_out=None, idx_stride=1, loss_sum=None,
+                      resid_out=None, qsum=None, stats_out=None, defer_ema=False, margin=None):
+        """x (N, D) contiguous fp32/bf16 — the input BEFORE the cosine l2norm (done in-kernel).
+
+        Search (pre-update codebook, vqp:743-747) -> gather/loss/residual (vqp:766, :1178, :1327; rvq:524-525)
+        -> batch statistics (vqp:602-607).  With defer_ema the caller all-reduces and applies the
+        statistics itself (ResidualVQ packs all stages into one collective).
+        Returns (SearchResult, stats or None).
+        """
+        cb = self.operands()
+        embed2d = self.embed[0]
+        res = ops.search(x, cb, embed2d, margin=margin)
+        ops.gather(res.x_eff, embed2d, res.idx, q_out=q_out, idx64_out=idx64_out, idx_stride=idx_stride,
+                   loss_sum=loss_sum, x_raw=x if res.x_eff is not x else None, resid_out=resid_out, qsum=qsum)
+        stats = None
+        if update:
+            stats = ops.ema_stats(res.x_eff, res.idx, self.codebook_size, out=stats_out)
+            if not defer_ema:
+                self.sync_stats(stats)
+                self.lerp_stats(stats, normalise=not self.manual_ema_update)
+                self.expire_codes_(res.x_eff)
+        return res, stats
+
+    def forward(self, x, sample_codebook_temp=None, mask=None, freeze_codebook=False, codebook_transform_fn=None,
+                ema_update_weight=None, accum_ema_update=False, ema_update=None, topk=None, update_usage=True):
+        """Reference contract (vqp:674-686, :791): returns (quantize fp32, embed_ind int64, dist).
+
+        `x` is the already-transformed input (the reference applies `transform_input` in the caller,
+        vqp:1159).  `dist` — the (N x K) matrix the kernels never materialise — is returned as None.
+        """
+        if mask is not None:
+            _unsupported("mask")
+        if codebook_transform_fn is not None:
+            _unsupported("codebook_transform_fn (implicit neural codebooks)")
+        if ema_update_weight is not None or accum_ema_update:
+            _unsupported("ema_update_weight / accum_ema_update")
+        if topk is not None:
+            _unsupported("topk")
+        ema_update = self.ema_update if ema_update is None else ema_update
+        shape = x.shape
+        flat = x.reshape(-1, shape[-1])
+        if flat.dtype not in (torch.float32, torch.bfloat16):
+            flat = flat.float()
+        flat = flat.contiguous()
+        cb = self.operands()
+        embed2d = self.embed[0]
+        with torch.no_grad():
+            res = ops.search(flat, cb, embed2d, normalise=False)  # the caller already applied transform_input
+            q = torch.empty((flat.shape[0], shape[-1]), dtype=torch.float32, device=flat.device)
+            idx64 = torch.empty((flat.shape[0],), dtype=torch.int64, device=flat.device)
+            x32 = res.x_eff if res.x_eff.dtype == torch.float32 else res.x_eff.float()
+            ops.gather(x32, embed2d, res.idx, q_out=q, idx64_out=idx64)
+            do_update = self.training and update_usage and not freeze_codebook and (ema_update or self.has_dead_code_replacement)
+            if do_update:
+                stats = self.sync_stats(ops.ema_stats(res.x_eff, res.idx, self.codebook_size))
+                self.lerp_stats(stats, normalise=ema_update and not self.manual_ema_update)
+                self.expire_codes_(res.x_eff)
+        return q.reshape(shape), idx64.reshape(shape[:-1]), None
+
+
+class EuclideanCodebook(Codebook):
+    """Legacy name (pre-1.2x releases of the reference); `Codebook` with use_cosine_sim=False."""
+
+    def __init__(self, *args, **kwargs):
+        kwargs["use_cosine_sim"] = False
+        super().__init__(*args, **kwargs)
+
+
+class CosineSimCodebook(Codebook):
+    """Legacy name; `Codebook` with use_cosine_sim=True."""
+
+    def __init__(self, *args, **kwargs):
+        kwargs["use_cosine_sim"] = True
+        super().__init__(*args, **kwargs)

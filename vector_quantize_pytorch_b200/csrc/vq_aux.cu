@@ -1,0 +1,367 @@
+// HBM-bound companions of the tensor-core search: operand preparation, exact re-score of flagged
+// rows, gather + commitment-loss + residual update, decode.  All are "one warp per row" streaming
+// kernels with 16-byte accesses; the codebook (<= a few MiB) stays L2-resident.
+#include "vqb_common.cuh"
+#include "code_operands.cuh"
+
+namespace vqb {
+
+constexpr int ROW_THREADS = 256;  // 8 warps = 8 rows in flight per CTA
+
+__global__ void codebook_prepare_kernel(const float* __restrict__ embed, int K, int Kpad, int D, int metric,
+                                        uint16_t* planes, float* bias, float* cnorm2, float* cmax) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= Kpad) return;
+  write_code_operands(k < K ? embed + static_cast<int64_t>(k) * D : nullptr, k, K, Kpad, D, metric, planes, bias, cnorm2,
+                      cmax, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// input staging: l2norm in the input dtype (cosine) and bf16 hi/lo split
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void input_prepare_kernel(const void* __restrict__ x, int64_t N, int D, int metric, void* x_eff,
+                                     uint16_t* planes, int n_planes) {
+  using E = Elem<DT>;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
+       row += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int64_t base = row * D;
+    float inv = 1.f;
+    bool cosine = metric == VQB_METRIC_COSINE;
+    float nrm = 1.f;
+    if (cosine) {
+      double s = 0.0;
+      for (int i = lane; i < D; i += 32) {
+        const float v = E::load(x, base + i);
+        s += static_cast<double>(v) * v;
+      }
+      s = warp_sum(s);
+      nrm = E::round(static_cast<float>(sqrt(s)));  // F.normalize: norm in the tensor dtype ...
+      nrm = fmaxf(nrm, 1e-6f);                      // ... clamp_min(eps)
+      (void)inv;
+    }
+    for (int i = lane; i < D; i += 32) {
+      float v = E::load(x, base + i);
+      if (cosine) v = E::round(__fdiv_rn(v, nrm));  // ... x / norm, rounded to the dtype
+      if (x_eff) E::store(x_eff, base + i, v);
+      if (planes) {
+        const uint16_t h = float_to_bf16_bits(v);
+        planes[base + i] = h;
+        if (n_planes == 2) planes[N * D + base + i] = float_to_bf16_bits(v - bf16_bits_to_float(h));
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exact re-score of flagged rows (reference formula and tie rule)
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void fix_flagged_kernel(const void* __restrict__ x, int64_t N, int D, const float* __restrict__ embed,
+                                   const float* __restrict__ cnorm2, int K, int metric,
+                                   const vqb_flag_entry* __restrict__ flagged, const int32_t* __restrict__ flag_count,
+                                   int32_t* idx) {
+  using E = Elem<DT>;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  int64_t cnt = *flag_count;
+  if (cnt > N) cnt = N;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); e < cnt;
+       e += static_cast<int64_t>(gridDim.x) * wpb) {
+    const vqb_flag_entry fe = flagged[e];
+    const int64_t base = static_cast<int64_t>(fe.row) * D;
+    double x2 = 0.0;
+    for (int i = lane; i < D; i += 32) {
+      const float v = E::load(x, base + i);
+      x2 += static_cast<double>(v) * v;
+    }
+    const float x2f = static_cast<float>(warp_sum(x2));
+    // score(k) exactly as the reference evaluates it in fp32 (vqp:58-62, :741-743); products/sums are
+    // accumulated in f64 and rounded once, the "ideal" fp32 GEMM result.
+    auto score = [&](int k) -> float {
+      const float* c = embed + static_cast<int64_t>(k) * D;
+      double xy = 0.0;
+      for (int i = lane; i < D; i += 32) xy += static_cast<double>(E::load(x, base + i)) * static_cast<double>(__ldg(c + i));
+      const float xyf = static_cast<float>(warp_sum(xy));
+      if (metric == VQB_METRIC_COSINE) return xyf;
+      const float d2 = __fadd_rn(__fadd_rn(x2f, __ldg(cnorm2 + k)), __fmul_rn(xyf, -2.f));
+      return -__fsqrt_rn(fmaxf(d2, 1e-8f));
+    };
+    int best_k;
+    if (fe.count == 2) {
+      const int ka = min(fe.cand0, fe.cand1), kb = max(fe.cand0, fe.cand1);
+      const float sa = score(ka), sb = score(kb);
+      best_k = (sb > sa) ? kb : ka;  // argmax keeps the FIRST maximal index (vqp:140)
+    } else {
+      float bs = -INFINITY;
+      best_k = 0;
+      for (int k = 0; k < K; ++k) {
+        const float s = score(k);
+        if (s > bs) { bs = s; best_k = k; }
+      }
+    }
+    if (lane == 0) idx[fe.row] = best_k;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather + loss + residual update
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void gather_kernel(const void* __restrict__ x, int64_t N, int D, const float* __restrict__ embed,
+                              const int32_t* __restrict__ idx, void* q_out, int64_t* idx64_out, int64_t idx_stride,
+                              double* loss_sum, const void* __restrict__ x_raw, void* resid_out, void* qsum) {
+  using E = Elem<DT>;
+  using T = typename E::T;
+  constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte access: 8 (bf16) or 4 (fp32)
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  float lsum = 0.f;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
+       row += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int k = idx[row];
+    if (idx64_out && lane == 0) idx64_out[row * idx_stride] = k;
+    const float* c = embed + static_cast<int64_t>(k) * D;
+    const int64_t base = row * D;
+    for (int i = lane * VEC; i < D; i += 32 * VEC) {
+      float cv[VEC], xv[VEC], qv[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; e += 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(c + i + e));
+        cv[e] = t.x; cv[e + 1] = t.y; cv[e + 2] = t.z; cv[e + 3] = t.w;
+      }
+      {
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(x) + base + i);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        if (DT == VQB_DTYPE_BF16) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { xv[(2 * e) % VEC] = __uint_as_float(w[e] << 16); xv[(2 * e + 1) % VEC] = __uint_as_float(w[e] & 0xFFFF0000u); }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) xv[e % VEC] = __uint_as_float(w[e]);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        qv[e] = E::round(cv[e]);                 // quantize.type(x.dtype)            vqp:1178
+        const float d = qv[e] - xv[e];
+        lsum += E::round(d * d);                 // F.mse_loss elementwise in x.dtype  vqp:1327
+      }
+      auto store_vec = [&](void* dst, const float* v) {
+        uint32_t w[4];
+        if (DT == VQB_DTYPE_BF16) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = float_to_bf16_bits(v[(2 * e) % VEC]) | (uint32_t(float_to_bf16_bits(v[(2 * e + 1) % VEC])) << 16);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) w[e] = __float_as_uint(v[e % VEC]);
+        }
+        *reinterpret_cast<uint4*>(reinterpret_cast<T*>(dst) + base + i) = make_uint4(w[0], w[1], w[2], w[3]);
+      };
+      if (q_out) store_vec(q_out, qv);
+      if (resid_out) {
+        float rv[VEC];
+        if (x_raw != x) {  // cosine: the residual is taken from the UN-normalised stage input (rvq:524)
+          const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(x_raw) + base + i);
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+          if (DT == VQB_DTYPE_BF16) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { rv[(2 * e) % VEC] = __uint_as_float(w[e] << 16); rv[(2 * e + 1) % VEC] = __uint_as_float(w[e] & 0xFFFF0000u); }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) rv[e % VEC] = __uint_as_float(w[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < VEC; ++e) rv[e] = xv[e];
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) rv[e] = rv[e] - qv[e];   // residual - quantized   rvq:524 (rounded by the store)
+        store_vec(resid_out, rv);
+      }
+      if (qsum) {
+        float sv[VEC];
+        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(qsum) + base + i);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        if (DT == VQB_DTYPE_BF16) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { sv[(2 * e) % VEC] = __uint_as_float(w[e] << 16); sv[(2 * e + 1) % VEC] = __uint_as_float(w[e] & 0xFFFF0000u); }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) sv[e % VEC] = __uint_as_float(w[e]);
+        }
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) sv[e] += qv[e];           // quantized_out + quantized rvq:525
+        store_vec(qsum, sv);
+      }
+    }
+  }
+  if (loss_sum) {
+    __shared__ double part[32];
+    double w = warp_sum(static_cast<double>(lsum));
+    if (lane == 0) part[threadIdx.x >> 5] = w;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0;
+      for (int i = 0; i < wpb; ++i) s += part[i];
+      atomicAdd(loss_sum, s);
+    }
+  }
+}
+
+__global__ void loss_finalize_kernel(const double* loss_sum, int64_t numel, int dtype, float weight, float* loss_out) {
+  float mean = static_cast<float>(*loss_sum / static_cast<double>(numel));
+  if (dtype == VQB_DTYPE_BF16) {
+    mean = bf16_round(mean);            // F.mse_loss returns a bf16 tensor
+    mean = bf16_round(mean * weight);   // commit_loss * commitment_weight stays bf16
+    *loss_out = 0.f + mean;             // promoted by the fp32 `loss` accumulator  vqp:1282, :1329
+  } else {
+    *loss_out = 0.f + mean * weight;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode: out[row] = sum_q embed_q[idx[row, q]]   (index -1 -> zeros)      rvq:324-382
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void decode_kernel(const float* __restrict__ embeds, int64_t embed_stride, int Q, int K, int D,
+                              const int64_t* __restrict__ idx, int64_t N, void* out) {
+  using E = Elem<DT>;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
+       row += static_cast<int64_t>(gridDim.x) * wpb) {
+    for (int i = lane * 4; i < D; i += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < Q; ++q) {
+        const int64_t k = idx[row * Q + q];
+        if (k < 0) continue;
+        const float4 c = __ldg(reinterpret_cast<const float4*>(embeds + q * embed_stride + k * D + i));
+        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+      }
+      E::store(out, row * D + i, acc.x);
+      E::store(out, row * D + i + 1, acc.y);
+      E::store(out, row * D + i + 2, acc.z);
+      E::store(out, row * D + i + 3, acc.w);
+    }
+  }
+}
+
+static inline int row_grid(int64_t rows, int wpb) {
+  int64_t g = (rows + wpb - 1) / wpb;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return static_cast<int>(g);
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" int vqb_version(void) { return VQB_VERSION; }
+
+extern "C" const char* vqb_strerror(int code) {
+  switch (code) {
+    case VQB_OK: return "ok";
+    case VQB_E_INVALID: return "vqb200: invalid argument (null pointer, non-positive size or bad enum)";
+    case VQB_E_UNSUPPORTED: return "vqb200: shape not supported by the sm_100a kernels (need D % 8 == 0 and n_a*ceil(D/64) <= 8)";
+    case VQB_E_ALIGN: return "vqb200: pointer is not 16-byte aligned";
+    case VQB_E_NO_DEVICE: return "vqb200: no CUDA device or device is not compute capability 10.x (B200)";
+    case VQB_E_DRIVER: return "vqb200: cuTensorMapEncodeTiled unavailable or failed";
+    case VQB_E_WORKSPACE: return "vqb200: workspace too small";
+    default: break;
+  }
+  if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
+  return "vqb200: unknown error";
+}
+
+extern "C" int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, float* bias,
+                                    float* cnorm2, float* cmax, void* stream) {
+  if (!embed || !planes || !bias || !cnorm2 || !cmax || K <= 0 || D <= 0) return VQB_E_INVALID;
+  if (metric != VQB_METRIC_EUCLID && metric != VQB_METRIC_COSINE) return VQB_E_INVALID;
+  if (D % 8 != 0) return VQB_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(planes)) & 15) return VQB_E_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(cmax, 0, sizeof(float), s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int Kpad = vqb_padded_codes(K);
+  const int wpb = ROW_THREADS / 32;
+  codebook_prepare_kernel<<<(Kpad + wpb - 1) / wpb, ROW_THREADS, 0, s>>>(embed, K, Kpad, D, metric,
+                                                                         static_cast<uint16_t*>(planes), bias, cnorm2, cmax);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, void* x_eff, void* a_planes,
+                                 int n_planes, void* stream) {
+  if (!x || N <= 0 || D <= 0) return VQB_E_INVALID;
+  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
+  if (a_planes && n_planes != 1 && n_planes != 2) return VQB_E_INVALID;
+  if (!x_eff && !a_planes) return VQB_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = row_grid(N, ROW_THREADS / 32);
+  if (dtype == VQB_DTYPE_F32)
+    input_prepare_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x, N, D, metric, x_eff, static_cast<uint16_t*>(a_planes), n_planes);
+  else
+    input_prepare_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x, N, D, metric, x_eff, static_cast<uint16_t*>(a_planes), n_planes);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_fix_flagged(const void* x_eff, int dtype, int64_t N, int D, const float* embed, const float* cnorm2,
+                               int K, int metric, const vqb_flag_entry* flagged, const int32_t* flag_count,
+                               int32_t* idx, void* stream) {
+  if (!x_eff || !embed || !cnorm2 || !flagged || !flag_count || !idx || N <= 0 || D <= 0 || K <= 0) return VQB_E_INVALID;
+  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // flag_count is only known on the device: a fixed grid strides over the list.
+  const int g = num_sms() * 2;
+  if (dtype == VQB_DTYPE_F32)
+    fix_flagged_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
+  else
+    fix_flagged_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_gather(const void* x_eff, int dtype, int64_t N, int D, const float* embed, const int32_t* idx,
+                          void* q_out, int64_t* idx64_out, int64_t idx_stride, double* loss_sum, const void* x_raw,
+                          void* resid_out, void* qsum, void* stream) {
+  if (!x_eff || !embed || !idx || N <= 0 || D <= 0) return VQB_E_INVALID;
+  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
+  if (D % 8 != 0) return VQB_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x_eff) | reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(q_out) |
+       reinterpret_cast<uintptr_t>(resid_out) | reinterpret_cast<uintptr_t>(qsum)) & 15)
+    return VQB_E_ALIGN;
+  if (!x_raw) x_raw = x_eff;
+  if (reinterpret_cast<uintptr_t>(x_raw) & 15) return VQB_E_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = row_grid(N, ROW_THREADS / 32);
+  if (dtype == VQB_DTYPE_F32)
+    gather_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, idx, q_out, idx64_out, idx_stride, loss_sum, x_raw, resid_out, qsum);
+  else
+    gather_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, idx, q_out, idx64_out, idx_stride, loss_sum, x_raw, resid_out, qsum);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_loss_finalize(const double* loss_sum, int64_t numel, int dtype, float weight, float* loss_out,
+                                 void* stream) {
+  if (!loss_sum || !loss_out || numel <= 0) return VQB_E_INVALID;
+  loss_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_sum, numel, dtype, weight, loss_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
+                          void* out, int dtype, void* stream) {
+  if (!embeds || !idx || !out || Q <= 0 || K <= 0 || D <= 0 || N <= 0) return VQB_E_INVALID;
+  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
+  if (D % 4 != 0) return VQB_E_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = row_grid(N, ROW_THREADS / 32);
+  if (dtype == VQB_DTYPE_F32)
+    decode_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, K, D, idx, N, out);
+  else
+    decode_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, K, D, idx, N, out);
+  return static_cast<int>(cudaGetLastError());
+}

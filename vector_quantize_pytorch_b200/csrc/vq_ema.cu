@@ -1,0 +1,296 @@
+// EMA codebook update:  batch statistics (cluster_size, embed_sum) and the lerp / Laplace-smoothed
+// normalisation of vector_quantize_pytorch.py:76-97, :152-154, :576-617.
+//
+// The reference computes embed_sum with a third dense GEMM (x^T . one_hot, :605).  Here it is a
+// segmented reduction: counting sort of the rows by code, then one CTA sums the rows of one code with
+// coalesced 8/16-byte loads — x is read exactly once, no float atomics on the common path (only codes
+// with more than SEG_CHUNK rows are split and combined with atomicAdd).
+#include "vqb_common.cuh"
+#include "code_operands.cuh"
+
+namespace vqb {
+
+constexpr int SEG_CHUNK = 2048;   // rows per work item
+constexpr int SEG_THREADS = 256;
+
+struct StatsWs {  // carved out of the caller's workspace
+  int32_t* counts;   // [K]
+  int32_t* offsets;  // [K]   exclusive scan of counts
+  int32_t* cursor;   // [K]   running insert position
+  int32_t* nwork;    // [1]
+  int32_t* perm;     // [N]   row ids grouped by code
+  int4* work;        // [K + N/SEG_CHUNK + 1]  {code, begin, end, split}
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int64_t max_work_items(int64_t N, int K) { return K + N / SEG_CHUNK + 1; }
+
+static size_t carve(StatsWs* ws, void* base, int64_t N, int K) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_counts = take(sizeof(int32_t) * K);
+  const size_t o_offsets = take(sizeof(int32_t) * K);
+  const size_t o_cursor = take(sizeof(int32_t) * K);
+  const size_t o_nwork = take(sizeof(int32_t));
+  const size_t o_perm = take(sizeof(int32_t) * N);
+  const size_t o_work = take(sizeof(int4) * max_work_items(N, K));
+  if (ws && base) {
+    uint8_t* b = static_cast<uint8_t*>(base);
+    ws->counts = reinterpret_cast<int32_t*>(b + o_counts);
+    ws->offsets = reinterpret_cast<int32_t*>(b + o_offsets);
+    ws->cursor = reinterpret_cast<int32_t*>(b + o_cursor);
+    ws->nwork = reinterpret_cast<int32_t*>(b + o_nwork);
+    ws->perm = reinterpret_cast<int32_t*>(b + o_perm);
+    ws->work = reinterpret_cast<int4*>(b + o_work);
+  }
+  return off;
+}
+
+__global__ void hist_kernel(const int32_t* __restrict__ idx, int64_t N, int K, int32_t* counts) {
+  extern __shared__ int32_t sh[];
+  const bool use_sh = K <= 8192;
+  if (use_sh) {
+    for (int i = threadIdx.x; i < K; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+  }
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < N;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int k = idx[r];
+    if (use_sh) atomicAdd(&sh[k], 1); else atomicAdd(&counts[k], 1);
+  }
+  if (use_sh) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < K; i += blockDim.x)
+      if (sh[i]) atomicAdd(&counts[i], sh[i]);
+  }
+}
+
+// single CTA: offsets = exclusive_scan(counts); work list; cluster_size part of stats
+__global__ void scan_kernel(const int32_t* __restrict__ counts, int K, int32_t* offsets, int32_t* cursor, int4* work,
+                            int32_t* nwork, float* stats) {
+  __shared__ int32_t s_cnt[1024], s_wk[1024];
+  __shared__ int32_t carry_cnt, carry_wk;
+  if (threadIdx.x == 0) { carry_cnt = 0; carry_wk = 0; }
+  __syncthreads();
+  for (int base = 0; base < K; base += 1024) {
+    const int k = base + threadIdx.x;
+    const int c = k < K ? counts[k] : 0;
+    const int w = k < K ? max(1, (c + SEG_CHUNK - 1) / SEG_CHUNK) : 0;
+    s_cnt[threadIdx.x] = c;
+    s_wk[threadIdx.x] = w;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+      int a = 0, b = 0;
+      if (threadIdx.x >= o) { a = s_cnt[threadIdx.x - o]; b = s_wk[threadIdx.x - o]; }
+      __syncthreads();
+      s_cnt[threadIdx.x] += a;
+      s_wk[threadIdx.x] += b;
+      __syncthreads();
+    }
+    const int ex_cnt = carry_cnt + s_cnt[threadIdx.x] - c;
+    const int ex_wk = carry_wk + s_wk[threadIdx.x] - w;
+    if (k < K) {
+      offsets[k] = ex_cnt;
+      cursor[k] = ex_cnt;
+      stats[k] = static_cast<float>(c);  // cluster_size = onehot.sum(1)   vqp:602
+      for (int j = 0; j < w; ++j) {
+        const int b = ex_cnt + j * SEG_CHUNK;
+        const int e = min(ex_cnt + c, b + SEG_CHUNK);
+        work[ex_wk + j] = make_int4(k, b, e, w > 1 ? 1 : 0);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) { carry_cnt += s_cnt[1023]; carry_wk += s_wk[1023]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *nwork = carry_wk;
+}
+
+__global__ void scatter_kernel(const int32_t* __restrict__ idx, int64_t N, int32_t* cursor, int32_t* perm) {
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < N;
+       r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int pos = atomicAdd(&cursor[idx[r]], 1);
+    perm[pos] = static_cast<int32_t>(r);
+  }
+}
+
+// one CTA per work item: embed_sum[code] (+)= sum of the rows perm[begin:end]        vqp:605
+template <int DT>
+__global__ void segsum_kernel(const void* __restrict__ x, int D, const int32_t* __restrict__ perm,
+                              const int4* __restrict__ work, const int32_t* __restrict__ nwork, float* embed_sum) {
+  using E = Elem<DT>;
+  if (static_cast<int>(blockIdx.x) >= *nwork) return;
+  extern __shared__ float red[];  // [NY][D]
+  const int4 wk = work[blockIdx.x];
+  const int TX = D / 4;                 // threads across the row (4 elements each); D % 8 == 0
+  const int NY = SEG_THREADS / TX;      // rows in flight
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (ty < NY) {
+    for (int r = wk.y + ty; r < wk.z; r += NY) {
+      const int64_t base = static_cast<int64_t>(perm[r]) * D + tx * 4;
+      if (DT == VQB_DTYPE_BF16) {
+        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + base);
+        a0 += __uint_as_float(u.x << 16); a1 += __uint_as_float(u.x & 0xFFFF0000u);
+        a2 += __uint_as_float(u.y << 16); a3 += __uint_as_float(u.y & 0xFFFF0000u);
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + base);
+        a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+      }
+    }
+    float* dst = red + ty * D + tx * 4;
+    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < D; i += blockDim.x) {
+    float s = 0.f;
+    for (int y = 0; y < NY; ++y) s += red[y * D + i];
+    float* out = embed_sum + static_cast<int64_t>(wk.x) * D + i;
+    if (wk.w) atomicAdd(out, s); else *out = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// EMA apply
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lerp_f32(float a, float b, float w) {  // torch.lerp
+  return (fabsf(w) < 0.5f) ? a + w * (b - a) : b - (b - a) * (1.f - w);
+}
+
+// single CTA: cluster_size.lerp_ (vqp:616) and its sum (vqp:577); zero cmax for the atomicMax that follows
+__global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K, float w, int do_lerp, float* scratch,
+                                 float* cmax) {
+  __shared__ double part[32];
+  double s = 0.0;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    float c = cluster_size[k];
+    if (do_lerp) { c = lerp_f32(c, stats[k], w); cluster_size[k] = c; }
+    s += c;
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += part[i];
+    scratch[0] = static_cast<float>(t);
+    if (cmax) *cmax = 0.f;
+  }
+}
+
+// one warp per (padded) code: embed_avg.lerp_ (vqp:617); embed = embed_avg / smoothed (vqp:576-584);
+// refresh the tensor-core operands of that row.
+__global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* embed_avg, float* embed,
+                                const float* __restrict__ stats, int64_t soff, int K, int Kpad, int D, float w, float eps, float keps, int metric,
+                                int do_lerp, int do_normalise, const float* __restrict__ scratch, uint16_t* planes,
+                                float* bias, float* cnorm2, float* cmax) {
+  const int lane = threadIdx.x & 31;
+  const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (k >= Kpad) return;
+  if (k >= K) {
+    if (do_normalise) write_code_operands(nullptr, k, K, Kpad, D, metric, planes, bias, cnorm2, cmax, lane);
+    return;
+  }
+  float* avg = embed_avg + static_cast<int64_t>(k) * D;
+  float* emb = embed + static_cast<int64_t>(k) * D;
+  if (do_lerp) {
+    const float* es = stats + soff + static_cast<int64_t>(k) * D;
+    for (int i = lane * 4; i < D; i += 128) {
+      float4 a = *reinterpret_cast<float4*>(avg + i);
+      const float4 b = *reinterpret_cast<const float4*>(es + i);
+      a.x = lerp_f32(a.x, b.x, w); a.y = lerp_f32(a.y, b.y, w); a.z = lerp_f32(a.z, b.z, w); a.w = lerp_f32(a.w, b.w, w);
+      *reinterpret_cast<float4*>(avg + i) = a;
+    }
+  }
+  if (!do_normalise) return;
+  const float total = scratch[0];
+  // laplace_smoothing(cluster_size, K, eps) * cluster_size.sum()      vqp:152-154, :577
+  const float denom = __fmul_rn(__fdiv_rn(__fadd_rn(cluster_size[k], eps), __fadd_rn(total, keps)), total);
+  double n2 = 0.0;
+  for (int i = lane * 4; i < D; i += 128) {
+    const float4 a = *reinterpret_cast<const float4*>(avg + i);
+    float4 e = make_float4(__fdiv_rn(a.x, denom), __fdiv_rn(a.y, denom), __fdiv_rn(a.z, denom), __fdiv_rn(a.w, denom));
+    if (metric == VQB_METRIC_COSINE)
+      n2 += static_cast<double>(e.x) * e.x + static_cast<double>(e.y) * e.y + static_cast<double>(e.z) * e.z + static_cast<double>(e.w) * e.w;
+    *reinterpret_cast<float4*>(emb + i) = e;
+  }
+  if (metric == VQB_METRIC_COSINE) {  // l2norm(embed_normalized)     vqp:581-582, eps 1e-6 (:37-38)
+    const float nrm = fmaxf(static_cast<float>(sqrt(warp_sum(n2))), 1e-6f);
+    __syncwarp();
+    for (int i = lane * 4; i < D; i += 128) {
+      float4 e = *reinterpret_cast<float4*>(emb + i);
+      e.x = __fdiv_rn(e.x, nrm); e.y = __fdiv_rn(e.y, nrm); e.z = __fdiv_rn(e.z, nrm); e.w = __fdiv_rn(e.w, nrm);
+      *reinterpret_cast<float4*>(emb + i) = e;
+    }
+  }
+  __syncwarp();
+  write_code_operands(emb, k, K, Kpad, D, metric, planes, bias, cnorm2, cmax, lane);
+}
+
+}  // namespace vqb
+
+using namespace vqb;
+
+extern "C" int64_t vqb_stats_offset(int K) { return K <= 0 ? 0 : (static_cast<int64_t>(K) + 3) / 4 * 4; }
+extern "C" int64_t vqb_stats_floats(int K, int D) { return (K <= 0 || D <= 0) ? 0 : vqb_stats_offset(K) + static_cast<int64_t>(K) * D; }
+
+extern "C" size_t vqb_ema_stats_workspace(int64_t N, int K) {
+  if (N <= 0 || K <= 0) return 0;
+  return carve(nullptr, nullptr, N, K);
+}
+
+extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x_eff || !idx || !stats || !workspace || N <= 0 || D <= 0 || K <= 0) return VQB_E_INVALID;
+  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
+  if (D % 8 != 0 || D > 4 * SEG_THREADS) return VQB_E_UNSUPPORTED;
+  if (N >= (static_cast<int64_t>(1) << 31)) return VQB_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(x_eff) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(stats)) & 15)
+    return VQB_E_ALIGN;
+  StatsWs ws;
+  if (carve(&ws, workspace, N, K) > workspace_bytes) return VQB_E_WORKSPACE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(ws.counts, 0, sizeof(int32_t) * K, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  const int64_t soff = vqb_stats_offset(K);
+  e = cudaMemsetAsync(stats + soff, 0, sizeof(float) * static_cast<size_t>(K) * D, s);  // split items accumulate
+  if (e != cudaSuccess) return static_cast<int>(e);
+  int g = static_cast<int>((N + 1023) / 1024);
+  const int cap = num_sms() * 4;
+  if (g > cap) g = cap;
+  hist_kernel<<<g, 256, K <= 8192 ? K * sizeof(int32_t) : 0, s>>>(idx, N, K, ws.counts);
+  scan_kernel<<<1, 1024, 0, s>>>(ws.counts, K, ws.offsets, ws.cursor, ws.work, ws.nwork, stats);
+  scatter_kernel<<<g, 256, 0, s>>>(idx, N, ws.cursor, ws.perm);
+  const int items = static_cast<int>(max_work_items(N, K));
+  const int TX = D / 4;
+  const size_t red_bytes = static_cast<size_t>(SEG_THREADS / TX) * D * sizeof(float);
+  if (dtype == VQB_DTYPE_F32)
+    segsum_kernel<VQB_DTYPE_F32><<<items, SEG_THREADS, red_bytes, s>>>(x_eff, D, ws.perm, ws.work, ws.nwork, stats + soff);
+  else
+    segsum_kernel<VQB_DTYPE_BF16><<<items, SEG_THREADS, red_bytes, s>>>(x_eff, D, ws.perm, ws.work, ws.nwork, stats + soff);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+                             double decay, double eps, int metric, int do_lerp, int do_normalise, void* planes,
+                             float* bias, float* cnorm2, float* cmax, float* scratch, void* stream) {
+  if (!cluster_size || !embed_avg || !embed || !scratch || K <= 0 || D <= 0) return VQB_E_INVALID;
+  if (do_lerp && !stats) return VQB_E_INVALID;
+  if (do_normalise && (!planes || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
+  if (D % 8 != 0) return VQB_E_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(embed_avg) | reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(planes)) & 15)
+    return VQB_E_ALIGN;
+  const int64_t soff = vqb_stats_offset(K);
+  if (do_lerp && ((reinterpret_cast<uintptr_t>(stats) | reinterpret_cast<uintptr_t>(stats + soff)) & 15)) return VQB_E_ALIGN;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const float w = static_cast<float>(1.0 - decay);  // (1. - decay) evaluated in python float, then fp32 (vqp:97)
+  const float epsf = static_cast<float>(eps);
+  const float keps = static_cast<float>(static_cast<double>(K) * eps);  // n_categories * eps in python float (vqp:154)
+  ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, w, do_lerp, scratch, do_normalise ? cmax : nullptr);
+  const int Kpad = vqb_padded_codes(K);
+  const int wpb = 8;
+  ema_rows_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(cluster_size, embed_avg, embed, stats, soff, K, Kpad, D, w, epsf, keps,
+                                                            metric, do_lerp, do_normalise, scratch,
+                                                            static_cast<uint16_t*>(planes), bias, cnorm2, cmax);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,73 @@
+// Shared host/device helpers for the vqb200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/vqb200.h"
+
+namespace vqb {
+
+// MMA N-tile (codes per accumulator): 256 for real codebooks, the 16-rounded size for tiny ones.
+__host__ __device__ inline int code_tile(int K) { return K >= 256 ? 256 : ((K + 15) / 16) * 16; }
+
+inline int device_props(int* sms, int* major) {
+  static int cached_dev = -1, c_sms = 0, c_major = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return VQB_E_NO_DEVICE;
+  if (dev != cached_dev) {
+    if (cudaDeviceGetAttribute(&c_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return VQB_E_NO_DEVICE;
+    if (cudaDeviceGetAttribute(&c_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return VQB_E_NO_DEVICE;
+    cached_dev = dev;
+  }
+  *sms = c_sms;
+  *major = c_major;
+  return VQB_OK;
+}
+inline int check_device() {
+  int sms, major;
+  int rc = device_props(&sms, &major);
+  if (rc) return rc;
+  return major == 10 ? VQB_OK : VQB_E_NO_DEVICE;
+}
+inline int num_sms() {
+  int sms = 1, major;
+  device_props(&sms, &major);
+  return sms;
+}
+
+__device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(static_cast<uint32_t>(b) << 16); }
+// round-to-nearest-even float -> bf16 bits (finite inputs)
+__device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
+  return __bfloat16_as_ushort(__float2bfloat16_rn(f));
+}
+__device__ __forceinline__ float bf16_round(float f) { return bf16_bits_to_float(float_to_bf16_bits(f)); }
+
+template <int DT> struct Elem;
+template <> struct Elem<VQB_DTYPE_F32> {
+  using T = float;
+  static __device__ __forceinline__ float load(const void* p, int64_t i) { return reinterpret_cast<const float*>(p)[i]; }
+  static __device__ __forceinline__ void store(void* p, int64_t i, float v) { reinterpret_cast<float*>(p)[i] = v; }
+  static __device__ __forceinline__ float round(float v) { return v; }
+};
+template <> struct Elem<VQB_DTYPE_BF16> {
+  using T = uint16_t;
+  static __device__ __forceinline__ float load(const void* p, int64_t i) { return bf16_bits_to_float(reinterpret_cast<const uint16_t*>(p)[i]); }
+  static __device__ __forceinline__ void store(void* p, int64_t i, float v) { reinterpret_cast<uint16_t*>(p)[i] = float_to_bf16_bits(v); }
+  static __device__ __forceinline__ float round(float v) { return bf16_round(v); }
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace vqb

@@ -1,0 +1,222 @@
+"""Functional layer over the C ABI: torch tensors in, torch tensors out, everything enqueued on the
+current CUDA stream.  Mirrors the arithmetic steps of `Codebook.forward`
+(reference vector_quantize_pytorch.py:674-791); the nn.Modules in this package are glue around these.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _C
+from ._C import lib, check
+
+# A row is certified by the tensor-core pass when its best score leads all others by more than
+# 2*margin*||x||*max||c||.  2^-16 is above the worst-case error of the split-bf16 passes
+# (|c - hi - lo| <= 2^-18 |c| per element, plus fp32 accumulation), see DESIGN.md.
+DEFAULT_MARGIN = 2.0 ** -16
+
+_DT = {torch.float32: _C.DTYPE_F32, torch.bfloat16: _C.DTYPE_BF16}
+
+# bench.py instrumentation: when PROFILE_EVENTS is a list, `search` brackets the tcgen05 kernel with CUDA
+# events on the launching stream; LAUNCHES counts the kernels this library enqueues.
+PROFILE_EVENTS = None
+LAUNCHES = 0
+
+
+def _count(n):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"vqb200 supports float32 and bfloat16 inputs, got {t.dtype}") from None
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vqb200 has no CPU path: tensors must live on a CUDA (B200, sm_100) device")
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def padded_codes(K: int) -> int:
+    return lib.vqb_padded_codes(K)
+
+
+@dataclass
+class CodebookOperands:
+    """Tensor-core view of one codebook (see vqb_codebook_prepare in include/vqb200.h)."""
+    planes: torch.Tensor  # bf16 (2, Kpad, D)
+    bias: torch.Tensor  # f32 (Kpad,)
+    cnorm2: torch.Tensor  # f32 (K,)
+    cmax: torch.Tensor  # f32 (1,)
+    scratch: torch.Tensor  # f32 (2,)
+    K: int
+    D: int
+    cosine: bool
+
+    @staticmethod
+    def allocate(K: int, D: int, cosine: bool, device) -> "CodebookOperands":
+        Kpad = padded_codes(K)
+        return CodebookOperands(
+            planes=torch.empty((2, Kpad, D), dtype=torch.bfloat16, device=device),
+            bias=torch.empty((Kpad,), dtype=torch.float32, device=device),
+            cnorm2=torch.empty((K,), dtype=torch.float32, device=device),
+            cmax=torch.zeros((1,), dtype=torch.float32, device=device),
+            scratch=torch.zeros((2,), dtype=torch.float32, device=device),
+            K=K, D=D, cosine=cosine)
+
+
+def prepare_codebook(embed: torch.Tensor, cosine: bool, out: CodebookOperands | None = None) -> CodebookOperands:
+    """embed (K, D) fp32 contiguous -> operands for `search`."""
+    _require_cuda(embed)
+    assert embed.dtype == torch.float32 and embed.dim() == 2 and embed.is_contiguous()
+    K, D = embed.shape
+    ops = out if out is not None else CodebookOperands.allocate(K, D, cosine, embed.device)
+    with torch.cuda.device(embed.device):
+        check(lib.vqb_codebook_prepare(_p(embed), K, D, int(cosine), _p(ops.planes), _p(ops.bias), _p(ops.cnorm2),
+                                       _p(ops.cmax), _stream()), "vqb_codebook_prepare")
+    _count(1)
+    return ops
+
+
+@dataclass
+class SearchResult:
+    idx: torch.Tensor  # int32 (N,)
+    x_eff: torch.Tensor  # (N, D) input as the codebook sees it (l2-normalised for cosine), in x.dtype
+    flag_count: torch.Tensor  # int32 (1,) rows re-scored exactly
+    flagged: torch.Tensor  # int32 (N, 4)
+    best: torch.Tensor | None = None
+
+
+def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margin: float | None = None, n_passes: int = 0,
+           debug_best: bool = False, fix: bool = True, normalise: bool = True) -> SearchResult:
+    """Nearest code of every row of x (N, D).  Replaces cdist/einsum + argmax (vqp:58-62, :741-747, :130-145)."""
+    _require_cuda(x, embed)
+    assert x.dim() == 2 and x.is_contiguous()
+    N, D = x.shape
+    assert D == ops.D
+    dt = _dtype_code(x)
+    cosine = ops.cosine
+    l2 = cosine and normalise  # normalise=False: the caller already applied l2norm (Codebook.forward contract)
+    dev = x.device
+    margin = DEFAULT_MARGIN if margin is None else margin
+    with torch.cuda.device(dev):
+        st = _stream()
+        if x.dtype == torch.bfloat16:
+            if l2:  # l2norm in bf16 (vqp:1159 -> :376); the normalised bf16 rows are the A operand
+                x_eff = torch.empty_like(x)
+                check(lib.vqb_input_prepare(_p(x), dt, N, D, 1, _p(x_eff), None, 0, st), "vqb_input_prepare")
+                _count(1)
+            else:
+                x_eff = x
+            a_planes, n_a = x_eff, 1
+        else:
+            a_planes = torch.empty((2, N, D), dtype=torch.bfloat16, device=dev)
+            x_eff = torch.empty_like(x) if l2 else x
+            check(lib.vqb_input_prepare(_p(x), dt, N, D, int(l2), _p(x_eff) if l2 else None, _p(a_planes), 2, st),
+                  "vqb_input_prepare")
+            _count(1)
+            n_a = 2
+        idx = torch.empty((N,), dtype=torch.int32, device=dev)
+        flagged = torch.empty((N, 4), dtype=torch.int32, device=dev)
+        count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        best = torch.empty((N,), dtype=torch.float32, device=dev) if debug_best else None
+        prof = PROFILE_EVENTS
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        check(lib.vqb_assign(_p(a_planes), n_a, N, D, _p(ops.planes), _p(ops.bias), _p(ops.cmax), ops.K, float(margin),
+                             int(n_passes), _p(idx), _p(flagged), _p(count), _p(best), st), "vqb_assign")
+        if prof is not None:
+            ev1.record()
+            prof.append((ev0, ev1))
+        _count(1 + int(fix))
+        if fix:
+            check(lib.vqb_fix_flagged(_p(x_eff), dt, N, D, _p(embed), _p(ops.cnorm2), ops.K, int(cosine), _p(flagged),
+                                      _p(count), _p(idx), st), "vqb_fix_flagged")
+    return SearchResult(idx, x_eff, count, flagged, best)
+
+
+def gather(x_eff: torch.Tensor, embed: torch.Tensor, idx: torch.Tensor, *, q_out: torch.Tensor | None = None,
+           idx64_out: torch.Tensor | None = None, idx_stride: int = 1, loss_sum: torch.Tensor | None = None,
+           x_raw: torch.Tensor | None = None, resid_out: torch.Tensor | None = None,
+           qsum: torch.Tensor | None = None) -> None:
+    """quantize = embed[idx].type(x.dtype) (vqp:766/:779-781, :1178) fused with the mse partial sum (vqp:1327)
+    and, for ResidualVQ, residual -= q ; quantized_out += q (rvq:524-525)."""
+    _require_cuda(x_eff, embed, idx)
+    N, D = x_eff.shape
+    with torch.cuda.device(x_eff.device):
+        check(lib.vqb_gather(_p(x_eff), _dtype_code(x_eff), N, D, _p(embed), _p(idx), _p(q_out), _p(idx64_out),
+                             int(idx_stride), _p(loss_sum), _p(x_raw), _p(resid_out), _p(qsum), _stream()), "vqb_gather")
+    _count(1)
+
+
+def loss_finalize(loss_sum: torch.Tensor, numel: int, dtype: torch.dtype, weight: float, out: torch.Tensor) -> None:
+    with torch.cuda.device(loss_sum.device):
+        check(lib.vqb_loss_finalize(_p(loss_sum), int(numel), _DT[dtype], float(weight), _p(out), _stream()),
+              "vqb_loss_finalize")
+    _count(1)
+
+
+def stats_floats(K: int, D: int) -> int:
+    return lib.vqb_stats_floats(K, D)
+
+
+def stats_offset(K: int) -> int:
+    return lib.vqb_stats_offset(K)
+
+
+def ema_stats(x_eff: torch.Tensor, idx: torch.Tensor, K: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Packed [cluster_size | embed_sum] of this batch (vqp:602, :605) — ready for ONE all-reduce."""
+    _require_cuda(x_eff, idx)
+    N, D = x_eff.shape
+    dev = x_eff.device
+    stats = out if out is not None else torch.empty((stats_floats(K, D),), dtype=torch.float32, device=dev)
+    ws_bytes = lib.vqb_ema_stats_workspace(N, K)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib.vqb_ema_stats(_p(x_eff), _dtype_code(x_eff), N, D, _p(idx), K, _p(stats), _p(ws), ws_bytes, _stream()),
+              "vqb_ema_stats")
+    _count(4)
+    return stats
+
+
+def ema_apply(cluster_size: torch.Tensor, embed_avg: torch.Tensor, embed: torch.Tensor, stats: torch.Tensor | None,
+              ops: CodebookOperands, *, decay: float, eps: float, do_lerp: bool, do_normalise: bool) -> None:
+    """lerp_ of cluster_size / embed_avg (vqp:616-617) and update_ema (vqp:576-584); refreshes `ops`."""
+    _require_cuda(cluster_size, embed_avg, embed)
+    K, D = embed.shape
+    with torch.cuda.device(embed.device):
+        check(lib.vqb_ema_apply(_p(cluster_size), _p(embed_avg), _p(embed), _p(stats), K, D, float(decay), float(eps),
+                                int(ops.cosine), int(do_lerp), int(do_normalise), _p(ops.planes), _p(ops.bias),
+                                _p(ops.cnorm2), _p(ops.cmax), _p(ops.scratch), _stream()), "vqb_ema_apply")
+    _count(2)
+
+
+def decode(embeds: torch.Tensor, indices: torch.Tensor, out_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """sum_q embeds[q][indices[..., q]] with -1 -> zeros (rvq:324-382).  embeds (Q, K, D) fp32 or (K, D)."""
+    _require_cuda(embeds, indices)
+    if embeds.dim() == 2:
+        embeds = embeds.unsqueeze(0)
+    Q, K, D = embeds.shape
+    assert indices.shape[-1] == Q and indices.dtype == torch.int64
+    embeds = embeds.contiguous()
+    flat = indices.reshape(-1, Q).contiguous()
+    N = flat.shape[0]
+    out = torch.empty((N, D), dtype=out_dtype, device=embeds.device)
+    with torch.cuda.device(embeds.device):
+        check(lib.vqb_decode(_p(embeds), K * D, Q, K, D, _p(flat), N, _p(out), _DT[out_dtype], _stream()), "vqb_decode")
+    _count(1)
+    return out.reshape(*indices.shape[:-1], D)

@@ -1,0 +1,279 @@
+"""`ResidualVQ` / `GroupedResidualVQ` — drop-ins for residual_vq.py:166-630 and :634-724 of the reference
+on the plain path (no beam search, no quantize-dropout, no implicit neural codebook, no mask).
+
+The Q-stage recurrence  residual -= q ; quantized_out += q  (rvq:524-525) runs inside the gather
+kernel of every stage (rounded to the input dtype exactly where the reference rounds), indices are
+written straight into the (..., Q) int64 result, and the EMA statistics of ALL stages (and, for the
+grouped module, all groups) are packed into one buffer so that multi-GPU training needs ONE all-reduce
+per forward instead of the reference's 2 per codebook per stage.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as distributed
+from torch import nn
+
+from . import ops
+from .codebook import _unsupported
+from .vector_quantize import VectorQuantize
+
+
+class ResidualVQ(nn.Module):
+    def __init__(
+        self,
+        *,
+        dim,
+        num_quantizers=None,
+        codebook_size,
+        codebook_dim=None,
+        shared_codebook=False,
+        diveq=False,
+        heads=1,
+        quantize_dropout=False,
+        quantize_dropout_cutoff_index=0,
+        quantize_dropout_multiple_of=1,
+        accept_image_fmap=False,
+        implicit_neural_codebook=False,
+        mlp_kwargs: dict = dict(),
+        beam_size=None,
+        eval_beam_size=None,
+        beam_score_quantizer_weights=None,
+        quant_grad_frac=0.,
+        **vq_kwargs,
+    ):
+        super().__init__()
+        assert heads == 1, "residual vq is not compatible with multi-headed codes"  # rvq:191
+        assert num_quantizers is not None or isinstance(codebook_size, tuple)  # rvq:192
+        if diveq or implicit_neural_codebook:
+            _unsupported("diveq / implicit_neural_codebook")
+        if quantize_dropout:
+            _unsupported("quantize_dropout")
+        if (beam_size is not None and beam_size > 1) or (eval_beam_size is not None and eval_beam_size > 1):
+            _unsupported("beam search")
+        if accept_image_fmap:
+            _unsupported("ResidualVQ(accept_image_fmap=True)")
+        if quant_grad_frac != 0.:
+            _unsupported("quant_grad_frac != 0")
+
+        codebook_dim = dim if codebook_dim is None else codebook_dim
+        self.codebook_dim = codebook_dim
+        requires_projection = codebook_dim != dim
+        self.project_in = nn.Linear(dim, codebook_dim) if requires_projection else nn.Identity()
+        self.project_out = nn.Linear(codebook_dim, dim) if requires_projection else nn.Identity()
+        self.has_projections = requires_projection
+        self.accept_image_fmap = accept_image_fmap
+
+        if shared_codebook:  # rvq:213-217
+            vq_kwargs.update(manual_ema_update=True)
+
+        codebook_sizes = codebook_size if isinstance(codebook_size, tuple) else (codebook_size,) * num_quantizers
+        num_quantizers = len(codebook_sizes) if num_quantizers is None else num_quantizers
+        assert len(codebook_sizes) == num_quantizers
+        self.num_quantizers = num_quantizers
+        self.codebook_sizes = codebook_sizes
+        self.uniform_codebook_size = len(set(codebook_sizes)) == 1
+
+        self.layers = nn.ModuleList([
+            VectorQuantize(dim=codebook_dim, codebook_size=k, codebook_dim=codebook_dim, **vq_kwargs) for k in codebook_sizes
+        ])  # rvq:249
+        self.quantize_dropout = False
+        self.vq_is_ema_updating = self.layers[0].ema_update
+        self.quant_grad_frac = 0.
+        self.shared_codebook = shared_codebook
+        if shared_codebook:  # rvq:295-306: every layer aliases ONE Codebook
+            assert self.uniform_codebook_size
+            codebook = self.layers[0]._codebook
+            for vq in self.layers[1:]:
+                vq._codebook = codebook
+
+    # ------------------------------------------------------------------ reference surface
+    @property
+    def codebook_size(self):
+        return self.layers[0].codebook_size
+
+    @property
+    def codebooks(self):  # rvq:312-322
+        books = tuple(layer._codebook.embed[0] for layer in self.layers)
+        return torch.stack(books) if self.uniform_codebook_size else books
+
+    def get_codes_from_indices(self, indices):  # rvq:324-376
+        if indices.shape[-1] < self.num_quantizers:
+            _unsupported("decoding fewer than num_quantizers indices (quantize dropout)")
+        if self.uniform_codebook_size:
+            q_idx = indices.reshape(-1, self.num_quantizers)
+            codes = [ops.decode(self.layers[q]._codebook.embed[0], q_idx[:, q:q + 1].contiguous()) for q in range(self.num_quantizers)]
+        else:
+            q_idx = indices.reshape(-1, self.num_quantizers)
+            codes = [ops.decode(self.layers[q]._codebook.embed[0], q_idx[:, q:q + 1].contiguous()) for q in range(self.num_quantizers)]
+        return torch.stack(codes).reshape(self.num_quantizers, *indices.shape[:-1], self.codebook_dim)
+
+    def get_output_from_indices(self, indices):  # rvq:378-382: sum over quantizers in ONE gather kernel
+        if indices.shape[-1] < self.num_quantizers:
+            _unsupported("decoding fewer than num_quantizers indices (quantize dropout)")
+        if self.uniform_codebook_size:
+            out = ops.decode(self.codebooks.contiguous(), indices)
+        else:
+            out = self.get_codes_from_indices(indices).sum(dim=0)
+        return self.project_out(out)
+
+    # ------------------------------------------------------------------ forward
+    def _stage_plan(self):
+        return [vq._codebook for vq in self.layers]
+
+    def forward(self, x, mask=None, indices=None, return_all_codes=False, sample_codebook_temp=None,
+                freeze_codebook=False, beam_size=None, rand_quantize_dropout_fixed_seed=None,
+                _stats_sink=None):
+        if mask is not None or indices is not None:
+            _unsupported("ResidualVQ.forward(mask=/indices=)")
+        if beam_size is not None and beam_size > 1:
+            _unsupported("beam search")
+        if not x.is_cuda:
+            raise RuntimeError("vqb200 has no CPU path: inputs must live on a CUDA (B200, sm_100) device")
+        if x.requires_grad and torch.is_grad_enabled():
+            # gradients need the per-stage straight-through/rotation glue of VectorQuantize: take the layered path
+            return self._forward_layered(x, freeze_codebook, return_all_codes)
+
+        x = self.project_in(x)
+        shape, dtype = x.shape, x.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"vqb200 supports float32 and bfloat16 inputs, got {dtype}")
+        flat = x.detach().reshape(-1, shape[-1]).contiguous()
+        N, D = flat.shape
+        Q = self.num_quantizers
+        dev = flat.device
+        training = self.training
+        books = self._stage_plan()
+
+        quantized_out = torch.zeros_like(flat)  # rvq:410
+        all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)
+        loss_sums = torch.zeros((Q,), dtype=torch.float64, device=dev)
+        losses = torch.zeros((Q,), dtype=torch.float32, device=dev)
+        bufs = [torch.empty_like(flat), torch.empty_like(flat)]
+        residual = flat  # rvq:411 (never written: stage 0 reads the caller's tensor)
+
+        do_update = [training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
+        stat_sizes = [ops.stats_floats(b.codebook_size, D) if u else 0 for b, u in zip(books, do_update)]
+        packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
+        offs = [sum(stat_sizes[:i]) for i in range(Q)]
+
+        for q, book in enumerate(books):  # rvq:469
+            nxt = bufs[q & 1]
+            want_loss = training and self.layers[q].has_commitment_loss
+            book.quantize_rows(
+                residual, update=do_update[q], idx64_out=all_idx[:, q], idx_stride=Q,
+                loss_sum=loss_sums[q:q + 1] if want_loss else None,
+                resid_out=nxt if q + 1 < Q else None, qsum=quantized_out,
+                stats_out=packed[offs[q]:offs[q] + stat_sizes[q]] if do_update[q] else None, defer_ema=True)
+            if want_loss:
+                ops.loss_finalize(loss_sums[q:q + 1], N * D, dtype, self.layers[q].commitment_weight, losses[q:q + 1])
+            residual = nxt
+
+        if packed is not None:
+            if _stats_sink is not None:  # GroupedResidualVQ gathers every group's statistics into one collective
+                _stats_sink.append((self, packed, offs, stat_sizes, do_update, flat))
+            else:
+                self._finish_update(packed, offs, stat_sizes, do_update, flat, synced=False)
+
+        quantized_out = self.project_out(quantized_out.reshape(shape))  # rvq:610
+        ret = (quantized_out, all_idx.reshape(*shape[:-1], Q), losses)
+        if return_all_codes:
+            ret = (*ret, self.get_codes_from_indices(ret[1]))
+        return ret
+
+    def _finish_update(self, packed, offs, stat_sizes, do_update, flat, synced):
+        """ONE all-reduce for all stages (reference: 2 per stage, vqp:603/:607), then the per-stage lerps in
+        order (vqp:616-617) and update_ema — once at the end for a shared codebook (rvq:593-597)."""
+        books = self._stage_plan()
+        if not synced and any(b.use_ddp for b in books):
+            distributed.all_reduce(packed)
+        for q, book in enumerate(books):
+            if not do_update[q]:
+                continue
+            stats = packed[offs[q]:offs[q] + stat_sizes[q]]
+            book.lerp_stats(stats, normalise=book.ema_update and not book.manual_ema_update)
+        if self.training and self.shared_codebook:
+            shared = books[0]
+            if self.vq_is_ema_updating and any(do_update):
+                shared.update_ema()
+            if shared.has_dead_code_replacement:
+                _unsupported("dead-code expiry over all residuals of a shared codebook")
+
+    def _forward_layered(self, x, freeze_codebook, return_all_codes):
+        """Differentiable path: the reference's Python loop (rvq:469-568) over our VectorQuantize layers."""
+        x = self.project_in(x)
+        quantized_out = torch.zeros_like(x)
+        residual = x
+        all_idx, all_losses = [], []
+        for vq in self.layers:
+            quantized, ind, loss = vq(residual, freeze_codebook=freeze_codebook)
+            residual = residual - quantized.detach()
+            quantized_out = quantized_out + quantized
+            all_idx.append(ind)
+            all_losses.append(loss)
+        if self.training and self.shared_codebook and self.vq_is_ema_updating and not freeze_codebook:
+            self.layers[0]._codebook.update_ema()
+        ret = (self.project_out(quantized_out), torch.stack(all_idx, dim=-1), torch.stack(all_losses))
+        if return_all_codes:
+            ret = (*ret, self.get_codes_from_indices(ret[1]))
+        return ret
+
+
+class GroupedResidualVQ(nn.Module):
+    def __init__(self, *, dim, groups=1, accept_image_fmap=False, **kwargs):
+        super().__init__()
+        self.dim = dim
+        self.groups = groups
+        assert (dim % groups) == 0  # rvq:646
+        if accept_image_fmap:
+            _unsupported("GroupedResidualVQ(accept_image_fmap=True)")
+        self.accept_image_fmap = accept_image_fmap
+        self.rvqs = nn.ModuleList([ResidualVQ(dim=dim // groups, **kwargs) for _ in range(groups)])  # rvq:651-658
+
+    @property
+    def codebooks(self):
+        return torch.stack(tuple(rvq.codebooks for rvq in self.rvqs))
+
+    @property
+    def split_dim(self):
+        return -1
+
+    def get_codes_from_indices(self, indices):
+        return torch.stack(tuple(rvq.get_codes_from_indices(i) for rvq, i in zip(self.rvqs, indices)))
+
+    def get_output_from_indices(self, indices):
+        return torch.cat(tuple(rvq.get_output_from_indices(i) for rvq, i in zip(self.rvqs, indices)), dim=-1)
+
+    def forward(self, x, indices=None, return_all_codes=False, sample_codebook_temp=None, freeze_codebook=False, mask=None):
+        if indices is not None or mask is not None:
+            _unsupported("GroupedResidualVQ.forward(indices=/mask=)")
+        assert x.shape[-1] == self.dim
+        chunks = x.chunk(self.groups, dim=-1)  # rvq:690
+        if self.training:
+            # the reference draws one torch.randint here even without quantize-dropout (rvq:701 -> :96-103);
+            # consume it too so that seeded runs stay aligned with the reference's RNG stream.
+            seed = torch.randint(0, 10_000, (), device=x.device)
+            if distributed.is_available() and distributed.is_initialized() and distributed.get_world_size() > 1:
+                distributed.all_reduce(seed)
+        sink = []
+        outs = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _stats_sink=sink)
+                for rvq, c in zip(self.rvqs, chunks)]  # rvq:706
+        if sink:
+            need_sync = any(b.use_ddp for rvq, *_ in sink for b in rvq._stage_plan())
+            if need_sync:  # ONE collective for every codebook of every group
+                flat_all = torch.cat([p for _, p, *_ in sink])
+                distributed.all_reduce(flat_all)
+                pos = 0
+                for rvq, packed, offs, sizes, upd, flat in sink:
+                    n = packed.numel()
+                    rvq._finish_update(flat_all[pos:pos + n], offs, sizes, upd, flat, synced=True)
+                    pos += n
+            else:
+                for rvq, packed, offs, sizes, upd, flat in sink:
+                    rvq._finish_update(packed, offs, sizes, upd, flat, synced=True)
+        quantized = torch.cat([o[0] for o in outs], dim=-1)  # rvq:719-721
+        all_indices = torch.stack([o[1] for o in outs])
+        commit_losses = torch.stack([o[2] for o in outs])
+        ret = (quantized, all_indices, commit_losses)
+        if return_all_codes:
+            ret = (*ret, torch.stack([o[3] for o in outs]))
+        return ret

@@ -1,0 +1,297 @@
+"""`VectorQuantize` — drop-in for the reference module (vector_quantize_pytorch.py:802-1403) on the
+default path: heads=1, no mask, Euclidean or cosine codebook with EMA updates.
+
+forward(x) -> (quantize [x.dtype, x.shape], embed_ind [int64, x.shape[:-1]], loss [fp32 scalar]).
+Layout handling, projections, STE / rotation trick stay PyTorch glue; the search, gather, commitment
+loss and EMA run in the sm_100a kernels.  Unsupported constructor / forward options raise.
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import ops
+from .codebook import Codebook, _unsupported
+
+LossBreakdown = namedtuple("LossBreakdown", ["commitment", "codebook_diversity", "orthogonal_reg", "inplace_optimize"])
+
+
+def _is_distributed():
+    import torch.distributed as dist
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def _safe_div(num, den, eps=1e-6):
+    return num / den.clamp(min=eps)
+
+
+def straight_through(src, tgt):  # vqp:282-283
+    return src + (tgt - src).detach()
+
+
+def rotate_to(src, tgt):
+    """Rotation-trick gradient estimator (arXiv:2410.06424 §4.2; reference vqp:287-318), PyTorch glue."""
+    shape = src.shape
+    src = src.reshape(-1, shape[-1])
+    tgt = tgt.reshape(-1, shape[-1])
+    norm_src = src.norm(dim=-1, keepdim=True)
+    norm_tgt = tgt.norm(dim=-1, keepdim=True)
+    u = _safe_div(src, norm_src)
+    q = _safe_div(tgt, norm_tgt)
+    e = src.unsqueeze(1)
+    w = F.normalize(u + q, p=2, dim=1, eps=1e-6).detach()
+    out = (e - 2 * (e @ w.unsqueeze(-1) @ w.unsqueeze(1)) + 2 * (e @ u.unsqueeze(-1).detach() @ q.unsqueeze(1).detach()))
+    rotated = out.squeeze(1) * _safe_div(norm_tgt, norm_src).detach()
+    return rotated.reshape(shape)
+
+
+class VectorQuantize(nn.Module):
+    def __init__(
+        self,
+        dim,
+        codebook_size,
+        codebook_dim=None,
+        heads=1,
+        separate_codebook_per_head=False,
+        decay=0.8,
+        eps=1e-5,
+        freeze_codebook=False,
+        kmeans_init=False,
+        kmeans_iters=10,
+        sync_kmeans=True,
+        use_cosine_sim=False,
+        layernorm_after_project_in=False,
+        threshold_ema_dead_code=0,
+        channel_last=True,
+        accept_image_fmap=False,
+        accept_3d_fmap=False,
+        commitment_weight=1.,
+        commitment_use_cross_entropy_loss=False,
+        orthogonal_reg_weight=0.,
+        orthogonal_reg_active_codes_only=False,
+        orthogonal_reg_max_codes=None,
+        codebook_diversity_loss_weight=0.,
+        codebook_diversity_temperature=100.,
+        stochastic_sample_codes=False,
+        sample_codebook_temp=1.,
+        straight_through=False,
+        rotation_trick=None,
+        directional_reparam=False,
+        directional_reparam_variance=5e-3,
+        sync_codebook=None,
+        sync_affine_param=False,
+        ema_update=None,
+        vq_bridge=None,
+        manual_ema_update=False,
+        learnable_codebook=None,
+        in_place_codebook_optimizer=None,
+        manual_in_place_optimizer_update=False,
+        affine_param=False,
+        affine_param_batch_decay=0.99,
+        affine_param_codebook_decay=0.9,
+        sync_update_v=0.,
+        return_zeros_for_masked_padding=True,
+        route_gradients_to_input=True,
+    ):
+        super().__init__()
+        # ---- options outside the accelerated path fail loudly
+        if heads != 1 or separate_codebook_per_head:
+            _unsupported("heads > 1")
+        if directional_reparam or vq_bridge is not None or learnable_codebook:
+            _unsupported("directional_reparam / vq_bridge / learnable_codebook")
+        if in_place_codebook_optimizer is not None:
+            _unsupported("in_place_codebook_optimizer")
+        if affine_param:
+            _unsupported("affine_param")
+        if stochastic_sample_codes or straight_through:
+            _unsupported("stochastic_sample_codes / gumbel straight_through")
+        if commitment_use_cross_entropy_loss or orthogonal_reg_weight > 0 or codebook_diversity_loss_weight > 0:
+            _unsupported("cross-entropy / orthogonal / diversity losses (they need the N x K distance matrix)")
+        if sync_update_v > 0:
+            _unsupported("sync_update_v")
+        if kmeans_init:
+            _unsupported("kmeans_init")
+
+        ema_update = True if ema_update is None else ema_update  # vqp:854
+        if not ema_update:
+            # a frozen, non-learnable codebook is still a valid use of the search kernels
+            pass
+        rotation_trick = (dim > 1) if rotation_trick is None else rotation_trick  # vqp:856
+
+        self.dim = dim
+        self.heads = heads
+        self.separate_codebook_per_head = separate_codebook_per_head
+        codebook_dim = dim if codebook_dim is None else codebook_dim
+        codebook_input_dim = codebook_dim * heads
+        requires_projection = codebook_input_dim != dim
+        if requires_projection:  # vqp:867-874
+            layers = [nn.Linear(dim, codebook_input_dim)]
+            if layernorm_after_project_in:
+                layers.append(nn.LayerNorm(codebook_input_dim))
+            self.project_in = layers[0] if len(layers) == 1 else nn.Sequential(*layers)
+            self.project_out = nn.Linear(codebook_input_dim, dim)
+        else:
+            self.project_in = nn.Identity()
+            self.project_out = nn.Identity()
+        self.has_projections = requires_projection
+
+        self.eps = eps
+        self.has_commitment_loss = commitment_weight > 0.
+        self.commitment_weight = commitment_weight
+        self.learnable_codebook = False
+        self.rotation_trick = rotation_trick
+        self.route_gradients_to_input = route_gradients_to_input
+
+        if sync_codebook is None:  # vqp:925-926
+            sync_codebook = _is_distributed()
+
+        self.use_cosine_sim = use_cosine_sim
+        self._codebook = Codebook(
+            dim=codebook_dim,
+            num_codebooks=1,
+            codebook_size=codebook_size,
+            decay=decay,
+            eps=eps,
+            threshold_ema_dead_code=threshold_ema_dead_code,
+            use_ddp=sync_codebook,
+            sync_kmeans=sync_kmeans,
+            sample_codebook_temp=sample_codebook_temp,
+            ema_update=ema_update,
+            manual_ema_update=manual_ema_update,
+            use_cosine_sim=use_cosine_sim,
+        )
+        self.codebook_size = codebook_size
+        self.accept_image_fmap = accept_image_fmap
+        self.accept_3d_fmap = accept_3d_fmap
+        self.channel_last = channel_last
+        self.register_buffer("zero", torch.tensor(0.), persistent=False)  # vqp:970
+        self.return_zeros_for_masked_padding = return_zeros_for_masked_padding
+        self.freeze_codebook = freeze_codebook
+
+    # ------------------------------------------------------------------ reference surface
+    @property
+    def ema_update(self):
+        return self._codebook.ema_update
+
+    @property
+    def codebook(self):  # vqp:982-989
+        return self._codebook.embed[0]
+
+    @codebook.setter
+    def codebook(self, codes):  # vqp:991-996
+        self._codebook.embed.copy_(codes.unsqueeze(0))
+
+    def get_codes_from_indices(self, indices):  # vqp:998-1018
+        codes = ops.decode(self.codebook, indices.unsqueeze(-1))
+        if not self.channel_last or self.accept_image_fmap or self.accept_3d_fmap:
+            codes = codes.movedim(-1, 1)
+        return codes
+
+    def get_output_from_indices(self, indices):  # vqp:1020-1022
+        return self.project_out(self.get_codes_from_indices(indices))
+
+    def expire_codes_(self, x):
+        self._codebook.expire_codes_(self._codebook.transform_input(x))
+
+    def update_indices(self, x, indices, mask=None):  # vqp:1056-1091
+        if mask is not None:
+            _unsupported("update_indices with a mask")
+        x, _ = self._to_rows_layout(x)
+        x = self.project_in(x)
+        x = self._codebook.transform_input(x)
+        self._codebook.update_indices(x, indices.reshape(x.shape[:-1]))
+
+    update_ema_indices = update_indices
+
+    # ------------------------------------------------------------------ layout glue (vqp:1136-1147)
+    def _to_rows_layout(self, x):
+        restore = None
+        if self.accept_image_fmap:
+            b, c, h, w = x.shape
+            x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+            restore = ("image", (h, w))
+        elif self.accept_3d_fmap:
+            b, c, d, h, w = x.shape
+            x = x.permute(0, 2, 3, 4, 1).reshape(b, d * h * w, c)
+            restore = ("3d", (d, h, w))
+        elif not self.channel_last:
+            x = x.transpose(1, 2)
+            restore = ("transpose", None)
+        return x, restore
+
+    def forward(self, x, indices=None, mask=None, lens=None, topk=None, sample_codebook_temp=None, freeze_codebook=None,
+                return_loss_breakdown=False, codebook_transform_fn=None, ema_update_weight=None, accum_ema_update=False,
+                ema_update=None):
+        if indices is not None:
+            _unsupported("forward(indices=...) cross-entropy loss")
+        if mask is not None or lens is not None:
+            _unsupported("mask / lens")
+        if topk is not None or codebook_transform_fn is not None or ema_update_weight is not None or accum_ema_update:
+            _unsupported("topk / codebook_transform_fn / ema_update_weight / accum_ema_update")
+        if not x.is_cuda:
+            raise RuntimeError("vqb200 has no CPU path: inputs must live on a CUDA (B200, sm_100) device")
+
+        input_requires_grad = x.requires_grad and torch.is_grad_enabled()
+        freeze_codebook = self.freeze_codebook if freeze_codebook is None else freeze_codebook
+        ema_update = self._codebook.ema_update if ema_update is None else ema_update
+
+        only_one = x.ndim == 2
+        if only_one:
+            x = x.unsqueeze(1)
+        x, restore = self._to_rows_layout(x)
+        x = self.project_in(x)  # vqp:1151
+        shape, dtype = x.shape, x.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"vqb200 supports float32 and bfloat16 inputs, got {dtype}")
+
+        flat = x.detach().reshape(-1, shape[-1]).contiguous()
+        N, D = flat.shape
+        cbk = self._codebook
+        training = self.training
+        do_update = training and not freeze_codebook and (ema_update or cbk.has_dead_code_replacement)
+        fused_loss = training and self.has_commitment_loss and not input_requires_grad
+
+        q = torch.empty_like(flat)
+        idx64 = torch.empty((N,), dtype=torch.int64, device=flat.device)
+        loss_sum = torch.zeros((1,), dtype=torch.float64, device=flat.device) if fused_loss else None
+        res, _ = cbk.quantize_rows(flat, update=do_update, q_out=q, idx64_out=idx64, loss_sum=loss_sum)
+
+        quantize = q.reshape(shape)
+        embed_ind = idx64.reshape(shape[:-1])
+        commit_loss = self.zero
+
+        loss = torch.tensor(0., device=flat.device, requires_grad=training)  # vqp:1282
+        if training:
+            if self.has_commitment_loss:
+                if fused_loss:
+                    commit_loss = torch.empty((), dtype=torch.float32, device=flat.device)
+                    # kernel returns weight * mse already rounded like F.mse_loss in x.dtype (vqp:1327-1329)
+                    ops.loss_finalize(loss_sum, N * D, dtype, self.commitment_weight, commit_loss)
+                    loss = loss + commit_loss
+                else:  # differentiable w.r.t. the input: PyTorch glue on the kernel's outputs
+                    x_t = cbk.transform_input(x)
+                    commit_loss = F.mse_loss(quantize.detach(), x_t)
+                    loss = loss + commit_loss * self.commitment_weight
+            if input_requires_grad and self.route_gradients_to_input:  # vqp:1225-1233
+                x_t = cbk.transform_input(x)
+                quantize = rotate_to(x_t, quantize) if self.rotation_trick else straight_through(x_t, quantize)
+
+        quantize = self.project_out(quantize)  # vqp:1360
+        if restore is not None:  # vqp:1364-1373, :1265-1275
+            kind, dims = restore
+            if kind == "transpose":
+                quantize = quantize.transpose(1, 2)
+            else:
+                b = quantize.shape[0]
+                quantize = quantize.reshape(b, *dims, quantize.shape[-1]).movedim(-1, 1)
+                embed_ind = embed_ind.reshape(b, *dims)
+        if only_one:
+            quantize = quantize.squeeze(1)
+            embed_ind = embed_ind.squeeze(1)
+
+        if not return_loss_breakdown:
+            return quantize, embed_ind, loss
+        return quantize, embed_ind, loss, LossBreakdown(commit_loss, self.zero, self.zero, self.zero)
