@@ -90,20 +90,91 @@ __global__ void fix_flagged_kernel(const void* __restrict__ x, int64_t N, int D,
       const float d2 = __fadd_rn(__fadd_rn(x2f, __ldg(cnorm2 + k)), __fmul_rn(xyf, -2.f));
       return -__fsqrt_rn(fmaxf(d2, 1e-8f));
     };
-    int best_k;
-    if (fe.count == 2) {
-      const int ka = min(fe.cand0, fe.cand1), kb = max(fe.cand0, fe.cand1);
-      const float sa = score(ka), sb = score(kb);
-      best_k = (sb > sa) ? kb : ka;  // argmax keeps the FIRST maximal index (vqp:140)
-    } else {
-      float bs = -INFINITY;
-      best_k = 0;
-      for (int k = 0; k < K; ++k) {
-        const float s = score(k);
-        if (s > bs) { bs = s; best_k = k; }
+    if (fe.count != 2) continue;  // >2 candidates: whole-row rescan by fix_overflow_kernel
+    const int ka = min(fe.cand0, fe.cand1), kb = max(fe.cand0, fe.cand1);
+    const float sa = score(ka), sb = score(kb);
+    const int best_k = (sb > sa) ? kb : ka;  // argmax keeps the FIRST maximal index (vqp:140)
+    if (lane == 0) idx[fe.row] = best_k;
+  }
+}
+
+// Rows with more than two codes inside the error band: exact rescan of the WHOLE codebook row by one CTA
+// (8 warps split the codes; each lane keeps its slice of x in registers; f64 accumulation, reference
+// formula and tie rule).  Rare (a few rows per million), but must not cost milliseconds when it happens.
+template <int DT>
+__global__ void __launch_bounds__(256)
+fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* __restrict__ embed,
+                    const float* __restrict__ cnorm2, int K, int metric, const vqb_flag_entry* __restrict__ flagged,
+                    const int32_t* __restrict__ flag_count, int32_t* idx) {
+  using E = Elem<DT>;
+  constexpr int MAXJ = 8;  // D <= 1024
+  __shared__ float s_best[8];
+  __shared__ int s_idx[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t cnt = *flag_count;
+  if (cnt > N) cnt = N;
+  for (int64_t e = blockIdx.x; e < cnt; e += gridDim.x) {
+    const vqb_flag_entry fe = flagged[e];
+    if (fe.count <= 2) continue;
+    const int64_t base = static_cast<int64_t>(fe.row) * D;
+    float xr[MAXJ][4];
+    double x2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      const int i = lane * 4 + j * 128;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        xr[j][t] = (i + t < D) ? E::load(x, base + i + t) : 0.f;
+        x2 += static_cast<double>(xr[j][t]) * xr[j][t];
       }
     }
-    if (lane == 0) idx[fe.row] = best_k;
+    const float x2f = static_cast<float>(warp_sum(x2));
+    float bs = -INFINITY;
+    int bk = 0x7fffffff;
+    for (int k0 = warp * 2; k0 < K; k0 += 16) {  // two codes per iteration for ILP
+      double acc[2] = {0.0, 0.0};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = k0 + u;
+        if (k < K) {
+          const float* c = embed + static_cast<int64_t>(k) * D;
+#pragma unroll
+          for (int j = 0; j < MAXJ; ++j) {
+            const int i = lane * 4 + j * 128;
+            if (i < D) {
+              const float4 cv = __ldg(reinterpret_cast<const float4*>(c + i));
+              acc[u] += static_cast<double>(xr[j][0]) * cv.x + static_cast<double>(xr[j][1]) * cv.y +
+                        static_cast<double>(xr[j][2]) * cv.z + static_cast<double>(xr[j][3]) * cv.w;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int k = k0 + u;
+        const float xyf = static_cast<float>(warp_sum(acc[u]));
+        if (k < K) {
+          float sc;
+          if (metric == VQB_METRIC_COSINE) {
+            sc = xyf;
+          } else {
+            const float d2 = __fadd_rn(__fadd_rn(x2f, __ldg(cnorm2 + k)), __fmul_rn(xyf, -2.f));
+            sc = -__fsqrt_rn(fmaxf(d2, 1e-8f));
+          }
+          if (sc > bs) { bs = sc; bk = k; }  // ascending k within the warp: first maximal index wins
+        }
+      }
+    }
+    if (lane == 0) { s_best[warp] = bs; s_idx[warp] = bk; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float b = s_best[0];
+      int k = s_idx[0];
+      for (int w = 1; w < 8; ++w)
+        if (s_best[w] > b || (s_best[w] == b && s_idx[w] < k)) { b = s_best[w]; k = s_idx[w]; }
+      idx[fe.row] = k;
+    }
+    __syncthreads();
   }
 }
 
@@ -318,10 +389,14 @@ extern "C" int vqb_fix_flagged(const void* x_eff, int dtype, int64_t N, int D, c
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // flag_count is only known on the device: a fixed grid strides over the list.
   const int g = num_sms() * 2;
-  if (dtype == VQB_DTYPE_F32)
+  if (D > 1024) return VQB_E_UNSUPPORTED;
+  if (dtype == VQB_DTYPE_F32) {
     fix_flagged_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
-  else
+    fix_overflow_kernel<VQB_DTYPE_F32><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
+  } else {
     fix_flagged_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
+    fix_overflow_kernel<VQB_DTYPE_BF16><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
+  }
   return static_cast<int>(cudaGetLastError());
 }
 

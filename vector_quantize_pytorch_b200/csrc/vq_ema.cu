@@ -127,17 +127,44 @@ __global__ void segsum_kernel(const void* __restrict__ x, int D, const int32_t* 
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (ty < NY) {
-    for (int r = wk.y + ty; r < wk.z; r += NY) {
-      const int64_t base = static_cast<int64_t>(perm[r]) * D + tx * 4;
+    // 4 independent row gathers in flight per thread: the loop is latency-bound otherwise
+    auto add_row = [&](int prow) {
+      const int64_t base = static_cast<int64_t>(prow) * D + tx * 4;
       if (DT == VQB_DTYPE_BF16) {
-        const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + base);
+        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + base));
         a0 += __uint_as_float(u.x << 16); a1 += __uint_as_float(u.x & 0xFFFF0000u);
         a2 += __uint_as_float(u.y << 16); a3 += __uint_as_float(u.y & 0xFFFF0000u);
       } else {
-        const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + base);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + base));
         a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
       }
+    };
+    int r = wk.y + ty;
+    for (; r + 3 * NY < wk.z; r += 4 * NY) {
+      const int p0 = perm[r], p1 = perm[r + NY], p2 = perm[r + 2 * NY], p3 = perm[r + 3 * NY];
+      if (DT == VQB_DTYPE_BF16) {
+        const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + tx * 4;
+        const uint2 u0 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p0) * D));
+        const uint2 u1 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p1) * D));
+        const uint2 u2 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p2) * D));
+        const uint2 u3 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p3) * D));
+        const uint2 us[4] = {u0, u1, u2, u3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          a0 += __uint_as_float(us[q].x << 16); a1 += __uint_as_float(us[q].x & 0xFFFF0000u);
+          a2 += __uint_as_float(us[q].y << 16); a3 += __uint_as_float(us[q].y & 0xFFFF0000u);
+        }
+      } else {
+        const float* xb = reinterpret_cast<const float*>(x) + tx * 4;
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p0) * D));
+        const float4 v1 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p1) * D));
+        const float4 v2 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p2) * D));
+        const float4 v3 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p3) * D));
+        a0 += (v0.x + v1.x) + (v2.x + v3.x); a1 += (v0.y + v1.y) + (v2.y + v3.y);
+        a2 += (v0.z + v1.z) + (v2.z + v3.z); a3 += (v0.w + v1.w) + (v2.w + v3.w);
+      }
     }
+    for (; r < wk.z; r += NY) add_row(perm[r]);
     float* dst = red + ty * D + tx * 4;
     dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
   }
