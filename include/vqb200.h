@@ -55,13 +55,15 @@ int vqb_padded_codes(int K);
 
 /* Derive the tensor-core operands of a codebook from its fp32 rows (embed, K x D):
  *   planes  bf16 [2][Kpad][D] : hi = bf16(c), lo = bf16(c - hi)   (rows >= K are zero)
- *   bias    f32  [Kpad]       : euclid 0.5*||c||^2, cosine 0, rows >= K +inf
+ *   bext    bf16 [Kpad][16]   : -bias as three bf16 terms in columns 0..2 (rest 0); rows >= K hold -3e38.
+ *                               A K=16 MMA against [1 1 1 0..] seeds the accumulator with -bias.
+ *   bias    f32  [Kpad]       : euclid 0.5*||c||^2, cosine 0, rows >= K +inf (informational)
  *   cnorm2  f32  [K]          : ||c||^2 (f64-accumulated), used by the exact re-score
  *   cmax    f32  [1]          : max_k ||c||
  * Replaces nothing in the reference (it searches the fp32 rows directly, :710-712, :743); this is
  * the layout change that lets the search run on tcgen05.  Also done by vqb_ema_apply. */
-int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, float* bias, float* cnorm2,
-                         float* cmax, void* stream);
+int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, void* bext, float* bias,
+                         float* cnorm2, float* cmax, void* stream);
 
 /* Input staging (only needed for fp32 inputs and/or the cosine metric):
  *   x_eff    [N][D] in `dtype`: l2norm(x) evaluated in the input dtype (:1159 -> :376); may be NULL for euclid
@@ -74,14 +76,14 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
  * materialising the (N x K) distance matrix.  tcgen05 MMA over TMA-staged tiles, fp32 accumulate in
  * TMEM, fused running arg-max.  Scores are x.c - 0.5||c||^2 (euclid) or x.c (cosine).
  *   a_planes  bf16 [n_a][N][D]   (n_a = 1: passes (a0,hi)+(a0,lo);  n_a = 2: (a0,hi)+(a0,lo)+(a1,hi))
- *   b_planes/bias/cmax           from vqb_codebook_prepare / vqb_ema_apply
+ *   b_planes/bext/cmax           from vqb_codebook_prepare / vqb_ema_apply
  *   margin_rel                   a row is certified when its best score leads every other code by more
  *                                than 2*margin_rel*||x||*cmax; otherwise it is appended to `flagged`
  *   idx       i32 [N]            winner of the tensor-core pass (final for unflagged rows)
  *   flagged   [N] entries, flag_count i32[1] (caller zeroes it)  -> vqb_fix_flagged
  *   dbg_best  f32 [N] or NULL    best score per row (tests)
  * Supported: D % 8 == 0, 8 <= D, n_a * ceil(D/64) <= 8, 1 <= K, N >= 1, sm_100 device. */
-int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const float* bias,
+int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, vqb_flag_entry* flagged,
                int32_t* flag_count, float* dbg_best, void* stream);
 
@@ -118,11 +120,11 @@ int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, const int32_t*
  *   decay, eps   : python floats of the reference (doubles), rounded to fp32 where torch rounds them
  *   do_lerp      : cluster_size.lerp_(stats[:K], 1-decay); embed_avg.lerp_(stats[off:], 1-decay)
  *   do_normalise : embed = embed_avg / (laplace(cluster_size) * sum(cluster_size)); l2norm if cosine;
- *                  planes / bias / cnorm2 / cmax are regenerated (all four required then)
+ *                  planes / bext / bias / cnorm2 / cmax are regenerated (all five required then)
  *   scratch      : f32[2] used internally */
 int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D, double decay,
-                  double eps, int metric, int do_lerp, int do_normalise, void* planes, float* bias, float* cnorm2,
-                  float* cmax, float* scratch, void* stream);
+                  double eps, int metric, int do_lerp, int do_normalise, void* planes, void* bext, float* bias,
+                  float* cnorm2, float* cmax, float* scratch, void* stream);
 
 /* Decode (next row of SURVEY 8f): out[row] = sum_q embed_q[idx[row, q]], index -1 contributes zeros
  * (vector_quantize_pytorch.py:998-1022, residual_vq.py:324-382).  embeds: Q codebooks stacked [Q][K][D] f32

@@ -18,7 +18,7 @@ SIGNATURES = {
     "vqb_version": (_i32, []),
     "vqb_strerror": (_c.c_char_p, [_i32]),
     "vqb_padded_codes": (_i32, [_i32]),
-    "vqb_codebook_prepare": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_codebook_prepare": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqb_input_prepare": (_i32, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
     "vqb_assign": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vqb_fix_flagged": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
@@ -28,7 +28,7 @@ SIGNATURES = {
     "vqb_stats_floats": (_i64, [_i32, _i32]),
     "vqb_ema_stats_workspace": (_sz, [_i64, _i32]),
     "vqb_ema_stats": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
-    "vqb_ema_apply": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_ema_apply": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqb_decode": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
 }
 

@@ -3,14 +3,19 @@
 // Replaces the reference's   dist = -cdist(x, embed) | einsum(x, embed) ; ind = dist.argmax(-1)
 // (vector_quantize_pytorch.py:58-62, :741-747, :130-145) without materialising the (N x K) matrix.
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer : x tile (A, 128 rows, stationary in smem for the whole code sweep) and
-//                              codebook tiles (B, BN codes x 64 dims per stage) -> 128B-swizzled smem
-//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32) into TMEM;
-//                              split-precision passes (a0,c_hi)+(a0,c_lo)[+(a1,c_hi)] accumulate into
-//                              the SAME accumulator, two accumulator stages (2 x 256 TMEM columns)
-//   warps 2..5  epilogue     : tcgen05.ld (lane == row, so a thread owns a whole row of scores),
-//                              score = acc - bias, running arg-max with an error-band candidate list
+// One persistent CTA per SM, warp-specialised (10 warps):
+//   warp 0      TMA producer : x tile (A: 128 rows, stationary in smem for the whole code sweep, refilled
+//                              k-block by k-block as the last sweep of the previous tile releases it),
+//                              codebook tiles (B: BN codes x 64 dims per stage) and the per-tile bias
+//                              block (Bext: BN codes x 16) -> swizzled smem
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32) into TMEM.
+//                              Per code tile: one K=16 MMA  [1 1 1 0..] x [-b1 -b2 -b3 0..]^T  that seeds
+//                              the accumulator with -0.5||c||^2 (three bf16 terms = exact fp32), then the
+//                              split-precision passes (a0,c_hi)+(a0,c_lo)[+(a1,c_hi)] accumulate on top.
+//                              Two accumulator stages (2 x 256 TMEM columns).
+//   warps 2..9  epilogue     : tcgen05.ld (lane == row).  Warps w and w+4 share a TMEM lane group and split
+//                              the columns; a thread keeps the running arg-max of its row slice plus an
+//                              error-band candidate list, the two slices are merged once per row tile.
 //
 // Exactness: the tensor-core score of a (row, code) pair differs from the exact fp32 value by at most
 // tau = margin_rel * ||x|| * max||c||.  A row is certified when its best score leads every other score
@@ -28,19 +33,20 @@ constexpr int A_SUB_BYTES = BM * BK * 2;  // 16 KiB: one (plane, k-block) sub-ti
 constexpr int MAX_A_SUB = 8;    // n_a * ceil(D/64) <= 8  -> A <= 128 KiB
 constexpr int MAX_STAGES = 6;
 constexpr int TMEM_COLS = 512;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_CTRL_BYTES = 1024;  // barriers + tmem ptr + row norms
-constexpr int SMEM_LIMIT = 232448;     // 227 KiB opt-in maximum per CTA
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
+constexpr int SMEM_CTRL_BYTES = 6144;     // barriers + tmem ptr + row norms + merge area
+constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
   int64_t N;
   int D, K, Kpad, BN;
   int n_a, n_passes;   // passes: 0:(a0,hi) 1:(a0,lo) 2:(a1,hi)
   int KB;              // ceil(D / 64)
-  int n_stages;
+  int n_stages, n_xstages;
   int num_row_tiles, num_code_tiles;
   float margin_rel;
-  const float* bias;   // [Kpad]
   const float* cmax;   // [1]
   int32_t* idx;
   vqb_flag_entry* flagged;
@@ -48,44 +54,65 @@ struct AssignParams {
   float* dbg_best;
 };
 
-struct Ctrl {  // lives at the start of dynamic smem
-  uint64_t a_full, a_empty;
-  uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
-  uint64_t t_full[2], t_empty[2];
-  uint32_t tmem_base;
-  uint32_t pad;
-  float xn2[BM];
-};
-static_assert(sizeof(Ctrl) <= SMEM_CTRL_BYTES, "control block too large");
-
-// Candidate-band update for one score (slow path; entered for ~ln(K) elements per row).
-struct RowState {
+struct RowState {  // running arg-max of one row (slice) + candidates inside the error band
   float best, thr, W;
   int i0, i1, n;
-  __device__ __forceinline__ void update(float v, int c) {
-    if (v > thr) {
-      if (v > best) {
-        if (v - best > W) { n = 1; } else { n += 1; i1 = i0; }
-        best = v;
-        i0 = c;
-      } else {
-        n += 1;
-        i1 = c;
-      }
-      thr = best - W;
-    }
+  __device__ __forceinline__ void init(float w) { W = w; best = -INFINITY; thr = -INFINITY; i0 = 0; i1 = -1; n = 0; }
+  // called only for elements with v > thr
+  __device__ __forceinline__ void hit(float v, int c) {
+    const bool nb = v > best;
+    n = (v - best > W) ? 1 : n + 1;   // a clear new leader drops every earlier candidate out of the band
+    i1 = nb ? i0 : c;
+    i0 = nb ? c : i0;
+    best = fmaxf(best, v);
+    thr = best - W;
   }
 };
 
+struct MergeSlot { float best; int i0, i1, n; };
+
+struct Ctrl {  // lives at the start of dynamic smem
+  uint64_t a_full[MAX_A_SUB], a_empty[MAX_A_SUB];
+  uint64_t a_read;                       // epilogue finished reading A (row norms)
+  uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
+  uint64_t x_full[2], x_empty[2];        // bias blocks
+  uint64_t t_full[2], t_empty[2];        // TMEM accumulator stages
+  uint32_t tmem_base;
+  uint32_t pad;
+  float xn2[2][BM];                      // row norms, one copy per column-half (no cross-warp sync needed)
+  MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
+};
+static_assert(sizeof(Ctrl) <= SMEM_CTRL_BYTES, "control block too large");
+
+// 32-byte-swizzle K-major descriptor (the [rows][16 bf16] bias operands): 8-row groups are 256 B apart.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;  // SWIZZLE_32B
+  return d;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AssignParams p) {
+vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmX, const AssignParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(smem);
   const uint32_t smem_base = smem_u32(smem);
-  const uint32_t a_base = (smem_base + SMEM_CTRL_BYTES + 1023u) & ~1023u;    // swizzle-128B tiles need 1024 B alignment
+  const uint32_t a_base = (smem_base + SMEM_CTRL_BYTES + 1023u) & ~1023u;    // swizzled tiles need 1024 B alignment
   const uint8_t* a_gen = smem + (a_base - smem_base);                         // same place, generic address
-  const uint32_t b_base = a_base + p.n_a * p.KB * A_SUB_BYTES;               // 1024-aligned
+  const int n_sub = p.n_a * p.KB;
+  const uint32_t aext_base = a_base + n_sub * A_SUB_BYTES;                    // 4 KiB
   const uint32_t b_stage_bytes = p.BN * BK * 2;
+  const uint32_t x_stage_bytes = p.BN * 32;
+  const uint32_t xb_base = aext_base + AEXT_BYTES;                            // n_xstages * BN*32
+  const uint32_t b_base = (xb_base + p.n_xstages * x_stage_bytes + 1023u) & ~1023u;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,15 +121,21 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    mbar_init(smem_u32(&ctrl->a_full), 1);
-    mbar_init(smem_u32(&ctrl->a_empty), 1 + 4);  // MMA commit + 4 epilogue warps (they read A for the row norms)
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < n_sub; ++s) {
+      mbar_init(smem_u32(&ctrl->a_full[s]), 1);
+      mbar_init(smem_u32(&ctrl->a_empty[s]), 1);
+    }
+    mbar_init(smem_u32(&ctrl->a_read), NUM_EPI_WARPS);
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(smem_u32(&ctrl->b_full[s]), 1);
       mbar_init(smem_u32(&ctrl->b_empty[s]), 1);
     }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&ctrl->x_full[s]), 1);
+      mbar_init(smem_u32(&ctrl->x_empty[s]), 1);
       mbar_init(smem_u32(&ctrl->t_full[s]), 1);
-      mbar_init(smem_u32(&ctrl->t_empty[s]), 4);
+      mbar_init(smem_u32(&ctrl->t_empty[s]), NUM_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -110,30 +143,54 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_alloc(smem_u32(&ctrl->tmem_base), TMEM_COLS);
     tmem_relinquish();
   }
+  if (threadIdx.x < BM) {
+    // constant A-side bias operand: row r = [1 1 1 0 ... 0] (16 bf16 = two 16-byte chunks), 32-byte swizzle:
+    // chunk j of row r lives at r*32 + ((j ^ ((r >> 2) & 1)) << 4)
+    const int r = threadIdx.x;
+    uint8_t* row = const_cast<uint8_t*>(a_gen) + (aext_base - a_base) + r * 32;
+    const int sw = (r >> 2) & 1;
+    *reinterpret_cast<uint4*>(row + ((0 ^ sw) << 4)) = make_uint4(0x3F803F80u, 0x00003F80u, 0u, 0u);
+    *reinterpret_cast<uint4*>(row + ((1 ^ sw) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
   const int my_tiles = (p.num_row_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  // plane used by pass ps: A plane = (ps == 2), B plane = (ps == 1)
+  const int last_pass_a0 = p.n_passes >= 2 ? 1 : 0;  // last pass that reads A plane 0
 
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t ph = 0;
+      uint32_t it = 0;
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = blockIdx.x + t * gridDim.x;
         const int row0 = tile * BM;
-        mbar_wait(smem_u32(&ctrl->a_empty), (t & 1) ^ 1);
-        mbar_arrive_expect_tx(smem_u32(&ctrl->a_full), p.n_a * p.KB * A_SUB_BYTES);
-        for (int pl = 0; pl < p.n_a; ++pl)
-          for (int kb = 0; kb < p.KB; ++kb)
-            tma_load_3d(a_base + (pl * p.KB + kb) * A_SUB_BYTES, &tmA, smem_u32(&ctrl->a_full), kb * BK, row0, pl);
-        for (int ct = 0; ct < p.num_code_tiles; ++ct) {
+        if (t > 0) mbar_wait(smem_u32(&ctrl->a_read), (t - 1) & 1);  // norms of the previous tile were read
+        for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
+          {  // bias block of this code tile
+            const uint32_t xs = p.n_xstages == 2 ? (it & 1) : 0;
+            const uint32_t xph = p.n_xstages == 2 ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(smem_u32(&ctrl->x_empty[xs]), xph ^ 1);
+            mbar_arrive_expect_tx(smem_u32(&ctrl->x_full[xs]), x_stage_bytes);
+            tma_load_3d(xb_base + xs * x_stage_bytes, &tmX, smem_u32(&ctrl->x_full[xs]), 0, ct * p.BN, 0);
+          }
           for (int ps = 0; ps < p.n_passes; ++ps) {
             const int bplane = (ps == 1) ? 1 : 0;
+            const int aplane = (ps == 2) ? 1 : 0;
+            const bool first_use = (ct == 0) && (ps == 0 || ps == 2);
             for (int kb = 0; kb < p.KB; ++kb) {
+              if (first_use) {  // refill this A sub-tile as soon as the previous row tile released it
+                const int sub = aplane * p.KB + kb;
+                mbar_wait(smem_u32(&ctrl->a_empty[sub]), (t & 1) ^ 1);
+                mbar_arrive_expect_tx(smem_u32(&ctrl->a_full[sub]), A_SUB_BYTES);
+                tma_load_3d(a_base + sub * A_SUB_BYTES, &tmA, smem_u32(&ctrl->a_full[sub]), kb * BK, row0, aplane);
+              }
               mbar_wait(smem_u32(&ctrl->b_empty[stage]), ph ^ 1);
               mbar_arrive_expect_tx(smem_u32(&ctrl->b_full[stage]), b_stage_bytes);
               tma_load_3d(b_base + stage * b_stage_bytes, &tmB, smem_u32(&ctrl->b_full[stage]), kb * BK, ct * p.BN, bplane);
@@ -147,51 +204,61 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BM, p.BN);
+      const uint64_t aext_desc = umma_smem_desc_sw32(aext_base);
       int stage = 0;
       uint32_t ph = 0;
       uint32_t it = 0;  // accumulator iteration counter (across row tiles)
       for (int t = 0; t < my_tiles; ++t) {
-        mbar_wait(smem_u32(&ctrl->a_full), t & 1);
-        tc_fence_after();
         for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
           const uint32_t as = it & 1;
           mbar_wait(smem_u32(&ctrl->t_empty[as]), ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
           const uint32_t d_tmem = tmem_base + as * 256;
-          uint32_t acc = 0;
+          {  // seed the accumulator with -bias
+            const uint32_t xs = p.n_xstages == 2 ? (it & 1) : 0;
+            const uint32_t xph = p.n_xstages == 2 ? ((it >> 1) & 1) : (it & 1);
+            mbar_wait(smem_u32(&ctrl->x_full[xs]), xph);
+            tc_fence_after();
+            umma_bf16_ss(d_tmem, aext_desc, umma_smem_desc_sw32(xb_base + xs * x_stage_bytes), idesc, 0u);
+            umma_commit(smem_u32(&ctrl->x_empty[xs]));
+          }
           for (int ps = 0; ps < p.n_passes; ++ps) {
             const int aplane = (ps == 2) ? 1 : 0;
+            const bool last_use = (ct == p.num_code_tiles - 1) && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
             for (int kb = 0; kb < p.KB; ++kb) {
+              const int sub = aplane * p.KB + kb;
+              if (ct == 0) mbar_wait(smem_u32(&ctrl->a_full[sub]), t & 1);
               mbar_wait(smem_u32(&ctrl->b_full[stage]), ph);
               tc_fence_after();
-              const uint32_t a_addr = a_base + (aplane * p.KB + kb) * A_SUB_BYTES;
+              const uint32_t a_addr = a_base + sub * A_SUB_BYTES;
               const uint32_t b_addr = b_base + stage * b_stage_bytes;
               const int rem = p.D - kb * BK;
               const int ksteps = rem >= BK ? (BK / UMMA_K) : (rem + UMMA_K - 1) / UMMA_K;
-              for (int k = 0; k < ksteps; ++k) {
+              for (int k = 0; k < ksteps; ++k)
                 umma_bf16_ss(d_tmem, umma_smem_desc_sw128(a_addr + k * UMMA_K * 2),
-                             umma_smem_desc_sw128(b_addr + k * UMMA_K * 2), idesc, acc);
-                acc = 1;
-              }
-              umma_commit(smem_u32(&ctrl->b_empty[stage]));  // stage reusable once these MMAs retire
+                             umma_smem_desc_sw128(b_addr + k * UMMA_K * 2), idesc, 1u);
+              umma_commit(smem_u32(&ctrl->b_empty[stage]));              // B stage reusable once these MMAs retire
+              if (last_use) umma_commit(smem_u32(&ctrl->a_empty[sub])); // ... and this A sub-tile too
               if (++stage == p.n_stages) { stage = 0; ph ^= 1; }
             }
           }
           umma_commit(smem_u32(&ctrl->t_full[as]));  // accumulator complete -> epilogue
         }
-        umma_commit(smem_u32(&ctrl->a_empty));  // all MMAs reading this A tile retired
       }
     }
   } else {
-    // ================================================================ epilogue (warps 2..5)
+    // ================================================================ epilogue (warps 2..9)
+    const int ew = warp - 2;                 // 0..7
     const int lg = warp & 3;                 // TMEM lane group this warp may access
+    const int half = ew >> 2;                // column half: chunk parity handled by this warp
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
+    const int pair_bar = 1 + lg;             // named barrier shared by the two warps of a lane group
     const float cmax = __ldg(p.cmax);
+    const int n_chunks = (p.BN + 31) / 32;
     uint32_t it = 0;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = blockIdx.x + t * gridDim.x;
       // ---- row norms from the A tile in smem (conflict-free: a warp reads 4 full 128 B rows per request)
-      mbar_wait(smem_u32(&ctrl->a_full), t & 1);
+      for (int s = 0; s < n_sub; ++s) mbar_wait(smem_u32(&ctrl->a_full[s]), t & 1);
       {
         const int sub = lane >> 3, chunk = lane & 7;
         for (int i = 0; i < 8; ++i) {
@@ -201,7 +268,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int kb = 0; kb < p.KB; ++kb) {
             float v[8];
             {
-              uint4 u = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off);
+              const uint4 u = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off);
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -210,7 +277,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
             if (p.n_a == 2) {
-              uint4 u = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off);
+              const uint4 u = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off);
               const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -224,19 +291,14 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
           acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
           acc2 += __shfl_xor_sync(0xffffffffu, acc2, 4);
-          if (chunk == 0) ctrl->xn2[r] = acc2;
+          if (chunk == 0) ctrl->xn2[half][r] = acc2;
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_empty));
+        if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_read));
       }
       RowState st;
-      st.W = 2.f * p.margin_rel * sqrtf(ctrl->xn2[row_in_tile]) * cmax + 1e-30f;
-      st.best = -INFINITY;
-      st.thr = -INFINITY;
-      st.i0 = 0;
-      st.i1 = -1;
-      st.n = 0;
-      __syncwarp();  // xn2 reads done before the next tile's writers (same warp) run
+      st.init(2.f * p.margin_rel * sqrtf(ctrl->xn2[half][row_in_tile]) * cmax + 1e-30f);
+      __syncwarp();  // xn2 reads done before this warp rewrites it for the next tile
 
       for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
         const uint32_t as = it & 1;
@@ -244,26 +306,28 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * 256;
         const int code0 = ct * p.BN;
-        for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        for (int ci = half; ci < n_chunks; ci += 2) {
+          const int c0 = ci * 32;
           if (p.BN - c0 >= 32) {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_addr + c0, r);
             tmem_wait_ld();
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + code0 + c0);
+            float m[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = __ldg(bp + j);
-              const float v0 = __uint_as_float(r[4 * j + 0]) - bb.x;
-              const float v1 = __uint_as_float(r[4 * j + 1]) - bb.y;
-              const float v2 = __uint_as_float(r[4 * j + 2]) - bb.z;
-              const float v3 = __uint_as_float(r[4 * j + 3]) - bb.w;
-              const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-              if (m > st.thr) {
-                const int c = code0 + c0 + 4 * j;
-                st.update(v0, c);
-                st.update(v1, c + 1);
-                st.update(v2, c + 2);
-                st.update(v3, c + 3);
+            for (int j = 0; j < 8; ++j)
+              m[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
+                           fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+            const float mm = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+            if (mm > st.thr) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (m[j] > st.thr) {
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float v = __uint_as_float(r[4 * j + e]);
+                    if (v > st.thr) st.hit(v, code0 + c0 + 4 * j + e);
+                  }
+                }
               }
             }
           } else {  // BN is a multiple of 16: one 16-column tail
@@ -271,25 +335,46 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld_32x32b_x16(t_addr + c0, r);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) st.update(__uint_as_float(r[j]) - __ldg(p.bias + code0 + c0 + j), code0 + c0 + j);
+            for (int j = 0; j < 16; ++j) {
+              const float v = __uint_as_float(r[j]);
+              if (v > st.thr) st.hit(v, code0 + c0 + j);
+            }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&ctrl->t_empty[as]));
       }
-      const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
-      if (row < p.N) {
-        p.idx[row] = st.i0;
-        if (p.dbg_best) p.dbg_best[row] = st.best;
-        if (st.n >= 2) {
-          const int slot = atomicAdd(p.flag_count, 1);
-          vqb_flag_entry e;
-          e.row = static_cast<int32_t>(row);
-          e.cand0 = st.i0;
-          e.cand1 = st.i1;
-          e.count = st.n;
-          p.flagged[slot] = e;
+
+      // ---- merge the two column slices of each row (upper half publishes, lower half finishes the row)
+      MergeSlot* slot = &ctrl->merge[t & 1][row_in_tile];
+      if (half == 1) {
+        slot->best = st.best; slot->i0 = st.i0; slot->i1 = st.i1; slot->n = st.n;
+        named_bar_sync(pair_bar, 64);
+      } else {
+        named_bar_sync(pair_bar, 64);
+        const float ob = slot->best;
+        const int oi0 = slot->i0, oi1 = slot->i1, on = slot->n;
+        // candidates of a slice count only if that slice's best is inside the band of the overall best
+        const float best = fmaxf(st.best, ob);
+        const bool mine_in = st.best >= best - st.W, other_in = ob >= best - st.W;
+        const int n = (mine_in ? st.n : 0) + (other_in ? on : 0);
+        int i0, i1;
+        if (st.best > ob || (st.best == ob && st.i0 < oi0)) { i0 = st.i0; i1 = (mine_in && st.n >= 2) ? st.i1 : oi0; }
+        else { i0 = oi0; i1 = (other_in && on >= 2) ? oi1 : st.i0; }
+        const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
+        if (row < p.N) {
+          p.idx[row] = i0;
+          if (p.dbg_best) p.dbg_best[row] = best;
+          if (n >= 2) {
+            const int s = atomicAdd(p.flag_count, 1);
+            vqb_flag_entry e;
+            e.row = static_cast<int32_t>(row);
+            e.cand0 = i0;
+            e.cand1 = i1;
+            e.count = n;
+            p.flagged[s] = e;
+          }
         }
       }
     }
@@ -323,18 +408,18 @@ static PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// bf16 tensor [planes][rows][D] (row-major) -> boxes of {64 dims, box_rows rows, 1 plane}, 128B swizzle,
+// bf16 tensor [planes][rows][cols] (row-major) -> boxes of {box_cols, box_rows, 1}, swizzle span == box row bytes,
 // out-of-bounds elements read as zero (ragged N / K / D are handled by the zero fill).
-static int make_map(CUtensorMap* m, const void* base, int D, int64_t rows, int planes, int box_rows) {
+static int make_map(CUtensorMap* m, const void* base, int cols, int64_t rows, int planes, int box_cols, int box_rows,
+                    CUtensorMapSwizzle swz) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return VQB_E_DRIVER;
-  cuuint64_t dims[3] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
-  cuuint64_t strides[2] = {static_cast<cuuint64_t>(D) * 2, static_cast<cuuint64_t>(D) * 2 * static_cast<cuuint64_t>(rows)};
-  cuuint32_t box[3] = {BK, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint64_t dims[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, static_cast<cuuint64_t>(cols) * 2 * static_cast<cuuint64_t>(rows)};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows), 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? VQB_OK : VQB_E_DRIVER;
 }
 
@@ -348,10 +433,10 @@ extern "C" int vqb_padded_codes(int K) {
   return (K + BN - 1) / BN * BN;
 }
 
-extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const float* bias,
+extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                           const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx,
                           vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best, void* stream) {
-  if (!a_planes || !b_planes || !bias || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
+  if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
   if (n_passes == 0) n_passes = (n_a == 2) ? 3 : 2;
   if (n_passes < 1 || n_passes > 3 || (n_passes == 3 && n_a != 2)) return VQB_E_INVALID;
@@ -359,7 +444,7 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
   const int KB = (D + BK - 1) / BK;
   if (n_a * KB > MAX_A_SUB) return VQB_E_UNSUPPORTED;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(a_planes) | reinterpret_cast<uintptr_t>(b_planes) | reinterpret_cast<uintptr_t>(bias)) & 15)
+  if ((reinterpret_cast<uintptr_t>(a_planes) | reinterpret_cast<uintptr_t>(b_planes) | reinterpret_cast<uintptr_t>(bext)) & 15)
     return VQB_E_ALIGN;
   int rc = check_device();
   if (rc) return rc;
@@ -368,23 +453,34 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
   p.N = N; p.D = D; p.K = K;
   p.BN = code_tile(K);
   p.Kpad = vqb_padded_codes(K);
+  if (n_passes < 3) n_a = 1;  // plane 1 of A is only read by pass 2
   p.n_a = n_a; p.n_passes = n_passes; p.KB = KB;
   p.num_row_tiles = static_cast<int>((N + BM - 1) / BM);
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
-  p.bias = bias; p.cmax = cmax; p.idx = idx; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
+  p.cmax = cmax; p.idx = idx; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
   const int a_bytes = n_a * KB * A_SUB_BYTES;
   const int b_stage = p.BN * BK * 2;
-  int stages = (SMEM_LIMIT - SMEM_CTRL_BYTES - 1024 /*align slack*/ - a_bytes) / b_stage;
+  const int x_stage = p.BN * 32;
+  const int fixed = SMEM_CTRL_BYTES + 1024 /*align*/ + a_bytes + AEXT_BYTES + 1024 /*align of B ring*/;
+  int xstages = 2;
+  int stages = (SMEM_LIMIT - fixed - xstages * x_stage) / b_stage;
+  if (stages < 3) {  // tight (fp32 split input, D = 256): single-buffer the bias block to keep B stages
+    xstages = 1;
+    stages = (SMEM_LIMIT - fixed - xstages * x_stage) / b_stage;
+  }
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages < 2) return VQB_E_UNSUPPORTED;
   p.n_stages = stages;
-  const int smem_bytes = SMEM_CTRL_BYTES + 1024 + a_bytes + stages * b_stage;
+  p.n_xstages = xstages;
+  const int smem_bytes = fixed + xstages * x_stage + stages * b_stage;
 
-  CUtensorMap tmA, tmB;
-  rc = make_map(&tmA, a_planes, D, N, n_a, BM);
+  CUtensorMap tmA, tmB, tmX;
+  rc = make_map(&tmA, a_planes, D, N, n_a, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);  // plane stride = N*D either way
   if (rc) return rc;
-  rc = make_map(&tmB, b_planes, D, p.Kpad, 2, p.BN);
+  rc = make_map(&tmB, b_planes, D, p.Kpad, 2, BK, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  rc = make_map(&tmX, bext, 16, p.Kpad, 1, 16, p.BN, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;
 
   static bool attr_set = false;
@@ -394,6 +490,6 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
     attr_set = true;
   }
   int grid = p.num_row_tiles < num_sms() ? p.num_row_tiles : num_sms();
-  vq_assign_kernel<<<grid, NUM_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, p);
+  vq_assign_kernel<<<grid, NUM_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmX, p);
   return static_cast<int>(cudaGetLastError());
 }

@@ -9,12 +9,12 @@ namespace vqb {
 constexpr int ROW_THREADS = 256;  // 8 warps = 8 rows in flight per CTA
 
 __global__ void codebook_prepare_kernel(const float* __restrict__ embed, int K, int Kpad, int D, int metric,
-                                        uint16_t* planes, float* bias, float* cnorm2, float* cmax) {
+                                        uint16_t* planes, uint16_t* bext, float* bias, float* cnorm2, float* cmax) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= Kpad) return;
-  write_code_operands(k < K ? embed + static_cast<int64_t>(k) * D : nullptr, k, K, Kpad, D, metric, planes, bias, cnorm2,
-                      cmax, lane);
+  write_code_operands(k < K ? embed + static_cast<int64_t>(k) * D : nullptr, k, K, Kpad, D, metric, planes, bext, bias,
+                      cnorm2, cmax, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -350,9 +350,9 @@ extern "C" const char* vqb_strerror(int code) {
   return "vqb200: unknown error";
 }
 
-extern "C" int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, float* bias,
+extern "C" int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, void* bext, float* bias,
                                     float* cnorm2, float* cmax, void* stream) {
-  if (!embed || !planes || !bias || !cnorm2 || !cmax || K <= 0 || D <= 0) return VQB_E_INVALID;
+  if (!embed || !planes || !bext || !bias || !cnorm2 || !cmax || K <= 0 || D <= 0) return VQB_E_INVALID;
   if (metric != VQB_METRIC_EUCLID && metric != VQB_METRIC_COSINE) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(planes)) & 15) return VQB_E_ALIGN;
@@ -362,7 +362,7 @@ extern "C" int vqb_codebook_prepare(const float* embed, int K, int D, int metric
   const int Kpad = vqb_padded_codes(K);
   const int wpb = ROW_THREADS / 32;
   codebook_prepare_kernel<<<(Kpad + wpb - 1) / wpb, ROW_THREADS, 0, s>>>(embed, K, Kpad, D, metric,
-                                                                         static_cast<uint16_t*>(planes), bias, cnorm2, cmax);
+                                                                         static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
   return static_cast<int>(cudaGetLastError());
 }
 

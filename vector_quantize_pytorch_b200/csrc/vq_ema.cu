@@ -115,58 +115,53 @@ __global__ void scatter_kernel(const int32_t* __restrict__ idx, int64_t N, int32
 }
 
 // one CTA per work item: embed_sum[code] (+)= sum of the rows perm[begin:end]        vqp:605
+// The row ids of the segment are staged in smem first, so the gather loop has a single dependent global
+// load per row and keeps UNROLL independent 16-byte row loads in flight per thread.
 template <int DT>
-__global__ void segsum_kernel(const void* __restrict__ x, int D, const int32_t* __restrict__ perm,
-                              const int4* __restrict__ work, const int32_t* __restrict__ nwork, float* embed_sum) {
-  using E = Elem<DT>;
+__global__ void __launch_bounds__(SEG_THREADS)
+segsum_kernel(const void* __restrict__ x, int D, const int32_t* __restrict__ perm, const int4* __restrict__ work,
+              const int32_t* __restrict__ nwork, float* embed_sum) {
   if (static_cast<int>(blockIdx.x) >= *nwork) return;
-  extern __shared__ float red[];  // [NY][D]
+  constexpr int VEC = (DT == VQB_DTYPE_BF16) ? 8 : 4;  // elements per 16-byte load
+  constexpr int UNROLL = 8;
+  extern __shared__ __align__(16) uint8_t seg_smem[];
+  int32_t* s_perm = reinterpret_cast<int32_t*>(seg_smem);                 // [SEG_CHUNK]
+  float* red = reinterpret_cast<float*>(seg_smem + SEG_CHUNK * sizeof(int32_t));  // [NY][D]
   const int4 wk = work[blockIdx.x];
-  const int TX = D / 4;                 // threads across the row (4 elements each); D % 8 == 0
-  const int NY = SEG_THREADS / TX;      // rows in flight
+  const int nrows = wk.z - wk.y;
+  for (int i = threadIdx.x; i < nrows; i += SEG_THREADS) s_perm[i] = perm[wk.y + i];
+  __syncthreads();
+  const int TX = D / VEC;               // threads across one row (D % 8 == 0)
+  const int NY = SEG_THREADS / TX;      // row lanes
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  float acc[VEC];
+#pragma unroll
+  for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
   if (ty < NY) {
-    // 4 independent row gathers in flight per thread: the loop is latency-bound otherwise
-    auto add_row = [&](int prow) {
-      const int64_t base = static_cast<int64_t>(prow) * D + tx * 4;
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + static_cast<size_t>(tx) * 16;
+    const size_t row_bytes = static_cast<size_t>(D) * (DT == VQB_DTYPE_BF16 ? 2 : 4);
+    auto accumulate = [&](const uint4& u) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
       if (DT == VQB_DTYPE_BF16) {
-        const uint2 u = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(x) + base));
-        a0 += __uint_as_float(u.x << 16); a1 += __uint_as_float(u.x & 0xFFFF0000u);
-        a2 += __uint_as_float(u.y << 16); a3 += __uint_as_float(u.y & 0xFFFF0000u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { acc[(2 * e) % VEC] += __uint_as_float(w[e] << 16); acc[(2 * e + 1) % VEC] += __uint_as_float(w[e] & 0xFFFF0000u); }
       } else {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + base));
-        a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e % VEC] += __uint_as_float(w[e]);
       }
     };
-    int r = wk.y + ty;
-    for (; r + 3 * NY < wk.z; r += 4 * NY) {
-      const int p0 = perm[r], p1 = perm[r + NY], p2 = perm[r + 2 * NY], p3 = perm[r + 3 * NY];
-      if (DT == VQB_DTYPE_BF16) {
-        const uint16_t* xb = reinterpret_cast<const uint16_t*>(x) + tx * 4;
-        const uint2 u0 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p0) * D));
-        const uint2 u1 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p1) * D));
-        const uint2 u2 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p2) * D));
-        const uint2 u3 = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<int64_t>(p3) * D));
-        const uint2 us[4] = {u0, u1, u2, u3};
+    int r = ty;
+    for (; r + (UNROLL - 1) * NY < nrows; r += UNROLL * NY) {
+      uint4 u[UNROLL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          a0 += __uint_as_float(us[q].x << 16); a1 += __uint_as_float(us[q].x & 0xFFFF0000u);
-          a2 += __uint_as_float(us[q].y << 16); a3 += __uint_as_float(us[q].y & 0xFFFF0000u);
-        }
-      } else {
-        const float* xb = reinterpret_cast<const float*>(x) + tx * 4;
-        const float4 v0 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p0) * D));
-        const float4 v1 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p1) * D));
-        const float4 v2 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p2) * D));
-        const float4 v3 = __ldg(reinterpret_cast<const float4*>(xb + static_cast<int64_t>(p3) * D));
-        a0 += (v0.x + v1.x) + (v2.x + v3.x); a1 += (v0.y + v1.y) + (v2.y + v3.y);
-        a2 += (v0.z + v1.z) + (v2.z + v3.z); a3 += (v0.w + v1.w) + (v2.w + v3.w);
-      }
+      for (int q = 0; q < UNROLL; ++q) u[q] = __ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(s_perm[r + q * NY]) * row_bytes));
+#pragma unroll
+      for (int q = 0; q < UNROLL; ++q) accumulate(u[q]);
     }
-    for (; r < wk.z; r += NY) add_row(perm[r]);
-    float* dst = red + ty * D + tx * 4;
-    dst[0] = a0; dst[1] = a1; dst[2] = a2; dst[3] = a3;
+    for (; r < nrows; r += NY) accumulate(__ldg(reinterpret_cast<const uint4*>(xb + static_cast<size_t>(s_perm[r]) * row_bytes)));
+    float* dst = red + ty * D + tx * VEC;
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) dst[e] = acc[e];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < D; i += blockDim.x) {
@@ -210,12 +205,12 @@ __global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K,
 __global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* embed_avg, float* embed,
                                 const float* __restrict__ stats, int64_t soff, int K, int Kpad, int D, float w, float eps, float keps, int metric,
                                 int do_lerp, int do_normalise, const float* __restrict__ scratch, uint16_t* planes,
-                                float* bias, float* cnorm2, float* cmax) {
+                                uint16_t* bext, float* bias, float* cnorm2, float* cmax) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= Kpad) return;
   if (k >= K) {
-    if (do_normalise) write_code_operands(nullptr, k, K, Kpad, D, metric, planes, bias, cnorm2, cmax, lane);
+    if (do_normalise) write_code_operands(nullptr, k, K, Kpad, D, metric, planes, bext, bias, cnorm2, cmax, lane);
     return;
   }
   float* avg = embed_avg + static_cast<int64_t>(k) * D;
@@ -251,7 +246,7 @@ __global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* e
     }
   }
   __syncwarp();
-  write_code_operands(emb, k, K, Kpad, D, metric, planes, bias, cnorm2, cmax, lane);
+  write_code_operands(emb, k, K, Kpad, D, metric, planes, bext, bias, cnorm2, cmax, lane);
 }
 
 }  // namespace vqb
@@ -270,7 +265,7 @@ extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, con
                              void* workspace, size_t workspace_bytes, void* stream) {
   if (!x_eff || !idx || !stats || !workspace || N <= 0 || D <= 0 || K <= 0) return VQB_E_INVALID;
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
-  if (D % 8 != 0 || D > 4 * SEG_THREADS) return VQB_E_UNSUPPORTED;
+  if (D % 8 != 0 || D > 4 * SEG_THREADS) return VQB_E_UNSUPPORTED;  // TX = D/VEC <= SEG_THREADS
   if (N >= (static_cast<int64_t>(1) << 31)) return VQB_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x_eff) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(stats)) & 15)
     return VQB_E_ALIGN;
@@ -289,8 +284,8 @@ extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, con
   scan_kernel<<<1, 1024, 0, s>>>(ws.counts, K, ws.offsets, ws.cursor, ws.work, ws.nwork, stats);
   scatter_kernel<<<g, 256, 0, s>>>(idx, N, ws.cursor, ws.perm);
   const int items = static_cast<int>(max_work_items(N, K));
-  const int TX = D / 4;
-  const size_t red_bytes = static_cast<size_t>(SEG_THREADS / TX) * D * sizeof(float);
+  const int TX = D / (dtype == VQB_DTYPE_BF16 ? 8 : 4);
+  const size_t red_bytes = SEG_CHUNK * sizeof(int32_t) + static_cast<size_t>(SEG_THREADS / TX) * D * sizeof(float);
   if (dtype == VQB_DTYPE_F32)
     segsum_kernel<VQB_DTYPE_F32><<<items, SEG_THREADS, red_bytes, s>>>(x_eff, D, ws.perm, ws.work, ws.nwork, stats + soff);
   else
@@ -300,10 +295,10 @@ extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, con
 
 extern "C" int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
                              double decay, double eps, int metric, int do_lerp, int do_normalise, void* planes,
-                             float* bias, float* cnorm2, float* cmax, float* scratch, void* stream) {
+                             void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream) {
   if (!cluster_size || !embed_avg || !embed || !scratch || K <= 0 || D <= 0) return VQB_E_INVALID;
   if (do_lerp && !stats) return VQB_E_INVALID;
-  if (do_normalise && (!planes || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
+  if (do_normalise && (!planes || !bext || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(embed_avg) | reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(planes)) & 15)
     return VQB_E_ALIGN;
@@ -318,6 +313,6 @@ extern "C" int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed
   const int wpb = 8;
   ema_rows_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(cluster_size, embed_avg, embed, stats, soff, K, Kpad, D, w, epsf, keps,
                                                             metric, do_lerp, do_normalise, scratch,
-                                                            static_cast<uint16_t*>(planes), bias, cnorm2, cmax);
+                                                            static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
   return static_cast<int>(cudaGetLastError());
 }

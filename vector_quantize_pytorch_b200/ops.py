@@ -58,6 +58,7 @@ def padded_codes(K: int) -> int:
 class CodebookOperands:
     """Tensor-core view of one codebook (see vqb_codebook_prepare in include/vqb200.h)."""
     planes: torch.Tensor  # bf16 (2, Kpad, D)
+    bext: torch.Tensor  # bf16 (Kpad, 16): -bias as three bf16 terms (the operand of the "bias MMA")
     bias: torch.Tensor  # f32 (Kpad,)
     cnorm2: torch.Tensor  # f32 (K,)
     cmax: torch.Tensor  # f32 (1,)
@@ -71,6 +72,7 @@ class CodebookOperands:
         Kpad = padded_codes(K)
         return CodebookOperands(
             planes=torch.empty((2, Kpad, D), dtype=torch.bfloat16, device=device),
+            bext=torch.empty((Kpad, 16), dtype=torch.bfloat16, device=device),
             bias=torch.empty((Kpad,), dtype=torch.float32, device=device),
             cnorm2=torch.empty((K,), dtype=torch.float32, device=device),
             cmax=torch.zeros((1,), dtype=torch.float32, device=device),
@@ -85,7 +87,7 @@ def prepare_codebook(embed: torch.Tensor, cosine: bool, out: CodebookOperands | 
     K, D = embed.shape
     ops = out if out is not None else CodebookOperands.allocate(K, D, cosine, embed.device)
     with torch.cuda.device(embed.device):
-        check(lib.vqb_codebook_prepare(_p(embed), K, D, int(cosine), _p(ops.planes), _p(ops.bias), _p(ops.cnorm2),
+        check(lib.vqb_codebook_prepare(_p(embed), K, D, int(cosine), _p(ops.planes), _p(ops.bext), _p(ops.bias), _p(ops.cnorm2),
                                        _p(ops.cmax), _stream()), "vqb_codebook_prepare")
     _count(1)
     return ops
@@ -137,7 +139,7 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        check(lib.vqb_assign(_p(a_planes), n_a, N, D, _p(ops.planes), _p(ops.bias), _p(ops.cmax), ops.K, float(margin),
+        check(lib.vqb_assign(_p(a_planes), n_a, N, D, _p(ops.planes), _p(ops.bext), _p(ops.cmax), ops.K, float(margin),
                              int(n_passes), _p(idx), _p(flagged), _p(count), _p(best), st), "vqb_assign")
         if prof is not None:
             ev1.record()
@@ -200,7 +202,7 @@ def ema_apply(cluster_size: torch.Tensor, embed_avg: torch.Tensor, embed: torch.
     K, D = embed.shape
     with torch.cuda.device(embed.device):
         check(lib.vqb_ema_apply(_p(cluster_size), _p(embed_avg), _p(embed), _p(stats), K, D, float(decay), float(eps),
-                                int(ops.cosine), int(do_lerp), int(do_normalise), _p(ops.planes), _p(ops.bias),
+                                int(ops.cosine), int(do_lerp), int(do_normalise), _p(ops.planes), _p(ops.bext), _p(ops.bias),
                                 _p(ops.cnorm2), _p(ops.cmax), _p(ops.scratch), _stream()), "vqb_ema_apply")
     _count(2)
 
