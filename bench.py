@@ -43,10 +43,13 @@ def load_peaks():
 # CPU arm: the oracle port (reference algorithm on the host cores)
 # ------------------------------------------------------------------------------------------------
 
-def cpu_reference_step_factory():
+CPU_THREADS = [None]
+
+
+def cpu_reference_step_factory(threads=None):
     import torch
     from oracle import vq_oracle_torch as T  # the reference's own ATen op sequence (bit-identical on the goldens)
-    torch.set_num_threads(os.cpu_count())
+    torch.set_num_threads(threads or os.cpu_count())
     gen = torch.Generator().manual_seed(1234)
     x = torch.randn(CPU_SAMPLE_VECTORS // 16, 16, D, generator=gen).bfloat16()
     state = T.State(torch.randn(K, D, generator=gen))
@@ -58,20 +61,29 @@ def cpu_reference_step_factory():
 
 
 def time_cpu(steps, warmup):
-    step = cpu_reference_step_factory()
-    for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return CPU_SAMPLE_VECTORS * steps / dt, dt / steps * 1e3
+    """All host cores is torch's default (and what the reference would use); on many-core hosts a smaller pool is
+    faster for this GEMM size, so both are timed and the FASTER one is reported (its thread count in `cores`)."""
+    best = None
+    for threads in sorted({os.cpu_count(), min(32, os.cpu_count())}, reverse=True):
+        step = cpu_reference_step_factory(threads)
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+        cand = (CPU_SAMPLE_VECTORS * steps / dt, dt / steps * 1e3, threads)
+        if best is None or cand[0] > best[0]:
+            best = cand
+    CPU_THREADS[0] = best[2]
+    return best[0], best[1]
 
 
 def cpu_baseline_block(value):
-    return {"value": value, "unit": "vectors/s", "cores": os.cpu_count(), "kind": "port",
+    return {"value": value, "unit": "vectors/s", "cores": CPU_THREADS[0] or os.cpu_count(), "host_cores": os.cpu_count(),
+            "kind": "port",
             "sample": f"{CPU_SAMPLE_VECTORS} of the {B * T} vectors of one step per CPU step; oracle/vq_oracle_torch.py "
-                      f"(the reference's ATen op sequence: N x K fp32 distances, one-hot, 3 sgemm), torch threads = all host cores"}
+                      f"(the reference's ATen op sequence: N x K fp32 distances, one-hot, 3 sgemm), best of torch threads in {{all host cores, 32}}"}
 
 
 def run_reference_arm(args):
@@ -212,6 +224,7 @@ def run_gpu_arm(args):
     ops.PROFILE_EVENTS = None
     clocks = sampler.stop(t_start, t_end)
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    prof = [pr for pr in prof if pr is not None]
     assign_ms = statistics.mean(a.elapsed_time(b) for a, b in prof) if prof else None
 
     # ---------------- end-to-end timing (`e2e`): pinned host input -> module -> host outputs

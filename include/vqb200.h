@@ -42,10 +42,28 @@ extern "C" {
 
 typedef struct vqb_flag_entry { /* one row whose winner the tensor-core pass could not certify */
   int32_t row;                  /* vector index                                                   */
+  int32_t count;                /* candidates inside the band; > 2 means "rescan the whole row"    */
   int32_t cand0;                /* best candidate of the tensor-core pass                         */
   int32_t cand1;                /* the other candidate inside the error band (valid if count==2)  */
-  int32_t count;                /* candidates inside the band; > 2 means "rescan the whole row"    */
+                                /* (cand0, cand1) double as a 64-bit arg-max key during the rescan */
 } vqb_flag_entry;
+
+/* Optional fused tail of the search (gather + loss + residual update, see vqb_gather for the meaning of
+ * every field).  Passed to vqb_assign, the certified rows are finished by the kernel's store warps while the
+ * tensor cores work on the next tile; pass the same struct to vqb_fix_flagged, which finishes the re-scored
+ * rows.  Host struct of device pointers. */
+typedef struct vqb_fused_outputs {
+  const void* x_eff;   /* [N][D] dtype, the rows as searched (l2-normalised for cosine)      */
+  const float* embed;  /* [K][D] fp32 codebook                                                 */
+  void* q_out;         /* [N][D] dtype or NULL                                                 */
+  int64_t* idx64_out;  /* written at idx64_out[row*idx_stride] or NULL                         */
+  int64_t idx_stride;
+  double* loss_sum;    /* f64[1] += sum((q-x)^2) or NULL                                       */
+  const void* x_raw;   /* NULL = x_eff                                                         */
+  void* resid_out;     /* [N][D] dtype = x_raw - q or NULL                                     */
+  void* qsum;          /* [N][D] dtype += q or NULL                                            */
+  int dtype;           /* VQB_DTYPE_*                                                          */
+} vqb_fused_outputs;
 
 int vqb_version(void);
 const char* vqb_strerror(int code);
@@ -85,12 +103,17 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
  * Supported: D % 8 == 0, 8 <= D, n_a * ceil(D/64) <= 8, 1 <= K, N >= 1, sm_100 device. */
 int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, vqb_flag_entry* flagged,
-               int32_t* flag_count, float* dbg_best, void* stream);
+               int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused /* NULL: search only */, void* stream);
+
+/* Diagnostics: i64 [grid][16] per-role cycle counters written by subsequent vqb_assign calls (NULL disables). */
+int vqb_debug_set_profile_buffer(void* device_buffer);
+int vqb_debug_set_mode(int mode); /* bit0: skip the epilogue's TMEM sweep (timing experiments only; results invalid) */
 
 /* Exact re-score of the flagged rows with the reference's own fp32 formula and tie rule
  * (-(x2 + y2 - 2xy).clamp(1e-8).sqrt(), first maximal index; :58-62, :140).  Rewrites idx[row]. */
 int vqb_fix_flagged(const void* x_eff, int dtype, int64_t N, int D, const float* embed, const float* cnorm2, int K,
-                    int metric, const vqb_flag_entry* flagged, const int32_t* flag_count, int32_t* idx, void* stream);
+                    int metric, vqb_flag_entry* flagged, const int32_t* flag_count, int32_t* idx,
+                    const vqb_fused_outputs* fused /* NULL: indices only */, void* stream);
 
 /* Gather + tail of VectorQuantize.forward / one ResidualVQ stage:
  *   q_out     [N][D] dtype : embed[idx] cast to the input dtype                       (:766/:779-781, :1178)
@@ -125,6 +148,35 @@ int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, const int32_t*
 int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D, double decay,
                   double eps, int metric, int do_lerp, int do_normalise, void* planes, void* bext, float* bias,
                   float* cnorm2, float* cmax, float* scratch, void* stream);
+
+/* One-call composite of VectorQuantize.forward's arithmetic (or one ResidualVQ stage): input staging ->
+ * vqb_assign (+ fused tail) -> vqb_fix_flagged -> vqb_loss_finalize -> vqb_ema_stats -> vqb_ema_apply, all
+ * enqueued from C++ (the Python glue pays one FFI call instead of ~20).  Replaces vqp:1159-1178 + :674-791. */
+typedef struct vqb_vq_forward_args {
+  const void* x;            /* [N][D] dtype, BEFORE the cosine l2norm                                         */
+  int dtype, metric;
+  int64_t N;
+  int D, K;
+  int already_normalised;   /* cosine only: x is already unit-norm (Codebook.forward contract)                 */
+  float* cluster_size;      /* [K]      state (update == 2)                                                    */
+  float* embed_avg;         /* [K][D]   state (update == 2)                                                    */
+  float* embed;             /* [K][D]   fp32 codebook (always)                                                 */
+  void* planes; void* bext; float* bias; float* cnorm2; float* cmax; float* scratch; /* vqb_codebook_prepare     */
+  void* q_out;              /* [N][D] dtype or NULL                                                            */
+  int64_t* idx64_out; int64_t idx_stride;   /* int64 indices (NULL to skip)                                    */
+  float* loss_out; float loss_weight;       /* f32[1] = weight * mse (NULL to skip)                            */
+  void* resid_out; void* qsum;              /* ResidualVQ recurrence (NULL to skip)                            */
+  int32_t* idx32;           /* [N] int32 indices (always written; input of the statistics)                     */
+  int update;               /* 0: none; 1: statistics only (caller all-reduces, then vqb_ema_apply); 2: + apply */
+  int do_normalise;         /* update == 2: also embed = embed_avg / smoothed cluster_size                      */
+  double decay, eps;
+  float* stats;             /* [vqb_stats_floats(K, D)] (update != 0)                                          */
+  float margin_rel;
+  void* workspace; size_t workspace_bytes;  /* >= vqb_vq_forward_workspace(...), 256-byte aligned              */
+  void* ev_search_begin; void* ev_search_end; /* optional cudaEvent_t recorded around the search kernel (profiling) */
+} vqb_vq_forward_args;
+size_t vqb_vq_forward_workspace(int64_t N, int D, int K, int dtype, int metric, int update);
+int vqb_vq_forward(const vqb_vq_forward_args* args, void* stream);
 
 /* Decode (next row of SURVEY 8f): out[row] = sum_q embed_q[idx[row, q]], index -1 contributes zeros
  * (vector_quantize_pytorch.py:998-1022, residual_vq.py:324-382).  embeds: Q codebooks stacked [Q][K][D] f32

@@ -35,7 +35,7 @@ def run(N, D, K, dtype, cosine=False, n_passes=0):
     t_fix = ev_time(lambda: ops.search(x, cb, c, n_passes=n_passes))
     r = ops.search(x, cb, c, n_passes=n_passes)
     cnt = r.flag_count.item()
-    over = int((r.flagged[:cnt, 3] > 2).sum().item()) if cnt else 0
+    over = int((r.flagged[:cnt, 1] > 2).sum().item()) if cnt else 0
     q = torch.empty_like(x); i64 = torch.empty(N, dtype=torch.int64, device=dev); ls = torch.zeros(1, dtype=torch.float64, device=dev)
     t_gather = ev_time(lambda: ops.gather(r.x_eff, c, r.idx, q_out=q, idx64_out=i64, loss_sum=ls))
     t_stats = ev_time(lambda: ops.ema_stats(r.x_eff, r.idx, K))

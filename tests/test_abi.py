@@ -45,7 +45,7 @@ def test_argument_errors_are_return_codes_not_crashes():
     from vector_quantize_pytorch_b200 import _C
     lib = _C.lib
     assert lib.vqb_codebook_prepare(None, 10, 8, 0, None, None, None, None, None, None) == -1
-    assert lib.vqb_assign(None, 1, 10, 8, None, None, None, 4, 0.0, 0, None, None, None, None, None) == -1
+    assert lib.vqb_assign(None, 1, 10, 8, None, None, None, 4, 0.0, 0, None, None, None, None, None, None) == -1
     assert lib.vqb_gather(None, 0, 1, 8, None, None, None, None, 1, None, None, None, None, None) == -1
     assert lib.vqb_ema_stats(None, 0, 1, 8, None, 4, None, None, 0, None) == -1
     assert lib.vqb_decode(None, 0, 1, 1, 8, None, 1, None, 0, None) == -1

@@ -14,14 +14,31 @@ _i32, _i64, _f32, _f64, _vp, _sz = _c.c_int, _c.c_int64, _c.c_float, _c.c_double
 DTYPE_F32, DTYPE_BF16 = 0, 1
 METRIC_EUCLID, METRIC_COSINE = 0, 1
 
+class FusedOutputs(ctypes.Structure):
+    """Mirror of `vqb_fused_outputs` (include/vqb200.h)."""
+    _fields_ = [("x_eff", _vp), ("embed", _vp), ("q_out", _vp), ("idx64_out", _vp), ("idx_stride", _i64),
+                ("loss_sum", _vp), ("x_raw", _vp), ("resid_out", _vp), ("qsum", _vp), ("dtype", _i32)]
+
+
+class VQForwardArgs(ctypes.Structure):
+    """Mirror of `vqb_vq_forward_args` (include/vqb200.h)."""
+    _fields_ = [("x", _vp), ("dtype", _i32), ("metric", _i32), ("N", _i64), ("D", _i32), ("K", _i32),
+                ("already_normalised", _i32), ("cluster_size", _vp), ("embed_avg", _vp), ("embed", _vp),
+                ("planes", _vp), ("bext", _vp), ("bias", _vp), ("cnorm2", _vp), ("cmax", _vp), ("scratch", _vp),
+                ("q_out", _vp), ("idx64_out", _vp), ("idx_stride", _i64), ("loss_out", _vp), ("loss_weight", _f32),
+                ("resid_out", _vp), ("qsum", _vp), ("idx32", _vp), ("update", _i32), ("do_normalise", _i32),
+                ("decay", _f64), ("eps", _f64), ("stats", _vp), ("margin_rel", _f32), ("workspace", _vp),
+                ("workspace_bytes", _sz), ("ev_search_begin", _vp), ("ev_search_end", _vp)]
+
+
 SIGNATURES = {
     "vqb_version": (_i32, []),
     "vqb_strerror": (_c.c_char_p, [_i32]),
     "vqb_padded_codes": (_i32, [_i32]),
     "vqb_codebook_prepare": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqb_input_prepare": (_i32, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
-    "vqb_assign": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp]),
-    "vqb_fix_flagged": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "vqb_assign": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_fix_flagged": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vqb_gather": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "vqb_loss_finalize": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp]),
     "vqb_stats_offset": (_i64, [_i32]),
@@ -29,6 +46,10 @@ SIGNATURES = {
     "vqb_ema_stats_workspace": (_sz, [_i64, _i32]),
     "vqb_ema_stats": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "vqb_ema_apply": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_vq_forward_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32]),
+    "vqb_vq_forward": (_i32, [_vp, _vp]),
+    "vqb_debug_set_profile_buffer": (_i32, [_vp]),
+    "vqb_debug_set_mode": (_i32, [_i32]),
     "vqb_decode": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
 }
 

@@ -13,6 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
+from .dist import allreduce_packed
 
 
 def _uniform_init(*shape):
@@ -126,7 +127,7 @@ class Codebook(nn.Module):
         """The reference all-reduces cluster_size and embed_sum separately (vqp:603, :607); the packed
         buffer needs ONE all-reduce (NCCL over NVLink on B200)."""
         if self.use_ddp:
-            distributed.all_reduce(stats)
+            allreduce_packed(stats)
         return stats
 
     def lerp_stats(self, stats: torch.Tensor, normalise: bool):
@@ -184,28 +185,32 @@ class Codebook(nn.Module):
 
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
-    def quantize_rows(self, x: torch.Tensor, *, update: bool, q_out=None, idx64_out=None, idx_stride=1, loss_sum=None,
-                      resid_out=None, qsum=None, stats_out=None, defer_ema=False, margin=None):
+    def quantize_rows(self, x: torch.Tensor, *, update: bool, q_out=None, idx64_out=None, idx_stride=1, loss_out=None,
+                      loss_weight=1.0, resid_out=None, qsum=None, stats_out=None, defer_ema=False, margin=None):
         """x (N, D) contiguous fp32/bf16 — the input BEFORE the cosine l2norm (done in-kernel).
 
-        Search (pre-update codebook, vqp:743-747) -> gather/loss/residual (vqp:766, :1178, :1327; rvq:524-525)
-        -> batch statistics (vqp:602-607).  With defer_ema the caller all-reduces and applies the
-        statistics itself (ResidualVQ packs all stages into one collective).
-        Returns (SearchResult, stats or None).
+        One C call: search (pre-update codebook, vqp:743-747) with the fused gather / loss / residual tail
+        (vqp:766, :1178, :1327; rvq:524-525) -> batch statistics (vqp:602-607) -> EMA apply (vqp:616-617, :576-584).
+        With defer_ema (or when the statistics must be all-reduced first) the EMA apply is left to the caller.
+        Returns (idx32, stats or None).
         """
         cb = self.operands()
-        embed2d = self.embed[0]
-        res = ops.search(x, cb, embed2d, margin=margin)
-        ops.gather(res.x_eff, embed2d, res.idx, q_out=q_out, idx64_out=idx64_out, idx_stride=idx_stride,
-                   loss_sum=loss_sum, x_raw=x if res.x_eff is not x else None, resid_out=resid_out, qsum=qsum)
-        stats = None
-        if update:
-            stats = ops.ema_stats(res.x_eff, res.idx, self.codebook_size, out=stats_out)
-            if not defer_ema:
+        apply_here = update and not defer_ema and not self.use_ddp
+        mode = 0 if not update else (2 if apply_here else 1)
+        normalise = self.ema_update and not self.manual_ema_update
+        idx32, stats = ops.vq_forward(
+            x, cb, self._state2d(), update=mode, do_normalise=normalise, decay=self.decay, eps=self.eps, q_out=q_out,
+            idx64_out=idx64_out, idx_stride=idx_stride, loss_out=loss_out, loss_weight=loss_weight, resid_out=resid_out,
+            qsum=qsum, stats=stats_out, margin=margin, ws_key=id(self))
+        if mode == 2 and normalise:
+            self._mark_operands_fresh()
+        if update and not defer_ema:
+            if mode == 1:
                 self.sync_stats(stats)
-                self.lerp_stats(stats, normalise=not self.manual_ema_update)
-                self.expire_codes_(res.x_eff)
-        return res, stats
+                self.lerp_stats(stats, normalise=normalise)
+            if self.has_dead_code_replacement:
+                self.expire_codes_(self.transform_input(x))
+        return idx32, stats
 
     def forward(self, x, sample_codebook_temp=None, mask=None, freeze_codebook=False, codebook_transform_fn=None,
                 ema_update_weight=None, accum_ema_update=False, ema_update=None, topk=None, update_usage=True):

@@ -3,12 +3,17 @@
 // Replaces the reference's   dist = -cdist(x, embed) | einsum(x, embed) ; ind = dist.argmax(-1)
 // (vector_quantize_pytorch.py:58-62, :741-747, :130-145) without materialising the (N x K) matrix.
 //
-// One persistent CTA per SM, warp-specialised (10 warps):
+// Persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2): the two CTAs of a pair quantize two adjacent
+// 128-row tiles against the same codebook sweep.  Each CTA stages only HALF of every codebook tile
+// (BN/2 codes) — the M=256 MMA reads both halves — which halves the L2->SM operand traffic that bounded
+// the single-CTA version (measured: 53 B/clk/SM of B-tile ingest at 2 passes).
+// Per CTA, warp-specialised (10 warps):
 //   warp 0      TMA producer : x tile (A: 128 rows, stationary in smem for the whole code sweep, refilled
 //                              k-block by k-block as the last sweep of the previous tile releases it),
 //                              codebook tiles (B: BN codes x 64 dims per stage) and the per-tile bias
 //                              block (Bext: BN codes x 16) -> swizzled smem
-//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::f16 (bf16 x bf16 -> fp32) into TMEM.
+//   warp 1      MMA issuer   : (leader CTA only) tcgen05.mma.cta_group::2.kind::f16, M=256 (128 rows per CTA),
+//                              bf16 x bf16 -> fp32 into the TMEM of both CTAs.
 //                              Per code tile: one K=16 MMA  [1 1 1 0..] x [-b1 -b2 -b3 0..]^T  that seeds
 //                              the accumulator with -0.5||c||^2 (three bf16 terms = exact fp32), then the
 //                              split-precision passes (a0,c_hi)+(a0,c_lo)[+(a1,c_hi)] accumulate on top.
@@ -23,6 +28,7 @@
 // it with the reference's exact formula.  The band test is conservative (may over-flag, never under-flag).
 #include "ptx.cuh"
 #include "vqb_common.cuh"
+#include "gather_row.cuh"
 
 namespace vqb {
 
@@ -31,10 +37,11 @@ constexpr int BK = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int UMMA_K = 16;      // K of one tcgen05.mma for 16-bit inputs
 constexpr int A_SUB_BYTES = BM * BK * 2;  // 16 KiB: one (plane, k-block) sub-tile of A
 constexpr int MAX_A_SUB = 8;    // n_a * ceil(D/64) <= 8  -> A <= 128 KiB
-constexpr int MAX_STAGES = 6;
+constexpr int MAX_STAGES = 8;
 constexpr int TMEM_COLS = 512;
 constexpr int NUM_EPI_WARPS = 8;
-constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS) * 32;
+constexpr int NUM_STORE_WARPS = 4;  // fused gather / loss / residual tail of the certified rows
+constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS + NUM_STORE_WARPS) * 32;
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
 constexpr int SMEM_CTRL_BYTES = 6144;     // barriers + tmem ptr + row norms + merge area
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
@@ -52,6 +59,9 @@ struct AssignParams {
   vqb_flag_entry* flagged;
   int32_t* flag_count;
   float* dbg_best;
+  long long* prof;     // optional [gridDim][16] cycle counters (diagnostics)
+  FusedOut fo;         // optional fused gather tail (fo.enabled)
+  int dbg_mode;        // diagnostics: bit0 = epilogue skips the TMEM sweep, bit1 = skip B loads+MMAs except bias
 };
 
 struct RowState {  // running arg-max of one row (slice) + candidates inside the error band
@@ -77,10 +87,12 @@ struct Ctrl {  // lives at the start of dynamic smem
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
   uint64_t x_full[2], x_empty[2];        // bias blocks
   uint64_t t_full[2], t_empty[2];        // TMEM accumulator stages
+  uint64_t g_full[2], g_empty[2];        // winners of a row tile handed to the store warps
   uint32_t tmem_base;
   uint32_t pad;
-  float xn2[2][BM];                      // row norms, one copy per column-half (no cross-warp sync needed)
+  float xn2[BM];                         // row norms of the current tile
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
+  int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
 };
 static_assert(sizeof(Ctrl) <= SMEM_CTRL_BYTES, "control block too large");
 
@@ -109,8 +121,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint8_t* a_gen = smem + (a_base - smem_base);                         // same place, generic address
   const int n_sub = p.n_a * p.KB;
   const uint32_t aext_base = a_base + n_sub * A_SUB_BYTES;                    // 4 KiB
-  const uint32_t b_stage_bytes = p.BN * BK * 2;
-  const uint32_t x_stage_bytes = p.BN * 32;
+  const uint32_t b_stage_bytes = (p.BN / 2) * BK * 2;   // this CTA's half of a codebook tile
+  const uint32_t x_stage_bytes = (p.BN / 2) * 32;
   const uint32_t xb_base = aext_base + AEXT_BYTES;                            // n_xstages * BN*32
   const uint32_t b_base = (xb_base + p.n_xstages * x_stage_bytes + 1023u) & ~1023u;
 
@@ -135,13 +147,15 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&ctrl->x_full[s]), 1);
       mbar_init(smem_u32(&ctrl->x_empty[s]), 1);
       mbar_init(smem_u32(&ctrl->t_full[s]), 1);
-      mbar_init(smem_u32(&ctrl->t_empty[s]), NUM_EPI_WARPS);
+      mbar_init(smem_u32(&ctrl->t_empty[s]), 2 * NUM_EPI_WARPS);  // leader's copy collects both CTAs' epilogues
+      mbar_init(smem_u32(&ctrl->g_full[s]), NUM_EPI_WARPS / 2);
+      mbar_init(smem_u32(&ctrl->g_empty[s]), NUM_STORE_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&ctrl->tmem_base), TMEM_COLS);
-    tmem_relinquish();
+    tmem_alloc_2sm(smem_u32(&ctrl->tmem_base), TMEM_COLS);
+    tmem_relinquish_2sm();
   }
   if (threadIdx.x < BM) {
     // constant A-side bias operand: row r = [1 1 1 0 ... 0] (16 bf16 = two 16-byte chunks), 32-byte swizzle:
@@ -155,30 +169,40 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();        // the peer's barriers are initialised before anything signals them remotely
   tc_fence_after();
   const uint32_t tmem_base = ctrl->tmem_base;
 
-  const int my_tiles = (p.num_row_tiles - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const uint32_t rank = cluster_ctarank();          // 0 = leader (issues the MMAs)
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_pairs = (p.num_row_tiles + 1) >> 1;  // a pair of CTAs quantizes two adjacent row tiles
+  const int my_tiles = (num_pairs - cluster_id + num_clusters - 1) / num_clusters;
   // plane used by pass ps: A plane = (ps == 2), B plane = (ps == 1)
   const int last_pass_a0 = p.n_passes >= 2 ? 1 : 0;  // last pass that reads A plane 0
 
   if (warp == 0) {
     // ================================================================ TMA producer
     if (lane == 0) {
+      long long prof_acc[2] = {0, 0};
+      const long long pstart = clock64();
       int stage = 0;
       uint32_t ph = 0;
       uint32_t it = 0;
+      const int code_half = static_cast<int>(rank) * (p.BN / 2);
       for (int t = 0; t < my_tiles; ++t) {
-        const int tile = blockIdx.x + t * gridDim.x;
-        const int row0 = tile * BM;
+        const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
+        const int row0 = tile * BM;  // may lie beyond N for the odd last pair: TMA zero-fills, nothing is written back
         if (t > 0) mbar_wait(smem_u32(&ctrl->a_read), (t - 1) & 1);  // norms of the previous tile were read
         for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
-          {  // bias block of this code tile
+          {  // bias block of this code tile (this CTA's half of the codes)
             const uint32_t xs = p.n_xstages == 2 ? (it & 1) : 0;
             const uint32_t xph = p.n_xstages == 2 ? ((it >> 1) & 1) : (it & 1);
             mbar_wait(smem_u32(&ctrl->x_empty[xs]), xph ^ 1);
-            mbar_arrive_expect_tx(smem_u32(&ctrl->x_full[xs]), x_stage_bytes);
-            tma_load_3d(xb_base + xs * x_stage_bytes, &tmX, smem_u32(&ctrl->x_full[xs]), 0, ct * p.BN, 0);
+            if (leader) mbar_arrive_expect_tx(smem_u32(&ctrl->x_full[xs]), 2 * x_stage_bytes);
+            tma_load_3d_2sm(xb_base + xs * x_stage_bytes, &tmX, smem_u32(&ctrl->x_full[xs]) & kPeerBitMask, 0,
+                            ct * p.BN + code_half, 0);
           }
           for (int ps = 0; ps < p.n_passes; ++ps) {
             const int bplane = (ps == 1) ? 1 : 0;
@@ -188,22 +212,32 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (first_use) {  // refill this A sub-tile as soon as the previous row tile released it
                 const int sub = aplane * p.KB + kb;
                 mbar_wait(smem_u32(&ctrl->a_empty[sub]), (t & 1) ^ 1);
-                mbar_arrive_expect_tx(smem_u32(&ctrl->a_full[sub]), A_SUB_BYTES);
-                tma_load_3d(a_base + sub * A_SUB_BYTES, &tmA, smem_u32(&ctrl->a_full[sub]), kb * BK, row0, aplane);
+                if (leader) mbar_arrive_expect_tx(smem_u32(&ctrl->a_full[sub]), 2 * A_SUB_BYTES);
+                tma_load_3d_2sm(a_base + sub * A_SUB_BYTES, &tmA, smem_u32(&ctrl->a_full[sub]) & kPeerBitMask, kb * BK, row0,
+                                aplane);
               }
-              mbar_wait(smem_u32(&ctrl->b_empty[stage]), ph ^ 1);
-              mbar_arrive_expect_tx(smem_u32(&ctrl->b_full[stage]), b_stage_bytes);
-              tma_load_3d(b_base + stage * b_stage_bytes, &tmB, smem_u32(&ctrl->b_full[stage]), kb * BK, ct * p.BN, bplane);
+              { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->b_empty[stage]), ph ^ 1); prof_acc[0] += clock64() - c0; }
+              if (p.dbg_mode & 4) {  // timing experiment: no codebook traffic, the MMAs run on stale smem
+                if (leader) mbar_arrive(smem_u32(&ctrl->b_full[stage]));
+              } else {
+                if (leader) mbar_arrive_expect_tx(smem_u32(&ctrl->b_full[stage]), 2 * b_stage_bytes);
+                tma_load_3d_2sm(b_base + stage * b_stage_bytes, &tmB, smem_u32(&ctrl->b_full[stage]) & kPeerBitMask, kb * BK,
+                                ct * p.BN + code_half, bplane);
+              }
               if (++stage == p.n_stages) { stage = 0; ph ^= 1; }
             }
           }
         }
       }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = prof_acc[0]; p.prof[blockIdx.x * 16 + 1] = clock64() - pstart; }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(BM, p.BN);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);
+      constexpr uint16_t kBoth = 0x3;
+      long long w_tempty = 0, w_bfull = 0, w_xfull = 0, w_afull = 0;
+      const long long mstart = clock64();
       const uint64_t aext_desc = umma_smem_desc_sw32(aext_base);
       int stage = 0;
       uint32_t ph = 0;
@@ -211,41 +245,45 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = 0; t < my_tiles; ++t) {
         for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
           const uint32_t as = it & 1;
-          mbar_wait(smem_u32(&ctrl->t_empty[as]), ((it >> 1) & 1) ^ 1);
+          { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->t_empty[as]), ((it >> 1) & 1) ^ 1); w_tempty += clock64() - c0; }
           const uint32_t d_tmem = tmem_base + as * 256;
           {  // seed the accumulator with -bias
             const uint32_t xs = p.n_xstages == 2 ? (it & 1) : 0;
             const uint32_t xph = p.n_xstages == 2 ? ((it >> 1) & 1) : (it & 1);
-            mbar_wait(smem_u32(&ctrl->x_full[xs]), xph);
+            { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->x_full[xs]), xph); w_xfull += clock64() - c0; }
             tc_fence_after();
-            umma_bf16_ss(d_tmem, aext_desc, umma_smem_desc_sw32(xb_base + xs * x_stage_bytes), idesc, 0u);
-            umma_commit(smem_u32(&ctrl->x_empty[xs]));
+            umma_bf16_ss_2sm(d_tmem, aext_desc, umma_smem_desc_sw32(xb_base + xs * x_stage_bytes), idesc, 0u);
+            umma_commit_2sm(smem_u32(&ctrl->x_empty[xs]), kBoth);
           }
           for (int ps = 0; ps < p.n_passes; ++ps) {
             const int aplane = (ps == 2) ? 1 : 0;
             const bool last_use = (ct == p.num_code_tiles - 1) && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
             for (int kb = 0; kb < p.KB; ++kb) {
               const int sub = aplane * p.KB + kb;
-              if (ct == 0) mbar_wait(smem_u32(&ctrl->a_full[sub]), t & 1);
-              mbar_wait(smem_u32(&ctrl->b_full[stage]), ph);
+              if (ct == 0) { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->a_full[sub]), t & 1); w_afull += clock64() - c0; }
+              { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->b_full[stage]), ph); w_bfull += clock64() - c0; }
               tc_fence_after();
               const uint32_t a_addr = a_base + sub * A_SUB_BYTES;
               const uint32_t b_addr = b_base + stage * b_stage_bytes;
               const int rem = p.D - kb * BK;
               const int ksteps = rem >= BK ? (BK / UMMA_K) : (rem + UMMA_K - 1) / UMMA_K;
               for (int k = 0; k < ksteps; ++k)
-                umma_bf16_ss(d_tmem, umma_smem_desc_sw128(a_addr + k * UMMA_K * 2),
-                             umma_smem_desc_sw128(b_addr + k * UMMA_K * 2), idesc, 1u);
-              umma_commit(smem_u32(&ctrl->b_empty[stage]));              // B stage reusable once these MMAs retire
-              if (last_use) umma_commit(smem_u32(&ctrl->a_empty[sub])); // ... and this A sub-tile too
+                umma_bf16_ss_2sm(d_tmem, umma_smem_desc_sw128(a_addr + k * UMMA_K * 2),
+                                 umma_smem_desc_sw128(b_addr + k * UMMA_K * 2), idesc, 1u);
+              umma_commit_2sm(smem_u32(&ctrl->b_empty[stage]), kBoth);              // B stage reusable once these MMAs retire
+              if (last_use) umma_commit_2sm(smem_u32(&ctrl->a_empty[sub]), kBoth); // ... and this A sub-tile too
               if (++stage == p.n_stages) { stage = 0; ph ^= 1; }
             }
           }
-          umma_commit(smem_u32(&ctrl->t_full[as]));  // accumulator complete -> epilogue
+          umma_commit_2sm(smem_u32(&ctrl->t_full[as]), kBoth);  // accumulator complete -> both epilogues
         }
       }
+      if (p.prof) {
+        long long* o = p.prof + blockIdx.x * 16;
+        o[2] = w_tempty; o[3] = w_bfull; o[4] = w_xfull; o[5] = w_afull; o[6] = clock64() - mstart;
+      }
     }
-  } else {
+  } else if (warp < 2 + NUM_EPI_WARPS) {
     // ================================================================ epilogue (warps 2..9)
     const int ew = warp - 2;                 // 0..7
     const int lg = warp & 3;                 // TMEM lane group this warp may access
@@ -255,58 +293,64 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const float cmax = __ldg(p.cmax);
     const int n_chunks = (p.BN + 31) / 32;
     uint32_t it = 0;
+    long long w_tfull = 0, w_work = 0, w_merge = 0;
+    const long long estart = clock64();
     for (int t = 0; t < my_tiles; ++t) {
-      const int tile = blockIdx.x + t * gridDim.x;
-      // ---- row norms from the A tile in smem (conflict-free: a warp reads 4 full 128 B rows per request)
-      for (int s = 0; s < n_sub; ++s) mbar_wait(smem_u32(&ctrl->a_full[s]), t & 1);
-      {
-        const int sub = lane >> 3, chunk = lane & 7;
-        for (int i = 0; i < 8; ++i) {
-          const int r = lg * 32 + i * 4 + sub;
-          const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
-          float acc2 = 0.f;
-          for (int kb = 0; kb < p.KB; ++kb) {
-            float v[8];
-            {
-              const uint4 u = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[2 * e] = __uint_as_float(w[e] << 16);
-                v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
-              }
-            }
-            if (p.n_a == 2) {
-              const uint4 u = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off);
-              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[2 * e] += __uint_as_float(w[e] << 16);
-                v[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-              }
-            }
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc2 = fmaf(v[e], v[e], acc2);
-          }
-          acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
-          acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
-          acc2 += __shfl_xor_sync(0xffffffffu, acc2, 4);
-          if (chunk == 0) ctrl->xn2[half][r] = acc2;
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_read));
-      }
+      const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
       RowState st;
-      st.init(2.f * p.margin_rel * sqrtf(ctrl->xn2[half][row_in_tile]) * cmax + 1e-30f);
-      __syncwarp();  // xn2 reads done before this warp rewrites it for the next tile
 
       for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
         const uint32_t as = it & 1;
-        mbar_wait(smem_u32(&ctrl->t_full[as]), (it >> 1) & 1);
+        { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->t_full[as]), (it >> 1) & 1); w_tfull += clock64() - c0; }
+        const long long cw0 = clock64();
         tc_fence_after();
+        if (ct == 0) {
+          // ---- row norms from the A tile in smem.  The first accumulator being complete implies that every A
+          // sub-tile of both CTAs has landed (only the leader's barriers see the TMA bytes).
+          // Conflict-free: a warp reads 4 full 128 B rows per request.
+      {
+            const int sub = lane >> 3, chunk = lane & 7;
+            for (int i = half * 4; i < half * 4 + 4; ++i) {  // the two warps of a lane group split its 32 rows
+              const int r = lg * 32 + i * 4 + sub;
+              const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
+              float acc2 = 0.f;
+              for (int kb = 0; kb < p.KB; ++kb) {
+                float v[8];
+                {
+                  const uint4 u = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off);
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    v[2 * e] = __uint_as_float(w[e] << 16);
+                    v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
+                  }
+                }
+                if (p.n_a == 2) {
+                  const uint4 u = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off);
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    v[2 * e] += __uint_as_float(w[e] << 16);
+                    v[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
+                  }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc2 = fmaf(v[e], v[e], acc2);
+              }
+              acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
+              acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
+              acc2 += __shfl_xor_sync(0xffffffffu, acc2, 4);
+              if (chunk == 0) ctrl->xn2[r] = acc2;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_read));
+          }
+          named_bar_sync(pair_bar, 64);  // both halves' norms visible (the end-of-tile merge barrier orders reuse)
+          st.init(2.f * p.margin_rel * sqrtf(ctrl->xn2[row_in_tile]) * cmax + 1e-30f);
+        }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * 256;
         const int code0 = ct * p.BN;
-        for (int ci = half; ci < n_chunks; ci += 2) {
+        for (int ci = half; ci < n_chunks && !(p.dbg_mode & 1); ci += 2) {
           const int c0 = ci * 32;
           if (p.BN - c0 >= 32) {
             uint32_t r[32];
@@ -343,8 +387,13 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&ctrl->t_empty[as]));
+        if (lane == 0) {  // the leader's barrier gates the MMA issue into this accumulator stage of BOTH CTAs
+          if (leader) mbar_arrive(smem_u32(&ctrl->t_empty[as]));
+          else mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->t_empty[as]), 0));
+        }
+        w_work += clock64() - cw0;
       }
+      const long long cm0 = clock64();
 
       // ---- merge the two column slices of each row (upper half publishes, lower half finishes the row)
       MergeSlot* slot = &ctrl->merge[t & 1][row_in_tile];
@@ -363,6 +412,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (st.best > ob || (st.best == ob && st.i0 < oi0)) { i0 = st.i0; i1 = (mine_in && st.n >= 2) ? st.i1 : oi0; }
         else { i0 = oi0; i1 = (other_in && on >= 2) ? oi1 : st.i0; }
         const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
+        if (p.fo.enabled) {  // hand the certified winners of this tile to the store warps
+          mbar_wait(smem_u32(&ctrl->g_empty[t & 1]), ((t >> 1) & 1) ^ 1);
+          ctrl->gidx[t & 1][row_in_tile] = (row < p.N && n < 2) ? i0 : -1;
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_full[t & 1]));
+        }
         if (row < p.N) {
           p.idx[row] = i0;
           if (p.dbg_best) p.dbg_best[row] = best;
@@ -377,13 +432,51 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+      w_merge += clock64() - cm0;
+    }
+    if (p.prof && lane == 0 && (ew == 0 || ew == 4)) {
+      long long* o = p.prof + blockIdx.x * 16 + 8 + (ew >> 2) * 4;
+      o[0] = w_tfull; o[1] = w_work; o[2] = w_merge; o[3] = clock64() - estart;
+    }
+  }
+
+  if (warp >= 2 + NUM_EPI_WARPS && p.fo.enabled) {
+    // ================================================================ store warps (fused gather tail)
+    const int sw = warp - 2 - NUM_EPI_WARPS;
+    float lsum = 0.f;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
+      mbar_wait(smem_u32(&ctrl->g_full[t & 1]), (t >> 1) & 1);
+      const int* gi = ctrl->gidx[t & 1] + sw * 32;
+      constexpr int GB = 4;
+      for (int r0 = 0; r0 < 32; r0 += GB) {
+        int64_t rows[GB];
+        int ks[GB];
+        bool any = false;
+#pragma unroll
+        for (int b = 0; b < GB; ++b) {
+          ks[b] = gi[r0 + b];
+          rows[b] = ks[b] >= 0 ? static_cast<int64_t>(tile) * BM + sw * 32 + r0 + b : -1;
+          any |= ks[b] >= 0;
+        }
+        if (!any) continue;
+        if (p.fo.dtype == VQB_DTYPE_BF16) lsum += gather_rows<VQB_DTYPE_BF16, GB>(p.fo, rows, ks, p.D, lane);
+        else lsum += gather_rows<VQB_DTYPE_F32, GB>(p.fo, rows, ks, p.D, lane);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_empty[t & 1]));
+    }
+    if (p.fo.loss_sum) {
+      const double w = warp_sum(static_cast<double>(lsum));
+      if (lane == 0) atomicAdd(p.fo.loss_sum, w);
     }
   }
 
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal / read it
+  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -433,9 +526,17 @@ extern "C" int vqb_padded_codes(int K) {
   return (K + BN - 1) / BN * BN;
 }
 
+// validate + copy the optional fused-tail description (shared with vq_aux.cu through vqb_common.cuh)
+static long long* g_prof = nullptr;
+static int g_dbg_mode = 0;
+extern "C" int vqb_debug_set_mode(int mode) { g_dbg_mode = mode; return VQB_OK; }
+// diagnostics: device buffer of [grid][16] int64 cycle counters filled by the next vqb_assign calls (NULL = off)
+extern "C" int vqb_debug_set_profile_buffer(void* buf) { g_prof = static_cast<long long*>(buf); return VQB_OK; }
+
 extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                           const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx,
-                          vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best, void* stream) {
+                          vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
+                          const vqb_fused_outputs* fused, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
   if (n_passes == 0) n_passes = (n_a == 2) ? 3 : 2;
@@ -459,9 +560,13 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
   p.cmax = cmax; p.idx = idx; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
+  p.prof = g_prof;
+  p.dbg_mode = g_dbg_mode;
+  rc = make_fused(&p.fo, fused, D);
+  if (rc) return rc;
   const int a_bytes = n_a * KB * A_SUB_BYTES;
-  const int b_stage = p.BN * BK * 2;
-  const int x_stage = p.BN * 32;
+  const int b_stage = (p.BN / 2) * BK * 2;
+  const int x_stage = (p.BN / 2) * 32;
   const int fixed = SMEM_CTRL_BYTES + 1024 /*align*/ + a_bytes + AEXT_BYTES + 1024 /*align of B ring*/;
   int xstages = 2;
   int stages = (SMEM_LIMIT - fixed - xstages * x_stage) / b_stage;
@@ -478,9 +583,9 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
   CUtensorMap tmA, tmB, tmX;
   rc = make_map(&tmA, a_planes, D, N, n_a, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);  // plane stride = N*D either way
   if (rc) return rc;
-  rc = make_map(&tmB, b_planes, D, p.Kpad, 2, BK, p.BN, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_map(&tmB, b_planes, D, p.Kpad, 2, BK, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
-  rc = make_map(&tmX, bext, 16, p.Kpad, 1, 16, p.BN, CU_TENSOR_MAP_SWIZZLE_32B);
+  rc = make_map(&tmX, bext, 16, p.Kpad, 1, 16, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;
 
   static bool attr_set = false;
@@ -489,7 +594,22 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
-  int grid = p.num_row_tiles < num_sms() ? p.num_row_tiles : num_sms();
-  vq_assign_kernel<<<grid, NUM_THREADS, smem_bytes, static_cast<cudaStream_t>(stream)>>>(tmA, tmB, tmX, p);
+  const int num_pairs = (p.num_row_tiles + 1) / 2;
+  const int max_clusters = num_sms() / 2;
+  const int clusters = num_pairs < max_clusters ? num_pairs : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * clusters);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = static_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, vq_assign_kernel, tmA, tmB, tmX, p);
+  if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }

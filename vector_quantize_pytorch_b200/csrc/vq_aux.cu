@@ -3,6 +3,7 @@
 // kernels with 16-byte accesses; the codebook (<= a few MiB) stays L2-resident.
 #include "vqb_common.cuh"
 #include "code_operands.cuh"
+#include "gather_row.cuh"
 
 namespace vqb {
 
@@ -62,8 +63,8 @@ __global__ void input_prepare_kernel(const void* __restrict__ x, int64_t N, int 
 template <int DT>
 __global__ void fix_flagged_kernel(const void* __restrict__ x, int64_t N, int D, const float* __restrict__ embed,
                                    const float* __restrict__ cnorm2, int K, int metric,
-                                   const vqb_flag_entry* __restrict__ flagged, const int32_t* __restrict__ flag_count,
-                                   int32_t* idx) {
+                                   vqb_flag_entry* __restrict__ flagged, const int32_t* __restrict__ flag_count,
+                                   int32_t* idx, const FusedOut fo) {
   using E = Elem<DT>;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
@@ -90,32 +91,52 @@ __global__ void fix_flagged_kernel(const void* __restrict__ x, int64_t N, int D,
       const float d2 = __fadd_rn(__fadd_rn(x2f, __ldg(cnorm2 + k)), __fmul_rn(xyf, -2.f));
       return -__fsqrt_rn(fmaxf(d2, 1e-8f));
     };
-    if (fe.count != 2) continue;  // >2 candidates: whole-row rescan by fix_overflow_kernel
+    if (fe.count != 2) {  // >2 candidates: whole-row rescan (fix_overflow_kernel); reset its arg-max key
+      if (lane == 0) *reinterpret_cast<unsigned long long*>(&flagged[e].cand0) = 0ull;
+      continue;
+    }
     const int ka = min(fe.cand0, fe.cand1), kb = max(fe.cand0, fe.cand1);
     const float sa = score(ka), sb = score(kb);
     const int best_k = (sb > sa) ? kb : ka;  // argmax keeps the FIRST maximal index (vqp:140)
     if (lane == 0) idx[fe.row] = best_k;
+    if (fo.enabled) {  // finish the row the search kernel left to us: gather / loss / residual
+      const double l = warp_sum(static_cast<double>(gather_row<DT>(fo, fe.row, best_k, D, lane)));
+      if (fo.loss_sum && lane == 0) atomicAdd(fo.loss_sum, l);
+    }
   }
 }
 
-// Rows with more than two codes inside the error band: exact rescan of the WHOLE codebook row by one CTA
-// (8 warps split the codes; each lane keeps its slice of x in registers; f64 accumulation, reference
-// formula and tie rule).  Rare (a few rows per million), but must not cost milliseconds when it happens.
+// Rows with more than two codes inside the error band: exact rescan of the WHOLE codebook row.  Work items are
+// (flagged entry, chunk of OVF_CHUNK codes) pairs spread over the grid, so one unlucky row of a 16384-code codebook
+// is scanned by 128 CTAs in parallel instead of one.  Each item folds its chunk winner into the entry's 64-bit key
+// [orderable(score) : ~index] with atomicMax (larger score wins; equal scores: the LOWER index, vqp:140);
+// fix_finish_kernel then writes the index and the gather tail.  f64 accumulation, reference formula.
+constexpr int OVF_CHUNK = 128;
+
+__device__ __forceinline__ uint32_t orderable(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256)
 fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* __restrict__ embed,
-                    const float* __restrict__ cnorm2, int K, int metric, const vqb_flag_entry* __restrict__ flagged,
-                    const int32_t* __restrict__ flag_count, int32_t* idx) {
+                    const float* __restrict__ cnorm2, int K, int metric, vqb_flag_entry* __restrict__ flagged,
+                    const int32_t* __restrict__ flag_count) {
   using E = Elem<DT>;
   constexpr int MAXJ = 8;  // D <= 1024
-  __shared__ float s_best[8];
-  __shared__ int s_idx[8];
+  constexpr int CPI = 8;   // codes per warp iteration: independent L2 gathers in flight
+  __shared__ unsigned long long s_key[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int64_t cnt = *flag_count;
   if (cnt > N) cnt = N;
-  for (int64_t e = blockIdx.x; e < cnt; e += gridDim.x) {
+  const int n_chunks = (K + OVF_CHUNK - 1) / OVF_CHUNK;
+  const int64_t items = cnt * n_chunks;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t e = it / n_chunks;
+    const int chunk = static_cast<int>(it - e * n_chunks);
     const vqb_flag_entry fe = flagged[e];
-    if (fe.count <= 2) continue;
+    if (fe.count <= 2) continue;  // block-uniform
     const int64_t base = static_cast<int64_t>(fe.row) * D;
     float xr[MAXJ][4];
     double x2 = 0.0;
@@ -129,14 +150,16 @@ fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* _
       }
     }
     const float x2f = static_cast<float>(warp_sum(x2));
-    float bs = -INFINITY;
-    int bk = 0x7fffffff;
-    for (int k0 = warp * 2; k0 < K; k0 += 16) {  // two codes per iteration for ILP
-      double acc[2] = {0.0, 0.0};
+    unsigned long long key = 0ull;
+    const int k_end = min(K, (chunk + 1) * OVF_CHUNK);
+    for (int k0 = chunk * OVF_CHUNK + warp * CPI; k0 < k_end; k0 += 8 * CPI) {
+      double acc[CPI];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < CPI; ++u) acc[u] = 0.0;
+#pragma unroll
+      for (int u = 0; u < CPI; ++u) {
         const int k = k0 + u;
-        if (k < K) {
+        if (k < k_end) {
           const float* c = embed + static_cast<int64_t>(k) * D;
 #pragma unroll
           for (int j = 0; j < MAXJ; ++j) {
@@ -150,10 +173,10 @@ fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* _
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < CPI; ++u) {
         const int k = k0 + u;
         const float xyf = static_cast<float>(warp_sum(acc[u]));
-        if (k < K) {
+        if (k < k_end) {
           float sc;
           if (metric == VQB_METRIC_COSINE) {
             sc = xyf;
@@ -161,20 +184,40 @@ fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* _
             const float d2 = __fadd_rn(__fadd_rn(x2f, __ldg(cnorm2 + k)), __fmul_rn(xyf, -2.f));
             sc = -__fsqrt_rn(fmaxf(d2, 1e-8f));
           }
-          if (sc > bs) { bs = sc; bk = k; }  // ascending k within the warp: first maximal index wins
+          const unsigned long long cand = (static_cast<unsigned long long>(orderable(sc)) << 32) | (0xFFFFFFFFu - static_cast<uint32_t>(k));
+          key = cand > key ? cand : key;
         }
       }
     }
-    if (lane == 0) { s_best[warp] = bs; s_idx[warp] = bk; }
+    if (lane == 0) s_key[warp] = key;
     __syncthreads();
     if (threadIdx.x == 0) {
-      float b = s_best[0];
-      int k = s_idx[0];
-      for (int w = 1; w < 8; ++w)
-        if (s_best[w] > b || (s_best[w] == b && s_idx[w] < k)) { b = s_best[w]; k = s_idx[w]; }
-      idx[fe.row] = k;
+      unsigned long long kk = s_key[0];
+      for (int w = 1; w < 8; ++w) kk = s_key[w] > kk ? s_key[w] : kk;
+      atomicMax(reinterpret_cast<unsigned long long*>(&flagged[e].cand0), kk);
     }
     __syncthreads();
+  }
+}
+
+template <int DT>
+__global__ void fix_finish_kernel(int64_t N, int D, const vqb_flag_entry* __restrict__ flagged,
+                                  const int32_t* __restrict__ flag_count, int32_t* idx, const FusedOut fo) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  int64_t cnt = *flag_count;
+  if (cnt > N) cnt = N;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); e < cnt;
+       e += static_cast<int64_t>(gridDim.x) * wpb) {
+    const vqb_flag_entry fe = flagged[e];
+    if (fe.count <= 2) continue;
+    const unsigned long long key = *reinterpret_cast<const unsigned long long*>(&flagged[e].cand0);
+    const int k = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
+    if (lane == 0) idx[fe.row] = k;
+    if (fo.enabled) {
+      const double l = warp_sum(static_cast<double>(gather_row<DT>(fo, fe.row, k, D, lane)));
+      if (fo.loss_sum && lane == 0) atomicAdd(fo.loss_sum, l);
+    }
   }
 }
 
@@ -182,103 +225,22 @@ fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* _
 // gather + loss + residual update
 // ---------------------------------------------------------------------------------------------
 template <int DT>
-__global__ void gather_kernel(const void* __restrict__ x, int64_t N, int D, const float* __restrict__ embed,
-                              const int32_t* __restrict__ idx, void* q_out, int64_t* idx64_out, int64_t idx_stride,
-                              double* loss_sum, const void* __restrict__ x_raw, void* resid_out, void* qsum) {
-  using E = Elem<DT>;
-  using T = typename E::T;
-  constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte access: 8 (bf16) or 4 (fp32)
+__global__ void gather_kernel(int64_t N, int D, const int32_t* __restrict__ idx, const FusedOut fo) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   float lsum = 0.f;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
-       row += static_cast<int64_t>(gridDim.x) * wpb) {
-    const int k = idx[row];
-    if (idx64_out && lane == 0) idx64_out[row * idx_stride] = k;
-    const float* c = embed + static_cast<int64_t>(k) * D;
-    const int64_t base = row * D;
-    for (int i = lane * VEC; i < D; i += 32 * VEC) {
-      float cv[VEC], xv[VEC], qv[VEC];
-#pragma unroll
-      for (int e = 0; e < VEC; e += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(c + i + e));
-        cv[e] = t.x; cv[e + 1] = t.y; cv[e + 2] = t.z; cv[e + 3] = t.w;
-      }
-      {
-        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(x) + base + i);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        if (DT == VQB_DTYPE_BF16) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { xv[(2 * e) % VEC] = __uint_as_float(w[e] << 16); xv[(2 * e + 1) % VEC] = __uint_as_float(w[e] & 0xFFFF0000u); }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) xv[e % VEC] = __uint_as_float(w[e]);
-        }
-      }
-#pragma unroll
-      for (int e = 0; e < VEC; ++e) {
-        qv[e] = E::round(cv[e]);                 // quantize.type(x.dtype)            vqp:1178
-        const float d = qv[e] - xv[e];
-        lsum += E::round(d * d);                 // F.mse_loss elementwise in x.dtype  vqp:1327
-      }
-      auto store_vec = [&](void* dst, const float* v) {
-        uint32_t w[4];
-        if (DT == VQB_DTYPE_BF16) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = float_to_bf16_bits(v[(2 * e) % VEC]) | (uint32_t(float_to_bf16_bits(v[(2 * e + 1) % VEC])) << 16);
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = __float_as_uint(v[e % VEC]);
-        }
-        *reinterpret_cast<uint4*>(reinterpret_cast<T*>(dst) + base + i) = make_uint4(w[0], w[1], w[2], w[3]);
-      };
-      if (q_out) store_vec(q_out, qv);
-      if (resid_out) {
-        float rv[VEC];
-        if (x_raw != x) {  // cosine: the residual is taken from the UN-normalised stage input (rvq:524)
-          const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(x_raw) + base + i);
-          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-          if (DT == VQB_DTYPE_BF16) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) { rv[(2 * e) % VEC] = __uint_as_float(w[e] << 16); rv[(2 * e + 1) % VEC] = __uint_as_float(w[e] & 0xFFFF0000u); }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) rv[e % VEC] = __uint_as_float(w[e]);
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < VEC; ++e) rv[e] = xv[e];
-        }
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) rv[e] = rv[e] - qv[e];   // residual - quantized   rvq:524 (rounded by the store)
-        store_vec(resid_out, rv);
-      }
-      if (qsum) {
-        float sv[VEC];
-        const uint4 u = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(qsum) + base + i);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-        if (DT == VQB_DTYPE_BF16) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) { sv[(2 * e) % VEC] = __uint_as_float(w[e] << 16); sv[(2 * e + 1) % VEC] = __uint_as_float(w[e] & 0xFFFF0000u); }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) sv[e % VEC] = __uint_as_float(w[e]);
-        }
-#pragma unroll
-        for (int e = 0; e < VEC; ++e) sv[e] += qv[e];           // quantized_out + quantized rvq:525
-        store_vec(qsum, sv);
-      }
-    }
-  }
-  if (loss_sum) {
+       row += static_cast<int64_t>(gridDim.x) * wpb)
+    lsum += gather_row<DT>(fo, row, idx[row], D, lane);
+  if (fo.loss_sum) {
     __shared__ double part[32];
-    double w = warp_sum(static_cast<double>(lsum));
+    const double w = warp_sum(static_cast<double>(lsum));
     if (lane == 0) part[threadIdx.x >> 5] = w;
     __syncthreads();
     if (threadIdx.x == 0) {
       double s = 0.0;
       for (int i = 0; i < wpb; ++i) s += part[i];
-      atomicAdd(loss_sum, s);
+      atomicAdd(fo.loss_sum, s);
     }
   }
 }
@@ -382,20 +344,26 @@ extern "C" int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int
 }
 
 extern "C" int vqb_fix_flagged(const void* x_eff, int dtype, int64_t N, int D, const float* embed, const float* cnorm2,
-                               int K, int metric, const vqb_flag_entry* flagged, const int32_t* flag_count,
-                               int32_t* idx, void* stream) {
+                               int K, int metric, vqb_flag_entry* flagged, const int32_t* flag_count,
+                               int32_t* idx, const vqb_fused_outputs* fused, void* stream) {
   if (!x_eff || !embed || !cnorm2 || !flagged || !flag_count || !idx || N <= 0 || D <= 0 || K <= 0) return VQB_E_INVALID;
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // flag_count is only known on the device: a fixed grid strides over the list.
-  const int g = num_sms() * 2;
   if (D > 1024) return VQB_E_UNSUPPORTED;
+  FusedOut fo;
+  int rc = make_fused(&fo, fused, D);
+  if (rc) return rc;
+  if (fo.enabled && fo.dtype != dtype) return VQB_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // flag_count is only known on the device: fixed grids stride over the list.
+  const int g = num_sms() * 2;
   if (dtype == VQB_DTYPE_F32) {
-    fix_flagged_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
-    fix_overflow_kernel<VQB_DTYPE_F32><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
+    fix_flagged_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx, fo);
+    fix_overflow_kernel<VQB_DTYPE_F32><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count);
+    fix_finish_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(N, D, flagged, flag_count, idx, fo);
   } else {
-    fix_flagged_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
-    fix_overflow_kernel<VQB_DTYPE_BF16><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx);
+    fix_flagged_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx, fo);
+    fix_overflow_kernel<VQB_DTYPE_BF16><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count);
+    fix_finish_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(N, D, flagged, flag_count, idx, fo);
   }
   return static_cast<int>(cudaGetLastError());
 }
@@ -404,19 +372,16 @@ extern "C" int vqb_gather(const void* x_eff, int dtype, int64_t N, int D, const 
                           void* q_out, int64_t* idx64_out, int64_t idx_stride, double* loss_sum, const void* x_raw,
                           void* resid_out, void* qsum, void* stream) {
   if (!x_eff || !embed || !idx || N <= 0 || D <= 0) return VQB_E_INVALID;
-  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
-  if (D % 8 != 0) return VQB_E_UNSUPPORTED;
-  if ((reinterpret_cast<uintptr_t>(x_eff) | reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(q_out) |
-       reinterpret_cast<uintptr_t>(resid_out) | reinterpret_cast<uintptr_t>(qsum)) & 15)
-    return VQB_E_ALIGN;
-  if (!x_raw) x_raw = x_eff;
-  if (reinterpret_cast<uintptr_t>(x_raw) & 15) return VQB_E_ALIGN;
+  vqb_fused_outputs f;
+  f.x_eff = x_eff; f.embed = embed; f.q_out = q_out; f.idx64_out = idx64_out; f.idx_stride = idx_stride;
+  f.loss_sum = loss_sum; f.x_raw = x_raw; f.resid_out = resid_out; f.qsum = qsum; f.dtype = dtype;
+  FusedOut fo;
+  const int rc = make_fused(&fo, &f, D);
+  if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int g = row_grid(N, ROW_THREADS / 32);
-  if (dtype == VQB_DTYPE_F32)
-    gather_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, idx, q_out, idx64_out, idx_stride, loss_sum, x_raw, resid_out, qsum);
-  else
-    gather_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, idx, q_out, idx64_out, idx_stride, loss_sum, x_raw, resid_out, qsum);
+  if (dtype == VQB_DTYPE_F32) gather_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(N, D, idx, fo);
+  else gather_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(N, D, idx, fo);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -4,6 +4,7 @@ current CUDA stream.  Mirrors the arithmetic steps of `Codebook.forward`
 """
 from __future__ import annotations
 
+import ctypes
 from dataclasses import dataclass
 
 import torch
@@ -98,13 +99,17 @@ class SearchResult:
     idx: torch.Tensor  # int32 (N,)
     x_eff: torch.Tensor  # (N, D) input as the codebook sees it (l2-normalised for cosine), in x.dtype
     flag_count: torch.Tensor  # int32 (1,) rows re-scored exactly
-    flagged: torch.Tensor  # int32 (N, 4)
+    flagged: torch.Tensor  # int32 (N, 4): (row, count, cand0, cand1)
     best: torch.Tensor | None = None
 
 
 def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margin: float | None = None, n_passes: int = 0,
-           debug_best: bool = False, fix: bool = True, normalise: bool = True) -> SearchResult:
-    """Nearest code of every row of x (N, D).  Replaces cdist/einsum + argmax (vqp:58-62, :741-747, :130-145)."""
+           debug_best: bool = False, fix: bool = True, normalise: bool = True, fused: dict | None = None) -> SearchResult:
+    """Nearest code of every row of x (N, D).  Replaces cdist/einsum + argmax (vqp:58-62, :741-747, :130-145).
+
+    fused: optional dict(q_out=, idx64_out=, idx_stride=, loss_sum=, resid_out=, qsum=) of output tensors — the
+    gather / commitment-loss / residual tail (see `gather`) then runs INSIDE the search kernel (store warps) and
+    the re-score kernels, and no separate gather launch is needed."""
     _require_cuda(x, embed)
     assert x.dim() == 2 and x.is_contiguous()
     N, D = x.shape
@@ -135,20 +140,80 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
         flagged = torch.empty((N, 4), dtype=torch.int32, device=dev)
         count = torch.zeros((1,), dtype=torch.int32, device=dev)
         best = torch.empty((N,), dtype=torch.float32, device=dev) if debug_best else None
+        fo = None
+        if fused is not None:
+            fo = _C.FusedOutputs(x_eff=_p(x_eff), embed=_p(embed), q_out=_p(fused.get("q_out")),
+                                 idx64_out=_p(fused.get("idx64_out")), idx_stride=int(fused.get("idx_stride", 1)),
+                                 loss_sum=_p(fused.get("loss_sum")), x_raw=_p(x) if x_eff is not x else None,
+                                 resid_out=_p(fused.get("resid_out")), qsum=_p(fused.get("qsum")), dtype=dt)
+        fo_ref = ctypes.byref(fo) if fo is not None else None
         prof = PROFILE_EVENTS
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
         check(lib.vqb_assign(_p(a_planes), n_a, N, D, _p(ops.planes), _p(ops.bext), _p(ops.cmax), ops.K, float(margin),
-                             int(n_passes), _p(idx), _p(flagged), _p(count), _p(best), st), "vqb_assign")
+                             int(n_passes), _p(idx), _p(flagged), _p(count), _p(best), fo_ref, st), "vqb_assign")
         if prof is not None:
             ev1.record()
             prof.append((ev0, ev1))
-        _count(1 + int(fix))
+        _count(1 + 3 * int(fix))
         if fix:
             check(lib.vqb_fix_flagged(_p(x_eff), dt, N, D, _p(embed), _p(ops.cnorm2), ops.K, int(cosine), _p(flagged),
-                                      _p(count), _p(idx), st), "vqb_fix_flagged")
+                                      _p(count), _p(idx), fo_ref, st), "vqb_fix_flagged")
     return SearchResult(idx, x_eff, count, flagged, best)
+
+
+_WS_CACHE: dict = {}
+
+
+def _workspace(key, nbytes: int, device) -> torch.Tensor:
+    """Scratch buffers are reused across calls (same stream => ordered); keyed by shape/device."""
+    buf = _WS_CACHE.get(key)
+    if buf is None or buf.numel() < nbytes or buf.device != device:
+        buf = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = buf
+    return buf
+
+
+def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: int, do_normalise: bool, decay: float,
+               eps: float, q_out=None, idx64_out=None, idx_stride: int = 1, loss_out=None, loss_weight: float = 1.0,
+               resid_out=None, qsum=None, stats=None, margin: float | None = None, already_normalised: bool = False,
+               ws_key=None) -> tuple[torch.Tensor, torch.Tensor | None]:
+    """ONE C call for the arithmetic of VectorQuantize.forward / one ResidualVQ stage (vqb_vq_forward).
+
+    state = (cluster_size (K,), embed_avg (K, D), embed (K, D)).  update: 0 none, 1 statistics only (returned
+    packed; the caller all-reduces and calls `ema_apply`), 2 statistics + EMA apply.  Returns (idx32, stats)."""
+    _require_cuda(x, state[2])
+    assert x.dim() == 2 and x.is_contiguous()
+    N, D = x.shape
+    K = ops.K
+    dt = _dtype_code(x)
+    dev = x.device
+    cs, ea, emb = state
+    idx32 = torch.empty((N,), dtype=torch.int32, device=dev)
+    if update and stats is None:
+        stats = torch.empty((stats_floats(K, D),), dtype=torch.float32, device=dev)
+    nbytes = lib.vqb_vq_forward_workspace(N, D, K, dt, int(ops.cosine), int(update))
+    ws = _workspace((ws_key, N, D, K, dt, dev.index), nbytes, dev)
+    a = _C.VQForwardArgs(
+        x=_p(x), dtype=dt, metric=int(ops.cosine), N=N, D=D, K=K, already_normalised=int(already_normalised),
+        cluster_size=_p(cs), embed_avg=_p(ea), embed=_p(emb), planes=_p(ops.planes), bext=_p(ops.bext), bias=_p(ops.bias),
+        cnorm2=_p(ops.cnorm2), cmax=_p(ops.cmax), scratch=_p(ops.scratch), q_out=_p(q_out), idx64_out=_p(idx64_out),
+        idx_stride=int(idx_stride), loss_out=_p(loss_out), loss_weight=float(loss_weight), resid_out=_p(resid_out),
+        qsum=_p(qsum), idx32=_p(idx32), update=int(update), do_normalise=int(do_normalise), decay=float(decay),
+        eps=float(eps), stats=_p(stats), margin_rel=float(DEFAULT_MARGIN if margin is None else margin),
+        workspace=_p(ws), workspace_bytes=ws.numel(), ev_search_begin=None, ev_search_end=None)
+    with torch.cuda.device(dev):
+        prof = PROFILE_EVENTS
+        if prof is not None:  # bench instrumentation: CUDA events around the search kernel, recorded from C
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(); ev1.record()  # materialise the handles
+            a.ev_search_begin, a.ev_search_end = ev0.cuda_event, ev1.cuda_event
+            prof.append((ev0, ev1))
+        check(lib.vqb_vq_forward(ctypes.byref(a), _stream()), "vqb_vq_forward")
+    _count(4 + (1 if dt == _C.DTYPE_F32 or ops.cosine else 0) + (1 if loss_out is not None else 0) + (4 if update else 0)
+           + (2 if update == 2 else 0))
+    return idx32, stats
 
 
 def gather(x_eff: torch.Tensor, embed: torch.Tensor, idx: torch.Tensor, *, q_out: torch.Tensor | None = None,

@@ -15,6 +15,7 @@ from torch import nn
 
 from . import ops
 from .codebook import _unsupported
+from .dist import allreduce_packed
 from .vector_quantize import VectorQuantize
 
 
@@ -146,7 +147,6 @@ class ResidualVQ(nn.Module):
 
         quantized_out = torch.zeros_like(flat)  # rvq:410
         all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)
-        loss_sums = torch.zeros((Q,), dtype=torch.float64, device=dev)
         losses = torch.zeros((Q,), dtype=torch.float32, device=dev)
         bufs = [torch.empty_like(flat), torch.empty_like(flat)]
         residual = flat  # rvq:411 (never written: stage 0 reads the caller's tensor)
@@ -161,11 +161,9 @@ class ResidualVQ(nn.Module):
             want_loss = training and self.layers[q].has_commitment_loss
             book.quantize_rows(
                 residual, update=do_update[q], idx64_out=all_idx[:, q], idx_stride=Q,
-                loss_sum=loss_sums[q:q + 1] if want_loss else None,
+                loss_out=losses[q:q + 1] if want_loss else None, loss_weight=self.layers[q].commitment_weight,
                 resid_out=nxt if q + 1 < Q else None, qsum=quantized_out,
                 stats_out=packed[offs[q]:offs[q] + stat_sizes[q]] if do_update[q] else None, defer_ema=True)
-            if want_loss:
-                ops.loss_finalize(loss_sums[q:q + 1], N * D, dtype, self.layers[q].commitment_weight, losses[q:q + 1])
             residual = nxt
 
         if packed is not None:
@@ -185,7 +183,7 @@ class ResidualVQ(nn.Module):
         order (vqp:616-617) and update_ema — once at the end for a shared codebook (rvq:593-597)."""
         books = self._stage_plan()
         if not synced and any(b.use_ddp for b in books):
-            distributed.all_reduce(packed)
+            allreduce_packed(packed)
         for q, book in enumerate(books):
             if not do_update[q]:
                 continue
@@ -261,7 +259,7 @@ class GroupedResidualVQ(nn.Module):
             need_sync = any(b.use_ddp for rvq, *_ in sink for b in rvq._stage_plan())
             if need_sync:  # ONE collective for every codebook of every group
                 flat_all = torch.cat([p for _, p, *_ in sink])
-                distributed.all_reduce(flat_all)
+                allreduce_packed(flat_all)
                 pos = 0
                 for rvq, packed, offs, sizes, upd, flat in sink:
                     n = packed.numel()

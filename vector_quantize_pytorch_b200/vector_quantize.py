@@ -256,21 +256,23 @@ class VectorQuantize(nn.Module):
 
         q = torch.empty_like(flat)
         idx64 = torch.empty((N,), dtype=torch.int64, device=flat.device)
-        loss_sum = torch.zeros((1,), dtype=torch.float64, device=flat.device) if fused_loss else None
-        res, _ = cbk.quantize_rows(flat, update=do_update, q_out=q, idx64_out=idx64, loss_sum=loss_sum)
+        # the kernel returns weight * mse already rounded like F.mse_loss in x.dtype (vqp:1327-1329)
+        commit_loss = torch.empty((), dtype=torch.float32, device=flat.device) if fused_loss else self.zero
+        cbk.quantize_rows(flat, update=do_update, q_out=q, idx64_out=idx64, loss_out=commit_loss if fused_loss else None,
+                          loss_weight=self.commitment_weight)
 
         quantize = q.reshape(shape)
         embed_ind = idx64.reshape(shape[:-1])
-        commit_loss = self.zero
 
-        loss = torch.tensor(0., device=flat.device, requires_grad=training)  # vqp:1282
+        if training and fused_loss:
+            # vqp:1282: `loss` is a fresh fp32 scalar that requires grad in training mode
+            loss = commit_loss.requires_grad_(torch.is_grad_enabled())
+        else:
+            loss = torch.tensor(0., device=flat.device, requires_grad=training and torch.is_grad_enabled())  # vqp:1282
         if training:
             if self.has_commitment_loss:
                 if fused_loss:
-                    commit_loss = torch.empty((), dtype=torch.float32, device=flat.device)
-                    # kernel returns weight * mse already rounded like F.mse_loss in x.dtype (vqp:1327-1329)
-                    ops.loss_finalize(loss_sum, N * D, dtype, self.commitment_weight, commit_loss)
-                    loss = loss + commit_loss
+                    pass
                 else:  # differentiable w.r.t. the input: PyTorch glue on the kernel's outputs
                     x_t = cbk.transform_input(x)
                     commit_loss = F.mse_loss(quantize.detach(), x_t)
