@@ -233,11 +233,8 @@ def run_gpu_arm(args):
     l_host = torch.empty((), dtype=torch.float32).pin_memory()
 
     def e2e_step():
-        xd = x_host.to(dev, non_blocking=True)
-        q, ind, loss = vq(xd)
-        q_host.copy_(q, non_blocking=True)
-        i_host.copy_(ind, non_blocking=True)
-        l_host.copy_(loss.detach(), non_blocking=True)
+        # public host-buffer API: pinned input -> chunk-pipelined H2D / kernels / D2H -> pinned outputs
+        vq.forward_host(x_host, n_chunks=8, out=(q_host, i_host, l_host))
 
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()

@@ -62,6 +62,8 @@ typedef struct vqb_fused_outputs {
   const void* x_raw;   /* NULL = x_eff                                                         */
   void* resid_out;     /* [N][D] dtype = x_raw - q or NULL                                     */
   void* qsum;          /* [N][D] dtype += q or NULL                                            */
+  float* stats_cnt;    /* [K] cluster_size += 1 per row, or NULL (caller zeroes)                 */
+  float* stats_sum;    /* [K][D] embed_sum += x_eff row (vector RED), or NULL (caller zeroes)    */
   int dtype;           /* VQB_DTYPE_*                                                          */
 } vqb_fused_outputs;
 
@@ -104,6 +106,14 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
 int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, vqb_flag_entry* flagged,
                int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused /* NULL: search only */, void* stream);
+
+/* vqb_assign + the metric / ||c||^2 (cnorm2 [K]) that the in-kernel commitment loss of the COSINE metric needs.
+ * When the fused tail asks for neither residual, running sum nor fused statistics, the tail degenerates to a row copy
+ * q <- codebook row (bf16 inputs: the bf16 hi plane) and the loss is read off the winning score. */
+int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
+                  const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, vqb_flag_entry* flagged,
+                  int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused, int metric, const float* cnorm2,
+                  void* stream);
 
 /* Diagnostics: i64 [grid][16] per-role cycle counters written by subsequent vqb_assign calls (NULL disables). */
 int vqb_debug_set_profile_buffer(void* device_buffer);
@@ -168,6 +178,9 @@ typedef struct vqb_vq_forward_args {
   void* resid_out; void* qsum;              /* ResidualVQ recurrence (NULL to skip)                            */
   int32_t* idx32;           /* [N] int32 indices (always written; input of the statistics)                     */
   int update;               /* 0: none; 1: statistics only (caller all-reduces, then vqb_ema_apply); 2: + apply */
+  int stats_mode;           /* 0: statistics accumulated by the search kernel's store warps (vector RED into L2);
+                               1: separate counting-sort + segmented-sum kernels (vqb_ema_stats)                 */
+  int stats_accumulate;     /* stats_mode 0: do not zero `stats` first (chunked batches sum their statistics)   */
   int do_normalise;         /* update == 2: also embed = embed_avg / smoothed cluster_size                      */
   double decay, eps;
   float* stats;             /* [vqb_stats_floats(K, D)] (update != 0)                                          */

@@ -223,6 +223,30 @@ def test_codebook_forward_contract_and_update_indices():
     assert torch.allclose(vq1.get_output_from_indices(ind), q)
 
 
+@pytest.mark.parametrize("dt,cosine", [("bf16", False), ("fp32", False), ("bf16", True)])
+def test_forward_host_matches_forward(dt, cosine):
+    """The chunk-pipelined host API must be the same function as forward() (one EMA update from summed statistics)."""
+    m = vqb()
+    torch.manual_seed(9)
+    a = m.VectorQuantize(dim=64, codebook_size=200, use_cosine_sim=cosine).to(DEV)
+    b = m.VectorQuantize(dim=64, codebook_size=200, use_cosine_sim=cosine).to(DEV)
+    _warm_codebook(a, 64, 200, cosine)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(7, 1000, 64).to(TDT[dt])
+    qa, ia, la = a(x.to(DEV))
+    qh, ih, lh = b.forward_host(x.pin_memory(), n_chunks=5)
+    torch.cuda.synchronize()
+    assert not qh.is_cuda and qh.shape == x.shape and ih.shape == x.shape[:-1]
+    assert torch.equal(ia.cpu(), ih) and torch.equal(qa.cpu(), qh)
+    assert abs(la.item() - lh.item()) <= (1e-5 if dt == "fp32" else 8e-3) * la.item()
+    for name in ("cluster_size", "embed_avg", "embed"):
+        assert torch.allclose(getattr(a._codebook, name), getattr(b._codebook, name), rtol=1e-5, atol=1e-5), name
+    # second call reuses the pipeline buffers
+    qh2, ih2, _ = b.forward_host(x.pin_memory(), n_chunks=5)
+    qa2, ia2, _ = a(x.to(DEV))
+    assert torch.equal(ia2.cpu(), ih2)
+
+
 def test_rvq_decode_invariant():
     """Reference tests/test_readme.py:74-103: sum of gathered codes == quantized_out (frozen codebook)."""
     m = vqb()

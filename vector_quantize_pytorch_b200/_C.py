@@ -17,7 +17,8 @@ METRIC_EUCLID, METRIC_COSINE = 0, 1
 class FusedOutputs(ctypes.Structure):
     """Mirror of `vqb_fused_outputs` (include/vqb200.h)."""
     _fields_ = [("x_eff", _vp), ("embed", _vp), ("q_out", _vp), ("idx64_out", _vp), ("idx_stride", _i64),
-                ("loss_sum", _vp), ("x_raw", _vp), ("resid_out", _vp), ("qsum", _vp), ("dtype", _i32)]
+                ("loss_sum", _vp), ("x_raw", _vp), ("resid_out", _vp), ("qsum", _vp), ("stats_cnt", _vp), ("stats_sum", _vp),
+                ("dtype", _i32)]
 
 
 class VQForwardArgs(ctypes.Structure):
@@ -26,7 +27,7 @@ class VQForwardArgs(ctypes.Structure):
                 ("already_normalised", _i32), ("cluster_size", _vp), ("embed_avg", _vp), ("embed", _vp),
                 ("planes", _vp), ("bext", _vp), ("bias", _vp), ("cnorm2", _vp), ("cmax", _vp), ("scratch", _vp),
                 ("q_out", _vp), ("idx64_out", _vp), ("idx_stride", _i64), ("loss_out", _vp), ("loss_weight", _f32),
-                ("resid_out", _vp), ("qsum", _vp), ("idx32", _vp), ("update", _i32), ("do_normalise", _i32),
+                ("resid_out", _vp), ("qsum", _vp), ("idx32", _vp), ("update", _i32), ("stats_mode", _i32), ("stats_accumulate", _i32), ("do_normalise", _i32),
                 ("decay", _f64), ("eps", _f64), ("stats", _vp), ("margin_rel", _f32), ("workspace", _vp),
                 ("workspace_bytes", _sz), ("ev_search_begin", _vp), ("ev_search_end", _vp)]
 
@@ -38,6 +39,7 @@ SIGNATURES = {
     "vqb_codebook_prepare": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqb_input_prepare": (_i32, [_vp, _i32, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
     "vqb_assign": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_assign_ex": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _i32, _f32, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "vqb_fix_flagged": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vqb_gather": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "vqb_loss_finalize": (_i32, [_vp, _i64, _i32, _f32, _vp, _vp]),

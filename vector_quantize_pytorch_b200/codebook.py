@@ -186,7 +186,8 @@ class Codebook(nn.Module):
     # ------------------------------------------------------------------ the hot path
     @torch.no_grad()
     def quantize_rows(self, x: torch.Tensor, *, update: bool, q_out=None, idx64_out=None, idx_stride=1, loss_out=None,
-                      loss_weight=1.0, resid_out=None, qsum=None, stats_out=None, defer_ema=False, margin=None):
+                      loss_weight=1.0, resid_out=None, qsum=None, stats_out=None, defer_ema=False, margin=None,
+                      stats_accumulate=False):
         """x (N, D) contiguous fp32/bf16 — the input BEFORE the cosine l2norm (done in-kernel).
 
         One C call: search (pre-update codebook, vqp:743-747) with the fused gather / loss / residual tail
@@ -201,7 +202,7 @@ class Codebook(nn.Module):
         idx32, stats = ops.vq_forward(
             x, cb, self._state2d(), update=mode, do_normalise=normalise, decay=self.decay, eps=self.eps, q_out=q_out,
             idx64_out=idx64_out, idx_stride=idx_stride, loss_out=loss_out, loss_weight=loss_weight, resid_out=resid_out,
-            qsum=qsum, stats=stats_out, margin=margin, ws_key=id(self))
+            qsum=qsum, stats=stats_out, margin=margin, ws_key=id(self), stats_accumulate=stats_accumulate)
         if mode == 2 and normalise:
             self._mark_operands_fresh()
         if update and not defer_ema:

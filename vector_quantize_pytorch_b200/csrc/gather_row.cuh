@@ -19,12 +19,16 @@ struct FusedOut {  // device-side copy of vqb_fused_outputs
   const void* x_raw;
   void* resid_out;
   void* qsum;
+  float* stats_cnt;   // optional: cluster_size[k] += 1        (vqp:602)
+  float* stats_sum;   // optional: embed_sum[k][:] += x_eff[row] (vqp:605), vector RED into the L2-resident buffer
   int dtype;
   int enabled;
 };
 
 inline int make_fused(FusedOut* o, const vqb_fused_outputs* f, int D) {
   o->enabled = 0;
+  o->stats_cnt = nullptr;
+  o->stats_sum = nullptr;
   if (!f) return VQB_OK;
   if (!f->x_eff || !f->embed) return VQB_E_INVALID;
   if (f->dtype != VQB_DTYPE_F32 && f->dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
@@ -36,7 +40,20 @@ inline int make_fused(FusedOut* o, const vqb_fused_outputs* f, int D) {
   o->x_eff = f->x_eff; o->embed = f->embed; o->q_out = f->q_out; o->idx64_out = f->idx64_out;
   o->idx_stride = f->idx_stride; o->loss_sum = f->loss_sum; o->x_raw = f->x_raw ? f->x_raw : f->x_eff;
   o->resid_out = f->resid_out; o->qsum = f->qsum; o->dtype = f->dtype; o->enabled = 1;
+  o->stats_cnt = f->stats_cnt; o->stats_sum = f->stats_sum;
+  if ((reinterpret_cast<uintptr_t>(f->stats_sum) & 15) != 0) return VQB_E_ALIGN;
   return VQB_OK;
+}
+
+// 16-byte vector reduction: four fp32 adds into global memory without a return value (sm_90+)
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+template <int VEC>
+__device__ __forceinline__ void stats_add(const FusedOut& o, int k, int D, int i, const float* xv) {
+  float* dst = o.stats_sum + static_cast<int64_t>(k) * D + i;
+  red_add_v4(dst, xv[0], xv[1], xv[2], xv[3]);
+  if (VEC == 8) red_add_v4(dst + 4, xv[4], xv[5], xv[6], xv[7]);
 }
 
 template <int DT>
@@ -71,6 +88,7 @@ __device__ __forceinline__ float gather_row(const FusedOut& o, int64_t row, int 
   constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte access: 8 (bf16) or 4 (fp32)
   float lsum = 0.f;
   if (o.idx64_out && lane == 0) o.idx64_out[row * o.idx_stride] = k;
+  if (o.stats_cnt && lane == 0) atomicAdd(o.stats_cnt + k, 1.f);
   const float* c = o.embed + static_cast<int64_t>(k) * D;
   const int64_t base = row * D;
   for (int i = lane * VEC; i < D; i += 32 * VEC) {
@@ -81,6 +99,7 @@ __device__ __forceinline__ float gather_row(const FusedOut& o, int64_t row, int 
       cv[e] = t.x; cv[e + 1] = t.y; cv[e + 2] = t.z; cv[e + 3] = t.w;
     }
     unpack16<DT>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(o.x_eff) + base + i), xv);
+    if (o.stats_sum) stats_add<VEC>(o, k, D, i, xv);
 #pragma unroll
     for (int e = 0; e < VEC; ++e) {
       qv[e] = E::round(cv[e]);
@@ -119,10 +138,15 @@ __device__ __forceinline__ float gather_rows(const FusedOut& o, const int64_t (&
   using T = typename E::T;
   constexpr int VEC = 16 / sizeof(T);
   float lsum = 0.f;
-  if (o.idx64_out && lane < B && rows[0] >= 0) {
+  if (o.idx64_out && lane < B) {
 #pragma unroll
     for (int b = 0; b < B; ++b)
       if (lane == b && rows[b] >= 0) o.idx64_out[rows[b] * o.idx_stride] = ks[b];
+  }
+  if (o.stats_cnt && lane < B) {
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+      if (lane == b && rows[b] >= 0) atomicAdd(o.stats_cnt + ks[b], 1.f);
   }
   for (int i = lane * VEC; i < D; i += 32 * VEC) {
     float4 cq[B][VEC / 4];
@@ -144,6 +168,7 @@ __device__ __forceinline__ float gather_rows(const FusedOut& o, const int64_t (&
       const int64_t off = rows[b] * D + i;
       float xv[8], qv[8];
       unpack16<DT>(xq[b], xv);
+      if (o.stats_sum) stats_add<VEC>(o, ks[b], D, i, xv);
 #pragma unroll
       for (int e = 0; e < VEC / 4; ++e) {
         qv[4 * e] = E::round(cq[b][e].x); qv[4 * e + 1] = E::round(cq[b][e].y);

@@ -30,6 +30,14 @@
 #include "vqb_common.cuh"
 #include "gather_row.cuh"
 
+// Per-role cycle accounting (scripts/gpu_roles.py): compile with -DVQB_PROFILE.  Off by default: the counters cost
+// registers in a kernel that runs at the 128-register cap.
+#ifdef VQB_PROFILE
+#define PROF_CLOCK() PROF_CLOCK()
+#else
+#define PROF_CLOCK() 0ll
+#endif
+
 namespace vqb {
 
 constexpr int BM = 128;         // rows of x per tile (UMMA M, one TMEM lane per row)
@@ -61,6 +69,10 @@ struct AssignParams {
   float* dbg_best;
   long long* prof;     // optional [gridDim][16] cycle counters (diagnostics)
   FusedOut fo;         // optional fused gather tail (fo.enabled)
+  int copy_mode;       // tail = pure row copy q <- codebook row (+ loss from the scores); no x re-read
+  int metric;
+  const uint16_t* b_hi;     // bf16 hi plane [Kpad][D]: bf16(c) == the quantized row for bf16 inputs
+  const float* cnorm2;      // [K] (cosine loss term)
   int dbg_mode;        // diagnostics: bit0 = epilogue skips the TMEM sweep, bit1 = skip B loads+MMAs except bias
 };
 
@@ -109,6 +121,14 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t saddr) {
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Generic fused tail of one batch of rows (needs x again: residual / running sum / fused statistics).  Kept out of
+// line so that its register appetite does not set the allocation of the whole persistent kernel.
+template <int GB>
+__device__ __forceinline__ float tail_rows(const FusedOut& fo, const int64_t (&rows)[GB], const int (&ks)[GB], int D, int lane) {
+  if (fo.dtype == VQB_DTYPE_BF16) return gather_rows<VQB_DTYPE_BF16, GB>(fo, rows, ks, D, lane);
+  return gather_rows<VQB_DTYPE_F32, GB>(fo, rows, ks, D, lane);
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -186,7 +206,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ================================================================ TMA producer
     if (lane == 0) {
       long long prof_acc[2] = {0, 0};
-      const long long pstart = clock64();
+      const long long pstart = PROF_CLOCK();
       int stage = 0;
       uint32_t ph = 0;
       uint32_t it = 0;
@@ -216,7 +236,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tma_load_3d_2sm(a_base + sub * A_SUB_BYTES, &tmA, smem_u32(&ctrl->a_full[sub]) & kPeerBitMask, kb * BK, row0,
                                 aplane);
               }
-              { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->b_empty[stage]), ph ^ 1); prof_acc[0] += clock64() - c0; }
+              { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_empty[stage]), ph ^ 1); prof_acc[0] += PROF_CLOCK() - c0; }
               if (p.dbg_mode & 4) {  // timing experiment: no codebook traffic, the MMAs run on stale smem
                 if (leader) mbar_arrive(smem_u32(&ctrl->b_full[stage]));
               } else {
@@ -229,7 +249,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = prof_acc[0]; p.prof[blockIdx.x * 16 + 1] = clock64() - pstart; }
+      if (p.prof) { p.prof[blockIdx.x * 16 + 0] = prof_acc[0]; p.prof[blockIdx.x * 16 + 1] = PROF_CLOCK() - pstart; }
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
@@ -237,7 +257,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);
       constexpr uint16_t kBoth = 0x3;
       long long w_tempty = 0, w_bfull = 0, w_xfull = 0, w_afull = 0;
-      const long long mstart = clock64();
+      const long long mstart = PROF_CLOCK();
       const uint64_t aext_desc = umma_smem_desc_sw32(aext_base);
       int stage = 0;
       uint32_t ph = 0;
@@ -245,12 +265,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = 0; t < my_tiles; ++t) {
         for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
           const uint32_t as = it & 1;
-          { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->t_empty[as]), ((it >> 1) & 1) ^ 1); w_tempty += clock64() - c0; }
+          { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->t_empty[as]), ((it >> 1) & 1) ^ 1); w_tempty += PROF_CLOCK() - c0; }
           const uint32_t d_tmem = tmem_base + as * 256;
           {  // seed the accumulator with -bias
             const uint32_t xs = p.n_xstages == 2 ? (it & 1) : 0;
             const uint32_t xph = p.n_xstages == 2 ? ((it >> 1) & 1) : (it & 1);
-            { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->x_full[xs]), xph); w_xfull += clock64() - c0; }
+            { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->x_full[xs]), xph); w_xfull += PROF_CLOCK() - c0; }
             tc_fence_after();
             umma_bf16_ss_2sm(d_tmem, aext_desc, umma_smem_desc_sw32(xb_base + xs * x_stage_bytes), idesc, 0u);
             umma_commit_2sm(smem_u32(&ctrl->x_empty[xs]), kBoth);
@@ -260,8 +280,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const bool last_use = (ct == p.num_code_tiles - 1) && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
             for (int kb = 0; kb < p.KB; ++kb) {
               const int sub = aplane * p.KB + kb;
-              if (ct == 0) { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->a_full[sub]), t & 1); w_afull += clock64() - c0; }
-              { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->b_full[stage]), ph); w_bfull += clock64() - c0; }
+              if (ct == 0) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[sub]), t & 1); w_afull += PROF_CLOCK() - c0; }
+              { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[stage]), ph); w_bfull += PROF_CLOCK() - c0; }
               tc_fence_after();
               const uint32_t a_addr = a_base + sub * A_SUB_BYTES;
               const uint32_t b_addr = b_base + stage * b_stage_bytes;
@@ -280,7 +300,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (p.prof) {
         long long* o = p.prof + blockIdx.x * 16;
-        o[2] = w_tempty; o[3] = w_bfull; o[4] = w_xfull; o[5] = w_afull; o[6] = clock64() - mstart;
+        o[2] = w_tempty; o[3] = w_bfull; o[4] = w_xfull; o[5] = w_afull; o[6] = PROF_CLOCK() - mstart;
       }
     }
   } else if (warp < 2 + NUM_EPI_WARPS) {
@@ -291,18 +311,18 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
     const int pair_bar = 1 + lg;             // named barrier shared by the two warps of a lane group
     const float cmax = __ldg(p.cmax);
-    const int n_chunks = (p.BN + 31) / 32;
     uint32_t it = 0;
     long long w_tfull = 0, w_work = 0, w_merge = 0;
-    const long long estart = clock64();
+    const long long estart = PROF_CLOCK();
+    float epi_loss = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
       RowState st;
 
       for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
         const uint32_t as = it & 1;
-        { const long long c0 = clock64(); mbar_wait(smem_u32(&ctrl->t_full[as]), (it >> 1) & 1); w_tfull += clock64() - c0; }
-        const long long cw0 = clock64();
+        { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->t_full[as]), (it >> 1) & 1); w_tfull += PROF_CLOCK() - c0; }
+        const long long cw0 = PROF_CLOCK();
         tc_fence_after();
         if (ct == 0) {
           // ---- row norms from the A tile in smem.  The first accumulator being complete implies that every A
@@ -350,39 +370,43 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * 256;
         const int code0 = ct * p.BN;
-        for (int ci = half; ci < n_chunks && !(p.dbg_mode & 1); ci += 2) {
-          const int c0 = ci * 32;
-          if (p.BN - c0 >= 32) {
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(t_addr + c0, r);
-            tmem_wait_ld();
-            float m[8];
+        // This warp owns the 16-column pieces 4q + 2*half + {0,1} of the tile.  Two register buffers: the
+        // tcgen05.ld of the next piece is in flight while the current one is scanned.
+        const int n_pieces_tile = p.BN >> 4;
+        auto piece_col = [&](int j) { return (4 * (j >> 1) + 2 * half + (j & 1)) << 4; };
+        int np = 0;
+        while (np < 64 && (piece_col(np) >> 4) < n_pieces_tile) ++np;
+        if (p.dbg_mode & 1) np = 0;
+        auto scan16 = [&](const uint32_t (&r)[16], int cbase) {
+          float m[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              m[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
-                           fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-            const float mm = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
-            if (mm > st.thr) {
+          for (int j = 0; j < 4; ++j)
+            m[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
+                         fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+          const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+          if (mm > st.thr) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                if (m[j] > st.thr) {
+            for (int j = 0; j < 4; ++j) {
+              if (m[j] > st.thr) {
 #pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float v = __uint_as_float(r[4 * j + e]);
-                    if (v > st.thr) st.hit(v, code0 + c0 + 4 * j + e);
-                  }
+                for (int e = 0; e < 4; ++e) {
+                  const float v = __uint_as_float(r[4 * j + e]);
+                  if (v > st.thr) st.hit(v, cbase + 4 * j + e);
                 }
               }
             }
-          } else {  // BN is a multiple of 16: one 16-column tail
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(t_addr + c0, r);
+          }
+        };
+        uint32_t buf0[16], buf1[16];
+        if (np > 0) tmem_ld_32x32b_x16(t_addr + piece_col(0), buf0);
+        for (int j = 0; j < np; j += 2) {
+          tmem_wait_ld();
+          if (j + 1 < np) tmem_ld_32x32b_x16(t_addr + piece_col(j + 1), buf1);
+          scan16(buf0, code0 + piece_col(j));
+          if (j + 1 < np) {
             tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float v = __uint_as_float(r[j]);
-              if (v > st.thr) st.hit(v, code0 + c0 + j);
-            }
+            if (j + 2 < np) tmem_ld_32x32b_x16(t_addr + piece_col(j + 2), buf0);
+            scan16(buf1, code0 + piece_col(j + 1));
           }
         }
         tc_fence_before();
@@ -391,9 +415,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (leader) mbar_arrive(smem_u32(&ctrl->t_empty[as]));
           else mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->t_empty[as]), 0));
         }
-        w_work += clock64() - cw0;
+        w_work += PROF_CLOCK() - cw0;
       }
-      const long long cm0 = clock64();
+      const long long cm0 = PROF_CLOCK();
 
       // ---- merge the two column slices of each row (upper half publishes, lower half finishes the row)
       MergeSlot* slot = &ctrl->merge[t & 1][row_in_tile];
@@ -412,6 +436,14 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (st.best > ob || (st.best == ob && st.i0 < oi0)) { i0 = st.i0; i1 = (mine_in && st.n >= 2) ? st.i1 : oi0; }
         else { i0 = oi0; i1 = (other_in && on >= 2) ? oi1 : st.i0; }
         const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
+        if (p.copy_mode && p.fo.loss_sum && row < p.N && n < 2) {
+          // ||q - x||^2 = ||x||^2 - 2(x.c - 0.5||c||^2)  — the score already holds it (cosine: bias is 0, add ||c||^2).
+          // Differs from the reference's bf16 evaluation by << 1e-3 relative; flagged rows get the
+          // exact evaluation in vqb_fix_flagged.
+          float d2 = ctrl->xn2[row_in_tile] - 2.f * best;
+          if (p.metric == VQB_METRIC_COSINE) d2 += __ldg(p.cnorm2 + i0);
+          epi_loss += fmaxf(d2, 0.f);
+        }
         if (p.fo.enabled) {  // hand the certified winners of this tile to the store warps
           mbar_wait(smem_u32(&ctrl->g_empty[t & 1]), ((t >> 1) & 1) ^ 1);
           ctrl->gidx[t & 1][row_in_tile] = (row < p.N && n < 2) ? i0 : -1;
@@ -432,11 +464,15 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
-      w_merge += clock64() - cm0;
+      w_merge += PROF_CLOCK() - cm0;
+    }
+    if (p.copy_mode && p.fo.loss_sum && half == 0) {
+      const double w = warp_sum(static_cast<double>(epi_loss));
+      if (lane == 0) atomicAdd(p.fo.loss_sum, w);
     }
     if (p.prof && lane == 0 && (ew == 0 || ew == 4)) {
       long long* o = p.prof + blockIdx.x * 16 + 8 + (ew >> 2) * 4;
-      o[0] = w_tfull; o[1] = w_work; o[2] = w_merge; o[3] = clock64() - estart;
+      o[0] = w_tfull; o[1] = w_work; o[2] = w_merge; o[3] = PROF_CLOCK() - estart;
     }
   }
 
@@ -448,7 +484,41 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
       mbar_wait(smem_u32(&ctrl->g_full[t & 1]), (t >> 1) & 1);
       const int* gi = ctrl->gidx[t & 1] + sw * 32;
-      constexpr int GB = 4;
+      if (p.copy_mode) {
+        // q[row] <- codebook row: bf16 inputs copy the bf16 hi plane (== embed.type(bf16)), fp32 inputs the fp32 row.
+        constexpr int CB = 4;  // rows per batch: independent 16-byte loads in flight per lane
+        const int row_bytes = p.D * (p.fo.dtype == VQB_DTYPE_BF16 ? 2 : 4);
+        const uint8_t* src = p.fo.dtype == VQB_DTYPE_BF16 ? reinterpret_cast<const uint8_t*>(p.b_hi)
+                                                          : reinterpret_cast<const uint8_t*>(p.fo.embed);
+        uint8_t* dst = static_cast<uint8_t*>(p.fo.q_out);
+        for (int r0 = 0; r0 < 32; r0 += CB) {
+          int ks[CB];
+#pragma unroll
+          for (int b = 0; b < CB; ++b) ks[b] = gi[r0 + b];
+          const int64_t row_base = static_cast<int64_t>(tile) * BM + sw * 32 + r0;
+          if (p.fo.idx64_out && lane < CB && ks[lane & (CB - 1)] >= 0) {
+            int kk = 0;
+#pragma unroll
+            for (int b = 0; b < CB; ++b) kk = (lane == b) ? ks[b] : kk;
+            p.fo.idx64_out[(row_base + lane) * p.fo.idx_stride] = kk;
+          }
+          if (dst) {
+            for (int off = lane * 16; off < row_bytes; off += 512) {
+              uint4 v[CB];
+#pragma unroll
+              for (int b = 0; b < CB; ++b)
+                if (ks[b] >= 0) v[b] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(ks[b]) * row_bytes + off));
+#pragma unroll
+              for (int b = 0; b < CB; ++b)
+                if (ks[b] >= 0) *reinterpret_cast<uint4*>(dst + (row_base + b) * row_bytes + off) = v[b];
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_empty[t & 1]));
+        continue;
+      }
+      constexpr int GB = 2;
       for (int r0 = 0; r0 < 32; r0 += GB) {
         int64_t rows[GB];
         int ks[GB];
@@ -460,13 +530,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           any |= ks[b] >= 0;
         }
         if (!any) continue;
-        if (p.fo.dtype == VQB_DTYPE_BF16) lsum += gather_rows<VQB_DTYPE_BF16, GB>(p.fo, rows, ks, p.D, lane);
-        else lsum += gather_rows<VQB_DTYPE_F32, GB>(p.fo, rows, ks, p.D, lane);
+        lsum += tail_rows<GB>(p.fo, rows, ks, p.D, lane);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_empty[t & 1]));
     }
-    if (p.fo.loss_sum) {
+    if (p.fo.loss_sum && !p.copy_mode) {
       const double w = warp_sum(static_cast<double>(lsum));
       if (lane == 0) atomicAdd(p.fo.loss_sum, w);
     }
@@ -537,6 +606,15 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
                           const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx,
                           vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
                           const vqb_fused_outputs* fused, void* stream) {
+  return vqb_assign_ex(a_planes, n_a, N, D, b_planes, bext, cmax, K, margin_rel, n_passes, idx, flagged, flag_count,
+                       dbg_best, fused, VQB_METRIC_EUCLID, nullptr, stream);
+}
+
+// Same, with the metric and ||c||^2 needed for the in-kernel commitment loss of the cosine metric.
+extern "C" int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
+                             const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx,
+                             vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
+                             const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
   if (n_passes == 0) n_passes = (n_a == 2) ? 3 : 2;
@@ -564,6 +642,12 @@ extern "C" int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const
   p.dbg_mode = g_dbg_mode;
   rc = make_fused(&p.fo, fused, D);
   if (rc) return rc;
+  p.metric = metric;
+  p.cnorm2 = cnorm2;
+  p.b_hi = static_cast<const uint16_t*>(b_planes);
+  // pure-copy tail: nothing needs x again (no residual / running sum / fused statistics); the cosine loss needs ||c||^2
+  p.copy_mode = p.fo.enabled && !p.fo.resid_out && !p.fo.qsum && !p.fo.stats_sum &&
+                !(metric == VQB_METRIC_COSINE && p.fo.loss_sum && !cnorm2);
   const int a_bytes = n_a * KB * A_SUB_BYTES;
   const int b_stage = (p.BN / 2) * BK * 2;
   const int x_stage = (p.BN / 2) * 32;

@@ -375,6 +375,7 @@ extern "C" int vqb_gather(const void* x_eff, int dtype, int64_t N, int D, const 
   vqb_fused_outputs f;
   f.x_eff = x_eff; f.embed = embed; f.q_out = q_out; f.idx64_out = idx64_out; f.idx_stride = idx_stride;
   f.loss_sum = loss_sum; f.x_raw = x_raw; f.resid_out = resid_out; f.qsum = qsum; f.dtype = dtype;
+  f.stats_cnt = nullptr; f.stats_sum = nullptr;
   FusedOut fo;
   const int rc = make_fused(&fo, &f, D);
   if (rc) return rc;

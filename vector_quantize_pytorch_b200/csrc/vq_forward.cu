@@ -85,11 +85,21 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   f.loss_sum = a->loss_out ? loss_sum : nullptr;
   f.x_raw = (x_eff != a->x) ? a->x : nullptr;
   f.resid_out = a->resid_out; f.qsum = a->qsum; f.dtype = a->dtype;
-  const bool want_tail = a->q_out || a->idx64_out || a->loss_out || a->resid_out || a->qsum;
+  const bool fused_stats = a->update && a->stats_mode == 0;
+  f.stats_cnt = nullptr; f.stats_sum = nullptr;
+  if (fused_stats) {  // statistics ride on the store warps: zero the packed buffer, accumulate with vector REDs
+    if (!a->stats_accumulate) {
+      e = cudaMemsetAsync(a->stats, 0, sizeof(float) * static_cast<size_t>(vqb_stats_floats(a->K, a->D)), s);
+      if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    f.stats_cnt = a->stats;
+    f.stats_sum = a->stats + vqb_stats_offset(a->K);
+  }
+  const bool want_tail = a->q_out || a->idx64_out || a->loss_out || a->resid_out || a->qsum || fused_stats;
   vqb_flag_entry* flagged = reinterpret_cast<vqb_flag_entry*>(ws + w.flagged);
   if (a->ev_search_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_begin), s);
-  rc = vqb_assign(a_planes, n_a, a->N, a->D, a->planes, a->bext, a->cmax, a->K, a->margin_rel, 0, a->idx32, flagged,
-                  flag_count, nullptr, want_tail ? &f : nullptr, stream);
+  rc = vqb_assign_ex(a_planes, n_a, a->N, a->D, a->planes, a->bext, a->cmax, a->K, a->margin_rel, 0, a->idx32, flagged,
+                     flag_count, nullptr, want_tail ? &f : nullptr, a->metric, a->cnorm2, stream);
   if (rc) return rc;
   if (a->ev_search_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_end), s);
   rc = vqb_fix_flagged(x_eff, a->dtype, a->N, a->D, a->embed, a->cnorm2, a->K, a->metric, flagged, flag_count, a->idx32,
@@ -100,10 +110,12 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
     if (rc) return rc;
   }
   // ---- EMA (vqp:586-617, :576-584)
-  if (a->update) {
+  if (a->update && !fused_stats) {
     rc = vqb_ema_stats(x_eff, a->dtype, a->N, a->D, a->idx32, a->K, a->stats, ws + w.stats_ws,
                        vqb_ema_stats_workspace(a->N, a->K), stream);
     if (rc) return rc;
+  }
+  if (a->update) {
     if (a->update == 2) {
       rc = vqb_ema_apply(a->cluster_size, a->embed_avg, a->embed, a->stats, a->K, a->D, a->decay, a->eps, a->metric, 1,
                          a->do_normalise, a->planes, a->bext, a->bias, a->cnorm2, a->cmax, a->scratch, stream);

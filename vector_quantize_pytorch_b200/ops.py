@@ -145,14 +145,15 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
             fo = _C.FusedOutputs(x_eff=_p(x_eff), embed=_p(embed), q_out=_p(fused.get("q_out")),
                                  idx64_out=_p(fused.get("idx64_out")), idx_stride=int(fused.get("idx_stride", 1)),
                                  loss_sum=_p(fused.get("loss_sum")), x_raw=_p(x) if x_eff is not x else None,
-                                 resid_out=_p(fused.get("resid_out")), qsum=_p(fused.get("qsum")), dtype=dt)
+                                 resid_out=_p(fused.get("resid_out")), qsum=_p(fused.get("qsum")), stats_cnt=None, stats_sum=None, dtype=dt)
         fo_ref = ctypes.byref(fo) if fo is not None else None
         prof = PROFILE_EVENTS
         if prof is not None:
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-        check(lib.vqb_assign(_p(a_planes), n_a, N, D, _p(ops.planes), _p(ops.bext), _p(ops.cmax), ops.K, float(margin),
-                             int(n_passes), _p(idx), _p(flagged), _p(count), _p(best), fo_ref, st), "vqb_assign")
+        check(lib.vqb_assign_ex(_p(a_planes), n_a, N, D, _p(ops.planes), _p(ops.bext), _p(ops.cmax), ops.K, float(margin),
+                                int(n_passes), _p(idx), _p(flagged), _p(count), _p(best), fo_ref, int(cosine),
+                                _p(ops.cnorm2), st), "vqb_assign")
         if prof is not None:
             ev1.record()
             prof.append((ev0, ev1))
@@ -163,6 +164,8 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
     return SearchResult(idx, x_eff, count, flagged, best)
 
 
+# 0: EMA statistics accumulated inside the search kernel (vector RED into L2); 1: separate sort + segmented sums
+STATS_MODE = int(__import__("os").environ.get("VQB_STATS_MODE", "1"))
 _WS_CACHE: dict = {}
 
 
@@ -178,7 +181,7 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
 def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: int, do_normalise: bool, decay: float,
                eps: float, q_out=None, idx64_out=None, idx_stride: int = 1, loss_out=None, loss_weight: float = 1.0,
                resid_out=None, qsum=None, stats=None, margin: float | None = None, already_normalised: bool = False,
-               ws_key=None) -> tuple[torch.Tensor, torch.Tensor | None]:
+               ws_key=None, stats_accumulate: bool = False) -> tuple[torch.Tensor, torch.Tensor | None]:
     """ONE C call for the arithmetic of VectorQuantize.forward / one ResidualVQ stage (vqb_vq_forward).
 
     state = (cluster_size (K,), embed_avg (K, D), embed (K, D)).  update: 0 none, 1 statistics only (returned
@@ -200,7 +203,7 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
         cluster_size=_p(cs), embed_avg=_p(ea), embed=_p(emb), planes=_p(ops.planes), bext=_p(ops.bext), bias=_p(ops.bias),
         cnorm2=_p(ops.cnorm2), cmax=_p(ops.cmax), scratch=_p(ops.scratch), q_out=_p(q_out), idx64_out=_p(idx64_out),
         idx_stride=int(idx_stride), loss_out=_p(loss_out), loss_weight=float(loss_weight), resid_out=_p(resid_out),
-        qsum=_p(qsum), idx32=_p(idx32), update=int(update), do_normalise=int(do_normalise), decay=float(decay),
+        qsum=_p(qsum), idx32=_p(idx32), update=int(update), stats_mode=STATS_MODE, stats_accumulate=int(stats_accumulate), do_normalise=int(do_normalise), decay=float(decay),
         eps=float(eps), stats=_p(stats), margin_rel=float(DEFAULT_MARGIN if margin is None else margin),
         workspace=_p(ws), workspace_bytes=ws.numel(), ev_search_begin=None, ev_search_end=None)
     with torch.cuda.device(dev):

@@ -222,6 +222,96 @@ class VectorQuantize(nn.Module):
             restore = ("transpose", None)
         return x, restore
 
+    # ------------------------------------------------------------------ host-resident batches
+    @torch.no_grad()
+    def forward_host(self, x_host: torch.Tensor, n_chunks: int = 8, out=None):
+        """forward() for a batch that lives in (pinned) HOST memory; results are returned in host memory.
+
+        The batch is streamed through the GPU in `n_chunks` row chunks on three streams — upload of chunk i+1,
+        kernels of chunk i and download of chunk i-1 overlap, so the call costs ~max(H2D, D2H) over PCIe instead
+        of H2D + kernels + D2H.  Same arithmetic as forward(): every chunk searches the pre-update codebook, the
+        chunks' EMA statistics are summed and the codebook is updated once at the end (vqp:586-617).
+        `out` = optional (quantize, indices, loss) host tensors to fill (pinned for full overlap)."""
+        if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last:
+            _unsupported("forward_host with projections / feature-map layouts")
+        cbk = self._codebook
+        emb = cbk.embed
+        if not emb.is_cuda:
+            raise RuntimeError("vqb200 has no CPU path: move the module to a CUDA (B200) device")
+        if x_host.is_cuda or x_host.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("forward_host expects a float32 / bfloat16 CPU tensor (pinned for full overlap)")
+        dev = emb.device
+        shape = x_host.shape
+        D = shape[-1]
+        xf = x_host.reshape(-1, D)
+        N = xf.shape[0]
+        training = self.training
+        do_update = training and not self.freeze_codebook and (cbk.ema_update or cbk.has_dead_code_replacement)
+        want_loss = training and self.has_commitment_loss
+        if out is None:
+            out = (torch.empty(shape, dtype=x_host.dtype).pin_memory(), torch.empty(shape[:-1], dtype=torch.int64).pin_memory(),
+                   torch.empty((), dtype=torch.float32).pin_memory())
+        q_host, i_host, l_host = out
+        qf, idf = q_host.reshape(-1, D), i_host.reshape(-1)
+        rows = -(-N // n_chunks)
+        rows = -(-rows // 256) * 256  # whole CTA-pair tiles per chunk
+        n_chunks = -(-N // rows)
+        key = (N, D, x_host.dtype, rows, dev)
+        st = getattr(self, "_host_pipe", None)
+        if st is None or st["key"] != key:
+            st = dict(key=key, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
+                      x=[torch.empty((rows, D), dtype=x_host.dtype, device=dev) for _ in range(2)],
+                      q=[torch.empty((rows, D), dtype=x_host.dtype, device=dev) for _ in range(2)],
+                      i=[torch.empty((rows,), dtype=torch.int64, device=dev) for _ in range(2)],
+                      loss=torch.zeros((n_chunks,), dtype=torch.float32, device=dev),
+                      stats=torch.empty((ops.stats_floats(cbk.codebook_size, D),), dtype=torch.float32, device=dev),
+                      stats_chunk=torch.empty((ops.stats_floats(cbk.codebook_size, D),), dtype=torch.float32, device=dev))
+            self._host_pipe = st
+        cur = torch.cuda.current_stream(dev)
+        up, down = st["h2d"], st["d2h"]
+        up.wait_stream(cur)
+        ev_up, ev_done, ev_down = [], [], []
+        weights = []
+        for c in range(n_chunks):
+            b = c & 1
+            r0, r1 = c * rows, min(N, (c + 1) * rows)
+            n = r1 - r0
+            weights.append(n / N)
+            with torch.cuda.stream(up):
+                if c >= 2:
+                    up.wait_event(ev_done[c - 2])  # x[b] is free once chunk c-2 has been searched
+                st["x"][b][:n].copy_(xf[r0:r1], non_blocking=True)
+                e = torch.cuda.Event(); e.record(up); ev_up.append(e)
+            cur.wait_event(ev_up[c])
+            if c >= 2:
+                cur.wait_event(ev_down[c - 2])  # q[b] / i[b] have been downloaded
+            in_place = ops.STATS_MODE == 0  # fused statistics accumulate straight into the running total
+            cbk.quantize_rows(st["x"][b][:n], update=do_update, q_out=st["q"][b], idx64_out=st["i"][b],
+                              loss_out=st["loss"][c:c + 1] if want_loss else None, loss_weight=self.commitment_weight,
+                              stats_out=(st["stats"] if (in_place or c == 0) else st["stats_chunk"]) if do_update else None,
+                              defer_ema=True, stats_accumulate=in_place and c > 0)
+            if do_update and not in_place and c > 0:
+                st["stats"].add_(st["stats_chunk"])
+            e = torch.cuda.Event(); e.record(cur); ev_done.append(e)
+            with torch.cuda.stream(down):
+                down.wait_event(ev_done[c])
+                qf[r0:r1].copy_(st["q"][b][:n], non_blocking=True)
+                idf[r0:r1].copy_(st["i"][b][:n], non_blocking=True)
+                e = torch.cuda.Event(); e.record(down); ev_down.append(e)
+        if do_update:
+            cbk.sync_stats(st["stats"])
+            cbk.lerp_stats(st["stats"], normalise=cbk.ema_update and not cbk.manual_ema_update)
+        if want_loss:
+            w = torch.tensor(weights, dtype=torch.float32, device=dev)
+            loss = (st["loss"][:n_chunks] * w).sum()
+            if x_host.dtype == torch.bfloat16:
+                loss = loss.bfloat16().float()
+            l_host.copy_(loss, non_blocking=True)
+        else:
+            l_host.zero_()
+        cur.wait_stream(down)
+        return q_host, i_host, l_host
+
     def forward(self, x, indices=None, mask=None, lens=None, topk=None, sample_codebook_temp=None, freeze_codebook=None,
                 return_loss_breakdown=False, codebook_transform_fn=None, ema_update_weight=None, accum_ema_update=False,
                 ema_update=None):
