@@ -247,6 +247,32 @@ def test_forward_host_matches_forward(dt, cosine):
     assert torch.equal(ia2.cpu(), ih2)
 
 
+def test_lens_mask_matches_unmasked_prefix():
+    """Reference tests/test_readme.py:49-72: a `lens`-masked call equals the call on the unpadded prefix; padding
+    comes back as zeros / index -1; masked rows take no part in the EMA update."""
+    m = vqb()
+    torch.manual_seed(2)
+    a = m.VectorQuantize(dim=64, codebook_size=100).to(DEV)
+    b = m.VectorQuantize(dim=64, codebook_size=100).to(DEV)
+    _warm_codebook(a, 64, 100)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(1, 300, 64, device=DEV)
+    lens = torch.tensor([211], device=DEV)
+    qm, im, lm = a(x, lens=lens)
+    qp, ip, lp = b(x[:, :211])
+    assert torch.equal(im[:, :211], ip) and (im[:, 211:] == -1).all()
+    assert torch.equal(qm[:, :211], qp) and (qm[:, 211:] == 0).all()
+    assert abs(lm.item() - lp.item()) <= 1e-6 * lp.item()
+    for name in ("cluster_size", "embed_avg", "embed"):
+        assert torch.allclose(getattr(a._codebook, name), getattr(b._codebook, name), rtol=1e-6, atol=1e-6), name
+    # boolean mask, eval mode, padding returned as the input
+    c = m.VectorQuantize(dim=64, codebook_size=100, return_zeros_for_masked_padding=False).to(DEV).eval()
+    mask = torch.rand(2, 50, device=DEV) > 0.3
+    y = torch.randn(2, 50, 64, device=DEV)
+    qc, ic, lc = c(y, mask=mask)
+    assert torch.equal(qc[~mask], y[~mask]) and (ic[~mask] == -1).all() and (ic[mask] >= 0).all() and lc.item() == 0.0
+
+
 def test_rvq_decode_invariant():
     """Reference tests/test_readme.py:74-103: sum of gathered codes == quantized_out (frozen codebook)."""
     m = vqb()

@@ -39,19 +39,34 @@ def is_stale():
 
 
 def build(force=False, verbose=False):
+    """Compile (if stale) under an exclusive file lock: with torchrun every rank imports the package at once."""
+    import fcntl
     if not force and not is_stale():
         return LIB
+    with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():  # another process built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError("vqb200: nvcc not found and libvqb200.so is missing/stale; cannot build the CUDA library")
     extra = ["-DVQB_PROFILE"] if os.environ.get("VQB_PROFILE") else []  # per-role cycle counters (scripts/gpu_roles.py)
-    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    tmp = LIB + ".tmp%d" % os.getpid()
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(PKG, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         raise RuntimeError("vqb200: nvcc failed\n" + log)
+    os.replace(tmp, LIB)  # atomic: a concurrently importing process never sees a half-written library
     if verbose:
         print(log)
     return LIB

@@ -33,7 +33,7 @@
 // Per-role cycle accounting (scripts/gpu_roles.py): compile with -DVQB_PROFILE.  Off by default: the counters cost
 // registers in a kernel that runs at the 128-register cap.
 #ifdef VQB_PROFILE
-#define PROF_CLOCK() PROF_CLOCK()
+#define PROF_CLOCK() clock64()
 #else
 #define PROF_CLOCK() 0ll
 #endif
@@ -86,6 +86,19 @@ struct RowState {  // running arg-max of one row (slice) + candidates inside the
     n = (v - best > W) ? 1 : n + 1;   // a clear new leader drops every earlier candidate out of the band
     i1 = nb ? i0 : c;
     i0 = nb ? c : i0;
+    best = fmaxf(best, v);
+    thr = best - W;
+  }
+  // Branch-free form of `if (v > thr) hit(v, c)`: pure select/compare code, only best -> thr is a loop-carried chain.
+  // The epilogue warps are branch-latency bound (32 independent rows per warp make almost every group of four columns
+  // a hit for SOME lane), so predication beats the nested per-element branches.
+  __device__ __forceinline__ void upd(float v, int c) {
+    const bool p = v > thr;
+    const bool nb = v > best;
+    const int n_hit = (v - best > W) ? 1 : n + 1;
+    n = p ? n_hit : n;
+    i1 = p ? (nb ? i0 : c) : i1;
+    i0 = nb ? c : i0;  // nb implies p (thr < best)
     best = fmaxf(best, v);
     thr = best - W;
   }
@@ -389,10 +402,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 4; ++j) {
               if (m[j] > st.thr) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const float v = __uint_as_float(r[4 * j + e]);
-                  if (v > st.thr) st.hit(v, cbase + 4 * j + e);
-                }
+                for (int e = 0; e < 4; ++e) st.upd(__uint_as_float(r[4 * j + e]), cbase + 4 * j + e);
               }
             }
           }

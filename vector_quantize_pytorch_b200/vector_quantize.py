@@ -312,13 +312,64 @@ class VectorQuantize(nn.Module):
         cur.wait_stream(down)
         return q_host, i_host, l_host
 
+    # ------------------------------------------------------------------ variable-length sequences (vqp:599-600, :1317-1325, :1378-1396)
+    def _forward_masked(self, x, mask, freeze_codebook, ema_update, return_loss_breakdown):
+        """mask (B, N) bool.  The kernels run on the compacted unmasked rows: masked positions take no part in the
+        statistics or the loss (the reference zeroes their one-hot rows, vqp:599-600, and averages the loss over the
+        unmasked elements against the ORIGINAL input, vqp:1317-1325) and come back as zeros / index -1."""
+        if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last:
+            _unsupported("mask / lens together with projections or feature-map layouts")
+        if x.requires_grad and torch.is_grad_enabled():
+            _unsupported("mask / lens on inputs that require grad")
+        if not x.is_cuda:
+            raise RuntimeError("vqb200 has no CPU path: inputs must live on a CUDA (B200, sm_100) device")
+        assert x.ndim == 3 and mask.shape == x.shape[:2]
+        freeze_codebook = self.freeze_codebook if freeze_codebook is None else freeze_codebook
+        cbk = self._codebook
+        ema_update = cbk.ema_update if ema_update is None else ema_update
+        training = self.training
+        B, N, D = x.shape
+        flat = x.detach().reshape(-1, D)
+        rows = mask.reshape(-1).nonzero(as_tuple=True)[0]  # host sync (the reference's masked path syncs as well)
+        quantize = torch.zeros_like(flat) if self.return_zeros_for_masked_padding else flat.clone()
+        embed_ind = torch.full((B * N,), -1, dtype=torch.int64, device=x.device)
+        loss = torch.tensor(0., device=x.device, requires_grad=training and torch.is_grad_enabled())
+        commit_loss = self.zero
+        if rows.numel() > 0:
+            xc = flat[rows].contiguous()
+            qc = torch.empty_like(xc)
+            ic = torch.empty((xc.shape[0],), dtype=torch.int64, device=x.device)
+            do_update = training and not freeze_codebook and (ema_update or cbk.has_dead_code_replacement)
+            fused = training and self.has_commitment_loss and not self.use_cosine_sim
+            commit = torch.empty((), dtype=torch.float32, device=x.device) if fused else None
+            cbk.quantize_rows(xc, update=do_update, q_out=qc, idx64_out=ic, loss_out=commit,
+                              loss_weight=self.commitment_weight)
+            quantize[rows] = qc
+            embed_ind[rows] = ic
+            if training and self.has_commitment_loss:
+                if fused:  # euclid: the original input IS what the codebook saw
+                    commit_loss = commit
+                    loss = commit.requires_grad_(torch.is_grad_enabled())
+                else:      # cosine: mse against the un-normalised original input (vqp:1319)
+                    commit_loss = F.mse_loss(qc, xc)
+                    loss = loss + commit_loss * self.commitment_weight
+        quantize = quantize.reshape(B, N, D)
+        embed_ind = embed_ind.reshape(B, N)
+        if not return_loss_breakdown:
+            return quantize, embed_ind, loss
+        return quantize, embed_ind, loss, LossBreakdown(commit_loss, self.zero, self.zero, self.zero)
+
     def forward(self, x, indices=None, mask=None, lens=None, topk=None, sample_codebook_temp=None, freeze_codebook=None,
                 return_loss_breakdown=False, codebook_transform_fn=None, ema_update_weight=None, accum_ema_update=False,
                 ema_update=None):
         if indices is not None:
             _unsupported("forward(indices=...) cross-entropy loss")
-        if mask is not None or lens is not None:
-            _unsupported("mask / lens")
+        if mask is not None and lens is not None:
+            raise AssertionError("pass either mask or lens")  # vqp:1116
+        if lens is not None:  # vqp:1118-1119, :99-101
+            mask = torch.arange(x.shape[1], device=lens.device) < lens[:, None]
+        if mask is not None:
+            return self._forward_masked(x, mask, freeze_codebook, ema_update, return_loss_breakdown)
         if topk is not None or codebook_transform_fn is not None or ema_update_weight is not None or accum_ema_update:
             _unsupported("topk / codebook_transform_fn / ema_update_weight / accum_ema_update")
         if not x.is_cuda:
