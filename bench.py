@@ -29,6 +29,7 @@ METRIC = "vectors quantized/sec at dim=256, codebook=1024; indices bit-exact vs 
 B, T, D, K = 64, 4096, 256, 1024
 WORKLOAD = "VectorQuantize dim=256 codebook_size=1024, x=(64,4096,256) bf16, EMA on (BASELINE.json configs[1])"
 CPU_SAMPLE_VECTORS = 65536  # 1/4 of the batch per CPU step (~0.7 s on 8 cores)
+E2E_CHUNKS = int(os.environ.get("VQB_E2E_CHUNKS", "16"))  # row chunks of the host-buffer pipeline (forward_host)
 
 
 def load_peaks():
@@ -234,8 +235,11 @@ def run_gpu_arm(args):
 
     def e2e_step():
         # public host-buffer API: pinned input -> chunk-pipelined H2D / kernels / D2H -> pinned outputs
-        vq.forward_host(x_host, n_chunks=8, out=(q_host, i_host, l_host))
+        vq.forward_host(x_host, n_chunks=E2E_CHUNKS, out=(q_host, i_host, l_host))
 
+    if os.environ.get("VQB_BENCH_SKIP_E2E"):  # profiling aid: keep the launch list to the device-resident steps
+        print(json.dumps({"ms_per_step": ms_dev, "kernel_ms": assign_ms, "gpu_launches": launches}))
+        return
     for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
     barrier()

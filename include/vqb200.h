@@ -117,6 +117,7 @@ int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, const void* b
 
 /* Diagnostics: i64 [grid][16] per-role cycle counters written by subsequent vqb_assign calls (NULL disables). */
 int vqb_debug_set_profile_buffer(void* device_buffer);
+int vqb_debug_active(void);
 int vqb_debug_set_mode(int mode); /* bit0: skip the epilogue's TMEM sweep (timing experiments only; results invalid) */
 
 /* Exact re-score of the flagged rows with the reference's own fp32 formula and tie rule
@@ -161,7 +162,8 @@ int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const flo
 
 /* One-call composite of VectorQuantize.forward's arithmetic (or one ResidualVQ stage): input staging ->
  * vqb_assign (+ fused tail) -> vqb_fix_flagged -> vqb_loss_finalize -> vqb_ema_stats -> vqb_ema_apply, all
- * enqueued from C++ (the Python glue pays one FFI call instead of ~20).  Replaces vqp:1159-1178 + :674-791. */
+ * enqueued from C++ (the Python glue pays one FFI call instead of ~20).  Replaces vqp:1159-1178 + :674-791.
+ * With VQB_GRAPH=1 repeated calls with identical arguments are replayed from a cached CUDA graph. */
 typedef struct vqb_vq_forward_args {
   const void* x;            /* [N][D] dtype, BEFORE the cosine l2norm                                         */
   int dtype, metric;

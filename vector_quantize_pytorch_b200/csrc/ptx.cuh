@@ -60,6 +60,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp (the others get false).  Issuing tcgen05 / TMA instructions under this predicate from
+// warp-uniform control flow lets ptxas keep their operands in uniform registers; under an `if (lane == 0)` region it
+// wraps every such instruction in an ELECT / BRA.U.ANY loop instead (measured: ~60 SM clocks more per MMA issue).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
@@ -173,6 +188,23 @@ __device__ __forceinline__ void umma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Lean issue form for the hot loop: the descriptors arrive as (lo, hi) words so that advancing along K is one 32-bit
+// add on `lo` (address field, units of 16 B), and the accumulate predicate is a compile-time constant.  The issuing
+// thread is latency-bound on the uniform datapath: every instruction removed here raises the MMA issue rate.
+__device__ __forceinline__ void umma_bf16_ss_2sm_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                     uint32_t b_hi, uint32_t idesc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "setp.eq.u32 p, 1, 1;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc)
       : "memory");
 }
 // Arrive (once every prior MMA of this thread retired) on the barrier at this offset in every CTA of `mask`.

@@ -113,6 +113,7 @@ struct Ctrl {  // lives at the start of dynamic smem
   uint64_t x_full[2], x_empty[2];        // bias blocks
   uint64_t t_full[2], t_empty[2];        // TMEM accumulator stages
   uint64_t g_full[2], g_empty[2];        // winners of a row tile handed to the store warps
+  uint64_t t_done[2];                    // follower CTA: its 8 epilogue warps released accumulator stage s
   uint32_t tmem_base;
   uint32_t pad;
   float xn2[BM];                         // row norms of the current tile
@@ -180,7 +181,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&ctrl->x_full[s]), 1);
       mbar_init(smem_u32(&ctrl->x_empty[s]), 1);
       mbar_init(smem_u32(&ctrl->t_full[s]), 1);
-      mbar_init(smem_u32(&ctrl->t_empty[s]), 2 * NUM_EPI_WARPS);  // leader's copy collects both CTAs' epilogues
+      mbar_init(smem_u32(&ctrl->t_empty[s]), NUM_EPI_WARPS + 1);  // leader's 8 epilogue warps + one forwarded arrive for the follower's
+      mbar_init(smem_u32(&ctrl->t_done[s]), NUM_EPI_WARPS);
       mbar_init(smem_u32(&ctrl->g_full[s]), NUM_EPI_WARPS / 2);
       mbar_init(smem_u32(&ctrl->g_empty[s]), NUM_STORE_WARPS);
     }
@@ -266,12 +268,21 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================================================ MMA issuer
-    if (lane == 0 && leader) {
+    if (leader) {  // the whole warp runs the loop (warp-uniform); one elected lane issues
       const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);
+      // timing experiment (results invalid): issue the pass MMAs with half the N extent
+      const uint32_t idesc_pass = (p.dbg_mode & 8) ? umma_idesc_bf16(2 * BM, p.BN / 2) : idesc;
       constexpr uint16_t kBoth = 0x3;
       long long w_tempty = 0, w_bfull = 0, w_xfull = 0, w_afull = 0;
       const long long mstart = PROF_CLOCK();
       const uint64_t aext_desc = umma_smem_desc_sw32(aext_base);
+      // K-major SW128 descriptors: constant high word, the low word is (address >> 4) | LBO; stepping 32 B along K or
+      // one sub-tile / stage further is an add on the low word
+      const uint64_t d0 = umma_smem_desc_sw128(a_base);
+      const uint32_t desc_hi = static_cast<uint32_t>(d0 >> 32);
+      const uint32_t a_desc_lo0 = static_cast<uint32_t>(d0);
+      const uint32_t b_desc_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(b_base));
+      const uint32_t b_stage_units = b_stage_bytes >> 4;
       int stage = 0;
       uint32_t ph = 0;
       uint32_t it = 0;  // accumulator iteration counter (across row tiles)
@@ -285,35 +296,59 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t xph = p.n_xstages == 2 ? ((it >> 1) & 1) : (it & 1);
             { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->x_full[xs]), xph); w_xfull += PROF_CLOCK() - c0; }
             tc_fence_after();
-            umma_bf16_ss_2sm(d_tmem, aext_desc, umma_smem_desc_sw32(xb_base + xs * x_stage_bytes), idesc, 0u);
-            umma_commit_2sm(smem_u32(&ctrl->x_empty[xs]), kBoth);
+            if (elect_one_sync()) {
+              umma_bf16_ss_2sm(d_tmem, aext_desc, umma_smem_desc_sw32(xb_base + xs * x_stage_bytes), idesc, 0u);
+              umma_commit_2sm(smem_u32(&ctrl->x_empty[xs]), kBoth);
+            }
+            __syncwarp();
           }
           for (int ps = 0; ps < p.n_passes; ++ps) {
             const int aplane = (ps == 2) ? 1 : 0;
             const bool last_use = (ct == p.num_code_tiles - 1) && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
-            for (int kb = 0; kb < p.KB; ++kb) {
+            uint32_t a_lo = a_desc_lo0 + static_cast<uint32_t>(aplane * p.KB) * (A_SUB_BYTES >> 4);
+            for (int kb = 0; kb < p.KB; ++kb, a_lo += (A_SUB_BYTES >> 4)) {
               const int sub = aplane * p.KB + kb;
               if (ct == 0) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[sub]), t & 1); w_afull += PROF_CLOCK() - c0; }
               { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[stage]), ph); w_bfull += PROF_CLOCK() - c0; }
               tc_fence_after();
-              const uint32_t a_addr = a_base + sub * A_SUB_BYTES;
-              const uint32_t b_addr = b_base + stage * b_stage_bytes;
-              const int rem = p.D - kb * BK;
-              const int ksteps = rem >= BK ? (BK / UMMA_K) : (rem + UMMA_K - 1) / UMMA_K;
-              for (int k = 0; k < ksteps; ++k)
-                umma_bf16_ss_2sm(d_tmem, umma_smem_desc_sw128(a_addr + k * UMMA_K * 2),
-                                 umma_smem_desc_sw128(b_addr + k * UMMA_K * 2), idesc, 1u);
-              umma_commit_2sm(smem_u32(&ctrl->b_empty[stage]), kBoth);              // B stage reusable once these MMAs retire
-              if (last_use) umma_commit_2sm(smem_u32(&ctrl->a_empty[sub]), kBoth); // ... and this A sub-tile too
+              const uint32_t b_lo = b_desc_lo0 + static_cast<uint32_t>(stage) * b_stage_units;
+              if (elect_one_sync()) {
+                if (kb + 1 < p.KB || (p.D & (BK - 1)) == 0) {  // full k-block: four K=16 steps, descriptors advance by 32 B
+                  umma_bf16_ss_2sm_acc(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc_pass);
+                  umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc_pass);
+                  umma_bf16_ss_2sm_acc(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc_pass);
+                  umma_bf16_ss_2sm_acc(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc_pass);
+                } else {  // ragged last k-block (D % 64 != 0): only the K steps that hold data (the rest is TMA zero fill)
+                  const int ksteps = ((p.D & (BK - 1)) + UMMA_K - 1) / UMMA_K;
+                  for (int k = 0; k < ksteps; ++k)
+                    umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc_pass);
+                }
+                umma_commit_2sm(smem_u32(&ctrl->b_empty[stage]), kBoth);              // B stage reusable once these MMAs retire
+                if (last_use) umma_commit_2sm(smem_u32(&ctrl->a_empty[sub]), kBoth); // ... and this A sub-tile too
+              }
+              __syncwarp();
               if (++stage == p.n_stages) { stage = 0; ph ^= 1; }
             }
           }
-          umma_commit_2sm(smem_u32(&ctrl->t_full[as]), kBoth);  // accumulator complete -> both epilogues
+          if (elect_one_sync()) umma_commit_2sm(smem_u32(&ctrl->t_full[as]), kBoth);  // accumulator complete -> both epilogues
+          __syncwarp();
         }
       }
-      if (p.prof) {
+      if (p.prof && lane == 0) {
         long long* o = p.prof + blockIdx.x * 16;
         o[2] = w_tempty; o[3] = w_bfull; o[4] = w_xfull; o[5] = w_afull; o[6] = PROF_CLOCK() - mstart;
+      }
+    } else if (lane == 0) {
+      // follower CTA: forward "my epilogue released accumulator stage s" to the leader's t_empty barrier.  A remote
+      // (release.cluster) arrive costs ~1 us; doing it once here instead of in each of the 8 epilogue warps took
+      // ~15 % off the follower's epilogue time.
+      const uint32_t total = static_cast<uint32_t>(my_tiles) * static_cast<uint32_t>(p.num_code_tiles);
+      const uint32_t remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
+      const uint32_t remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
+      for (uint32_t it = 0; it < total; ++it) {
+        const uint32_t as = it & 1;
+        mbar_wait(smem_u32(&ctrl->t_done[as]), (it >> 1) & 1);
+        mbar_arrive_cluster(as ? remote1 : remote0);
       }
     }
   } else if (warp < 2 + NUM_EPI_WARPS) {
@@ -346,29 +381,21 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int i = half * 4; i < half * 4 + 4; ++i) {  // the two warps of a lane group split its 32 rows
               const int r = lg * 32 + i * 4 + sub;
               const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
+              // ||x||^2 only scales the certification band (5x safety margin), so the squares of a 16-byte chunk are
+              // accumulated in packed bf16 (<= 2^-8 relative error) and only the hi plane of an fp32 input is read.
               float acc2 = 0.f;
               for (int kb = 0; kb < p.KB; ++kb) {
-                float v[8];
-                {
-                  const uint4 u = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off);
-                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    v[2 * e] = __uint_as_float(w[e] << 16);
-                    v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
-                  }
-                }
-                if (p.n_a == 2) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off);
-                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    v[2 * e] += __uint_as_float(w[e] << 16);
-                    v[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc2 = fmaf(v[e], v[e], acc2);
+                const uint4 u = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off);
+                const __nv_bfloat162 w0 = *reinterpret_cast<const __nv_bfloat162*>(&u.x);
+                const __nv_bfloat162 w1 = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+                const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162*>(&u.z);
+                const __nv_bfloat162 w3 = *reinterpret_cast<const __nv_bfloat162*>(&u.w);
+                __nv_bfloat162 sq = __hmul2(w0, w0);
+                sq = __hfma2(w1, w1, sq);
+                sq = __hfma2(w2, w2, sq);
+                sq = __hfma2(w3, w3, sq);
+                const float2 f = __bfloat1622float2(sq);
+                acc2 += f.x + f.y;
               }
               acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
               acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
@@ -421,10 +448,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {  // the leader's barrier gates the MMA issue into this accumulator stage of BOTH CTAs
-          if (leader) mbar_arrive(smem_u32(&ctrl->t_empty[as]));
-          else mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->t_empty[as]), 0));
-        }
+        if (lane == 0)  // the leader's barrier gates the MMA issue into this accumulator stage of BOTH CTAs; the
+                        // follower's warps arrive locally and its (otherwise idle) warp 1 forwards ONE remote arrive
+          mbar_arrive(smem_u32(leader ? &ctrl->t_empty[as] : &ctrl->t_done[as]));
         w_work += PROF_CLOCK() - cw0;
       }
       const long long cm0 = PROF_CLOCK();
@@ -609,6 +635,7 @@ extern "C" int vqb_padded_codes(int K) {
 static long long* g_prof = nullptr;
 static int g_dbg_mode = 0;
 extern "C" int vqb_debug_set_mode(int mode) { g_dbg_mode = mode; return VQB_OK; }
+extern "C" int vqb_debug_active(void) { return (g_prof != nullptr) || (g_dbg_mode != 0); }
 // diagnostics: device buffer of [grid][16] int64 cycle counters filled by the next vqb_assign calls (NULL = off)
 extern "C" int vqb_debug_set_profile_buffer(void* buf) { g_prof = static_cast<long long*>(buf); return VQB_OK; }
 
