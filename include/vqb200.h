@@ -163,7 +163,8 @@ int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const flo
 /* One-call composite of VectorQuantize.forward's arithmetic (or one ResidualVQ stage): input staging ->
  * vqb_assign (+ fused tail) -> vqb_fix_flagged -> vqb_loss_finalize -> vqb_ema_stats -> vqb_ema_apply, all
  * enqueued from C++ (the Python glue pays one FFI call instead of ~20).  Replaces vqp:1159-1178 + :674-791.
- * With VQB_GRAPH=1 repeated calls with identical arguments are replayed from a cached CUDA graph. */
+ * Repeated calls with identical arguments are replayed from a cached CUDA graph (VQB_GRAPH=0 disables); besides the
+ * launch gaps this removes the sensitivity of the step time to host-side scheduling jitter. */
 typedef struct vqb_vq_forward_args {
   const void* x;            /* [N][D] dtype, BEFORE the cosine l2norm                                         */
   int dtype, metric;

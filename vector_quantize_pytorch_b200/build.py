@@ -58,6 +58,7 @@ def _build_locked(verbose):
     if nvcc is None:
         raise RuntimeError("vqb200: nvcc not found and libvqb200.so is missing/stale; cannot build the CUDA library")
     extra = ["-DVQB_PROFILE"] if os.environ.get("VQB_PROFILE") else []  # per-role cycle counters (scripts/gpu_roles.py)
+    extra += os.environ.get("VQB_NVCC_EXTRA", "").split()  # A/B experiments, e.g. -DVQB_EPI_SIMPLE
     tmp = LIB + ".tmp%d" % os.getpid()
     cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)

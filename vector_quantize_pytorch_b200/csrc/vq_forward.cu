@@ -50,8 +50,8 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream);
 // CUDA-graph cache.  The chain is ~15 small launches around one big kernel; replaying it as a graph removes the
 // launch gaps.  A call is identified by every pointer / size / flag of its argument struct; the first occurrence
 // of a key is enqueued directly (also warms lazy module loading), the second is captured, later ones replay.
-// Opt-in (VQB_GRAPH=1): it only pays off when the caller reuses its output buffers, otherwise every new pointer
-// set costs a capture + instantiate (torch's allocator hands out varying addresses for small tensors).
+// It pays off when pointer sets repeat: the Python glue keeps its small outputs / scratch in persistent buffers and
+// torch's allocator cycles through a handful of large blocks for the per-call outputs.  VQB_GRAPH=0 disables.
 // Bypassed while profiling events are requested, or when the stream is already being captured
 // (then the launches simply become part of the caller's graph).
 // ---------------------------------------------------------------------------------------------
@@ -61,7 +61,9 @@ struct GraphEntry {
   cudaGraphExec_t exec;
   unsigned long long last_use;
 };
-constexpr int kMaxGraphs = 32;
+constexpr int kMaxGraphs = 128;
+int g_captures_since_replay = 0;  // safety valve: pointer sets that never repeat make capturing pure overhead
+bool g_graph_disabled = false;
 GraphEntry g_graphs[kMaxGraphs];
 int g_num_graphs = 0;
 unsigned long long g_tick = 0;
@@ -70,7 +72,7 @@ int graph_mode() {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("VQB_GRAPH");
-    mode = (e && e[0] == '1') ? 1 : 0;  // opt-in: callers whose output buffers are stable across calls
+    mode = (e && e[0] == '0') ? 0 : 1;
   }
   return mode;
 }
@@ -93,7 +95,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   if (!a) return VQB_E_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (!graph_mode() || a->ev_search_begin || a->ev_search_end || vqb_debug_active() ||
+  if (!graph_mode() || g_graph_disabled || a->ev_search_begin || a->ev_search_end || vqb_debug_active() ||
       cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
     return vq_forward_enqueue(a, stream);
   uint64_t key[40];
@@ -104,6 +106,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
     if (memcmp(g_graphs[i].key, key, sizeof(key)) == 0) { slot = i; break; }
   if (slot >= 0 && g_graphs[slot].exec) {  // replay
     g_graphs[slot].last_use = g_tick;
+    g_captures_since_replay = 0;
     const cudaError_t e = cudaGraphLaunch(g_graphs[slot].exec, s);
     return static_cast<int>(e);
   }
@@ -122,6 +125,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   }
   // second sighting: capture, instantiate, launch
   g_graphs[slot].last_use = g_tick;
+  if (++g_captures_since_replay > 48) g_graph_disabled = true;  // instantiations are not paying off: stop
   if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     return vq_forward_enqueue(a, stream);

@@ -194,7 +194,8 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
     dt = _dtype_code(x)
     dev = x.device
     cs, ea, emb = state
-    idx32 = torch.empty((N,), dtype=torch.int32, device=dev)
+    # internal scratch lives in reusable buffers: stable pointers keep the CUDA-graph cache of vqb_vq_forward hot
+    idx32 = _workspace(("idx32", ws_key, N, dev.index), 4 * N, dev).view(torch.int32)[:N]
     if update and stats is None:
         stats = torch.empty((stats_floats(K, D),), dtype=torch.float32, device=dev)
     nbytes = lib.vqb_vq_forward_workspace(N, D, K, dt, int(ops.cosine), int(update))

@@ -147,7 +147,13 @@ class ResidualVQ(nn.Module):
 
         quantized_out = torch.zeros_like(flat)  # rvq:410
         all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)
-        losses = torch.zeros((Q,), dtype=torch.float32, device=dev)
+        loss_buf = getattr(self, "_loss_buf", None)  # persistent (stable pointers for the graph cache), cloned out below
+        if loss_buf is None or loss_buf.device != dev or loss_buf.numel() != Q:
+            loss_buf = torch.zeros((Q,), dtype=torch.float32, device=dev)
+            self._loss_buf = loss_buf
+        if not training:
+            loss_buf.zero_()
+        losses = loss_buf
         bufs = [torch.empty_like(flat), torch.empty_like(flat)]
         residual = flat  # rvq:411 (never written: stage 0 reads the caller's tensor)
 
@@ -173,7 +179,7 @@ class ResidualVQ(nn.Module):
                 self._finish_update(packed, offs, stat_sizes, do_update, flat, synced=False)
 
         quantized_out = self.project_out(quantized_out.reshape(shape))  # rvq:610
-        ret = (quantized_out, all_idx.reshape(*shape[:-1], Q), losses)
+        ret = (quantized_out, all_idx.reshape(*shape[:-1], Q), losses.clone())
         if return_all_codes:
             ret = (*ret, self.get_codes_from_indices(ret[1]))
         return ret

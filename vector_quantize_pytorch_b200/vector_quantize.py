@@ -206,6 +206,13 @@ class VectorQuantize(nn.Module):
 
     update_ema_indices = update_indices
 
+    def _loss_scratch(self, device):
+        buf = getattr(self, "_loss_buf", None)
+        if buf is None or buf.device != device:
+            buf = torch.zeros((1,), dtype=torch.float32, device=device)
+            self._loss_buf = buf
+        return buf
+
     # ------------------------------------------------------------------ layout glue (vqp:1136-1147)
     def _to_rows_layout(self, x):
         restore = None
@@ -398,9 +405,11 @@ class VectorQuantize(nn.Module):
         q = torch.empty_like(flat)
         idx64 = torch.empty((N,), dtype=torch.int64, device=flat.device)
         # the kernel returns weight * mse already rounded like F.mse_loss in x.dtype (vqp:1327-1329)
-        commit_loss = torch.empty((), dtype=torch.float32, device=flat.device) if fused_loss else self.zero
-        cbk.quantize_rows(flat, update=do_update, q_out=q, idx64_out=idx64, loss_out=commit_loss if fused_loss else None,
+        # the loss lands in a persistent scalar (stable pointer for the graph cache) and is cloned out
+        loss_buf = self._loss_scratch(flat.device) if fused_loss else None
+        cbk.quantize_rows(flat, update=do_update, q_out=q, idx64_out=idx64, loss_out=loss_buf,
                           loss_weight=self.commitment_weight)
+        commit_loss = loss_buf.clone().reshape(()) if fused_loss else self.zero
 
         quantize = q.reshape(shape)
         embed_ind = idx64.reshape(shape[:-1])
