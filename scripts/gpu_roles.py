@@ -9,7 +9,8 @@ N, D, K = 262144, 256, 1024
 x = torch.randn(N, D, device=dev).bfloat16()
 c = torch.randn(K, D, device=dev)
 cb = ops.prepare_codebook(c, False)
-for passes, mode in ((2, 1), (2, 9)):
+MODES = [tuple(int(v) for v in a.split(",")) for a in sys.argv[1:]] or [(2, 0), (2, 1), (1, 0)]
+for passes, mode in MODES:
     _C.lib.vqb_debug_set_mode(mode)
     for _ in range(3):
         ops.search(x, cb, c, n_passes=passes, fix=False)

@@ -174,6 +174,7 @@ def test_flagged_rows_are_rescored_exactly():
     K, D, N = 512, 128, 4096
     c = torch.randn(K, D)
     c[300] = c[7]                        # exact duplicate: index 7 must always beat 300
+    c[301] = c[7]                        # ... and a third copy: > 2 candidates -> whole-row rescan path
     c[400] = c[9] * (1 + 3e-7)           # inside fp32 noise of code 9
     c[401] = c[11] + 1e-4 * torch.randn(D)  # resolvable only by the exact re-score
     x = torch.randn(N, D)
@@ -186,6 +187,8 @@ def test_flagged_rows_are_rescored_exactly():
         res = ops.search(xd, cb, cd)
         idx = res.idx.cpu().numpy()
         assert res.flag_count.item() >= 128
+        flagged = res.flagged[:res.flag_count.item()].cpu().numpy()  # (row, count, cand0, cand1)
+        assert (flagged[:, 1] > 2).sum() >= 64, "the triple tie must take the > 2 candidates path"
         assert (idx[:64] == 7).all()
         x_np = O.cast_like(x.numpy(), dt)
         ref = O.argmax_first(O.scores(x_np, c.numpy(), False))
