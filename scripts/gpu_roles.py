@@ -21,7 +21,7 @@ for passes, mode in MODES:
     _C.lib.vqb_debug_set_profile_buffer(None)
     p = prof.cpu().double()
     names = ["prod.wait_b_empty", "prod.total", "mma.wait_t_empty", "mma.wait_b_full", "mma.wait_x_full", "mma.wait_a_full",
-             "mma.total", "-", "epi0.wait_t_full", "epi0.work", "epi0.merge", "epi0.total", "epi1.wait_t_full", "epi1.work",
+             "mma.total", "epi0.wait_norms", "epi0.wait_t_full", "epi0.work", "epi0.merge", "epi0.total", "epi1.wait_t_full", "epi1.work",
              "epi1.merge", "epi1.total"]
     lead = p[0::2].mean(0); foll = p[1::2].mean(0)
     print(f"passes={passes} dbg_mode={mode} (kcycles, mean over CTAs; leader | follower)")

@@ -26,9 +26,7 @@ struct FusedOut {  // device-side copy of vqb_fused_outputs
 };
 
 inline int make_fused(FusedOut* o, const vqb_fused_outputs* f, int D) {
-  o->enabled = 0;
-  o->stats_cnt = nullptr;
-  o->stats_sum = nullptr;
+  *o = FusedOut{};  // every pointer null, enabled = 0: a disabled tail must be inert wherever the kernels test a field
   if (!f) return VQB_OK;
   if (!f->x_eff || !f->embed) return VQB_E_INVALID;
   if (f->dtype != VQB_DTYPE_F32 && f->dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;

@@ -60,6 +60,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait with cluster-scope acquire: pairs with a peer CTA's mbar_arrive_cluster (release.cluster).
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > VQB_WAIT_TIMEOUT_CYCLES) {
+      printf("vqb200: mbarrier wait timeout (block %d thread %d bar 0x%x parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+
 // One lane of a CONVERGED warp (the others get false).  Issuing tcgen05 / TMA instructions under this predicate from
 // warp-uniform control flow lets ptxas keep their operands in uniform registers; under an `if (lane == 0)` region it
 // wraps every such instruction in an ELECT / BRA.U.ANY loop instead (measured: ~60 SM clocks more per MMA issue).
@@ -159,6 +182,11 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) 
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Relaxed form: no memory ordering (and therefore no fence in front of it — the release form costs ~1 us).  Enough
+// when the only thing handed over is "my tcgen05.ld's have completed" (tcgen05.wait::ld precedes it).
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the byte count is credited to the barrier at the same offset in
 // the LEADER CTA (rank 0) — pass a barrier address with the peer bit cleared (see kPeerBitMask).

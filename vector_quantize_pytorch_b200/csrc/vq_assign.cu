@@ -51,7 +51,7 @@ constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_STORE_WARPS = 4;  // fused gather / loss / residual tail of the certified rows
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS + NUM_STORE_WARPS) * 32;
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 6144;     // barriers + tmem ptr + row norms + merge area
+constexpr int SMEM_CTRL_BYTES = 7168;     // barriers + tmem ptr + row norms + merge area
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
@@ -108,15 +108,16 @@ struct MergeSlot { float best; int i0, i1, n; };
 
 struct Ctrl {  // lives at the start of dynamic smem
   uint64_t a_full[MAX_A_SUB], a_empty[MAX_A_SUB];
-  uint64_t a_read;                       // epilogue finished reading A (row norms)
+  uint64_t a_read;                       // store warps finished reading A (row norms)
+  uint64_t a_ready;                      // follower CTA: its A tile has landed (forwarded by the leader's store warp 0)
+  uint64_t n_full[2];                    // row norms of a tile are in xn2[tile parity]
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
   uint64_t x_full[2], x_empty[2];        // bias blocks
   uint64_t t_full[2], t_empty[2];        // TMEM accumulator stages
   uint64_t g_full[2], g_empty[2];        // winners of a row tile handed to the store warps
-  uint64_t t_done[2];                    // follower CTA: its 8 epilogue warps released accumulator stage s
   uint32_t tmem_base;
   uint32_t pad;
-  float xn2[BM];                         // row norms of the current tile
+  float xn2[2][BM];                      // row norms, double buffered by row-tile parity
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
   int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
 };
@@ -172,7 +173,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&ctrl->a_full[s]), 1);
       mbar_init(smem_u32(&ctrl->a_empty[s]), 1);
     }
-    mbar_init(smem_u32(&ctrl->a_read), NUM_EPI_WARPS);
+    mbar_init(smem_u32(&ctrl->a_read), NUM_STORE_WARPS);
+    mbar_init(smem_u32(&ctrl->a_ready), 1);
+    mbar_init(smem_u32(&ctrl->n_full[0]), NUM_STORE_WARPS);
+    mbar_init(smem_u32(&ctrl->n_full[1]), NUM_STORE_WARPS);
     for (int s = 0; s < p.n_stages; ++s) {
       mbar_init(smem_u32(&ctrl->b_full[s]), 1);
       mbar_init(smem_u32(&ctrl->b_empty[s]), 1);
@@ -181,8 +185,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&ctrl->x_full[s]), 1);
       mbar_init(smem_u32(&ctrl->x_empty[s]), 1);
       mbar_init(smem_u32(&ctrl->t_full[s]), 1);
-      mbar_init(smem_u32(&ctrl->t_empty[s]), NUM_EPI_WARPS + 1);  // leader's 8 epilogue warps + one forwarded arrive for the follower's
-      mbar_init(smem_u32(&ctrl->t_done[s]), NUM_EPI_WARPS);
+      mbar_init(smem_u32(&ctrl->t_empty[s]), 2 * NUM_EPI_WARPS);  // the epilogue warps of BOTH CTAs (the follower's arrive remotely)
       mbar_init(smem_u32(&ctrl->g_full[s]), NUM_EPI_WARPS / 2);
       mbar_init(smem_u32(&ctrl->g_empty[s]), NUM_STORE_WARPS);
     }
@@ -338,18 +341,6 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         long long* o = p.prof + blockIdx.x * 16;
         o[2] = w_tempty; o[3] = w_bfull; o[4] = w_xfull; o[5] = w_afull; o[6] = PROF_CLOCK() - mstart;
       }
-    } else if (lane == 0) {
-      // follower CTA: forward "my epilogue released accumulator stage s" to the leader's t_empty barrier.  A remote
-      // (release.cluster) arrive costs ~1 us; doing it once here instead of in each of the 8 epilogue warps took
-      // ~15 % off the follower's epilogue time.
-      const uint32_t total = static_cast<uint32_t>(my_tiles) * static_cast<uint32_t>(p.num_code_tiles);
-      const uint32_t remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
-      const uint32_t remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
-      for (uint32_t it = 0; it < total; ++it) {
-        const uint32_t as = it & 1;
-        mbar_wait(smem_u32(&ctrl->t_done[as]), (it >> 1) & 1);
-        mbar_arrive_cluster(as ? remote1 : remote0);
-      }
     }
   } else if (warp < 2 + NUM_EPI_WARPS) {
     // ================================================================ epilogue (warps 2..9)
@@ -359,12 +350,14 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
     const int pair_bar = 1 + lg;             // named barrier shared by the two warps of a lane group
     const float cmax = __ldg(p.cmax);
+    const uint32_t te_remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
+    const uint32_t te_remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
     // number of 16-column pieces of a code tile owned by this warp (pieces 4q + 2*half + {0,1} below BN/16)
     int np_warp = 0;
     while (np_warp < 64 && (4 * (np_warp >> 1) + 2 * half + (np_warp & 1)) < (p.BN >> 4)) ++np_warp;
     if (p.dbg_mode & 1) np_warp = 0;
     uint32_t it = 0;
-    long long w_tfull = 0, w_work = 0, w_merge = 0;
+    long long w_tfull = 0, w_work = 0, w_merge = 0, w_nfull = 0;
     const long long estart = PROF_CLOCK();
     float epi_loss = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
@@ -376,51 +369,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->t_full[as]), (it >> 1) & 1); w_tfull += PROF_CLOCK() - c0; }
         const long long cw0 = PROF_CLOCK();
         tc_fence_after();
-        if (ct == 0) {
-          // ---- row norms from the A tile in smem.  The first accumulator being complete implies that every A
-          // sub-tile of both CTAs has landed (only the leader's barriers see the TMA bytes).
-          // Conflict-free: a warp reads 4 full 128 B rows per request.
-      {
-            const int sub = lane >> 3, chunk = lane & 7;
-            for (int i = half * 4; i < half * 4 + 4; ++i) {  // the two warps of a lane group split its 32 rows
-              const int r = lg * 32 + i * 4 + sub;
-              const uint32_t off = (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4);
-              // ||x||^2 in fp32: it scales the certification band AND carries the commitment loss
-              // (sum ||q - x||^2 = sum ||x||^2 - 2 score), so it must be as exact as the scores.
-              float acc2 = 0.f;
-              for (int kb = 0; kb < p.KB; ++kb) {
-                float v[8];
-                {
-                  const uint4 u = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off);
-                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    v[2 * e] = __uint_as_float(w[e] << 16);
-                    v[2 * e + 1] = __uint_as_float(w[e] & 0xFFFF0000u);
-                  }
-                }
-                if (p.n_a == 2) {
-                  const uint4 u = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off);
-                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    v[2 * e] += __uint_as_float(w[e] << 16);
-                    v[2 * e + 1] += __uint_as_float(w[e] & 0xFFFF0000u);
-                  }
-                }
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc2 = fmaf(v[e], v[e], acc2);
-              }
-              acc2 += __shfl_xor_sync(0xffffffffu, acc2, 1);
-              acc2 += __shfl_xor_sync(0xffffffffu, acc2, 2);
-              acc2 += __shfl_xor_sync(0xffffffffu, acc2, 4);
-              if (chunk == 0) ctrl->xn2[r] = acc2;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_read));
-          }
-          named_bar_sync(pair_bar, 64);  // both halves' norms visible (the end-of-tile merge barrier orders reuse)
-          st.init(2.f * p.margin_rel * sqrtf(ctrl->xn2[row_in_tile]) * cmax + 1e-30f);
+        if (ct == 0) {  // the store warps computed this tile's row norms while the first accumulator was being built
+          { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->n_full[t & 1]), (t >> 1) & 1); w_nfull += PROF_CLOCK() - c0; }
+          st.init(2.f * p.margin_rel * sqrtf(ctrl->xn2[t & 1][row_in_tile]) * cmax + 1e-30f);
         }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * 256;
         const int code0 = ct * p.BN;
@@ -453,23 +404,31 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #endif
           }
         };
+        // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld has completed (the
+        // final piece is scanned from registers afterwards): the release -> MMA -> t_full loop is the critical path.
+        auto release_stage = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {  // the leader's barrier gates the MMA issue into this accumulator stage of BOTH CTAs
+            if (leader) mbar_arrive(smem_u32(&ctrl->t_empty[as]));
+            else mbar_arrive_cluster_relaxed(as ? te_remote1 : te_remote0);
+          }
+        };
         uint32_t buf0[16], buf1[16];
         if (np > 0) tmem_ld_32x32b_x16(t_addr + piece_col(0), buf0);
+        else release_stage();
         for (int j = 0; j < np; j += 2) {
           tmem_wait_ld();
           if (j + 1 < np) tmem_ld_32x32b_x16(t_addr + piece_col(j + 1), buf1);
+          else release_stage();
           scan16(buf0, code0 + piece_col(j));
           if (j + 1 < np) {
             tmem_wait_ld();
             if (j + 2 < np) tmem_ld_32x32b_x16(t_addr + piece_col(j + 2), buf0);
+            else release_stage();
             scan16(buf1, code0 + piece_col(j + 1));
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0)  // the leader's barrier gates the MMA issue into this accumulator stage of BOTH CTAs; the
-                        // follower's warps arrive locally and its (otherwise idle) warp 1 forwards ONE remote arrive
-          mbar_arrive(smem_u32(leader ? &ctrl->t_empty[as] : &ctrl->t_done[as]));
         w_work += PROF_CLOCK() - cw0;
       }
       const long long cm0 = PROF_CLOCK();
@@ -495,7 +454,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // ||q - x||^2 = ||x||^2 - 2(x.c - 0.5||c||^2)  — the score already holds it (cosine: bias is 0, add ||c||^2).
           // Differs from the reference's bf16 evaluation by << 1e-3 relative; flagged rows get the
           // exact evaluation in vqb_fix_flagged.
-          float d2 = ctrl->xn2[row_in_tile] - 2.f * best;
+          float d2 = ctrl->xn2[t & 1][row_in_tile] - 2.f * best;
           if (p.metric == VQB_METRIC_COSINE) d2 += __ldg(p.cnorm2 + i0);
           epi_loss += fmaxf(d2, 0.f);
         }
@@ -528,15 +487,77 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (p.prof && lane == 0 && (ew == 0 || ew == 4)) {
       long long* o = p.prof + blockIdx.x * 16 + 8 + (ew >> 2) * 4;
       o[0] = w_tfull; o[1] = w_work; o[2] = w_merge; o[3] = PROF_CLOCK() - estart;
+      if (ew == 0) p.prof[blockIdx.x * 16 + 7] = w_nfull;
     }
   }
 
-  if (warp >= 2 + NUM_EPI_WARPS && p.fo.enabled) {
-    // ================================================================ store warps (fused gather tail)
+  if (warp >= 2 + NUM_EPI_WARPS) {
+    // ================================================================ store warps: row norms + fused gather tail
     const int sw = warp - 2 - NUM_EPI_WARPS;
     float lsum = 0.f;
+    // ||x||^2 of the 32 rows [sw*32, sw*32+32) of row tile t, from the A tile in smem, as soon as it has landed.
+    // Only the leader's barriers see the TMA bytes; its store warp 0 forwards "landed" to the follower.
+    // fp32 accumulation: the norm scales the certification band AND carries the commitment loss
+    // (sum ||q - x||^2 = sum ||x||^2 - 2 score), so it must be as exact as the scores.
+    auto row_norms = [&](int t) {
+      if (leader) {
+        for (int s2 = 0; s2 < n_sub; ++s2) mbar_wait(smem_u32(&ctrl->a_full[s2]), t & 1);
+        if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready), 1));
+      } else {
+        mbar_wait_cluster(smem_u32(&ctrl->a_ready), t & 1);
+      }
+      const int sub = lane >> 3, chunk = lane & 7;  // conflict-free: a warp reads 4 full 128 B rows per request
+      // two rows per lane in flight, two partial sums per row: the dependent-FMA chain, not smem, bounds this loop
+      for (int i = 0; i < 8; i += 2) {
+        const int r0 = sw * 32 + i * 4 + sub, r1 = r0 + 4;
+        const uint32_t off0 = (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4);
+        const uint32_t off1 = (r1 >> 3) * 1024 + (r1 & 7) * 128 + ((chunk ^ (r1 & 7)) << 4);
+        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll 4
+        for (int kb = 0; kb < p.KB; ++kb) {
+          uint4 u[2], l[2];
+          u[0] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off0);
+          u[1] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off1);
+          if (p.n_a == 2) {
+            l[0] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off0);
+            l[1] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off1);
+          } else {
+            l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
+          }
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const uint32_t w[4] = {u[b].x, u[b].y, u[b].z, u[b].w};
+            const uint32_t wl[4] = {l[b].x, l[b].y, l[b].z, l[b].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float v0 = __uint_as_float(w[e] << 16) + __uint_as_float(wl[e] << 16);
+              const float v1 = __uint_as_float(w[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+              acc[b][0] = fmaf(v0, v0, acc[b][0]);
+              acc[b][1] = fmaf(v1, v1, acc[b][1]);
+            }
+          }
+        }
+        float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1];
+#pragma unroll
+        for (int m = 1; m <= 4; m <<= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, m);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+        }
+        if (chunk == 0) { ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1; }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&ctrl->a_read));        // the producer may refill A once the MMAs are done with it too
+        mbar_arrive(smem_u32(&ctrl->n_full[t & 1])); // release: the xn2 writes above are visible to the epilogue
+      }
+    };
+    if (my_tiles > 0) row_norms(0);
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
+      // norms of the NEXT tile first: its A tile lands during this tile's last code tile, long before this tile's
+      // winners are published (xn2[(t+1)&1] was last read by the merge of tile t-1, which preceded our gather of t-1)
+      if (t + 1 < my_tiles) row_norms(t + 1);
+      if (!p.fo.enabled) continue;
       mbar_wait(smem_u32(&ctrl->g_full[t & 1]), (t >> 1) & 1);
       const int* gi = ctrl->gidx[t & 1] + sw * 32;
       if (p.copy_mode) {
@@ -590,7 +611,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_empty[t & 1]));
     }
-    if (p.fo.loss_sum && !p.copy_mode) {
+    if (p.fo.enabled && p.fo.loss_sum && !p.copy_mode) {
       const double w = warp_sum(static_cast<double>(lsum));
       if (lane == 0) atomicAdd(p.fo.loss_sum, w);
     }
