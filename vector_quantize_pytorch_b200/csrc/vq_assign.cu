@@ -7,20 +7,24 @@
 // 128-row tiles against the same codebook sweep.  Each CTA stages only HALF of every codebook tile
 // (BN/2 codes) — the M=256 MMA reads both halves — which halves the L2->SM operand traffic that bounded
 // the single-CTA version (measured: 53 B/clk/SM of B-tile ingest at 2 passes).
-// Per CTA, warp-specialised (10 warps):
-//   warp 0      TMA producer : x tile (A: 128 rows, stationary in smem for the whole code sweep, refilled
+// Per CTA, warp-specialised (14 warps).  The warp scheduler favours the HIGHER warp id of a scheduler partition when
+// several warps are ready, and the epilogue warps are always ready (alu-pipe bound) — so the two warps whose issue
+// latency gates everything else (MMA issuer, TMA producer) get the highest ids of their partitions:
+//   warps 0..7  epilogue     : tcgen05.ld (lane == row).  Warps w and w+4 share a TMEM lane group and split
+//                              the columns; a thread keeps a branch-free running top-3 of its row slice (RowState),
+//                              the two slices are merged once per row tile.
+//   warps 8..11 store        : row norms ||x||^2 of the next tile from the A tile in smem; fused gather tail
+//                              (quantized rows, int64 indices) of the tile just certified
+//   warp 12     TMA producer : x tile (A: 128 rows, stationary in smem for the whole code sweep, refilled
 //                              k-block by k-block as the last sweep of the previous tile releases it),
 //                              codebook tiles (B: BN codes x 64 dims per stage) and the per-tile bias
 //                              block (Bext: BN codes x 16) -> swizzled smem
-//   warp 1      MMA issuer   : (leader CTA only) tcgen05.mma.cta_group::2.kind::f16, M=256 (128 rows per CTA),
+//   warp 13     MMA issuer   : (leader CTA only) tcgen05.mma.cta_group::2.kind::f16, M=256 (128 rows per CTA),
 //                              bf16 x bf16 -> fp32 into the TMEM of both CTAs.
 //                              Per code tile: one K=16 MMA  [1 1 1 0..] x [-b1 -b2 -b3 0..]^T  that seeds
 //                              the accumulator with -0.5||c||^2 (three bf16 terms = exact fp32), then the
 //                              split-precision passes (a0,c_hi)+(a0,c_lo)[+(a1,c_hi)] accumulate on top.
 //                              Two accumulator stages (2 x 256 TMEM columns).
-//   warps 2..9  epilogue     : tcgen05.ld (lane == row).  Warps w and w+4 share a TMEM lane group and split
-//                              the columns; a thread keeps the running arg-max of its row slice plus an
-//                              error-band candidate list, the two slices are merged once per row tile.
 //
 // Exactness: the tensor-core score of a (row, code) pair differs from the exact fp32 value by at most
 // tau = margin_rel * ||x|| * max||c||.  A row is certified when its best score leads every other score
@@ -50,8 +54,10 @@ constexpr int TMEM_COLS = 512;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_STORE_WARPS = 4;  // fused gather / loss / residual tail of the certified rows
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS + NUM_STORE_WARPS) * 32;
+constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
+constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 7168;     // barriers + tmem ptr + row norms + merge area
+constexpr int SMEM_CTRL_BYTES = 9216;     // barriers + tmem ptr + row norms + merge area
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
@@ -73,38 +79,51 @@ struct AssignParams {
   int metric;
   const uint16_t* b_hi;     // bf16 hi plane [Kpad][D]: bf16(c) == the quantized row for bf16 inputs
   const float* cnorm2;      // [K] (cosine loss term)
+  uint32_t tagmask, mul1, mulm1;  // 0xFFFFFFF0, 1, -1: constants the compiler must not fold (RowState::piece)
   int dbg_mode;        // diagnostics: bit0 = epilogue skips the TMEM sweep, bit1 = skip B loads+MMAs except bias
 };
 
-struct RowState {  // running arg-max of one row (slice) + candidates inside the error band
-  float best, thr, W;
-  int i0, i1, n;
-  __device__ __forceinline__ void init(float w) { W = w; best = -INFINITY; thr = -INFINITY; i0 = 0; i1 = -1; n = 0; }
-  // called only for elements with v > thr
-  __device__ __forceinline__ void hit(float v, int c) {
-    const bool nb = v > best;
-    n = (v - best > W) ? 1 : n + 1;   // a clear new leader drops every earlier candidate out of the band
-    i1 = nb ? i0 : c;
-    i0 = nb ? c : i0;
-    best = fmaxf(best, v);
-    thr = best - W;
+// Running top-3 of one row (slice), branch-free.  Scores carry the element's position inside its 16-column piece in
+// their 4 low mantissa bits (tag = 15 - e, so that among equal truncated values the FIRST column wins a max), which
+// makes the whole update min/max arithmetic — no compare/select chains, no divergence between the 32 rows of a
+// warp.  The tag perturbs a score by < 16 ulp; the certification band W carries that slack (see st.init below).
+// t3 only answers "is there a third candidate inside the band" (-> whole-row exact re-scan).
+struct RowState {
+  float t1, t2, t3;   // tagged top-3 scores
+  float thr, W;       // thr = t1 - W: pieces whose exact maximum is <= thr cannot hold a candidate
+  float bexact;       // exact (untagged) running maximum: the score that carries the loss
+  int j1, j2;         // first column of the pieces t1 / t2 came from
+  __device__ __forceinline__ void init(float w) {
+    W = w; t1 = t2 = t3 = -3.4e38f; bexact = -3.4e38f; thr = -3.4e38f; j1 = 0; j2 = 0;
   }
-  // Branch-free form of `if (v > thr) hit(v, c)`: pure select/compare code, only best -> thr is a loop-carried chain.
-  // The epilogue warps are branch-latency bound (32 independent rows per warp make almost every group of four columns
-  // a hit for SOME lane), so predication beats the nested per-element branches.
-  __device__ __forceinline__ void upd(float v, int c) {
-    const bool p = v > thr;
-    const bool nb = v > best;
-    const int n_hit = (v - best > W) ? 1 : n + 1;
-    n = p ? n_hit : n;
-    i1 = p ? (nb ? i0 : c) : i1;
-    i0 = nb ? c : i0;  // nb implies p (thr < best)
-    best = fmaxf(best, v);
-    thr = best - W;
+  // Pipe balance: the SM's alu pipe (FMNMX, LOP3; one warp instruction per 2 clocks per scheduler) is what bounds
+  // the epilogue, the fma pipe idles.  So only the max of each compare-exchange is an FMNMX; the min is recovered on
+  // the fma pipe as an integer identity on the bit patterns, min = a + b - max (exact: max returns one of its inputs),
+  // written as IMADs with a multiplier ptxas cannot fold (mul1 = 1, mulm1 = -1 come in through the kernel params).
+  __device__ __forceinline__ void piece(const uint32_t (&r)[16], int cbase, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
+    const float o1 = t1, o2 = t2;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const uint32_t ku = (r[e] & tagmask) | static_cast<uint32_t>(15 - e);
+      const float n1 = fmaxf(t1, __uint_as_float(ku));
+      const uint32_t lo1 = __float_as_uint(n1) * mulm1 + (__float_as_uint(t1) * mul1 + ku);
+      const float n2 = fmaxf(t2, __uint_as_float(lo1));
+      const uint32_t lo2 = __float_as_uint(n2) * mulm1 + (__float_as_uint(t2) * mul1 + lo1);
+      t3 = fmaxf(t3, __uint_as_float(lo2));
+      t1 = n1;
+      t2 = n2;
+    }
+    // where did t1 / t2 come from?  Equal tagged scores in different pieces make this ambiguous, but then the
+    // equal score also sits in t2 or t3, the row has >= 3 candidates and is re-scanned exactly anyway.
+    const bool c1 = t1 != o1;
+    j2 = (t2 == o2) ? j2 : ((c1 && t2 == o1) ? j1 : cbase);
+    j1 = c1 ? cbase : j1;
+    thr = t1 - W;
   }
+  static __device__ __forceinline__ int col(float t, int j) { return j + 15 - static_cast<int>(__float_as_uint(t) & 15u); }
 };
 
-struct MergeSlot { float best; int i0, i1, n; };
+struct MergeSlot { float t1, t2, t3, bexact; int i0, i1; };
 
 struct Ctrl {  // lives at the start of dynamic smem
   uint64_t a_full[MAX_A_SUB], a_empty[MAX_A_SUB];
@@ -165,7 +184,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
 
   // ------------------------------------------------------------------ one-time setup
-  if (warp == 0 && lane == 0) {
+  if (warp == WARP_PROD && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmX);
@@ -191,7 +210,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tmem_alloc_2sm(smem_u32(&ctrl->tmem_base), TMEM_COLS);
     tmem_relinquish_2sm();
   }
@@ -220,7 +239,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // plane used by pass ps: A plane = (ps == 2), B plane = (ps == 1)
   const int last_pass_a0 = p.n_passes >= 2 ? 1 : 0;  // last pass that reads A plane 0
 
-  if (warp == 0) {
+  if (warp == WARP_PROD) {
     // ================================================================ TMA producer
     if (lane == 0) {
       long long prof_acc[2] = {0, 0};
@@ -269,7 +288,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       if (p.prof) { p.prof[blockIdx.x * 16 + 0] = prof_acc[0]; p.prof[blockIdx.x * 16 + 1] = PROF_CLOCK() - pstart; }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ================================================================ MMA issuer
     if (leader) {  // the whole warp runs the loop (warp-uniform); one elected lane issues
       const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);
@@ -342,9 +361,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         o[2] = w_tempty; o[3] = w_bfull; o[4] = w_xfull; o[5] = w_afull; o[6] = PROF_CLOCK() - mstart;
       }
     }
-  } else if (warp < 2 + NUM_EPI_WARPS) {
-    // ================================================================ epilogue (warps 2..9)
-    const int ew = warp - 2;                 // 0..7
+  } else if (warp < NUM_EPI_WARPS) {
+    // ================================================================ epilogue (warps 0..7)
+    const int ew = warp;                     // 0..7
     const int lg = warp & 3;                 // TMEM lane group this warp may access
     const int half = ew >> 2;                // column half: chunk parity handled by this warp
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
@@ -371,7 +390,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (ct == 0) {  // the store warps computed this tile's row norms while the first accumulator was being built
           { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->n_full[t & 1]), (t >> 1) & 1); w_nfull += PROF_CLOCK() - c0; }
-          st.init(2.f * p.margin_rel * sqrtf(ctrl->xn2[t & 1][row_in_tile]) * cmax + 1e-30f);
+          // band = 2 * (MMA error bound) + 2 * (tag perturbation: 16 ulp <= 2^-19 |score|, |score| <= |x||c| + |c|^2/2)
+          const float xc = sqrtf(ctrl->xn2[t & 1][row_in_tile]) * cmax;
+          st.init(2.f * p.margin_rel * xc + 0x1p-18f * (xc + (p.metric == VQB_METRIC_COSINE ? 0.f : 0.5f * cmax * cmax)) + 1e-30f);
         }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * 256;
         const int code0 = ct * p.BN;
@@ -386,23 +407,13 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             m[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
                          fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
           const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-          // Slow path (some lane of the warp has a candidate in this piece).  Measured on B200: branch-free selects
-          // beat clever branching here — the all-four-elements update per hit group (0.238 ms at config 2) is faster
-          // than "update only the group maximum unless a second element is in the band" (0.258 ms).
-          if (mm > st.thr) {
-#ifdef VQB_EPI_FLAT
-#pragma unroll
-            for (int e = 0; e < 16; ++e) st.upd(__uint_as_float(r[e]), cbase + e);
-#else
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (m[j] > st.thr) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) st.upd(__uint_as_float(r[4 * j + e]), cbase + 4 * j + e);
-              }
-            }
+          st.bexact = fmaxf(st.bexact, mm);
+#ifdef VQB_PROFILE
+          if (p.dbg_mode & 16) return;  // timing experiment: TMEM loads + max tree only
 #endif
-          }
+          // 32 independent rows per warp: for K ~ 1e3 some lane has a candidate in most pieces, so what matters is
+          // that the update itself is straight-line min/max code (measured history in DESIGN.md section 8)
+          if (mm > st.thr) st.piece(r, cbase, p.tagmask, p.mul1, p.mulm1);
         };
         // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld has completed (the
         // final piece is scanned from registers afterwards): the release -> MMA -> t_full loop is the critical path.
@@ -415,6 +426,19 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         };
         uint32_t buf0[16], buf1[16];
+#ifdef VQB_PROFILE
+        if (p.dbg_mode & 32) {  // timing experiment: the scan arithmetic alone, on (stale) registers
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { buf0[e] = __float_as_uint(st.t3) + e + it; buf1[e] = buf0[e] ^ 0x3000u; }
+          release_stage();
+          for (int j = 0; j < np; j += 2) {
+            scan16(buf0, code0 + piece_col(j));
+            if (j + 1 < np) scan16(buf1, code0 + piece_col(j + 1));
+          }
+          w_work += PROF_CLOCK() - cw0;
+          continue;
+        }
+#endif
         if (np > 0) tmem_ld_32x32b_x16(t_addr + piece_col(0), buf0);
         else release_stage();
         for (int j = 0; j < np; j += 2) {
@@ -436,19 +460,22 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ---- merge the two column slices of each row (upper half publishes, lower half finishes the row)
       MergeSlot* slot = &ctrl->merge[t & 1][row_in_tile];
       if (half == 1) {
-        slot->best = st.best; slot->i0 = st.i0; slot->i1 = st.i1; slot->n = st.n;
+        slot->t1 = st.t1; slot->t2 = st.t2; slot->t3 = st.t3; slot->bexact = st.bexact;
+        slot->i0 = RowState::col(st.t1, st.j1); slot->i1 = RowState::col(st.t2, st.j2);
         named_bar_sync(pair_bar, 64);
       } else {
         named_bar_sync(pair_bar, 64);
-        const float ob = slot->best;
-        const int oi0 = slot->i0, oi1 = slot->i1, on = slot->n;
-        // candidates of a slice count only if that slice's best is inside the band of the overall best
-        const float best = fmaxf(st.best, ob);
-        const bool mine_in = st.best >= best - st.W, other_in = ob >= best - st.W;
-        const int n = (mine_in ? st.n : 0) + (other_in ? on : 0);
+        const float b1 = slot->t1, b2 = slot->t2, b3 = slot->t3;
+        const int ib0 = slot->i0, ib1 = slot->i1;
+        const int ia0 = RowState::col(st.t1, st.j1), ia1 = RowState::col(st.t2, st.j2);
+        const float best = fmaxf(st.bexact, slot->bexact);   // exact score of the winner
+        // candidates = tagged scores inside the band below the tagged maximum, over both slices
+        const float tb = fmaxf(st.t1, b1);
+        const float band = tb - st.W;
+        const int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (b1 > band) + (b2 > band) + (b3 > band);
         int i0, i1;
-        if (st.best > ob || (st.best == ob && st.i0 < oi0)) { i0 = st.i0; i1 = (mine_in && st.n >= 2) ? st.i1 : oi0; }
-        else { i0 = oi0; i1 = (other_in && on >= 2) ? oi1 : st.i0; }
+        if (st.t1 > b1 || (st.t1 == b1 && ia0 < ib0)) { i0 = ia0; i1 = (st.t2 > b1) ? ia1 : ib0; }
+        else { i0 = ib0; i1 = (b2 > st.t1) ? ib1 : ia0; }
         const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
         if (p.copy_mode && p.fo.loss_sum && row < p.N && n < 2) {
           // ||q - x||^2 = ||x||^2 - 2(x.c - 0.5||c||^2)  — the score already holds it (cosine: bias is 0, add ||c||^2).
@@ -491,9 +518,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
 
-  if (warp >= 2 + NUM_EPI_WARPS) {
+  if (warp >= NUM_EPI_WARPS && warp < NUM_EPI_WARPS + NUM_STORE_WARPS) {
     // ================================================================ store warps: row norms + fused gather tail
-    const int sw = warp - 2 - NUM_EPI_WARPS;
+    const int sw = warp - NUM_EPI_WARPS;
     float lsum = 0.f;
     // ||x||^2 of the 32 rows [sw*32, sw*32+32) of row tile t, from the A tile in smem, as soon as it has landed.
     // Only the leader's barriers see the TMA bytes; its store warp 0 forwards "landed" to the follower.
@@ -621,7 +648,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // neither CTA may exit (or free TMEM) while its peer can still signal / read it
-  if (warp == 1) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  if (warp == WARP_MMA) tmem_dealloc_2sm(tmem_base, TMEM_COLS);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -717,6 +744,7 @@ extern "C" int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, co
   p.cmax = cmax; p.idx = idx; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
   p.prof = g_prof;
   p.dbg_mode = g_dbg_mode;
+  p.tagmask = 0xFFFFFFF0u; p.mul1 = 1u; p.mulm1 = 0xFFFFFFFFu;
   rc = make_fused(&p.fo, fused, D);
   if (rc) return rc;
   p.metric = metric;
