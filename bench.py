@@ -110,54 +110,70 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------------
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region, in-process through NVML.
+
+    A forked `nvidia-smi -lms` loop was measured to perturb the very region it watches: one query can hold a driver lock
+    for tens of milliseconds, and a 20-step timed region is only ~7 ms long (observed: 0.34 -> 1.5 / 3.1 ms per step when
+    a query landed inside it).  NVML calls from a thread cost microseconds and fork nothing.
+    """
+    PERIOD_S = 0.002
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (time, sm_mhz, reasons bitmask)
+        self.smax = None
+        self.handle = None
+        self.stop_flag = False
+        self.thread = None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes torch's visible devices; honour CUDA_VISIBLE_DEVICES when it lists plain indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.gpu
+            if vis:
+                parts = [v.strip() for v in vis.split(",") if v.strip()]
+                if self.gpu < len(parts) and parts[self.gpu].isdigit():
+                    idx = int(parts[self.gpu])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.thread = threading.Thread(target=self._loop, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.nv = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                self.rows.append((time.time(), sm, rs))
+            except Exception:
+                pass
+            time.sleep(self.PERIOD_S)
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], None, set()
-        for ts, line in self.rows:
-            if ts < t0 - 0.05 or ts > t1 + 0.15:
-                continue
-            f = [c.strip() for c in line.split(",")]
-            try:
-                sm.append(float(f[1]))
-                smax = float(f[2])
-            except Exception:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:  # the timed region was shorter than one sample: use whatever we have
-            for ts, line in self.rows[-3:]:
-                f = [c.strip() for c in line.split(",")]
-                try:
-                    sm.append(float(f[1])); smax = float(f[2])
-                except Exception:
-                    pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        nv = self.nv
+        names = (("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown),
+                 ("hw_thermal_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", nv.nvmlClocksEventReasonSwThermalSlowdown),
+                 ("sw_power_cap", nv.nvmlClocksEventReasonSwPowerCap))
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        if not inside:  # the timed region was shorter than one sample period: take the nearest samples
+            inside = sorted(self.rows, key=lambda r: min(abs(r[0] - t0), abs(r[0] - t1)))[:3]
+        sm = [r[1] for r in inside]
+        reasons = sorted({n for r in inside for n, bit in names if r[2] & bit})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                "samples": len(sm), "source": "nvml, in-process, 2 ms period"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -206,27 +222,43 @@ def run_gpu_arm(args):
     # W untimed warm-up steps as requested, plus enough extra untimed calls for the allocator / graph cache to reach
     # their steady state (every output-pointer set is enqueued directly once and captured once before it replays)
     for _ in range(max(args.warmup, 12)):
-        vq(x_dev)
+        q, ind, loss = vq(x_dev)   # same binding pattern as the timed loop: the allocator then cycles the same blocks
     barrier()
-    ops.PROFILE_EVENTS = []
+    ops.PROFILE_EVENTS = None
     ops.LAUNCHES = 0
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
+    time.sleep(0.05)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start = time.time()
     e0.record()
     for _ in range(args.steps):
         q, ind, loss = vq(x_dev)
+    t_host = time.time()
     e1.record()
     barrier()
     t_end = time.time()
     launches = ops.LAUNCHES
-    prof = ops.PROFILE_EVENTS
-    ops.PROFILE_EVENTS = None
     clocks = sampler.stop(t_start, t_end)
     ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    host_ms = (t_host - t_start) * 1e3 / args.steps   # CPU time to enqueue one step (must stay below ms_dev)
+
+    # ---------------- the dominant kernel's launch duration (roofline): the same K steps once more, now with a CUDA
+    # event pair recorded on the launching stream around vq_assign_kernel.  Kept out of the headline region because
+    # event records cannot live inside the step's CUDA graph: with them every launch of the chain is enqueued one by
+    # one and the step becomes sensitive to host jitter (observed 0.34 -> 1.1 ms on a noisy box).
+    ops.PROFILE_EVENTS = []
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    g0.record()
+    for _ in range(args.steps):
+        q, ind, loss = vq(x_dev)
+    g1.record()
+    barrier()
+    prof = ops.PROFILE_EVENTS
+    ops.PROFILE_EVENTS = None
+    ms_dev_events = g0.elapsed_time(g1) / args.steps
     prof = [pr for pr in prof if pr is not None]
     assign_ms = statistics.mean(a.elapsed_time(b) for a, b in prof) if prof else None
 
@@ -240,9 +272,9 @@ def run_gpu_arm(args):
         vq.forward_host(x_host, n_chunks=E2E_CHUNKS, out=(q_host, i_host, l_host))
 
     if os.environ.get("VQB_BENCH_SKIP_E2E"):  # profiling aid: keep the launch list to the device-resident steps
-        print(json.dumps({"ms_per_step": ms_dev, "kernel_ms": assign_ms, "gpu_launches": launches}))
+        print(json.dumps({"ms_per_step": ms_dev, "kernel_ms": assign_ms, "gpu_launches": launches, "host_ms_per_step": host_ms}))
         return
-    for _ in range(max(1, min(args.warmup, 3))):
+    for _ in range(max(3, min(args.warmup, 5))):   # >= 3: every chunk's pointer set is seen twice before it replays
         e2e_step()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -270,6 +302,9 @@ def run_gpu_arm(args):
             "frac": (flops / (assign_ms * 1e-3) / 1e12 / peak_tf) if assign_ms else None,
             "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside the step)",
             "kernel_ms": assign_ms, "kernel_share_of_step": assign_ms / ms_dev if assign_ms else None,
+            "measured": "CUDA event pair on the launching stream around every vq_assign_kernel launch, over the same K "
+                        "steps repeated right after the headline region (events split the step's CUDA graph)",
+            "ms_per_step_with_events": ms_dev_events,
             "algorithmic_flops_per_launch": flops, "executed_mma_passes": 2, "traffic": None}
     cpu_v, _ = time_cpu(steps=2, warmup=1)
     line = {
@@ -283,6 +318,7 @@ def run_gpu_arm(args):
         "e2e": {"value": world * n_vec / (ms_e2e * 1e-3), "unit": "vectors/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": launches,
+        "host_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": roof,
         "cpu_baseline": cpu_baseline_block(cpu_v),

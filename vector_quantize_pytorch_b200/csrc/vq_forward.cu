@@ -48,25 +48,38 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream);
 
 // ---------------------------------------------------------------------------------------------
 // CUDA-graph cache.  The chain is ~15 small launches around one big kernel; replaying it as a graph removes the
-// launch gaps.  A call is identified by every pointer / size / flag of its argument struct; the first occurrence
-// of a key is enqueued directly (also warms lazy module loading), the second is captured, later ones replay.
-// It pays off when pointer sets repeat: the Python glue keeps its small outputs / scratch in persistent buffers and
-// torch's allocator cycles through a handful of large blocks for the per-call outputs.  VQB_GRAPH=0 disables.
+// launch gaps.  A call has a STRUCTURAL key (sizes, flags, which optional pointers are set, the stream: everything
+// that decides the node topology) and a POINTER key.  Per structural key the cache keeps up to kVariants executable
+// graphs, one per pointer set: torch's allocator cycles through a handful of blocks for the per-call outputs and the
+// chunked host path uses one pointer set per chunk, so steady state is pure replay.  A pointer set that is not
+// cached re-captures the chain (host-only, tens of microseconds) and patches the least recently used executable
+// with cudaGraphExecUpdate instead of instantiating again — a miss never costs a GPU bubble, which is what made
+// step times jump from 0.34 to 0.7+ ms whenever the allocator produced a new address combination mid-run.
+// The first call of a structural key is enqueued directly (warms lazy module loading).  VQB_GRAPH=0 disables.
 // Bypassed while profiling events are requested, or when the stream is already being captured
 // (then the launches simply become part of the caller's graph).
 // ---------------------------------------------------------------------------------------------
 namespace {
-struct GraphEntry {
-  uint64_t key[40];
+constexpr int kKeyWords = 24;
+constexpr int kVariants = 32;     // executable graphs per structural key
+constexpr int kMaxStruct = 16;    // structural keys (LRU)
+constexpr int kCaptureFailed = -2147483647;
+struct Variant {
+  uint64_t pkey[kKeyWords];
   cudaGraphExec_t exec;
   unsigned long long last_use;
 };
-constexpr int kMaxGraphs = 128;
-int g_captures_since_replay = 0;  // safety valve: pointer sets that never repeat make capturing pure overhead
-bool g_graph_disabled = false;
-GraphEntry g_graphs[kMaxGraphs];
-int g_num_graphs = 0;
+struct StructEntry {
+  uint64_t skey[kKeyWords];
+  Variant var[kVariants];
+  int n_var;
+  unsigned long long last_use;
+  bool used;
+};
+StructEntry* g_struct = nullptr;  // [kMaxStruct], allocated on first use
 unsigned long long g_tick = 0;
+int g_graph_failures = 0;         // capture / instantiate / update failures: give up after a few
+bool g_graph_disabled = false;
 
 int graph_mode() {
   static int mode = -1;
@@ -77,17 +90,37 @@ int graph_mode() {
   return mode;
 }
 
-void make_key(const vqb_vq_forward_args* a, void* stream, uint64_t* k) {
-  int i = 0;
-  auto P = [&](const void* p) { k[i++] = reinterpret_cast<uint64_t>(p); };
-  auto I = [&](long long v) { k[i++] = static_cast<uint64_t>(v); };
-  auto F = [&](double v) { uint64_t u; memcpy(&u, &v, 8); k[i++] = u; };
-  P(a->x); I(a->dtype); I(a->metric); I(a->N); I(a->D); I(a->K); I(a->already_normalised);
-  P(a->cluster_size); P(a->embed_avg); P(a->embed); P(a->planes); P(a->bext); P(a->bias); P(a->cnorm2); P(a->cmax);
-  P(a->scratch); P(a->q_out); P(a->idx64_out); I(a->idx_stride); P(a->loss_out); F(a->loss_weight); P(a->resid_out);
-  P(a->qsum); P(a->idx32); I(a->update); I(a->stats_mode); I(a->stats_accumulate); I(a->do_normalise); F(a->decay);
-  F(a->eps); P(a->stats); F(a->margin_rel); P(a->workspace); I(static_cast<long long>(a->workspace_bytes)); P(stream);
-  while (i < 40) k[i++] = 0;
+void make_keys(const vqb_vq_forward_args* a, void* stream, uint64_t* sk, uint64_t* pk) {
+  int si = 0, pi = 0;
+  uint64_t present = 0;
+  int nbit = 0;
+  auto P = [&](const void* p) { pk[pi++] = reinterpret_cast<uint64_t>(p); present |= static_cast<uint64_t>(p != nullptr) << nbit++; };
+  auto I = [&](long long v) { sk[si++] = static_cast<uint64_t>(v); };
+  auto F = [&](double v) { uint64_t u; memcpy(&u, &v, 8); sk[si++] = u; };
+  P(a->x); P(a->cluster_size); P(a->embed_avg); P(a->embed); P(a->planes); P(a->bext); P(a->bias); P(a->cnorm2); P(a->cmax);
+  P(a->scratch); P(a->q_out); P(a->idx64_out); P(a->loss_out); P(a->resid_out); P(a->qsum); P(a->idx32); P(a->stats);
+  P(a->workspace);
+  I(a->dtype); I(a->metric); I(a->N); I(a->D); I(a->K); I(a->already_normalised); I(a->idx_stride); F(a->loss_weight);
+  I(a->update); I(a->stats_mode); I(a->stats_accumulate); I(a->do_normalise); F(a->decay); F(a->eps); F(a->margin_rel);
+  I(static_cast<long long>(a->workspace_bytes)); I(reinterpret_cast<long long>(stream)); I(static_cast<long long>(present));
+  while (si < kKeyWords) sk[si++] = 0;
+  while (pi < kKeyWords) pk[pi++] = 0;
+}
+
+// capture the chain for `a` into a fresh graph (nothing executes)
+int capture_chain(const vqb_vq_forward_args* a, cudaStream_t s, cudaGraph_t* out) {
+  *out = nullptr;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return kCaptureFailed; }
+  const int rc = vq_forward_enqueue(a, s);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ee = cudaStreamEndCapture(s, &graph);
+  if (rc != VQB_OK || ee != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc != VQB_OK ? rc : kCaptureFailed;
+  }
+  *out = graph;
+  return VQB_OK;
 }
 }  // namespace
 
@@ -98,56 +131,95 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   if (!graph_mode() || g_graph_disabled || a->ev_search_begin || a->ev_search_end || vqb_debug_active() ||
       cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
     return vq_forward_enqueue(a, stream);
-  uint64_t key[40];
-  make_key(a, stream, key);
+  if (!g_struct) {
+    g_struct = static_cast<StructEntry*>(calloc(kMaxStruct, sizeof(StructEntry)));
+    if (!g_struct) return vq_forward_enqueue(a, stream);
+  }
+  uint64_t sk[kKeyWords], pk[kKeyWords];
+  make_keys(a, stream, sk, pk);
   ++g_tick;
-  int slot = -1;
-  for (int i = 0; i < g_num_graphs; ++i)
-    if (memcmp(g_graphs[i].key, key, sizeof(key)) == 0) { slot = i; break; }
-  if (slot >= 0 && g_graphs[slot].exec) {  // replay
-    g_graphs[slot].last_use = g_tick;
-    g_captures_since_replay = 0;
-    const cudaError_t e = cudaGraphLaunch(g_graphs[slot].exec, s);
-    return static_cast<int>(e);
-  }
-  if (slot < 0) {  // first sighting: remember the key, run directly
-    if (g_num_graphs < kMaxGraphs) slot = g_num_graphs++;
-    else {
-      slot = 0;
-      for (int i = 1; i < kMaxGraphs; ++i)
-        if (g_graphs[i].last_use < g_graphs[slot].last_use) slot = i;
-      if (g_graphs[slot].exec) cudaGraphExecDestroy(g_graphs[slot].exec);
+  StructEntry* se = nullptr;
+  for (int i = 0; i < kMaxStruct; ++i)
+    if (g_struct[i].used && memcmp(g_struct[i].skey, sk, sizeof(sk)) == 0) { se = &g_struct[i]; break; }
+  if (!se) {  // first call of this structure: remember it, run directly
+    int slot = 0;
+    for (int i = 0; i < kMaxStruct; ++i) {
+      if (!g_struct[i].used) { slot = i; break; }
+      if (g_struct[i].last_use < g_struct[slot].last_use) slot = i;
     }
-    memcpy(g_graphs[slot].key, key, sizeof(key));
-    g_graphs[slot].exec = nullptr;
-    g_graphs[slot].last_use = g_tick;
+    se = &g_struct[slot];
+    for (int v = 0; v < se->n_var; ++v)
+      if (se->var[v].exec) cudaGraphExecDestroy(se->var[v].exec);
+    memset(se, 0, sizeof(*se));
+    memcpy(se->skey, sk, sizeof(sk));
+    se->used = true;
+    se->last_use = g_tick;
     return vq_forward_enqueue(a, stream);
   }
-  // second sighting: capture, instantiate, launch
-  g_graphs[slot].last_use = g_tick;
-  if (++g_captures_since_replay > 48) g_graph_disabled = true;  // instantiations are not paying off: stop
-  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-    cudaGetLastError();
-    return vq_forward_enqueue(a, stream);
-  }
-  const int rc = vq_forward_enqueue(a, stream);
+  se->last_use = g_tick;
+  for (int v = 0; v < se->n_var; ++v)
+    if (se->var[v].exec && memcmp(se->var[v].pkey, pk, sizeof(pk)) == 0) {  // replay
+      se->var[v].last_use = g_tick;
+      return static_cast<int>(cudaGraphLaunch(se->var[v].exec, s));
+    }
+  // New pointer set.  Instantiating an executable graph is the expensive step (it can synchronise with the device and
+  // stall the whole launch queue), so a set earns its own executable only on its SECOND sighting ("pending" record);
+  // until then the call is served by patching the least recently used executable in place.
   cudaGraph_t graph = nullptr;
-  const cudaError_t ee = cudaStreamEndCapture(s, &graph);
-  if (rc != VQB_OK || ee != cudaSuccess || !graph) {
-    if (graph) cudaGraphDestroy(graph);
-    cudaGetLastError();
-    if (rc != VQB_OK) return rc;
-    return vq_forward_enqueue(a, stream);  // capture failed: nothing ran, enqueue directly
+  const int rc = capture_chain(a, s, &graph);
+  if (rc != VQB_OK) {
+    if (rc != kCaptureFailed) return rc;              // error reported by the chain itself (nothing ran)
+    if (++g_graph_failures > 4) g_graph_disabled = true;
+    return vq_forward_enqueue(a, stream);             // capture failed: nothing ran, enqueue directly
   }
-  cudaGraphExec_t exec = nullptr;
-  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (ie != cudaSuccess || !exec) {
+  Variant* pend = nullptr;     // pending record of this pointer set
+  Variant* donor = nullptr;    // least recently used executable
+  Variant* spare = nullptr;    // free / least recently used pending record
+  for (int v = 0; v < se->n_var; ++v) {
+    Variant* q = &se->var[v];
+    if (q->exec) { if (!donor || q->last_use < donor->last_use) donor = q; }
+    else if (memcmp(q->pkey, pk, sizeof(pk)) == 0) pend = q;
+    else if (!spare || q->last_use < spare->last_use) spare = q;
+  }
+  if (se->n_var < kVariants) spare = &se->var[se->n_var];
+  auto fail = [&]() {
     cudaGetLastError();
+    cudaGraphDestroy(graph);
+    if (++g_graph_failures > 4) g_graph_disabled = true;
     return vq_forward_enqueue(a, stream);
+  };
+  Variant* use = nullptr;
+  if (pend || !donor) {  // second sighting (or nothing to patch yet): instantiate
+    use = pend ? pend : spare;
+    if (!use) return fail();
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess || !exec) return fail();
+    if (use == &se->var[se->n_var]) ++se->n_var;
+    use->exec = exec;
+  } else {
+    if (spare) {  // remember the sighting
+      if (spare == &se->var[se->n_var]) ++se->n_var;
+      memcpy(spare->pkey, pk, sizeof(pk));
+      spare->exec = nullptr;
+      spare->last_use = g_tick;
+    }
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(donor->exec, graph, &info) != cudaSuccess) {  // topology differs after all: rebuild it
+      cudaGetLastError();
+      cudaGraphExecDestroy(donor->exec);
+      donor->exec = nullptr;
+      if (cudaGraphInstantiate(&donor->exec, graph, 0) != cudaSuccess || !donor->exec) {
+        donor->exec = nullptr;
+        memset(donor->pkey, 0xFF, sizeof(donor->pkey));  // a pending record that matches nothing
+        return fail();
+      }
+    }
+    use = donor;
   }
-  g_graphs[slot].exec = exec;
-  return static_cast<int>(cudaGraphLaunch(exec, s));
+  cudaGraphDestroy(graph);
+  memcpy(use->pkey, pk, sizeof(pk));
+  use->last_use = g_tick;
+  return static_cast<int>(cudaGraphLaunch(use->exec, s));
 }
 
 static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {

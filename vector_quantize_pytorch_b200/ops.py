@@ -216,7 +216,7 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
             a.ev_search_begin, a.ev_search_end = ev0.cuda_event, ev1.cuda_event
             prof.append((ev0, ev1))
         check(lib.vqb_vq_forward(ctypes.byref(a), _stream()), "vqb_vq_forward")
-    _count(4 + (1 if dt == _C.DTYPE_F32 or ops.cosine else 0) + (1 if loss_out is not None else 0) + (4 if update else 0)
+    _count(4 + (1 if dt == _C.DTYPE_F32 or ops.cosine else 0) + (1 if loss_out is not None else 0) + (5 if update else 0)
            + (2 if update == 2 else 0))
     return idx32, stats
 
