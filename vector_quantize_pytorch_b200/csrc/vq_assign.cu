@@ -70,6 +70,7 @@ struct AssignParams {
   float margin_rel;
   const float* cmax;   // [1]
   int32_t* idx;
+  int32_t* idx_prov;   // optional: idx with -1 for flagged rows
   vqb_flag_entry* flagged;
   int32_t* flag_count;
   float* dbg_best;
@@ -493,6 +494,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (row < p.N) {
           p.idx[row] = i0;
+          if (p.idx_prov) p.idx_prov[row] = (n < 2) ? i0 : -1;
           if (p.dbg_best) p.dbg_best[row] = best;
           if (n >= 2) {
             const int s = atomicAdd(p.flag_count, 1);
@@ -719,6 +721,16 @@ extern "C" int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, co
                              const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx,
                              vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
                              const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream) {
+  return vqb::assign_launch(a_planes, n_a, N, D, b_planes, bext, cmax, K, margin_rel, n_passes, idx, nullptr, flagged,
+                            flag_count, dbg_best, fused, metric, cnorm2, stream);
+}
+
+// idx_prov (optional): like idx, but -1 for the rows handed to the exact re-score — lets the EMA sort start on the
+// certified rows while vqb_fix_flagged is still running (vq_forward.cu).
+int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
+                       const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, int32_t* idx_prov,
+                       vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused,
+                       int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
   if (n_passes == 0) n_passes = (n_a == 2) ? 3 : 2;
@@ -741,7 +753,7 @@ extern "C" int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, co
   p.num_row_tiles = static_cast<int>((N + BM - 1) / BM);
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
-  p.cmax = cmax; p.idx = idx; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
+  p.cmax = cmax; p.idx = idx; p.idx_prov = idx_prov; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
   p.prof = g_prof;
   p.dbg_mode = g_dbg_mode;
   p.tagmask = 0xFFFFFFF0u; p.mul1 = 1u; p.mulm1 = 0xFFFFFFFFu;

@@ -81,6 +81,7 @@ __global__ void hist_kernel(const int32_t* __restrict__ idx, int64_t N, int K, i
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < N;
        r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int k = idx[r];
+    if (k < 0) continue;
     if (use_sh) atomicAdd(&sh[k], 1); else atomicAdd(&counts[k], 1);
   }
   if (use_sh) {
@@ -98,7 +99,10 @@ hist_cta_kernel(const int32_t* __restrict__ idx, int64_t N, int K, int64_t rows_
   __syncthreads();
   const int64_t b = blockIdx.x * rows_per_cta;
   const int64_t e = min(N, b + rows_per_cta);
-  for (int64_t r = b + threadIdx.x; r < e; r += SORT_THREADS) atomicAdd(&sh[idx[r]], 1);
+  for (int64_t r = b + threadIdx.x; r < e; r += SORT_THREADS) {
+    const int k = idx[r];
+    if (k >= 0) atomicAdd(&sh[k], 1);   // -1: row accounted for elsewhere (stats_add_flagged)
+  }
   __syncthreads();
   int32_t* out = cta_counts + static_cast<size_t>(blockIdx.x) * K;
   for (int i = threadIdx.x; i < K; i += SORT_THREADS) out[i] = sh[i];
@@ -152,7 +156,9 @@ scatter_cta_kernel(const int32_t* __restrict__ idx, int64_t N, int K, int64_t ro
   const int64_t b = blockIdx.x * rows_per_cta;
   const int64_t e = min(N, b + rows_per_cta);
   for (int64_t r = b + threadIdx.x; r < e; r += SORT_THREADS) {
-    const int pos = atomicAdd(&sh[idx[r]], 1);
+    const int k = idx[r];
+    if (k < 0) continue;
+    const int pos = atomicAdd(&sh[k], 1);
     perm[pos] = static_cast<int32_t>(r);
   }
 }
@@ -201,7 +207,9 @@ __global__ void scan_kernel(const int32_t* __restrict__ counts, int K, int32_t* 
 __global__ void scatter_kernel(const int32_t* __restrict__ idx, int64_t N, int32_t* cursor, int32_t* perm) {
   for (int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; r < N;
        r += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int pos = atomicAdd(&cursor[idx[r]], 1);
+    const int k = idx[r];
+    if (k < 0) continue;
+    const int pos = atomicAdd(&cursor[k], 1);
     perm[pos] = static_cast<int32_t>(r);
   }
 }
@@ -261,6 +269,25 @@ segsum_kernel(const void* __restrict__ x, int D, const int32_t* __restrict__ per
     for (int y = 0; y < NY; ++y) s += red[y * D + i];
     float* out = embed_sum + static_cast<int64_t>(wk.x) * D + i;
     if (wk.w) atomicAdd(out, s); else *out = s;
+  }
+}
+
+// one warp per flagged row: cluster_size[k] += 1, embed_sum[k] += x[row]   (k = the row's final code)
+template <int DT>
+__global__ void stats_add_flagged_kernel(const void* __restrict__ x, int64_t N, int D, const vqb_flag_entry* __restrict__ flagged,
+                                         const int32_t* __restrict__ flag_count, const int32_t* __restrict__ idx,
+                                         float* stats, int64_t soff) {
+  using E = Elem<DT>;
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  int64_t cnt = *flag_count;
+  if (cnt > N) cnt = N;
+  for (int64_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < cnt; e += warps) {
+    const int row = flagged[e].row;
+    const int k = idx[row];
+    if (lane == 0) atomicAdd(stats + k, 1.f);
+    float* dst = stats + soff + static_cast<int64_t>(k) * D;
+    for (int i = lane; i < D; i += 32) atomicAdd(dst + i, E::load(x, static_cast<int64_t>(row) * D + i));
   }
 }
 
@@ -347,6 +374,17 @@ using namespace vqb;
 
 extern "C" int64_t vqb_stats_offset(int K) { return K <= 0 ? 0 : (static_cast<int64_t>(K) + 3) / 4 * 4; }
 extern "C" int64_t vqb_stats_floats(int K, int D) { return (K <= 0 || D <= 0) ? 0 : vqb_stats_offset(K) + static_cast<int64_t>(K) * D; }
+
+int vqb::stats_add_flagged(const void* x_eff, int dtype, int64_t N, int D, const vqb_flag_entry* flagged,
+                           const int32_t* flag_count, const int32_t* idx, int K, float* stats, void* stream) {
+  if (!x_eff || !flagged || !flag_count || !idx || !stats) return VQB_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = num_sms();
+  const int64_t soff = vqb_stats_offset(K);
+  if (dtype == VQB_DTYPE_F32) stats_add_flagged_kernel<VQB_DTYPE_F32><<<g, 256, 0, s>>>(x_eff, N, D, flagged, flag_count, idx, stats, soff);
+  else stats_add_flagged_kernel<VQB_DTYPE_BF16><<<g, 256, 0, s>>>(x_eff, N, D, flagged, flag_count, idx, stats, soff);
+  return static_cast<int>(cudaGetLastError());
+}
 
 extern "C" size_t vqb_ema_stats_workspace(int64_t N, int K) {
   if (N <= 0 || K <= 0) return 0;

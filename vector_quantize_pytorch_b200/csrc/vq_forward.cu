@@ -16,7 +16,7 @@ namespace {
 inline size_t up256(size_t v) { return (v + 255) / 256 * 256; }
 
 struct FwdWs {
-  size_t x_eff, a_planes, flagged, counters, stats_ws, total;
+  size_t x_eff, a_planes, flagged, counters, stats_ws, idx_prov, total;
 };
 
 FwdWs carve_fwd(int64_t N, int D, int K, int dtype, int metric, int update) {
@@ -34,6 +34,8 @@ FwdWs carve_fwd(int64_t N, int D, int K, int dtype, int metric, int update) {
   off = up256(off + 16);
   w.stats_ws = off;
   if (update) off = up256(off + vqb_ema_stats_workspace(N, K));
+  w.idx_prov = off;   // int32 [N]: search result with -1 for the rows that go through the exact re-score
+  if (update) off = up256(off + static_cast<size_t>(N) * sizeof(int32_t));
   w.total = off;
   return w;
 }
@@ -105,6 +107,25 @@ void make_keys(const vqb_vq_forward_args* a, void* stream, uint64_t* sk, uint64_
   I(static_cast<long long>(a->workspace_bytes)); I(reinterpret_cast<long long>(stream)); I(static_cast<long long>(present));
   while (si < kKeyWords) sk[si++] = 0;
   while (pi < kKeyWords) pk[pi++] = 0;
+}
+
+// Side stream of the forward chain: the EMA sort runs on it, next to the exact re-score on the caller's stream.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+SideStream* side_stream() {
+  static SideStream ss;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+    if (!ss.ok) cudaGetLastError();
+  }
+  return ss.ok ? &ss : nullptr;
 }
 
 // capture the chain for `a` into a fresh graph (nothing executes)
@@ -283,11 +304,27 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   const bool split_tail = (a->resid_out || a->qsum) && !fused_stats;
   const bool want_tail = !split_tail && (a->q_out || a->idx64_out || a->loss_out || fused_stats);
   vqb_flag_entry* flagged = reinterpret_cast<vqb_flag_entry*>(ws + w.flagged);
+  // The EMA sort (histogram -> scans -> scatter -> segmented sums) only needs the indices, and all but ~0.3 % of them
+  // are final when the search kernel ends.  So the search also writes a provisional index array (-1 for the rows
+  // it hands to the exact re-score), the sort of those runs on a side stream NEXT TO the re-score, and the few
+  // re-scored rows are added to the packed statistics afterwards.  Both chains are latency-bound strings of small
+  // kernels; overlapped they take max() instead of sum() (measured: DESIGN.md section 8).
+  SideStream* side = (a->update && !fused_stats) ? side_stream() : nullptr;
+  int32_t* idx_prov = side ? reinterpret_cast<int32_t*>(ws + w.idx_prov) : nullptr;
   if (a->ev_search_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_begin), s);
-  rc = vqb_assign_ex(a_planes, n_a, a->N, a->D, a->planes, a->bext, a->cmax, a->K, a->margin_rel, 0, a->idx32, flagged,
-                     flag_count, nullptr, want_tail ? &f : nullptr, a->metric, a->cnorm2, stream);
+  rc = assign_launch(a_planes, n_a, a->N, a->D, a->planes, a->bext, a->cmax, a->K, a->margin_rel, 0, a->idx32, idx_prov,
+                     flagged, flag_count, nullptr, want_tail ? &f : nullptr, a->metric, a->cnorm2, stream);
   if (rc) return rc;
   if (a->ev_search_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_end), s);
+  if (side) {  // fork: certified rows -> statistics
+    if (cudaEventRecord(side->fork, s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess)
+      return static_cast<int>(cudaGetLastError());
+    rc = vqb_ema_stats(x_eff, a->dtype, a->N, a->D, idx_prov, a->K, a->stats, ws + w.stats_ws,
+                       vqb_ema_stats_workspace(a->N, a->K), side->stream);
+    const cudaError_t je = cudaEventRecord(side->join, side->stream);
+    if (rc) return rc;
+    if (je != cudaSuccess) return static_cast<int>(cudaGetLastError());
+  }
   rc = vqb_fix_flagged(x_eff, a->dtype, a->N, a->D, a->embed, a->cnorm2, a->K, a->metric, flagged, flag_count, a->idx32,
                        want_tail ? &f : nullptr, stream);
   if (rc) return rc;
@@ -302,8 +339,13 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   }
   // ---- EMA (vqp:586-617, :576-584)
   if (a->update && !fused_stats) {
-    rc = vqb_ema_stats(x_eff, a->dtype, a->N, a->D, a->idx32, a->K, a->stats, ws + w.stats_ws,
-                       vqb_ema_stats_workspace(a->N, a->K), stream);
+    if (side) {  // join, then the re-scored rows are added to the statistics of the certified ones
+      if (cudaStreamWaitEvent(s, side->join, 0) != cudaSuccess) return static_cast<int>(cudaGetLastError());
+      rc = stats_add_flagged(x_eff, a->dtype, a->N, a->D, flagged, flag_count, a->idx32, a->K, a->stats, stream);
+    } else {
+      rc = vqb_ema_stats(x_eff, a->dtype, a->N, a->D, a->idx32, a->K, a->stats, ws + w.stats_ws,
+                         vqb_ema_stats_workspace(a->N, a->K), stream);
+    }
     if (rc) return rc;
   }
   if (a->update) {

@@ -70,4 +70,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+
+// ---- internal entry points shared between translation units (not part of the C ABI) ----
+// vq_assign.cu: vqb_assign_ex plus an optional provisional index array (-1 for rows handed to the exact re-score)
+int assign_launch(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
+                  const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, int32_t* idx_prov,
+                  vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused,
+                  int metric, const float* cnorm2, void* stream);
+// vq_ema.cu: add the rows listed in `flagged` (final code = idx[row]) to packed statistics that were built from an
+// index array in which those rows were marked -1
+int stats_add_flagged(const void* x_eff, int dtype, int64_t N, int D, const vqb_flag_entry* flagged,
+                      const int32_t* flag_count, const int32_t* idx, int K, float* stats, void* stream);
+
 }  // namespace vqb
