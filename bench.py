@@ -29,7 +29,7 @@ METRIC = "vectors quantized/sec at dim=256, codebook=1024; indices bit-exact vs 
 B, T, D, K = 64, 4096, 256, 1024
 WORKLOAD = "VectorQuantize dim=256 codebook_size=1024, x=(64,4096,256) bf16, EMA on (BASELINE.json configs[1])"
 CPU_SAMPLE_VECTORS = 65536  # 1/4 of the batch per CPU step (~0.7 s on 8 cores)
-E2E_CHUNKS = int(os.environ.get("VQB_E2E_CHUNKS", "16"))  # row chunks of the host-buffer pipeline (forward_host)
+E2E_CHUNKS = int(os.environ.get("VQB_E2E_CHUNKS", "10"))  # row chunks of the host-buffer pipeline (forward_host)
 
 
 def load_peaks():

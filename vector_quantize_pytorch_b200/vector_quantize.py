@@ -260,51 +260,60 @@ class VectorQuantize(nn.Module):
                    torch.empty((), dtype=torch.float32).pin_memory())
         q_host, i_host, l_host = out
         qf, idf = q_host.reshape(-1, D), i_host.reshape(-1)
-        rows = -(-N // n_chunks)
-        rows = -(-rows // 256) * 256  # whole CTA-pair tiles per chunk
-        n_chunks = -(-N // rows)
-        key = (N, D, x_host.dtype, rows, dev)
+        # Chunk sizes ramp up and down (1, 2, 3, 3, ..., 3, 2, 1 units): the first upload and the last download are
+        # not overlapped with anything, so they are kept short; the middle chunks are large to amortise per-chunk costs.
+        wts = [min(c + 1, n_chunks - c, 3) for c in range(n_chunks)]
+        unit = N / sum(wts)
+        bounds, acc = [0], 0.0
+        for wgt in wts:
+            acc += wgt * unit
+            b_ = min(N, -(-int(round(acc)) // 256) * 256)  # whole CTA-pair tiles per chunk
+            if b_ > bounds[-1]:
+                bounds.append(b_)
+        bounds[-1] = N
+        n_chunks = len(bounds) - 1
+        rows = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
+        key = (N, D, x_host.dtype, tuple(bounds), dev)
         st = getattr(self, "_host_pipe", None)
         if st is None or st["key"] != key:
+            # whole-batch device buffers (2 x 134 MB at BASELINE config 2): no upload ever waits for a buffer to be
+            # recycled, so all uploads are enqueued up front and PCIe never idles on the host's enqueue pace
             st = dict(key=key, h2d=torch.cuda.Stream(dev), d2h=torch.cuda.Stream(dev),
-                      x=[torch.empty((rows, D), dtype=x_host.dtype, device=dev) for _ in range(2)],
-                      q=[torch.empty((rows, D), dtype=x_host.dtype, device=dev) for _ in range(2)],
-                      i=[torch.empty((rows,), dtype=torch.int64, device=dev) for _ in range(2)],
+                      x=torch.empty((N, D), dtype=x_host.dtype, device=dev),
+                      q=torch.empty((N, D), dtype=x_host.dtype, device=dev),
+                      i=torch.empty((N,), dtype=torch.int64, device=dev),
                       loss=torch.zeros((n_chunks,), dtype=torch.float32, device=dev),
                       stats=torch.empty((ops.stats_floats(cbk.codebook_size, D),), dtype=torch.float32, device=dev),
                       stats_chunk=torch.empty((ops.stats_floats(cbk.codebook_size, D),), dtype=torch.float32, device=dev))
             self._host_pipe = st
         cur = torch.cuda.current_stream(dev)
         up, down = st["h2d"], st["d2h"]
-        up.wait_stream(cur)
-        ev_up, ev_done, ev_down = [], [], []
+        up.wait_stream(cur)     # the previous call's kernels are done with x
+        down.wait_stream(cur)
+        ev_up = []
+        with torch.cuda.stream(up):
+            for c in range(n_chunks):
+                r0, r1 = bounds[c], bounds[c + 1]
+                st["x"][r0:r1].copy_(xf[r0:r1], non_blocking=True)
+                e = torch.cuda.Event(); e.record(up); ev_up.append(e)
         weights = []
         for c in range(n_chunks):
-            b = c & 1
-            r0, r1 = c * rows, min(N, (c + 1) * rows)
+            r0, r1 = bounds[c], bounds[c + 1]
             n = r1 - r0
             weights.append(n / N)
-            with torch.cuda.stream(up):
-                if c >= 2:
-                    up.wait_event(ev_done[c - 2])  # x[b] is free once chunk c-2 has been searched
-                st["x"][b][:n].copy_(xf[r0:r1], non_blocking=True)
-                e = torch.cuda.Event(); e.record(up); ev_up.append(e)
             cur.wait_event(ev_up[c])
-            if c >= 2:
-                cur.wait_event(ev_down[c - 2])  # q[b] / i[b] have been downloaded
             in_place = ops.STATS_MODE == 0  # fused statistics accumulate straight into the running total
-            cbk.quantize_rows(st["x"][b][:n], update=do_update, q_out=st["q"][b], idx64_out=st["i"][b],
+            cbk.quantize_rows(st["x"][r0:r1], update=do_update, q_out=st["q"][r0:r1], idx64_out=st["i"][r0:r1],
                               loss_out=st["loss"][c:c + 1] if want_loss else None, loss_weight=self.commitment_weight,
                               stats_out=(st["stats"] if (in_place or c == 0) else st["stats_chunk"]) if do_update else None,
                               defer_ema=True, stats_accumulate=in_place and c > 0)
             if do_update and not in_place and c > 0:
                 st["stats"].add_(st["stats_chunk"])
-            e = torch.cuda.Event(); e.record(cur); ev_done.append(e)
+            e = torch.cuda.Event(); e.record(cur)
             with torch.cuda.stream(down):
-                down.wait_event(ev_done[c])
-                qf[r0:r1].copy_(st["q"][b][:n], non_blocking=True)
-                idf[r0:r1].copy_(st["i"][b][:n], non_blocking=True)
-                e = torch.cuda.Event(); e.record(down); ev_down.append(e)
+                down.wait_event(e)
+                qf[r0:r1].copy_(st["q"][r0:r1], non_blocking=True)
+                idf[r0:r1].copy_(st["i"][r0:r1], non_blocking=True)
         if do_update:
             cbk.sync_stats(st["stats"])
             cbk.lerp_stats(st["stats"], normalise=cbk.ema_update and not cbk.manual_ema_update)
