@@ -54,6 +54,7 @@ constexpr int TMEM_COLS = 512;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_STORE_WARPS = 4;  // fused gather / loss / residual tail of the certified rows
 constexpr int NUM_THREADS = (2 + NUM_EPI_WARPS + NUM_STORE_WARPS) * 32;
+constexpr int MMA_GROUP = 4;      // k-blocks issued per elected region of the MMA warp
 constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
 constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
@@ -306,6 +307,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t a_desc_lo0 = static_cast<uint32_t>(d0);
       const uint32_t b_desc_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(b_base));
       const uint32_t b_stage_units = b_stage_bytes >> 4;
+      const bool full_k = (p.D & (BK - 1)) == 0;
+      const int ksteps_last = full_k ? 4 : ((p.D & (BK - 1)) + UMMA_K - 1) / UMMA_K;
+      // a group never spans more than half of the B ring (the producer must be able to run ahead of it)
+      const int mma_group = p.n_stages >= 2 * MMA_GROUP ? MMA_GROUP : (p.n_stages >= 4 ? 2 : 1);
       int stage = 0;
       uint32_t ph = 0;
       uint32_t it = 0;  // accumulator iteration counter (across row tiles)
@@ -328,29 +333,50 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int ps = 0; ps < p.n_passes; ++ps) {
             const int aplane = (ps == 2) ? 1 : 0;
             const bool last_use = (ct == p.num_code_tiles - 1) && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
-            uint32_t a_lo = a_desc_lo0 + static_cast<uint32_t>(aplane * p.KB) * (A_SUB_BYTES >> 4);
-            for (int kb = 0; kb < p.KB; ++kb, a_lo += (A_SUB_BYTES >> 4)) {
-              const int sub = aplane * p.KB + kb;
-              if (ct == 0) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[sub]), t & 1); w_afull += PROF_CLOCK() - c0; }
-              { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[stage]), ph); w_bfull += PROF_CLOCK() - c0; }
-              tc_fence_after();
-              const uint32_t b_lo = b_desc_lo0 + static_cast<uint32_t>(stage) * b_stage_units;
-              if (elect_one_sync()) {
-                if (kb + 1 < p.KB || (p.D & (BK - 1)) == 0) {  // full k-block: four K=16 steps, descriptors advance by 32 B
-                  umma_bf16_ss_2sm_acc(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc_pass);
-                  umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc_pass);
-                  umma_bf16_ss_2sm_acc(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc_pass);
-                  umma_bf16_ss_2sm_acc(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc_pass);
-                } else {  // ragged last k-block (D % 64 != 0): only the K steps that hold data (the rest is TMA zero fill)
-                  const int ksteps = ((p.D & (BK - 1)) + UMMA_K - 1) / UMMA_K;
-                  for (int k = 0; k < ksteps; ++k)
-                    umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc_pass);
+            // Groups of up to MMA_GROUP k-blocks: wait for all their operands, then ONE elected region issues their
+            // MMAs back to back.  The issuing warp shares its scheduler with two always-ready epilogue warps; every
+            // instruction it does not execute (loop control, waits, elect, fences per k-block) is issue latency the
+            // tensor pipe does not see (measured: 103 -> see DESIGN.md section 8 clk per MMA).
+            for (int kb0 = 0; kb0 < p.KB; kb0 += mma_group) {
+              const int cnt = min(mma_group, p.KB - kb0);
+              int st_w = stage;
+              uint32_t ph_w = ph;
+#pragma unroll
+              for (int g = 0; g < MMA_GROUP; ++g) {
+                if (g < cnt) {
+                  if (ct == 0) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[aplane * p.KB + kb0 + g]), t & 1); w_afull += PROF_CLOCK() - c0; }
+                  { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[st_w]), ph_w); w_bfull += PROF_CLOCK() - c0; }
+                  if (++st_w == p.n_stages) { st_w = 0; ph_w ^= 1; }
                 }
-                umma_commit_2sm(smem_u32(&ctrl->b_empty[stage]), kBoth);              // B stage reusable once these MMAs retire
-                if (last_use) umma_commit_2sm(smem_u32(&ctrl->a_empty[sub]), kBoth); // ... and this A sub-tile too
+              }
+              tc_fence_after();
+              if (elect_one_sync()) {
+                int st_i = stage;
+#pragma unroll
+                for (int g = 0; g < MMA_GROUP; ++g) {
+                  if (g < cnt) {
+                    const int kb = kb0 + g;
+                    const int sub = aplane * p.KB + kb;
+                    const uint32_t a_lo = a_desc_lo0 + static_cast<uint32_t>(sub) * (A_SUB_BYTES >> 4);
+                    const uint32_t b_lo = b_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units;
+                    if (full_k || kb + 1 < p.KB) {  // full k-block: four K=16 steps, descriptors advance by 32 B
+                      umma_bf16_ss_2sm_acc(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc_pass);
+                      umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc_pass);
+                      umma_bf16_ss_2sm_acc(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc_pass);
+                      umma_bf16_ss_2sm_acc(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc_pass);
+                    } else {  // ragged last k-block (D % 64 != 0): only the K steps that hold data (the rest is TMA zero fill)
+                      for (int k = 0; k < ksteps_last; ++k)
+                        umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc_pass);
+                    }
+                    umma_commit_2sm(smem_u32(&ctrl->b_empty[st_i]), kBoth);              // B stage reusable once these MMAs retire
+                    if (last_use) umma_commit_2sm(smem_u32(&ctrl->a_empty[sub]), kBoth); // ... and this A sub-tile too
+                    if (++st_i == p.n_stages) st_i = 0;
+                  }
+                }
               }
               __syncwarp();
-              if (++stage == p.n_stages) { stage = 0; ph ^= 1; }
+              stage = st_w;
+              ph = ph_w;
             }
           }
           if (elect_one_sync()) umma_commit_2sm(smem_u32(&ctrl->t_full[as]), kBoth);  // accumulator complete -> both epilogues
@@ -414,7 +440,11 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #endif
           // 32 independent rows per warp: for K ~ 1e3 some lane has a candidate in most pieces, so what matters is
           // that the update itself is straight-line min/max code (measured history in DESIGN.md section 8)
+#ifdef VQB_EPI_NOSKIP
+          st.piece(r, cbase, p.tagmask, p.mul1, p.mulm1);
+#else
           if (mm > st.thr) st.piece(r, cbase, p.tagmask, p.mul1, p.mulm1);
+#endif
         };
         // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld has completed (the
         // final piece is scanned from registers afterwards): the release -> MMA -> t_full loop is the critical path.
