@@ -109,6 +109,22 @@ def run_reference_arm(args):
 # clocks sampler (B200_PROFILING.md "clocks line")
 # ------------------------------------------------------------------------------------------------
 
+def ncu_dram_bytes():
+    """dram read + write bytes of one vq_assign_kernel launch, from the committed ncu summary (None if it is missing)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_assign_final_summary.txt")
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    try:
+        for line in open(path):
+            if "dram__bytes_read.sum =" in line or "dram__bytes_write.sum =" in line:
+                val, unit = line.split("=")[1].split()[:2]
+                total += float(val) * mult[unit]
+                seen += 1
+    except Exception:
+        return None
+    return total if seen == 2 else None
+
+
 class ClockSampler:
     """SM clock + throttle reasons sampled DURING the timed region, in-process through NVML.
 
@@ -305,7 +321,10 @@ def run_gpu_arm(args):
             "measured": "CUDA event pair on the launching stream around every vq_assign_kernel launch, over the same K "
                         "steps repeated right after the headline region (events split the step's CUDA graph)",
             "ms_per_step_with_events": ms_dev_events,
-            "algorithmic_flops_per_launch": flops, "executed_mma_passes": 2, "traffic": None}
+            "algorithmic_flops_per_launch": flops, "executed_mma_passes": 2, "traffic": ncu_dram_bytes(),
+            "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_assign_final_summary.txt: "
+                            "`ncu --set full` capture of the search launch WITHOUT the fused tail; in the step the same launch "
+                            "also writes quantize, +134.2 MB)"}
     cpu_v, _ = time_cpu(steps=2, warmup=1)
     line = {
         "metric": METRIC, "value": world * n_vec / (ms_dev * 1e-3), "unit": "vectors/s", "n_gpus": world,

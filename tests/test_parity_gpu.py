@@ -302,6 +302,40 @@ def test_gradients_route_through_glue():
         assert x.grad is not None and torch.isfinite(x.grad).all()
 
 
+def test_graph_replay_and_patch_match_direct_enqueue():
+    """vqb_vq_forward replays / patches CUDA graphs when a call structure repeats (vq_forward.cu).  Twin modules see the
+    same batches: one through the graph cache (outputs kept alive in different patterns, so pointer sets repeat, alternate
+    and appear new), one with profiling events requested, which forces the launch-by-launch path.  Everything — outputs
+    and the EMA-updated codebook — must stay identical step after step (a stale pointer in a patched graph would not)."""
+    m = vqb()
+    from vector_quantize_pytorch_b200 import ops
+    torch.manual_seed(7)
+    a = m.VectorQuantize(dim=64, codebook_size=256).to(DEV)
+    b = m.VectorQuantize(dim=64, codebook_size=256).to(DEV)
+    _warm_codebook(a, 64, 256)
+    b.load_state_dict(a.state_dict())
+    keep = []
+    for step in range(10):
+        x = torch.randn(4, 1024, 64, device=DEV).bfloat16()
+        qa, ia, la = a(x)
+        ops.PROFILE_EVENTS = []
+        try:
+            qb, ib, lb = b(x)
+        finally:
+            ops.PROFILE_EVENTS = None
+        torch.cuda.synchronize()
+        assert torch.equal(ia, ib), f"indices differ at step {step}"
+        assert torch.equal(qa, qb), f"quantized differs at step {step}"
+        assert torch.allclose(la, lb, rtol=1e-6, atol=0), f"loss differs at step {step}"
+        # float atomics in the segmented sums make the statistics order-dependent in the last bits
+        torch.testing.assert_close(a._codebook.embed, b._codebook.embed, rtol=1e-5, atol=1e-6)
+        b.load_state_dict(a.state_dict())   # keep the twins in lock step
+        if step % 3 == 0:
+            keep.append((qa, ia))            # hold some outputs: the allocator hands out new blocks
+        elif step % 3 == 2:
+            keep.clear()
+
+
 # ------------------------------------------------------------------------------------------------
 # BASELINE.json full sizes: size-independent properties
 # ------------------------------------------------------------------------------------------------

@@ -118,14 +118,19 @@ struct SideStream {
 SideStream* side_stream() {
   static SideStream ss;
   static bool tried = false;
+  static int dev = -1;
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   if (!tried) {
     tried = true;
+    dev = cur;
     ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
     if (!ss.ok) cudaGetLastError();
   }
-  return ss.ok ? &ss : nullptr;
+  // one process drives one GPU; a call on another device simply runs the chain in one stream
+  return (ss.ok && cur == dev) ? &ss : nullptr;
 }
 
 // capture the chain for `a` into a fresh graph (nothing executes)
