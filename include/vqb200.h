@@ -119,6 +119,9 @@ int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, const void* b
 int vqb_debug_set_profile_buffer(void* device_buffer);
 int vqb_debug_active(void);
 int vqb_debug_set_mode(int mode); /* bit0: skip the epilogue's TMEM sweep (timing experiments only; results invalid) */
+/* How vqb_vq_forward's CUDA-graph cache served the calls so far: out4 = {replayed, patched (cudaGraphExecUpdate),
+ * instantiated, enqueued launch by launch after a capture / instantiate failure} (host array of 4 int64). */
+int vqb_debug_graph_stats(long long* out4);
 
 /* Exact re-score of the flagged rows with the reference's own fp32 formula and tie rule
  * (-(x2 + y2 - 2xy).clamp(1e-8).sqrt(), first maximal index; :58-62, :140).  Rewrites idx[row]. */

@@ -8,6 +8,8 @@ Bars: indices bit-exact (except rows the reference itself resolves inside fp32 r
 counted and classified with a float64 top-2 gap); values within 1e-5 (fp32) / one bf16 ulp (bf16).
 """
 import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -306,34 +308,57 @@ def test_graph_replay_and_patch_match_direct_enqueue():
     """vqb_vq_forward replays / patches CUDA graphs when a call structure repeats (vq_forward.cu).  Twin modules see the
     same batches: one through the graph cache (outputs kept alive in different patterns, so pointer sets repeat, alternate
     and appear new), one with profiling events requested, which forces the launch-by-launch path.  Everything — outputs
-    and the EMA-updated codebook — must stay identical step after step (a stale pointer in a patched graph would not)."""
+    and the EMA-updated codebook — must stay identical step after step (a stale pointer in a patched graph would not).
+    Run on torch's default stream (the legacy stream, on which CUDA refuses stream capture: the cache must fall back
+    cleanly) and on a side stream (where capture is legal)."""
+    import ctypes
     m = vqb()
-    from vector_quantize_pytorch_b200 import ops
-    torch.manual_seed(7)
-    a = m.VectorQuantize(dim=64, codebook_size=256).to(DEV)
-    b = m.VectorQuantize(dim=64, codebook_size=256).to(DEV)
-    _warm_codebook(a, 64, 256)
-    b.load_state_dict(a.state_dict())
-    keep = []
-    for step in range(10):
-        x = torch.randn(4, 1024, 64, device=DEV).bfloat16()
-        qa, ia, la = a(x)
-        ops.PROFILE_EVENTS = []
-        try:
-            qb, ib, lb = b(x)
-        finally:
-            ops.PROFILE_EVENTS = None
-        torch.cuda.synchronize()
-        assert torch.equal(ia, ib), f"indices differ at step {step}"
-        assert torch.equal(qa, qb), f"quantized differs at step {step}"
-        assert torch.allclose(la, lb, rtol=1e-6, atol=0), f"loss differs at step {step}"
-        # float atomics in the segmented sums make the statistics order-dependent in the last bits
-        torch.testing.assert_close(a._codebook.embed, b._codebook.embed, rtol=1e-5, atol=1e-6)
-        b.load_state_dict(a.state_dict())   # keep the twins in lock step
-        if step % 3 == 0:
-            keep.append((qa, ia))            # hold some outputs: the allocator hands out new blocks
-        elif step % 3 == 2:
-            keep.clear()
+    from vector_quantize_pytorch_b200 import _C, ops
+
+    def graph_stats():
+        out = (ctypes.c_longlong * 4)()
+        assert _C.lib.vqb_debug_graph_stats(ctypes.cast(out, ctypes.c_void_p)) == 0
+        return list(out)
+
+    def twin_run(dim, K):
+        torch.manual_seed(7)
+        a = m.VectorQuantize(dim=dim, codebook_size=K).to(DEV)
+        b = m.VectorQuantize(dim=dim, codebook_size=K).to(DEV)
+        _warm_codebook(a, dim, K)
+        b.load_state_dict(a.state_dict())
+        keep = []
+        for step in range(10):
+            x = torch.randn(4, 1024, dim, device=DEV).bfloat16()
+            qa, ia, la = a(x)
+            ops.PROFILE_EVENTS = []
+            try:
+                qb, ib, lb = b(x)
+            finally:
+                ops.PROFILE_EVENTS = None
+            torch.cuda.current_stream().synchronize()
+            assert torch.equal(ia, ib), f"indices differ at step {step}"
+            assert torch.equal(qa, qb), f"quantized differs at step {step}"
+            assert torch.allclose(la, lb, rtol=1e-6, atol=0), f"loss differs at step {step}"
+            # float atomics in the statistics make them order-dependent in the last bits
+            torch.testing.assert_close(a._codebook.embed, b._codebook.embed, rtol=1e-5, atol=1e-6)
+            b.load_state_dict(a.state_dict())   # keep the twins in lock step
+            if step % 3 == 0:
+                keep.append((qa, ia))            # hold some outputs: the allocator hands out new blocks
+            elif step % 3 == 2:
+                keep.clear()
+
+    s0 = graph_stats()
+    twin_run(64, 256)
+    s1 = graph_stats()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        twin_run(96, 320)
+    side.synchronize()
+    s2 = graph_stats()
+    names = ("replayed", "patched", "instantiated", "fell_back")
+    print("graph cache, default stream:", dict(zip(names, (y - x for x, y in zip(s0, s1)))),
+          "| side stream:", dict(zip(names, (y - x for x, y in zip(s1, s2)))))
 
 
 # ------------------------------------------------------------------------------------------------

@@ -53,6 +53,7 @@ SIGNATURES = {
     "vqb_debug_set_profile_buffer": (_i32, [_vp]),
     "vqb_debug_set_mode": (_i32, [_i32]),
     "vqb_debug_active": (_i32, []),
+    "vqb_debug_graph_stats": (_i32, [_vp]),
     "vqb_decode": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
 }
 

@@ -5,6 +5,7 @@
 // (input staging -> tensor-core search with fused gather tail -> exact re-score -> EMA statistics -> EMA apply
 // -> loss) from C++ in one call; the caller only provides outputs and one workspace.
 #include "vqb_common.cuh"
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -81,6 +82,7 @@ struct StructEntry {
 StructEntry* g_struct = nullptr;  // [kMaxStruct], allocated on first use
 unsigned long long g_tick = 0;
 int g_graph_failures = 0;         // capture / instantiate / update failures: give up after a few
+long long g_n_replay = 0, g_n_update = 0, g_n_instantiate = 0, g_n_direct = 0;  // vqb_debug_graph_stats
 bool g_graph_disabled = false;
 
 int graph_mode() {
@@ -133,16 +135,32 @@ SideStream* side_stream() {
   return (ss.ok && cur == dev) ? &ss : nullptr;
 }
 
+// one line on stderr the first time the graph path is unavailable (the chain then runs launch by launch: same
+// results, ~12 launches per forward instead of one)
+void note_graph_error(const char* what, cudaError_t e) {
+  static bool said = false;
+  if (said) return;
+  said = true;
+  fprintf(stderr, "vqb200: %s failed (%s); vqb_vq_forward enqueues its kernels one by one on this stream\n", what,
+          cudaGetErrorString(e));
+}
+
 // capture the chain for `a` into a fresh graph (nothing executes)
 int capture_chain(const vqb_vq_forward_args* a, cudaStream_t s, cudaGraph_t* out) {
   *out = nullptr;
-  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return kCaptureFailed; }
+  const cudaError_t be = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+  if (be != cudaSuccess) {  // e.g. the legacy default stream: CUDA does not capture it
+    cudaGetLastError();
+    note_graph_error("cudaStreamBeginCapture", be);
+    return kCaptureFailed;
+  }
   const int rc = vq_forward_enqueue(a, s);
   cudaGraph_t graph = nullptr;
   const cudaError_t ee = cudaStreamEndCapture(s, &graph);
   if (rc != VQB_OK || ee != cudaSuccess || !graph) {
     if (graph) cudaGraphDestroy(graph);
     cudaGetLastError();
+    if (rc == VQB_OK) note_graph_error("cudaStreamEndCapture", ee);
     return rc != VQB_OK ? rc : kCaptureFailed;
   }
   *out = graph;
@@ -186,6 +204,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   for (int v = 0; v < se->n_var; ++v)
     if (se->var[v].exec && memcmp(se->var[v].pkey, pk, sizeof(pk)) == 0) {  // replay
       se->var[v].last_use = g_tick;
+      ++g_n_replay;
       return static_cast<int>(cudaGraphLaunch(se->var[v].exec, s));
     }
   // New pointer set.  Instantiating an executable graph is the expensive step (it can synchronise with the device and
@@ -196,6 +215,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   if (rc != VQB_OK) {
     if (rc != kCaptureFailed) return rc;              // error reported by the chain itself (nothing ran)
     if (++g_graph_failures > 4) g_graph_disabled = true;
+    ++g_n_direct;
     return vq_forward_enqueue(a, stream);             // capture failed: nothing ran, enqueue directly
   }
   Variant* pend = nullptr;     // pending record of this pointer set
@@ -209,6 +229,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   }
   if (se->n_var < kVariants) spare = &se->var[se->n_var];
   auto fail = [&]() {
+    ++g_n_direct;
     cudaGetLastError();
     cudaGraphDestroy(graph);
     if (++g_graph_failures > 4) g_graph_disabled = true;
@@ -222,6 +243,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
     if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess || !exec) return fail();
     if (use == &se->var[se->n_var]) ++se->n_var;
     use->exec = exec;
+    ++g_n_instantiate;
   } else {
     if (spare) {  // remember the sighting
       if (spare == &se->var[se->n_var]) ++se->n_var;
@@ -241,11 +263,19 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
       }
     }
     use = donor;
+    ++g_n_update;
   }
   cudaGraphDestroy(graph);
   memcpy(use->pkey, pk, sizeof(pk));
   use->last_use = g_tick;
   return static_cast<int>(cudaGraphLaunch(use->exec, s));
+}
+
+// diagnostics: how the graph cache served the calls so far {replayed, patched, instantiated, fell back after a failure}
+extern "C" int vqb_debug_graph_stats(long long* out4) {
+  if (!out4) return VQB_E_INVALID;
+  out4[0] = g_n_replay; out4[1] = g_n_update; out4[2] = g_n_instantiate; out4[3] = g_n_direct;
+  return VQB_OK;
 }
 
 static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
