@@ -145,6 +145,19 @@ void note_graph_error(const char* what, cudaError_t e) {
           cudaGetErrorString(e));
 }
 
+// The chain is captured on an internal stream, never on the caller's: torch's default stream is the legacy stream,
+// which CUDA refuses to capture ("operation not permitted when stream is capturing"), while an executable graph may
+// be LAUNCHED into any stream.
+cudaStream_t capture_stream() {
+  static cudaStream_t cs = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); cs = nullptr; }
+  }
+  return cs;
+}
+
 // capture the chain for `a` into a fresh graph (nothing executes)
 int capture_chain(const vqb_vq_forward_args* a, cudaStream_t s, cudaGraph_t* out) {
   *out = nullptr;
@@ -179,6 +192,8 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
     g_struct = static_cast<StructEntry*>(calloc(kMaxStruct, sizeof(StructEntry)));
     if (!g_struct) return vq_forward_enqueue(a, stream);
   }
+  cudaStream_t cap_s = capture_stream();   // created here, outside any capture
+  if (!cap_s) return vq_forward_enqueue(a, stream);
   uint64_t sk[kKeyWords], pk[kKeyWords];
   make_keys(a, stream, sk, pk);
   ++g_tick;
@@ -211,7 +226,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   // stall the whole launch queue), so a set earns its own executable only on its SECOND sighting ("pending" record);
   // until then the call is served by patching the least recently used executable in place.
   cudaGraph_t graph = nullptr;
-  const int rc = capture_chain(a, s, &graph);
+  const int rc = capture_chain(a, cap_s, &graph);
   if (rc != VQB_OK) {
     if (rc != kCaptureFailed) return rc;              // error reported by the chain itself (nothing ran)
     if (++g_graph_failures > 4) g_graph_disabled = true;
