@@ -27,9 +27,10 @@
 //                              Two accumulator stages (2 x 256 TMEM columns).
 //
 // Exactness: the tensor-core score of a (row, code) pair differs from the exact fp32 value by at most
-// tau = margin_rel * ||x|| * max||c||.  A row is certified when its best score leads every other score
-// by more than W = 2*tau; otherwise (row, candidates) goes to `flagged` and vqb_fix_flagged re-scores
-// it with the reference's exact formula.  The band test is conservative (may over-flag, never under-flag).
+// tau = margin_rel * ||x|| * max||c||, and the epilogue's 4-bit column tag perturbs it by < 16 ulp.  A row is
+// certified when its best (tagged) score leads every other score by more than W = 2*tau + 2*(tag slack);
+// otherwise (row, two best candidates, candidate count) goes to `flagged` and vqb_fix_flagged re-scores it with
+// the reference's exact formula (count >= 3: whole-row rescan).  Conservative: may over-flag, never under-flag.
 #include "ptx.cuh"
 #include "vqb_common.cuh"
 #include "gather_row.cuh"
