@@ -48,6 +48,25 @@ def rotate_to(src, tgt):
     return rotated.reshape(shape)
 
 
+def host_chunk_bounds(N: int, n_chunks: int):
+    """Row boundaries [0, b1, ..., N] of the chunks `forward_host` streams through the GPU.
+
+    Chunk sizes ramp up and down (1, 2, 3, 3, ..., 3, 2, 1 units): the first upload and the last download are not
+    overlapped with anything, so they are kept short; the middle chunks are large to amortise per-chunk costs.
+    Interior boundaries are multiples of 256 rows (whole CTA-pair tiles, 16-byte aligned row offsets)."""
+    n_chunks = max(1, int(n_chunks))
+    wts = [min(c + 1, n_chunks - c, 3) for c in range(n_chunks)]
+    unit = N / sum(wts)
+    bounds, acc = [0], 0.0
+    for wgt in wts:
+        acc += wgt * unit
+        b_ = min(N, -(-int(round(acc)) // 256) * 256)
+        if b_ > bounds[-1]:
+            bounds.append(b_)
+    bounds[-1] = N
+    return bounds
+
+
 class VectorQuantize(nn.Module):
     def __init__(
         self,
@@ -260,17 +279,7 @@ class VectorQuantize(nn.Module):
                    torch.empty((), dtype=torch.float32).pin_memory())
         q_host, i_host, l_host = out
         qf, idf = q_host.reshape(-1, D), i_host.reshape(-1)
-        # Chunk sizes ramp up and down (1, 2, 3, 3, ..., 3, 2, 1 units): the first upload and the last download are
-        # not overlapped with anything, so they are kept short; the middle chunks are large to amortise per-chunk costs.
-        wts = [min(c + 1, n_chunks - c, 3) for c in range(n_chunks)]
-        unit = N / sum(wts)
-        bounds, acc = [0], 0.0
-        for wgt in wts:
-            acc += wgt * unit
-            b_ = min(N, -(-int(round(acc)) // 256) * 256)  # whole CTA-pair tiles per chunk
-            if b_ > bounds[-1]:
-                bounds.append(b_)
-        bounds[-1] = N
+        bounds = host_chunk_bounds(N, n_chunks)
         n_chunks = len(bounds) - 1
         rows = max(bounds[c + 1] - bounds[c] for c in range(n_chunks))
         key = (N, D, x_host.dtype, tuple(bounds), dev)
