@@ -91,6 +91,9 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 for its workers; the reference arm is entitled to every host thread
+    for var in ("OMP_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(var, None)
     steps = max(1, min(args.steps, 5))
     warm = max(1, min(args.warmup, 2))
     v, ms = time_cpu(steps, warm)
