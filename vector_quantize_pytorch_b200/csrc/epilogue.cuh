@@ -1,0 +1,160 @@
+// Row-wise arg-max with a certificate, as run by the epilogue warps of the search kernel (vq_assign.cu) on the
+// fp32 score tiles they read back from TMEM (one thread = one row slice).  Replaces the reference's
+// `dist.argmax(dim=-1)` over the materialised (N x K) matrix (vector_quantize_pytorch.py:130-145).
+//
+// Two layers:
+//   ScanState  the HOT loop.  Per group of G columns: a 3-input max tree (FMNMX3) and one compare against the row's
+//              running threshold thr = (best so far) - W.  Only a group whose maximum beats thr can hold a candidate; it
+//              is copied, raw, to a tiny per-thread queue of LIVE groups.  A group that beats the running maximum by
+//              more than W kills every older group (queue reset), so the queue almost always holds ONE group.
+//   RowState   the exact tagged top-3 (scores carry their column in 4 low mantissa bits).  In round 1 it was applied
+//              to every element (7.5 instructions per element, alu-pipe bound: 4550 clk per 128x256 tile); now it is
+//              rebuilt once per row sweep from the live groups only.
+// Measured (scripts/epi_bench.cu, B200): see DESIGN.md section 8.
+#pragma once
+#include <stdint.h>
+
+namespace vqb {
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+template <int G>
+__device__ __forceinline__ float max_group(const uint32_t* r) {
+  static_assert(G == 4 || G == 8 || G == 16, "group size");
+  if (G == 4) return fmaxf(fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2])), __uint_as_float(r[3]));
+  if (G == 8)
+    return fmax3(fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2])),
+                 fmax3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5])),
+                 fmaxf(__uint_as_float(r[6]), __uint_as_float(r[7])));
+  const float a = fmax3(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]));
+  const float b = fmax3(__uint_as_float(r[3]), __uint_as_float(r[4]), __uint_as_float(r[5]));
+  const float c = fmax3(__uint_as_float(r[6]), __uint_as_float(r[7]), __uint_as_float(r[8]));
+  const float d = fmax3(__uint_as_float(r[9]), __uint_as_float(r[10]), __uint_as_float(r[11]));
+  const float e = fmax3(__uint_as_float(r[12]), __uint_as_float(r[13]), __uint_as_float(r[14]));
+  return fmaxf(fmax3(a, b, c), fmax3(d, e, __uint_as_float(r[15])));
+}
+__device__ __forceinline__ float max16(const uint32_t (&r)[16]) { return max_group<16>(r); }
+
+// Running top-3 of one row (slice), branch-free.  Scores carry the element's position inside its group in their 4 low
+// mantissa bits (tag = 15 - e, so that among equal truncated values the FIRST column wins a max), which makes the whole
+// update min/max arithmetic — no compare/select chains, no divergence between the 32 rows of a warp.  The tag perturbs
+// a score by < 16 ulp; the certification band W carries that slack.  t3 only answers "is there a third candidate
+// inside the band" (-> whole-row exact re-scan).
+struct RowState {
+  float t1, t2, t3;   // tagged top-3 scores
+  float thr, W;       // thr = t1 - W: pieces whose exact maximum is <= thr cannot hold a candidate
+  float bexact;       // exact (untagged) running maximum: the score that carries the loss
+  int j1, j2;         // first column of the groups t1 / t2 came from
+  __device__ __forceinline__ void init(float w) {
+    W = w; t1 = t2 = t3 = -3.4e38f; bexact = -3.4e38f; thr = -3.4e38f; j1 = 0; j2 = 0;
+  }
+  // Pipe balance: only the max of each compare-exchange is an FMNMX (alu pipe); the min is recovered on the fma pipe as
+  // an integer identity on the bit patterns, min = a + b - max (exact: max returns one of its inputs), written as IMADs
+  // with a multiplier ptxas cannot fold (mul1 = 1, mulm1 = -1 come in through the kernel params).
+  template <int G>
+  __device__ __forceinline__ void insert(const uint32_t* r, int cbase, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
+    const float o1 = t1, o2 = t2;
+#pragma unroll
+    for (int e = 0; e < G; ++e) {
+      const uint32_t ku = (r[e] & tagmask) | static_cast<uint32_t>(15 - e);
+      const float n1 = fmaxf(t1, __uint_as_float(ku));
+      const uint32_t lo1 = __float_as_uint(n1) * mulm1 + (__float_as_uint(t1) * mul1 + ku);
+      const float n2 = fmaxf(t2, __uint_as_float(lo1));
+      const uint32_t lo2 = __float_as_uint(n2) * mulm1 + (__float_as_uint(t2) * mul1 + lo1);
+      t3 = fmaxf(t3, __uint_as_float(lo2));
+      t1 = n1;
+      t2 = n2;
+    }
+    // where did t1 / t2 come from?  Equal tagged scores in different groups make this ambiguous, but then the
+    // equal score also sits in t2 or t3, the row has >= 3 candidates and is re-scanned exactly anyway.
+    const bool c1 = t1 != o1;
+    j2 = (t2 == o2) ? j2 : ((c1 && t2 == o1) ? j1 : cbase);
+    j1 = c1 ? cbase : j1;
+    thr = t1 - W;
+  }
+  __device__ __forceinline__ void piece(const uint32_t (&r)[16], int cbase, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
+    insert<16>(r, cbase, tagmask, mul1, mulm1);
+  }
+  static __device__ __forceinline__ int col(float t, int j) { return j + 15 - static_cast<int>(__float_as_uint(t) & 15u); }
+};
+
+struct MergeSlot { float t1, t2, t3, bexact; int i0, i1; };
+
+// The hot loop (see the header comment).  G = columns per group.  The queue of live groups is a separate thread-local
+// array (dynamically indexed -> local memory); keeping it out of this struct keeps the scalars below in registers.
+template <int G>
+struct ScanQueue {
+  static constexpr int CAP = 4;      // live groups kept; one more = overflow -> the row is re-scanned exactly
+  uint4 v[CAP + 1][G / 4];           // raw scores of the live groups (+ one spare slot for branch-free stores)
+  int c[CAP + 1];                    // first column of each
+};
+
+template <int G>
+struct ScanState {
+  static constexpr int CAP = ScanQueue<G>::CAP;
+  float t1;      // exact running maximum of this thread's slice
+  float thr;     // max(own, partner slice) running maximum - W
+  float kill;    // t1 + W: a group maximum above it makes every queued group irrelevant
+  float W;
+  int cnt;       // queued groups (CAP + 1 = overflow)
+
+  __device__ __forceinline__ void init(float w) {
+    W = w; t1 = -3.4e38f; thr = -3.4e38f; kill = -3.4e38f; cnt = 0;
+  }
+  // the partner thread of this row (other column half) has reached `other`: nothing <= other - W can be a candidate
+  __device__ __forceinline__ void raise(float other) { thr = fmaxf(thr, other - W); }
+
+  // Branch-free: a group that is not a candidate (p false) or does not fit is written to the spare slot CAP.
+  __device__ __forceinline__ void push(ScanQueue<G>& q, const uint32_t* r, int col, float m, bool p) {
+    const int c0 = (m > kill) ? 0 : cnt;
+    const int slot = (p && c0 < CAP) ? c0 : CAP;
+#pragma unroll
+    for (int e = 0; e < G; e += 4) q.v[slot][e >> 2] = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+    q.c[slot] = col;
+    cnt = p ? min(c0 + 1, CAP + 1) : cnt;
+    t1 = fmaxf(t1, m);
+    thr = fmaxf(thr, t1 - W);
+    kill = t1 + W;
+  }
+
+  // One warp-uniform branch per 16-column piece; inside it the groups are pushed with straight-line code (32 rows per
+  // warp: at K ~ 1e3 some lane holds a running-maximum record in most pieces, so what counts is that the taken path is
+  // short and free of divergence — measured in scripts/epi_bench.cu).
+  __device__ __forceinline__ void scan16(ScanQueue<G>& q, const uint32_t (&r)[16], int cbase) {
+    float m[16 / G];
+    bool any = false;
+#pragma unroll
+    for (int g = 0; g < 16 / G; ++g) {
+      m[g] = max_group<G>(r + g * G);
+      any |= m[g] > thr;
+    }
+    if (__any_sync(0xffffffffu, any)) {
+#pragma unroll
+      for (int g = 0; g < 16 / G; ++g) push(q, r + g * G, cbase + g * G, m[g], m[g] > thr);
+    }
+  }
+
+  // Rebuild the exact tagged top-3 of this slice from the live groups (typically one).
+  __device__ __forceinline__ void finish(const ScanQueue<G>& q, RowState& st, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
+    const float w = W;
+    st.init(w);
+    st.bexact = t1;
+    const float live = t1 - w;
+    const int n = min(cnt, CAP);
+    for (int i = 0; i < n; ++i) {
+      uint32_t v[G];
+#pragma unroll
+      for (int e = 0; e < G; e += 4) {
+        const uint4 u = q.v[i][e >> 2];
+        v[e] = u.x; v[e + 1] = u.y; v[e + 2] = u.z; v[e + 3] = u.w;
+      }
+      if (max_group<G>(v) > live) st.template insert<G>(v, q.c[i], tagmask, mul1, mulm1);
+    }
+    if (cnt > CAP) { st.t2 = st.t1; st.t3 = st.t1; }  // overflow: more live groups than the queue holds -> >= 3 candidates
+  }
+};
+
+}  // namespace vqb
