@@ -163,6 +163,12 @@ int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const flo
                   double eps, int metric, int do_lerp, int do_normalise, void* planes, void* bext, float* bias,
                   float* cnorm2, float* cmax, float* scratch, void* stream);
 
+/* vqb_ema_apply with the reference's per-code `ema_update_weight` (:86-97, :609-610): the lerp weight of code k is
+ * (1 - decay) * code_weight[k] (fp32 product).  code_weight f32 [K] or NULL (= vqb_ema_apply). */
+int vqb_ema_apply_weighted(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+                           double decay, double eps, int metric, int do_lerp, int do_normalise, const float* code_weight,
+                           void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream);
+
 /* One-call composite of VectorQuantize.forward's arithmetic (or one ResidualVQ stage): input staging ->
  * vqb_assign (+ fused tail) -> vqb_fix_flagged -> vqb_loss_finalize -> vqb_ema_stats -> vqb_ema_apply, all
  * enqueued from C++ (the Python glue pays one FFI call instead of ~20).  Replaces vqp:1159-1178 + :674-791.

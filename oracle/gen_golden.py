@@ -54,7 +54,7 @@ def randomize_codebooks(module, gen, scale=1.0, cosine=False):
         cb.embed_avg.data.copy_(e)
 
 
-def run_case(name, build, x_shape, dtype, steps, meta, randomize=True, scale=1.0, clustered=False):
+def run_case(name, build, x_shape, dtype, steps, meta, randomize=True, scale=1.0, clustered=False, seed_steps=False):
     ref = load_reference()
     torch.manual_seed(1234)
     gen = torch.Generator().manual_seed(4321)
@@ -73,6 +73,8 @@ def run_case(name, build, x_shape, dtype, steps, meta, randomize=True, scale=1.0
                 x = cb0[pick] + 0.3 * x
         x = x.to(tdtype)
         module.train(mode == "train")
+        if seed_steps:  # dead-code expiry draws torch.randperm from the global RNG (vqp:156-163): make it replayable
+            torch.manual_seed(5000 + step)
         if step == 0:  # later steps: pre(step) == post(step-1)
             snap(module, "s0_pre", store)
         with torch.no_grad():
@@ -91,7 +93,28 @@ def run_case(name, build, x_shape, dtype, steps, meta, randomize=True, scale=1.0
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def expire_cases():
+    """Dead-code expiry (vqp:544-574, rvq:599-601): threshold 2 with 8-cluster data on 64 codes, so that most codes die.
+    The sampled replacement rows come from torch's global CPU RNG, re-seeded before every step (replayed by the tests)."""
+    T = "train"
+    run_case("expire_vq_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=64, threshold_ema_dead_code=2), (4, 96, 32), "fp32",
+             [T, T, T], dict(kind="vq", dim=32, codebook_size=64, threshold_ema_dead_code=2), clustered=True, seed_steps=True)
+    run_case("expire_vq_cosine_bf16", lambda r: r.VectorQuantize(dim=32, codebook_size=64, threshold_ema_dead_code=2, use_cosine_sim=True),
+             (4, 96, 32), "bf16", [T, T, T], dict(kind="vq", dim=32, codebook_size=64, threshold_ema_dead_code=2, use_cosine_sim=True),
+             seed_steps=True)
+    run_case("expire_rvq_shared_fp32", lambda r: r.ResidualVQ(dim=32, num_quantizers=3, codebook_size=64, shared_codebook=True,
+                                                              threshold_ema_dead_code=2), (3, 64, 32), "fp32", [T, T],
+             dict(kind="rvq", dim=32, codebook_size=64, num_quantizers=3, shared_codebook=True, threshold_ema_dead_code=2),
+             clustered=True, seed_steps=True)
+    run_case("expire_rvq_separate_fp32", lambda r: r.ResidualVQ(dim=32, num_quantizers=3, codebook_size=64, threshold_ema_dead_code=2),
+             (3, 64, 32), "fp32", [T, T],
+             dict(kind="rvq", dim=32, codebook_size=64, num_quantizers=3, shared_codebook=False, threshold_ema_dead_code=2),
+             clustered=True, seed_steps=True)
+
+
 def main():
+    if "--expire" in sys.argv:
+        return expire_cases()
     T, E = "train", "eval"
     # --- VectorQuantize (vqp.py:802) ---
     run_case("vq_euclid_fp32", lambda r: r.VectorQuantize(dim=64, codebook_size=96), (2, 80, 64), "fp32",

@@ -187,10 +187,32 @@ def track_stats(state: CodebookState, x: np.ndarray, ind: np.ndarray, decay: flo
 # --------------------------------------------------------------------------------------------
 
 
+def expire_codes(state: CodebookState, samples: np.ndarray, threshold: float, reset: float, pick_fn, cosine: bool = False,
+                 dtype: str = "fp32") -> int:
+    """vqp:564-574 + :544-562 (`replace`) + :156-163 (`sample_vectors`): codes whose EMA cluster size fell below
+    `threshold` are re-seeded from `samples` (N, D).  `pick_fn(n, num)` supplies the sampled row ids — the reference
+    draws torch.randperm(n)[:num] (n >= num) or torch.randint(0, n, (num,)); the caller replays the same RNG.
+    Returns the number of replaced codes."""
+    expired = state.cluster_size < F32(threshold)  # vqp:568
+    num = int(expired.sum())
+    if num == 0:  # vqp:570
+        return 0
+    samples = np.asarray(samples, dtype=F32).reshape(-1, samples.shape[-1])
+    if cosine:  # vqp:545-546, in the dtype the samples arrive in (fp32 from Codebook.forward, x.dtype from rvq:601)
+        samples = l2norm(samples, dtype)
+    picks = np.asarray(pick_fn(samples.shape[0], num)).astype(np.int64)
+    sampled = samples[picks]
+    state.embed[expired] = sampled  # vqp:560
+    state.cluster_size[expired] = F32(reset)  # vqp:561
+    state.embed_avg[expired] = sampled * F32(reset)  # vqp:562
+    return num
+
+
 def codebook_forward(x: np.ndarray, state: CodebookState, *, cosine: bool = False, training: bool = True,
                      decay: float = 0.8, eps: float = 1e-5, ema_update: bool = True,
                      manual_ema_update: bool = False, freeze_codebook: bool = False, all_reduce=None,
-                     ema_update_weight=None, faithful: bool = False):
+                     ema_update_weight=None, faithful: bool = False, threshold_ema_dead_code: float = 0,
+                     pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False):
     """x: (N, D) fp32 (already upcast, vqp:692; already l2-normalised if cosine, vqp:1159).
 
     Returns (quantize (N, D) fp32, embed_ind (N,) int64).  Mutates `state` like the reference:
@@ -206,10 +228,31 @@ def codebook_forward(x: np.ndarray, state: CodebookState, *, cosine: bool = Fals
         quantize = (onehot @ embed).astype(F32)
     else:  # vqp:779-781 gather; bit-identical to the one-hot product
         quantize = embed[ind].copy()
-    if training and not freeze_codebook and ema_update:  # vqp:783-784, :619-641
-        track_stats(state, x, ind, decay, all_reduce, ema_update_weight, faithful)
-        if not manual_ema_update:  # vqp:638-639
+    has_expiry = threshold_ema_dead_code > 0
+    if training and not freeze_codebook and (ema_update or has_expiry):  # vqp:783-784, :619-641
+        if accum is not None:  # vqp:70-74, :80-82, :612-614: statistics parked on `.grad` across calls
+            K = state.cluster_size.shape[0]
+            cs, es = batch_stats(x, ind, K, faithful)
+            if callable(ema_update_weight):
+                ema_update_weight = ema_update_weight(es, cs)
+            if accum_ema_update:
+                accum["cs"] = accum.get("cs", 0) + cs
+                accum["es"] = accum.get("es", 0) + es
+                return quantize, ind
+            cs = cs + accum.pop("cs", 0)
+            es = es + accum.pop("es", 0)
+            ema_inplace(state.cluster_size, cs, decay, ema_update_weight)
+            ema_inplace(state.embed_avg, es, decay, ema_update_weight)
+        else:
+            if callable(ema_update_weight):
+                K = state.cluster_size.shape[0]
+                cs, es = batch_stats(x, ind, K, faithful)
+                ema_update_weight = ema_update_weight(es, cs)
+            track_stats(state, x, ind, decay, all_reduce, ema_update_weight, faithful)
+        if ema_update and not manual_ema_update:  # vqp:638-639
             update_ema(state, eps, cosine)
+        if has_expiry:  # vqp:641
+            expire_codes(state, x, threshold_ema_dead_code, threshold_ema_dead_code, pick_fn, cosine)
     return quantize, ind
 
 
@@ -244,10 +287,12 @@ class VQConfig:
     commitment_weight: float = 1.0  # vqp:822
     manual_ema_update: bool = False
     ema_update: bool = True
+    threshold_ema_dead_code: float = 0  # vqp:818
 
 
 def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *, training: bool = True,
-               freeze_codebook: bool = False, all_reduce=None, faithful: bool = False):
+               freeze_codebook: bool = False, all_reduce=None, faithful: bool = False, ema_update_weight=None,
+               pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False):
     """x: (..., D) values of dtype `dtype` held in float32.  x.requires_grad is False (bench setting).
 
     Returns (quantize (..., D) in dtype, indices (...,) int64, loss fp32 scalar, loss_fp32_unrounded).
@@ -259,7 +304,8 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
     quantize, ind = codebook_forward(  # vqp:1176
         x, state, cosine=cfg.use_cosine_sim, training=training, decay=cfg.decay, eps=cfg.eps,
         ema_update=cfg.ema_update, manual_ema_update=cfg.manual_ema_update, freeze_codebook=freeze_codebook,
-        all_reduce=all_reduce, faithful=faithful)
+        all_reduce=all_reduce, faithful=faithful, ema_update_weight=ema_update_weight,
+        threshold_ema_dead_code=cfg.threshold_ema_dead_code, pick_fn=pick_fn, accum=accum, accum_ema_update=accum_ema_update)
     quantize = cast_like(quantize, dtype)  # vqp:1178
     loss = F32(0.0)
     loss_f32 = F32(0.0)
@@ -283,7 +329,7 @@ def _bin(a: np.ndarray, dtype: str) -> np.ndarray:
 
 
 def rvq_forward(x: np.ndarray, dtype: str, states: list, cfg: VQConfig, *, shared_codebook: bool = False,
-                training: bool = True, freeze_codebook: bool = False, all_reduce=None, faithful: bool = False):
+                training: bool = True, freeze_codebook: bool = False, all_reduce=None, faithful: bool = False, pick_fn=None):
     """states: list of Q CodebookState (for shared_codebook all entries are THE SAME object, rvq:302-306).
 
     Returns (quantized_out (..., D) in dtype, indices (..., Q) int64, losses (Q,) fp32, losses_fp32 (Q,)).
@@ -295,18 +341,29 @@ def rvq_forward(x: np.ndarray, dtype: str, states: list, cfg: VQConfig, *, share
     x = cast_like(x, dtype)
     quantized_out = np.zeros_like(x)  # rvq:410
     residual = x  # rvq:411
-    all_ind, all_loss, all_loss32 = [], [], []
+    all_ind, all_loss, all_loss32, all_residuals = [], [], [], []
     for q in range(Q):  # rvq:469
+        all_residuals.append(residual)  # rvq:489
         quantized, ind, loss, loss32 = vq_forward(residual, dtype, states[q], layer_cfg, training=training,
                                                   freeze_codebook=freeze_codebook, all_reduce=all_reduce,
-                                                  faithful=faithful)  # rvq:493
+                                                  faithful=faithful, pick_fn=pick_fn)  # rvq:493
         residual = _bin(residual - quantized, dtype)  # rvq:524 (quant_grad_frac=0 -> detach)
         quantized_out = _bin(quantized_out + quantized, dtype)  # rvq:525
         all_ind.append(ind)
         all_loss.append(loss)
         all_loss32.append(loss32)
-    if training and shared_codebook and cfg.ema_update and not freeze_codebook:  # rvq:593-597
-        update_ema(states[0], cfg.eps, cfg.use_cosine_sim)
+    if training and shared_codebook:  # rvq:593-601 (not gated by freeze_codebook in the reference either)
+        if cfg.ema_update:
+            update_ema(states[0], cfg.eps, cfg.use_cosine_sim)
+        if cfg.threshold_ema_dead_code > 0:
+            # rvq:599-601 -> vqp:1051-1054 -> :573-574: all_residuals '(b) n l d -> b (n l) d' reaches Codebook.expire_codes_
+            # whose 'h ... d -> h (...) d' reads the BATCH axis as the codebook axis; `replace` zips it with the (1, K)
+            # mask, so only batch element 0's rows are sampled from.  Reproduced as is.
+            allr = np.stack([r[0].reshape(-1, r.shape[-1]) for r in all_residuals], axis=1).reshape(-1, x.shape[-1])
+            if cfg.use_cosine_sim:
+                allr = l2norm(allr, dtype)
+            expire_codes(states[0], allr, cfg.threshold_ema_dead_code, cfg.threshold_ema_dead_code, pick_fn, cfg.use_cosine_sim,
+                         dtype)
     return (quantized_out, np.stack(all_ind, axis=-1), np.array(all_loss, dtype=F32),
             np.array(all_loss32, dtype=F32))
 

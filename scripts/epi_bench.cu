@@ -43,7 +43,8 @@ struct OutRow { int i0, i1, n; float best; };
 constexpr int BN = 256;
 
 // VARIANT: 0 = LDTM only, 1 = 2-input max tree, 2 = 3-input max tree, 3 = round-1 epilogue (tagged top-3, piece skip),
-//          4/8/16 = new scan (group size G), 32+G = new scan without the cross-part threshold exchange
+//          4/8/16 = queue scan (group size G), 32+G = the same without the cross-part threshold exchange,
+//          64+G = queue scan without the per-piece branch, 100 / 101 = register-resident live group (with / without branch)
 // NW = epilogue warps (8: two column halves per TMEM lane group, 16: four column quarters)
 template <int VARIANT, int NW>
 __global__ void __launch_bounds__(NW * 32, 1)
@@ -63,9 +64,12 @@ epi_bench_kernel(int K, int sweeps, float W, OutRow* out, long long* cycles, uin
   const int row_in_tile = lg * 32 + lane;
   const int tiles = K / BN;
   long long acc = 0;
-  constexpr int G = (VARIANT >= 32) ? (VARIANT - 32) : VARIANT;
+  constexpr bool kReg = VARIANT >= 100;
+  constexpr int G = kReg ? 16 : (VARIANT >= 64) ? (VARIANT - 64) : (VARIANT >= 32) ? (VARIANT - 32) : VARIANT;
   constexpr bool kNew = (VARIANT == 4 || VARIANT == 8 || VARIANT == 16 || VARIANT >= 32);
-  constexpr bool kShare = kNew && VARIANT < 32;
+  constexpr bool kShare = kNew && !(VARIANT >= 32 && VARIANT < 64);
+  constexpr bool kBranch = !(VARIANT >= 64 && VARIANT < 100) && VARIANT != 101;
+  constexpr bool kImad = VARIANT == 102;
   // piece j (0..NPC-1) of column part q: pieces come in adjacent pairs, pairs are dealt round-robin to the parts
   auto piece_col_of = [&](int q, int j) { return ((P * (j >> 1) + q) * 2 + (j & 1)) << 4; };
 
@@ -75,7 +79,9 @@ epi_bench_kernel(int K, int sweeps, float W, OutRow* out, long long* cycles, uin
     st.init(W);
     ScanState<(kNew ? G : 4)> sc;
     ScanQueue<(kNew ? G : 4)> sq;
+    ScanReg sr;
     sc.init(W);
+    sr.init(W);
     s_share[part][row_in_tile] = -3.4e38f;
     float sink = 0.f;
     for (int ct = 0; ct < tiles; ++ct) {
@@ -99,7 +105,7 @@ epi_bench_kernel(int K, int sweeps, float W, OutRow* out, long long* cycles, uin
       const int code0 = ct * BN;
       if (kShare) {
 #pragma unroll
-        for (int o = 1; o < P; ++o) sc.raise(s_share[(part + o) % P][row_in_tile]);
+        for (int o = 1; o < P; ++o) { sc.raise(s_share[(part + o) % P][row_in_tile]); sr.raise(s_share[(part + o) % P][row_in_tile]); }
       }
       auto scan16 = [&](const uint32_t (&r)[16], int cbase) {
         if (VARIANT == 0) { sink += __uint_as_float(r[0]); return; }
@@ -119,7 +125,8 @@ epi_bench_kernel(int K, int sweeps, float W, OutRow* out, long long* cycles, uin
           if (mm > st.thr) st.piece(r, cbase, tagmask, mul1, mulm1);
           return;
         }
-        if (kNew) sc.scan16(sq, r, cbase);
+        if (kReg) { if constexpr (G == 16) sr.template scan16<kBranch, kImad>(sq, r, cbase, mul1); }
+        else if (kNew) sc.template scan16<kBranch>(sq, r, cbase);
       };
       uint32_t buf0[16], buf1[16];
       tmem_ld_32x32b_x16(t_addr + piece_col(0), buf0);
@@ -131,7 +138,7 @@ epi_bench_kernel(int K, int sweeps, float W, OutRow* out, long long* cycles, uin
         if (j + 2 < NPC) tmem_ld_32x32b_x16(t_addr + piece_col(j + 2), buf0);
         scan16(buf1, code0 + piece_col(j + 1));
       }
-      if (kShare) s_share[part][row_in_tile] = sc.t1;
+      if (kShare) s_share[part][row_in_tile] = kReg ? sr.t1 : sc.t1;
       acc += clock64() - c0;
       tc_fence_before();
       __syncthreads();   // nobody refills a stage that a partner still reads
@@ -139,7 +146,8 @@ epi_bench_kernel(int K, int sweeps, float W, OutRow* out, long long* cycles, uin
     }
     // ---- end of the row sweep: (new scan) rebuild the tagged top-3 from the few live groups, then merge the parts
     const long long c1 = clock64();
-    if (kNew) sc.finish(sq, st, tagmask, mul1, mulm1);
+    if (kReg) { if constexpr (G == 16) sr.finish(sq, st, tagmask, mul1, mulm1); }
+    else if (kNew) sc.finish(sq, st, tagmask, mul1, mulm1);
     MergeSlot* slot = &s_merge[part][row_in_tile];
     slot->t1 = st.t1; slot->t2 = st.t2; slot->t3 = st.t3; slot->bexact = st.bexact;
     slot->i0 = RowState::col(st.t1, st.j1); slot->i1 = RowState::col(st.t2, st.j2);
@@ -222,20 +230,12 @@ int main(int argc, char** argv) {
   const int sweeps = argc > 1 ? atoi(argv[1]) : 14;
   for (int K : {1024, 16384}) {
     const int sw = K == 1024 ? sweeps : std::max(1, sweeps / 8);
-    run<0>("ldtm only", K, sw, false);
     run<2>("ldtm + max tree (3-input)", K, sw, false);
     run<3>("round-1 tagged top-3", K, sw, true);
-    run<4>("scan G=4  (shared thr)", K, sw, true);
-    run<8>("scan G=8  (shared thr)", K, sw, true);
-    run<16>("scan G=16 (shared thr)", K, sw, true);
-    run<40>("scan G=8  (own thr)", K, sw, true);
-    run<48>("scan G=16 (own thr)", K, sw, true);
-    run<0, 16>("ldtm only", K, sw, false);
-    run<2, 16>("ldtm + max tree (3-input)", K, sw, false);
-    run<3, 16>("round-1 tagged top-3", K, sw, true);
-    run<4, 16>("scan G=4  (shared thr)", K, sw, true);
-    run<8, 16>("scan G=8  (shared thr)", K, sw, true);
-    run<16, 16>("scan G=16 (shared thr)", K, sw, true);
+    run<100>("regs  G=16 (SEL)", K, sw, true);
+    run<102>("regs  G=16 (IMAD)", K, sw, true);
+    run<100, 16>("regs  G=16 (SEL)", K, sw, true);
+    run<102, 16>("regs  G=16 (IMAD)", K, sw, true);
   }
   return 0;
 }

@@ -11,7 +11,20 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def golden_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Small fixtures that store their inputs (the `big*` ones are replayed by tests/test_big_golden.py)."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not n.startswith("big"))
+
+
+def replayable_on_gpu(names):
+    """Fixtures whose outputs do not depend on the CPU RNG (dead-code expiry draws torch.randperm on the tensor's device)."""
+    return [n for n in names if not n.startswith("expire")]
+
+
+def cpu_pick_fn(n, num):
+    """sample_vectors (vqp:156-163) on torch's global CPU generator — the caller seeds it like oracle/gen_golden.py."""
+    import torch
+    return (torch.randperm(n)[:num] if n >= num else torch.randint(0, n, (num,))).numpy()
 
 
 class Golden:
@@ -29,7 +42,8 @@ class Golden:
         dim = m["dim"] // m.get("groups", 1)
         return O.VQConfig(dim=dim, codebook_size=m["codebook_size"], use_cosine_sim=m.get("use_cosine_sim", False),
                           decay=m.get("decay", 0.8), eps=m.get("eps", 1e-5),
-                          commitment_weight=m.get("commitment_weight", 1.0))
+                          commitment_weight=m.get("commitment_weight", 1.0),
+                          threshold_ema_dead_code=m.get("threshold_ema_dead_code", 0))
 
     def state(self, tag, i):
         return O.CodebookState(self.z[f"{tag}_cb{i}_embed"].copy(), self.z[f"{tag}_cb{i}_embed_avg"].copy(),

@@ -6,7 +6,7 @@ Bar: indices identical except on rows the reference itself resolves inside fp32 
 import numpy as np
 import pytest
 
-from golden_util import Golden, golden_names, near_tie_rows
+from golden_util import Golden, golden_names, near_tie_rows, cpu_pick_fn
 from oracle import vq_oracle as O
 
 
@@ -14,11 +14,14 @@ def run_oracle(g, step, states, faithful=False):
     m, cfg = g.meta, g.cfg
     x = g[f"s{step}_x"]
     training = m["steps"][step] == "train"
+    if m.get("threshold_ema_dead_code", 0) > 0:  # replay the reference's RNG stream (oracle/gen_golden.py seeds every step)
+        import torch
+        torch.manual_seed(5000 + step)
     if m["kind"] == "vq":
-        q, ind, loss, loss32 = O.vq_forward(x, m["dtype"], states, cfg, training=training, faithful=faithful)
+        q, ind, loss, loss32 = O.vq_forward(x, m["dtype"], states, cfg, training=training, faithful=faithful, pick_fn=cpu_pick_fn)
     elif m["kind"] == "rvq":
         q, ind, loss, loss32 = O.rvq_forward(x, m["dtype"], states, cfg, shared_codebook=m["shared_codebook"],
-                                              training=training, faithful=faithful)
+                                              training=training, faithful=faithful, pick_fn=cpu_pick_fn)
     else:
         q, ind, loss, loss32 = O.grouped_rvq_forward(x, m["dtype"], states, cfg, shared_codebook=m["shared_codebook"],
                                                       training=training, faithful=faithful)

@@ -13,7 +13,7 @@ import os
 import pytest
 import torch
 
-from golden_util import Golden, golden_names, near_tie_rows
+from golden_util import Golden, golden_names, near_tie_rows, replayable_on_gpu
 from oracle import vq_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -61,7 +61,7 @@ def load_state(module, g, tag):
             cb.cluster_size.copy_(torch.from_numpy(st.cluster_size)[None])
 
 
-@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("name", replayable_on_gpu(golden_names()))
 def test_modules_match_reference_goldens(name):
     g = Golden(name)
     m = g.meta

@@ -66,6 +66,8 @@ class Codebook(nn.Module):
             _unsupported("vq_bridge")
         if gumbel_sample is not None:
             _unsupported("a custom gumbel_sample (stochastic code sampling)")
+        if threshold_ema_dead_code > 0 and use_ddp and sync_kmeans:
+            _unsupported("dead-code replacement with distributed sampling (use_ddp + sync_kmeans, vqp:211-229)")
 
         self.dim = dim
         self.decay = decay
@@ -130,13 +132,46 @@ class Codebook(nn.Module):
             allreduce_packed(stats)
         return stats
 
-    def lerp_stats(self, stats: torch.Tensor, normalise: bool):
-        """ema_inplace of both buffers (vqp:616-617) and, unless manual, update_ema (vqp:638-639)."""
+    def _stat_views(self, stats: torch.Tensor):
+        """(cluster_size (1, K), embed_sum (1, K, D)) views of a packed statistics buffer."""
+        K, D = self.codebook_size, self.dim
+        off = ops.stats_offset(K)
+        return stats[:K].view(1, K), stats[off:off + K * D].view(1, K, D)
+
+    def lerp_stats(self, stats: torch.Tensor, normalise: bool, ema_update_weight=None, accum_ema_update: bool = False):
+        """track_cluster_size_and_embed_avg after the all-reduce (vqp:609-617): the custom per-code weight
+        (tensor (K,) / (1, K) or callable of (embed_sum, cluster_size), vqp:86-97, :609-610), `accum_ema_update`
+        (park the batch statistics on the buffers' `.grad`, vqp:70-74, :612-614 — folded into the next normal update,
+        vqp:80-82), then ema_inplace of both buffers and, unless manual, update_ema (vqp:638-639).
+        Returns False when the statistics were only accumulated (the reference then skips update_ema and expiry)."""
+        cs_new, es_new = self._stat_views(stats)
+        if callable(ema_update_weight):
+            ema_update_weight = ema_update_weight(es_new, cs_new)
+        if accum_ema_update:
+            for buf, new in ((self.cluster_size, cs_new), (self.embed_avg, es_new)):
+                if buf.grad is not None:
+                    buf.grad.add_(new)
+                else:
+                    buf.grad = new.clone().detach()
+            return False
+        for buf, new in ((self.cluster_size, cs_new), (self.embed_avg, es_new)):  # vqp:80-82
+            if buf.grad is not None:
+                new.add_(buf.grad)
+                buf.grad = None
+        weight = None
+        if ema_update_weight is not None:
+            if torch.is_tensor(ema_update_weight):
+                weight = ema_update_weight.to(device=stats.device, dtype=torch.float32).reshape(-1).contiguous()
+                assert weight.numel() == self.codebook_size, "ema_update_weight must have one entry per code"
+            else:  # a python scalar scales every code alike
+                weight = torch.full((self.codebook_size,), float(ema_update_weight), dtype=torch.float32, device=stats.device)
         cs, ea, emb = self._state2d()
         cb = self.operands()
-        ops.ema_apply(cs, ea, emb, stats, cb, decay=self.decay, eps=self.eps, do_lerp=True, do_normalise=normalise)
+        ops.ema_apply(cs, ea, emb, stats, cb, decay=self.decay, eps=self.eps, do_lerp=True, do_normalise=normalise,
+                      code_weight=weight)
         if normalise:
             self._mark_operands_fresh()
+        return True
 
     def update_ema(self):  # vqp:576-584
         cs, ea, emb = self._state2d()
@@ -146,13 +181,13 @@ class Codebook(nn.Module):
 
     @torch.no_grad()
     def expire_codes_(self, batch_samples):  # vqp:544-574 (PyTorch glue: RNG-bound, cold, off by default)
+        """`batch_samples` as the reference's call site passes them: the fp32 `flatten` from Codebook.forward (vqp:641),
+        tensors in the input dtype from ResidualVQ's final expiry (rvq:601) — `replace` re-normalises in THAT dtype."""
         if not self.has_dead_code_replacement or not self.training:
             return
         expired = self.cluster_size[0] < self.threshold_ema_dead_code
         if not torch.any(expired):  # host sync, exactly like the reference (vqp:570)
             return
-        if self.use_ddp and self.sync_kmeans:
-            _unsupported("distributed dead-code replacement (sample_vectors_distributed)")
         samples = batch_samples.reshape(-1, batch_samples.shape[-1])
         if self.use_cosine_sim:
             samples = F.normalize(samples, p=2, dim=-1, eps=1e-6)
@@ -166,20 +201,46 @@ class Codebook(nn.Module):
         self.embed.data[0][expired] = sampled
         self.cluster_size.data[0][expired] = self.reset_cluster_size
         self.embed_avg.data[0][expired] = sampled * self.reset_cluster_size
+        # `.data[...] =` does not bump embed._version: without this the next search would still use the bf16 planes /
+        # bias of the replaced rows
+        self._operands_key = None
 
     @torch.no_grad()
     def update_indices(self, x, embed_ind, mask=None, ema_update_weight=None, accum_ema_update=False, ema_update=None):
         """vqp:643-668: EMA update from (x, indices) alone (tests/test_beam.py:8-45 of the reference)."""
-        if mask is not None or ema_update_weight is not None or accum_ema_update:
-            _unsupported("update_indices with mask / ema_update_weight / accum_ema_update")
+        if mask is not None:
+            _unsupported("update_indices with a mask")
         ema_update = self.ema_update if ema_update is None else ema_update
         if not ema_update and not self.has_dead_code_replacement:
             return
-        flat = x.reshape(-1, x.shape[-1]).contiguous()
+        flat = x.reshape(-1, x.shape[-1])
+        if flat.dtype not in (torch.float32, torch.bfloat16):
+            flat = flat.float()
+        flat = flat.contiguous()
         idx = embed_ind.reshape(-1).to(torch.int32).clamp_min(0).contiguous()
         stats = self.sync_stats(ops.ema_stats(flat, idx, self.codebook_size))
-        self.lerp_stats(stats, normalise=ema_update and not self.manual_ema_update)
-        self.expire_codes_(flat)
+        if self.lerp_stats(stats, normalise=ema_update and not self.manual_ema_update,
+                           ema_update_weight=ema_update_weight, accum_ema_update=accum_ema_update):
+            self.expire_codes_(flat.float())
+
+    @torch.no_grad()
+    def update_codebook(self, flatten, embed_onehot, mask=None, ema_update_weight=None, accum_ema_update=False,
+                        ema_update=None):
+        """vqp:619-641.  The reference passes the one-hot assignment; the kernels work from indices."""
+        self.update_indices(flatten, embed_onehot.argmax(dim=-1), mask=mask, ema_update_weight=ema_update_weight,
+                            accum_ema_update=accum_ema_update, ema_update=ema_update)
+
+    @torch.no_grad()
+    def track_cluster_size_and_embed_avg(self, flatten, embed_onehot, mask=None, ema_update_weight=None,
+                                         accum_ema_update=False):
+        """vqp:586-617: batch statistics -> (all-reduce) -> lerp of cluster_size / embed_avg, nothing else."""
+        if mask is not None:
+            _unsupported("track_cluster_size_and_embed_avg with a mask")
+        flat = flatten.reshape(-1, flatten.shape[-1])
+        flat = (flat if flat.dtype in (torch.float32, torch.bfloat16) else flat.float()).contiguous()
+        idx = embed_onehot.argmax(dim=-1).reshape(-1).to(torch.int32).contiguous()
+        stats = self.sync_stats(ops.ema_stats(flat, idx, self.codebook_size))
+        self.lerp_stats(stats, normalise=False, ema_update_weight=ema_update_weight, accum_ema_update=accum_ema_update)
 
     update_ema_indices = update_indices
 
@@ -187,7 +248,7 @@ class Codebook(nn.Module):
     @torch.no_grad()
     def quantize_rows(self, x: torch.Tensor, *, update: bool, q_out=None, idx64_out=None, idx_stride=1, loss_out=None,
                       loss_weight=1.0, resid_out=None, qsum=None, stats_out=None, defer_ema=False, margin=None,
-                      stats_accumulate=False):
+                      stats_accumulate=False, ema_update=None, ema_update_weight=None, accum_ema_update=False):
         """x (N, D) contiguous fp32/bf16 — the input BEFORE the cosine l2norm (done in-kernel).
 
         One C call: search (pre-update codebook, vqp:743-747) with the fused gather / loss / residual tail
@@ -196,9 +257,12 @@ class Codebook(nn.Module):
         Returns (idx32, stats or None).
         """
         cb = self.operands()
-        apply_here = update and not defer_ema and not self.use_ddp
+        ema_update = self.ema_update if ema_update is None else ema_update   # per-call override (vqp:628)
+        custom = ema_update_weight is not None or accum_ema_update or any(
+            b.grad is not None for b in (self.cluster_size, self.embed_avg))
+        apply_here = update and not defer_ema and not self.use_ddp and not custom
         mode = 0 if not update else (2 if apply_here else 1)
-        normalise = self.ema_update and not self.manual_ema_update
+        normalise = ema_update and not self.manual_ema_update
         idx32, stats = ops.vq_forward(
             x, cb, self._state2d(), update=mode, do_normalise=normalise, decay=self.decay, eps=self.eps, q_out=q_out,
             idx64_out=idx64_out, idx_stride=idx_stride, loss_out=loss_out, loss_weight=loss_weight, resid_out=resid_out,
@@ -206,11 +270,13 @@ class Codebook(nn.Module):
         if mode == 2 and normalise:
             self._mark_operands_fresh()
         if update and not defer_ema:
+            applied = True
             if mode == 1:
                 self.sync_stats(stats)
-                self.lerp_stats(stats, normalise=normalise)
-            if self.has_dead_code_replacement:
-                self.expire_codes_(self.transform_input(x))
+                applied = self.lerp_stats(stats, normalise=normalise, ema_update_weight=ema_update_weight,
+                                          accum_ema_update=accum_ema_update)
+            if applied and self.has_dead_code_replacement:
+                self.expire_codes_(self.transform_input(x).float())  # vqp:692: `flatten` is fp32
         return idx32, stats
 
     def forward(self, x, sample_codebook_temp=None, mask=None, freeze_codebook=False, codebook_transform_fn=None,
@@ -224,8 +290,6 @@ class Codebook(nn.Module):
             _unsupported("mask")
         if codebook_transform_fn is not None:
             _unsupported("codebook_transform_fn (implicit neural codebooks)")
-        if ema_update_weight is not None or accum_ema_update:
-            _unsupported("ema_update_weight / accum_ema_update")
         if topk is not None:
             _unsupported("topk")
         ema_update = self.ema_update if ema_update is None else ema_update
@@ -245,8 +309,9 @@ class Codebook(nn.Module):
             do_update = self.training and update_usage and not freeze_codebook and (ema_update or self.has_dead_code_replacement)
             if do_update:
                 stats = self.sync_stats(ops.ema_stats(res.x_eff, res.idx, self.codebook_size))
-                self.lerp_stats(stats, normalise=ema_update and not self.manual_ema_update)
-                self.expire_codes_(res.x_eff)
+                if self.lerp_stats(stats, normalise=ema_update and not self.manual_ema_update,
+                                   ema_update_weight=ema_update_weight, accum_ema_update=accum_ema_update):
+                    self.expire_codes_(res.x_eff.float())
         return q.reshape(shape), idx64.reshape(shape[:-1]), None
 
 

@@ -107,22 +107,25 @@ struct ScanState {
   // the partner thread of this row (other column half) has reached `other`: nothing <= other - W can be a candidate
   __device__ __forceinline__ void raise(float other) { thr = fmaxf(thr, other - W); }
 
-  // Branch-free: a group that is not a candidate (p false) or does not fit is written to the spare slot CAP.
+  // Scalars are updated unconditionally (m <= thr changes none of them), only the stores are predicated: lanes
+  // without a candidate cause no memory traffic and the warp does not diverge.
   __device__ __forceinline__ void push(ScanQueue<G>& q, const uint32_t* r, int col, float m, bool p) {
     const int c0 = (m > kill) ? 0 : cnt;
-    const int slot = (p && c0 < CAP) ? c0 : CAP;
+    const int slot = min(c0, CAP);          // overflow lands in the spare slot
+    if (p) {
 #pragma unroll
-    for (int e = 0; e < G; e += 4) q.v[slot][e >> 2] = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
-    q.c[slot] = col;
+      for (int e = 0; e < G; e += 4) q.v[slot][e >> 2] = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+      q.c[slot] = col;
+    }
     cnt = p ? min(c0 + 1, CAP + 1) : cnt;
     t1 = fmaxf(t1, m);
     thr = fmaxf(thr, t1 - W);
     kill = t1 + W;
   }
 
-  // One warp-uniform branch per 16-column piece; inside it the groups are pushed with straight-line code (32 rows per
-  // warp: at K ~ 1e3 some lane holds a running-maximum record in most pieces, so what counts is that the taken path is
-  // short and free of divergence — measured in scripts/epi_bench.cu).
+  // One warp-uniform branch per 16-column piece (32 rows per warp: at K ~ 1e3 some lane holds a running-maximum
+  // record in most pieces, so what counts is that the taken path is short and free of divergence).
+  template <bool BRANCH = true>
   __device__ __forceinline__ void scan16(ScanQueue<G>& q, const uint32_t (&r)[16], int cbase) {
     float m[16 / G];
     bool any = false;
@@ -131,7 +134,7 @@ struct ScanState {
       m[g] = max_group<G>(r + g * G);
       any |= m[g] > thr;
     }
-    if (__any_sync(0xffffffffu, any)) {
+    if (!BRANCH || __any_sync(0xffffffffu, any)) {
 #pragma unroll
       for (int g = 0; g < 16 / G; ++g) push(q, r + g * G, cbase + g * G, m[g], m[g] > thr);
     }
@@ -154,6 +157,94 @@ struct ScanState {
       if (max_group<G>(v) > live) st.template insert<G>(v, q.c[i], tagmask, mul1, mulm1);
     }
     if (cnt > CAP) { st.t2 = st.t1; st.t3 = st.t1; }  // overflow: more live groups than the queue holds -> >= 3 candidates
+  }
+};
+
+// live[e] = pred ? r[e] : live[e] as PREDICATED IMADs (r * one + 0, `one` = 1 from the kernel parameters so that ptxas
+// cannot fold it into a SEL / MOV): the copy then runs on the fma pipe, which idles in the epilogue, instead of the alu
+// pipe that bounds it (FMNMX / SEL issue at half rate there).
+__device__ __forceinline__ void cond_copy8(uint32_t* live, const uint32_t* r, bool pred, uint32_t one) {
+  asm("{\n"
+      ".reg .pred q;\n"
+      "setp.ne.u32 q, %16, 0;\n"
+      "@q mad.lo.u32 %0, %8, %17, 0;\n"
+      "@q mad.lo.u32 %1, %9, %17, 0;\n"
+      "@q mad.lo.u32 %2, %10, %17, 0;\n"
+      "@q mad.lo.u32 %3, %11, %17, 0;\n"
+      "@q mad.lo.u32 %4, %12, %17, 0;\n"
+      "@q mad.lo.u32 %5, %13, %17, 0;\n"
+      "@q mad.lo.u32 %6, %14, %17, 0;\n"
+      "@q mad.lo.u32 %7, %15, %17, 0;\n"
+      "}"
+      : "+r"(live[0]), "+r"(live[1]), "+r"(live[2]), "+r"(live[3]), "+r"(live[4]), "+r"(live[5]), "+r"(live[6]), "+r"(live[7])
+      : "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(static_cast<uint32_t>(pred)), "r"(one));
+}
+
+// Register-resident variant of the hot loop: the (almost always single) live group of 16 columns is kept in registers
+// and replaced with predicated moves; only a second live group inside the band (a near tie) goes to the thread-local queue.
+struct ScanReg {
+  static constexpr int CAP = ScanQueue<16>::CAP;
+  float t1, thr, kill, W;
+  int cnt;            // groups in the queue besides `live` (CAP + 1 = overflow)
+  int lcol;           // first column of the live group (-1: none yet)
+  uint32_t live[16];
+
+  __device__ __forceinline__ void init(float w) {
+    W = w; t1 = -3.4e38f; thr = -3.4e38f; kill = -3.4e38f; cnt = 0; lcol = -1;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) live[e] = 0xFF7FFFFFu;  // -FLT_MAX
+  }
+  __device__ __forceinline__ void raise(float other) { thr = fmaxf(thr, other - W); }
+
+  template <bool BRANCH = true, bool IMAD = false>
+  __device__ __forceinline__ void scan16(ScanQueue<16>& q, const uint32_t (&r)[16], int cbase, uint32_t one = 1u) {
+    const float m = max_group<16>(r);
+    const bool p = m > thr;
+    if (!BRANCH || __any_sync(0xffffffffu, p)) {
+      const bool reset = m > kill;             // beats everything seen so far by more than W (implies p)
+      const bool tie = p && !reset;            // a second live group: rare
+      if (__any_sync(0xffffffffu, tie)) {
+        if (tie) {
+          const int slot = min(cnt, CAP);
+#pragma unroll
+          for (int e = 0; e < 16; e += 4) q.v[slot][e >> 2] = make_uint4(r[e], r[e + 1], r[e + 2], r[e + 3]);
+          q.c[slot] = cbase;
+          cnt = min(cnt + 1, CAP + 1);
+        }
+      }
+      if (IMAD) {
+        cond_copy8(live, r, reset, one);
+        cond_copy8(live + 8, r + 8, reset, one);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) live[e] = reset ? r[e] : live[e];
+      }
+      lcol = reset ? cbase : lcol;
+      cnt = reset ? 0 : cnt;
+      t1 = fmaxf(t1, m);
+      thr = fmaxf(thr, t1 - W);
+      kill = t1 + W;
+    }
+  }
+
+  __device__ __forceinline__ void finish(const ScanQueue<16>& q, RowState& st, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
+    const float w = W;
+    st.init(w);
+    st.bexact = t1;
+    if (lcol >= 0) st.template insert<16>(live, lcol, tagmask, mul1, mulm1);
+    const float lv = t1 - w;
+    const int n = min(cnt, CAP);
+    for (int i = 0; i < n; ++i) {
+      uint32_t v[16];
+#pragma unroll
+      for (int e = 0; e < 16; e += 4) {
+        const uint4 u = q.v[i][e >> 2];
+        v[e] = u.x; v[e + 1] = u.y; v[e + 2] = u.z; v[e + 3] = u.w;
+      }
+      if (max_group<16>(v) > lv) st.template insert<16>(v, q.c[i], tagmask, mul1, mulm1);
+    }
+    if (cnt > CAP) { st.t2 = st.t1; st.t3 = st.t1; }
   }
 };
 

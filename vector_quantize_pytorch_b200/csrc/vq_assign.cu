@@ -34,6 +34,7 @@
 #include "ptx.cuh"
 #include "vqb_common.cuh"
 #include "gather_row.cuh"
+#include "epilogue.cuh"
 
 // Per-role cycle accounting (scripts/gpu_roles.py): compile with -DVQB_PROFILE.  Off by default: the counters cost
 // registers in a kernel that runs at the 128-register cap.
@@ -59,7 +60,7 @@ constexpr int MMA_GROUP = 4;      // k-blocks issued per elected region of the M
 constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
 constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 9216;     // barriers + tmem ptr + row norms + merge area
+constexpr int SMEM_CTRL_BYTES = 11264;    // barriers + tmem ptr + row norms + merge area + threshold exchange
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
@@ -86,48 +87,6 @@ struct AssignParams {
   int dbg_mode;        // diagnostics: bit0 = epilogue skips the TMEM sweep, bit1 = skip B loads+MMAs except bias
 };
 
-// Running top-3 of one row (slice), branch-free.  Scores carry the element's position inside its 16-column piece in
-// their 4 low mantissa bits (tag = 15 - e, so that among equal truncated values the FIRST column wins a max), which
-// makes the whole update min/max arithmetic — no compare/select chains, no divergence between the 32 rows of a
-// warp.  The tag perturbs a score by < 16 ulp; the certification band W carries that slack (see st.init below).
-// t3 only answers "is there a third candidate inside the band" (-> whole-row exact re-scan).
-struct RowState {
-  float t1, t2, t3;   // tagged top-3 scores
-  float thr, W;       // thr = t1 - W: pieces whose exact maximum is <= thr cannot hold a candidate
-  float bexact;       // exact (untagged) running maximum: the score that carries the loss
-  int j1, j2;         // first column of the pieces t1 / t2 came from
-  __device__ __forceinline__ void init(float w) {
-    W = w; t1 = t2 = t3 = -3.4e38f; bexact = -3.4e38f; thr = -3.4e38f; j1 = 0; j2 = 0;
-  }
-  // Pipe balance: the SM's alu pipe (FMNMX, LOP3; one warp instruction per 2 clocks per scheduler) is what bounds
-  // the epilogue, the fma pipe idles.  So only the max of each compare-exchange is an FMNMX; the min is recovered on
-  // the fma pipe as an integer identity on the bit patterns, min = a + b - max (exact: max returns one of its inputs),
-  // written as IMADs with a multiplier ptxas cannot fold (mul1 = 1, mulm1 = -1 come in through the kernel params).
-  __device__ __forceinline__ void piece(const uint32_t (&r)[16], int cbase, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
-    const float o1 = t1, o2 = t2;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) {
-      const uint32_t ku = (r[e] & tagmask) | static_cast<uint32_t>(15 - e);
-      const float n1 = fmaxf(t1, __uint_as_float(ku));
-      const uint32_t lo1 = __float_as_uint(n1) * mulm1 + (__float_as_uint(t1) * mul1 + ku);
-      const float n2 = fmaxf(t2, __uint_as_float(lo1));
-      const uint32_t lo2 = __float_as_uint(n2) * mulm1 + (__float_as_uint(t2) * mul1 + lo1);
-      t3 = fmaxf(t3, __uint_as_float(lo2));
-      t1 = n1;
-      t2 = n2;
-    }
-    // where did t1 / t2 come from?  Equal tagged scores in different pieces make this ambiguous, but then the
-    // equal score also sits in t2 or t3, the row has >= 3 candidates and is re-scanned exactly anyway.
-    const bool c1 = t1 != o1;
-    j2 = (t2 == o2) ? j2 : ((c1 && t2 == o1) ? j1 : cbase);
-    j1 = c1 ? cbase : j1;
-    thr = t1 - W;
-  }
-  static __device__ __forceinline__ int col(float t, int j) { return j + 15 - static_cast<int>(__float_as_uint(t) & 15u); }
-};
-
-struct MergeSlot { float t1, t2, t3, bexact; int i0, i1; };
-
 struct Ctrl {  // lives at the start of dynamic smem
   uint64_t a_full[MAX_A_SUB], a_empty[MAX_A_SUB];
   uint64_t a_read;                       // store warps finished reading A (row norms)
@@ -142,6 +101,8 @@ struct Ctrl {  // lives at the start of dynamic smem
   float xn2[2][BM];                      // row norms, double buffered by row-tile parity
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
   int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
+  float share[2][2][BM];                 // [row-tile parity][column half][row]: running maximum of each slice, read by the
+                                         // partner warp to raise its skip threshold (stale values are merely conservative)
 };
 static_assert(sizeof(Ctrl) <= SMEM_CTRL_BYTES, "control block too large");
 
@@ -218,6 +179,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_relinquish_2sm();
   }
   if (threadIdx.x < BM) {
+    ctrl->share[0][0][threadIdx.x] = -3.4e38f; ctrl->share[0][1][threadIdx.x] = -3.4e38f;
     // constant A-side bias operand: row r = [1 1 1 0 ... 0] (16 bf16 = two 16-byte chunks), 32-byte swizzle:
     // chunk j of row r lives at r*32 + ((j ^ ((r >> 2) & 1)) << 4)
     const int r = threadIdx.x;
@@ -409,7 +371,11 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float epi_loss = 0.f;
     for (int t = 0; t < my_tiles; ++t) {
       const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
-      RowState st;
+      RowState st;                 // exact tagged top-3, rebuilt once per row sweep from the live groups
+      ScanReg sc;                  // hot-loop state: running maximum + the live 16-column group, in registers (epilogue.cuh)
+      ScanQueue<16> sq;            // further live groups of a near tie (thread-local memory, rarely touched)
+      float* my_share = &ctrl->share[t & 1][half][row_in_tile];
+      const float* partner_share = &ctrl->share[t & 1][1 - half][row_in_tile];
 
       for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
         const uint32_t as = it & 1;
@@ -419,8 +385,20 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (ct == 0) {  // the store warps computed this tile's row norms while the first accumulator was being built
           { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->n_full[t & 1]), (t >> 1) & 1); w_nfull += PROF_CLOCK() - c0; }
           // band = 2 * (MMA error bound) + 2 * (tag perturbation: 16 ulp <= 2^-19 |score|, |score| <= |x||c| + |c|^2/2)
-          const float xc = sqrtf(ctrl->xn2[t & 1][row_in_tile]) * cmax;
-          st.init(2.f * p.margin_rel * xc + 0x1p-18f * (xc + (p.metric == VQB_METRIC_COSINE ? 0.f : 0.5f * cmax * cmax)) + 1e-30f);
+          // + (Euclid) the width over which the reference's own evaluation collapses distinct d^2 into one distance:
+          // d = sqrt(fl(fl(x2 + y2) - 2xy)) has ~d^2 * 2^-23 of resolution in d^2 (vqp:58-62); with a small-norm codebook
+          // (the default init) that exceeds the MMA band.  Rows inside it go to the exact re-score, which evaluates the
+          // reference formula including the sqrt.  In score units (d^2 / 2), with a 2x safety factor:
+          const float x2 = ctrl->xn2[t & 1][row_in_tile];
+          const float xc = sqrtf(x2) * cmax;
+          const bool euclid = p.metric != VQB_METRIC_COSINE;
+          sc.init(2.f * p.margin_rel * xc + 0x1p-18f * (xc + (euclid ? 0.5f * cmax * cmax : 0.f)) +
+                  (euclid ? 0x1p-22f * (x2 + cmax * cmax) : 0.f) + 1e-30f);
+          // the slot of the NEXT row tile (same parity as the previous one) was last read before the pair barrier of
+          // that tile's merge, which both warps of the pair have passed
+          ctrl->share[(t + 1) & 1][half][row_in_tile] = -3.4e38f;
+        } else {
+          sc.raise(*partner_share);
         }
         const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + as * 256;
         const int code0 = ct * p.BN;
@@ -429,23 +407,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         auto piece_col = [&](int j) { return (4 * (j >> 1) + 2 * half + (j & 1)) << 4; };
         const int np = np_warp;
         auto scan16 = [&](const uint32_t (&r)[16], int cbase) {
-          float m[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            m[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
-                         fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
-          const float mm = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
-          st.bexact = fmaxf(st.bexact, mm);
 #ifdef VQB_PROFILE
-          if (p.dbg_mode & 16) return;  // timing experiment: TMEM loads + max tree only
+          if (p.dbg_mode & 16) { sc.t1 = fmaxf(sc.t1, max16(r)); return; }  // timing experiment: TMEM loads + max tree only
 #endif
-          // 32 independent rows per warp: for K ~ 1e3 some lane has a candidate in most pieces, so what matters is
-          // that the update itself is straight-line min/max code (measured history in DESIGN.md section 8)
-#ifdef VQB_EPI_NOSKIP
-          st.piece(r, cbase, p.tagmask, p.mul1, p.mulm1);
-#else
-          if (mm > st.thr) st.piece(r, cbase, p.tagmask, p.mul1, p.mulm1);
-#endif
+          sc.scan16<true, true>(sq, r, cbase, p.mul1);
         };
         // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld has completed (the
         // final piece is scanned from registers afterwards): the release -> MMA -> t_full loop is the critical path.
@@ -485,9 +450,11 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             scan16(buf1, code0 + piece_col(j + 1));
           }
         }
+        *my_share = sc.t1;
         w_work += PROF_CLOCK() - cw0;
       }
       const long long cm0 = PROF_CLOCK();
+      sc.finish(sq, st, p.tagmask, p.mul1, p.mulm1);
 
       // ---- merge the two column slices of each row (upper half publishes, lower half finishes the row)
       MergeSlot* slot = &ctrl->merge[t & 1][row_in_tile];

@@ -301,13 +301,17 @@ __device__ __forceinline__ float lerp_f32(float a, float b, float w) {  // torch
 }
 
 // single CTA: cluster_size.lerp_ (vqp:616) and its sum (vqp:577); zero cmax for the atomicMax that follows
-__global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K, float w, int do_lerp, float* scratch,
-                                 float* cmax) {
+__global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K, float w, const float* __restrict__ code_weight,
+                                 int do_lerp, float* scratch, float* cmax) {
   __shared__ double part[32];
   double s = 0.0;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float c = cluster_size[k];
-    if (do_lerp) { c = lerp_f32(c, stats[k], w); cluster_size[k] = c; }
+    if (do_lerp) {  // (1 - decay) * weight, an fp32 product (vqp:86-97)
+      const float wk = code_weight ? __fmul_rn(w, code_weight[k]) : w;
+      c = lerp_f32(c, stats[k], wk);
+      cluster_size[k] = c;
+    }
     s += c;
   }
   s = warp_sum(s);
@@ -324,7 +328,8 @@ __global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K,
 // one warp per (padded) code: embed_avg.lerp_ (vqp:617); embed = embed_avg / smoothed (vqp:576-584);
 // refresh the tensor-core operands of that row.
 __global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* embed_avg, float* embed,
-                                const float* __restrict__ stats, int64_t soff, int K, int Kpad, int D, float w, float eps, float keps, int metric,
+                                const float* __restrict__ stats, int64_t soff, int K, int Kpad, int D, float w,
+                                const float* __restrict__ code_weight, float eps, float keps, int metric,
                                 int do_lerp, int do_normalise, const float* __restrict__ scratch, uint16_t* planes,
                                 uint16_t* bext, float* bias, float* cnorm2, float* cmax) {
   const int lane = threadIdx.x & 31;
@@ -337,6 +342,7 @@ __global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* e
   float* avg = embed_avg + static_cast<int64_t>(k) * D;
   float* emb = embed + static_cast<int64_t>(k) * D;
   if (do_lerp) {
+    if (code_weight) w = __fmul_rn(w, code_weight[k]);
     const float* es = stats + soff + static_cast<int64_t>(k) * D;
     for (int i = lane * 4; i < D; i += 128) {
       float4 a = *reinterpret_cast<float4*>(avg + i);
@@ -444,6 +450,14 @@ extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, con
 extern "C" int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
                              double decay, double eps, int metric, int do_lerp, int do_normalise, void* planes,
                              void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream) {
+  return vqb_ema_apply_weighted(cluster_size, embed_avg, embed, stats, K, D, decay, eps, metric, do_lerp, do_normalise,
+                                nullptr, planes, bext, bias, cnorm2, cmax, scratch, stream);
+}
+
+extern "C" int vqb_ema_apply_weighted(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+                                      double decay, double eps, int metric, int do_lerp, int do_normalise,
+                                      const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2,
+                                      float* cmax, float* scratch, void* stream) {
   if (!cluster_size || !embed_avg || !embed || !scratch || K <= 0 || D <= 0) return VQB_E_INVALID;
   if (do_lerp && !stats) return VQB_E_INVALID;
   if (do_normalise && (!planes || !bext || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
@@ -456,10 +470,10 @@ extern "C" int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed
   const float w = static_cast<float>(1.0 - decay);  // (1. - decay) evaluated in python float, then fp32 (vqp:97)
   const float epsf = static_cast<float>(eps);
   const float keps = static_cast<float>(static_cast<double>(K) * eps);  // n_categories * eps in python float (vqp:154)
-  ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, w, do_lerp, scratch, do_normalise ? cmax : nullptr);
+  ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, w, code_weight, do_lerp, scratch, do_normalise ? cmax : nullptr);
   const int Kpad = vqb_padded_codes(K);
   const int wpb = 8;
-  ema_rows_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(cluster_size, embed_avg, embed, stats, soff, K, Kpad, D, w, epsf, keps,
+  ema_rows_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(cluster_size, embed_avg, embed, stats, soff, K, Kpad, D, w, code_weight, epsf, keps,
                                                             metric, do_lerp, do_normalise, scratch,
                                                             static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
   return static_cast<int>(cudaGetLastError());

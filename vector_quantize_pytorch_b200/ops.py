@@ -171,7 +171,8 @@ _WS_CACHE: dict = {}
 
 
 def _workspace(key, nbytes: int, device) -> torch.Tensor:
-    """Scratch buffers are reused across calls (same stream => ordered); keyed by shape/device."""
+    """Scratch buffers are reused across calls (same stream => ordered).  Keyed by owner / device only and grown on
+    demand: a masked batch that compacts to a different N every call must not pin a new buffer per N."""
     buf = _WS_CACHE.get(key)
     if buf is None or buf.numel() < nbytes or buf.device != device:
         buf = torch.empty((max(nbytes, 256),), dtype=torch.uint8, device=device)
@@ -195,11 +196,11 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
     dev = x.device
     cs, ea, emb = state
     # internal scratch lives in reusable buffers: stable pointers keep the CUDA-graph cache of vqb_vq_forward hot
-    idx32 = _workspace(("idx32", ws_key, N, dev.index), 4 * N, dev).view(torch.int32)[:N]
+    idx32 = _workspace(("idx32", ws_key, dev.index), 4 * N, dev)[:4 * N].view(torch.int32)
     if update and stats is None:
         stats = torch.empty((stats_floats(K, D),), dtype=torch.float32, device=dev)
     nbytes = lib.vqb_vq_forward_workspace(N, D, K, dt, int(ops.cosine), int(update))
-    ws = _workspace((ws_key, N, D, K, dt, dev.index), nbytes, dev)
+    ws = _workspace(("fwd", ws_key, dev.index), nbytes, dev)
     a = _C.VQForwardArgs(
         x=_p(x), dtype=dt, metric=int(ops.cosine), N=N, D=D, K=K, already_normalised=int(already_normalised),
         cluster_size=_p(cs), embed_avg=_p(ea), embed=_p(emb), planes=_p(ops.planes), bext=_p(ops.bext), bias=_p(ops.bias),
@@ -207,7 +208,7 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
         idx_stride=int(idx_stride), loss_out=_p(loss_out), loss_weight=float(loss_weight), resid_out=_p(resid_out),
         qsum=_p(qsum), idx32=_p(idx32), update=int(update), stats_mode=STATS_MODE, stats_accumulate=int(stats_accumulate), do_normalise=int(do_normalise), decay=float(decay),
         eps=float(eps), stats=_p(stats), margin_rel=float(DEFAULT_MARGIN if margin is None else margin),
-        workspace=_p(ws), workspace_bytes=ws.numel(), ev_search_begin=None, ev_search_end=None)
+        workspace=_p(ws), workspace_bytes=nbytes, ev_search_begin=None, ev_search_end=None)
     with torch.cuda.device(dev):
         prof = PROFILE_EVENTS
         if prof is not None:  # bench instrumentation: CUDA events around the search kernel, recorded from C
@@ -266,14 +267,19 @@ def ema_stats(x_eff: torch.Tensor, idx: torch.Tensor, K: int, out: torch.Tensor 
 
 
 def ema_apply(cluster_size: torch.Tensor, embed_avg: torch.Tensor, embed: torch.Tensor, stats: torch.Tensor | None,
-              ops: CodebookOperands, *, decay: float, eps: float, do_lerp: bool, do_normalise: bool) -> None:
-    """lerp_ of cluster_size / embed_avg (vqp:616-617) and update_ema (vqp:576-584); refreshes `ops`."""
-    _require_cuda(cluster_size, embed_avg, embed)
+              ops: CodebookOperands, *, decay: float, eps: float, do_lerp: bool, do_normalise: bool,
+              code_weight: torch.Tensor | None = None) -> None:
+    """lerp_ of cluster_size / embed_avg (vqp:616-617) and update_ema (vqp:576-584); refreshes `ops`.
+    code_weight (K,) fp32: the reference's per-code `ema_update_weight` (vqp:86-97)."""
+    _require_cuda(cluster_size, embed_avg, embed, code_weight)
     K, D = embed.shape
+    if code_weight is not None:
+        assert code_weight.dtype == torch.float32 and code_weight.is_contiguous() and code_weight.numel() == K
     with torch.cuda.device(embed.device):
-        check(lib.vqb_ema_apply(_p(cluster_size), _p(embed_avg), _p(embed), _p(stats), K, D, float(decay), float(eps),
-                                int(ops.cosine), int(do_lerp), int(do_normalise), _p(ops.planes), _p(ops.bext), _p(ops.bias),
-                                _p(ops.cnorm2), _p(ops.cmax), _p(ops.scratch), _stream()), "vqb_ema_apply")
+        check(lib.vqb_ema_apply_weighted(_p(cluster_size), _p(embed_avg), _p(embed), _p(stats), K, D, float(decay), float(eps),
+                                         int(ops.cosine), int(do_lerp), int(do_normalise), _p(code_weight), _p(ops.planes),
+                                         _p(ops.bext), _p(ops.bias), _p(ops.cnorm2), _p(ops.cmax), _p(ops.scratch), _stream()),
+              "vqb_ema_apply")
     _count(2)
 
 

@@ -130,11 +130,11 @@ class ResidualVQ(nn.Module):
             _unsupported("beam search")
         if not x.is_cuda:
             raise RuntimeError("vqb200 has no CPU path: inputs must live on a CUDA (B200, sm_100) device")
-        if x.requires_grad and torch.is_grad_enabled():
-            # gradients need the per-stage straight-through/rotation glue of VectorQuantize: take the layered path
-            return self._forward_layered(x, freeze_codebook, return_all_codes)
-
         x = self.project_in(x)
+        if x.requires_grad and torch.is_grad_enabled():
+            # gradients (to the input or to project_in, rvq:406) need the per-stage straight-through / rotation glue of
+            # VectorQuantize: take the layered path
+            return self._forward_layered(x, freeze_codebook, return_all_codes)
         shape, dtype = x.shape, x.dtype
         if dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"vqb200 supports float32 and bfloat16 inputs, got {dtype}")
@@ -154,29 +154,37 @@ class ResidualVQ(nn.Module):
         if not training:
             loss_buf.zero_()
         losses = loss_buf
-        bufs = [torch.empty_like(flat), torch.empty_like(flat)]
+        # dead-code expiry samples from the stage inputs after the (deferred) EMA update: keep them all then
+        keep_inputs = training and not freeze_codebook and any(b.has_dead_code_replacement for b in books)
+        bufs = [torch.empty_like(flat) for _ in range(Q - 1 if keep_inputs else min(2, Q - 1))]
         residual = flat  # rvq:411 (never written: stage 0 reads the caller's tensor)
+        stage_inputs = []
 
         do_update = [training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
-        stat_sizes = [ops.stats_floats(b.codebook_size, D) if u else 0 for b, u in zip(books, do_update)]
+        # A shared codebook that replaces dead codes is modified BETWEEN stages by the reference (every layer's
+        # update_codebook ends with expire_codes_, vqp:641, on the one aliased Codebook): such stages cannot be deferred.
+        inline = [u and self.shared_codebook and b.has_dead_code_replacement for b, u in zip(books, do_update)]
+        stat_sizes = [ops.stats_floats(b.codebook_size, D) if (u and not i) else 0 for b, u, i in zip(books, do_update, inline)]
         packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
         offs = [sum(stat_sizes[:i]) for i in range(Q)]
 
         for q, book in enumerate(books):  # rvq:469
-            nxt = bufs[q & 1]
+            nxt = (bufs[q] if keep_inputs else bufs[q & 1]) if q + 1 < Q else None
+            if keep_inputs:
+                stage_inputs.append(residual)
             want_loss = training and self.layers[q].has_commitment_loss
             book.quantize_rows(
                 residual, update=do_update[q], idx64_out=all_idx[:, q], idx_stride=Q,
                 loss_out=losses[q:q + 1] if want_loss else None, loss_weight=self.layers[q].commitment_weight,
-                resid_out=nxt if q + 1 < Q else None, qsum=quantized_out,
-                stats_out=packed[offs[q]:offs[q] + stat_sizes[q]] if do_update[q] else None, defer_ema=True)
+                resid_out=nxt, qsum=quantized_out,
+                stats_out=packed[offs[q]:offs[q] + stat_sizes[q]] if stat_sizes[q] else None, defer_ema=not inline[q])
             residual = nxt
 
-        if packed is not None:
+        if packed is not None or any(inline):
             if _stats_sink is not None:  # GroupedResidualVQ gathers every group's statistics into one collective
-                _stats_sink.append((self, packed, offs, stat_sizes, do_update, flat))
+                _stats_sink.append((self, packed, offs, stat_sizes, do_update, (stage_inputs, shape)))
             else:
-                self._finish_update(packed, offs, stat_sizes, do_update, flat, synced=False)
+                self._finish_update(packed, offs, stat_sizes, do_update, (stage_inputs, shape), synced=False)
 
         quantized_out = self.project_out(quantized_out.reshape(shape))  # rvq:610
         ret = (quantized_out, all_idx.reshape(*shape[:-1], Q), losses.clone())
@@ -184,27 +192,37 @@ class ResidualVQ(nn.Module):
             ret = (*ret, self.get_codes_from_indices(ret[1]))
         return ret
 
-    def _finish_update(self, packed, offs, stat_sizes, do_update, flat, synced):
+    def _finish_update(self, packed, offs, stat_sizes, do_update, stage_inputs, synced):
         """ONE all-reduce for all stages (reference: 2 per stage, vqp:603/:607), then the per-stage lerps in
-        order (vqp:616-617) and update_ema — once at the end for a shared codebook (rvq:593-597)."""
+        order (vqp:616-617) and update_ema — once at the end for a shared codebook (rvq:593-597) — and the dead-code
+        expiry: per stage from that stage's input (vqp:641), for a shared codebook once over all residuals (rvq:599-601).
+        stage_inputs: (the Q stage inputs (N, D) — kept only when some codebook replaces dead codes —, input shape)."""
+        stage_inputs, shape = stage_inputs
         books = self._stage_plan()
-        if not synced and any(b.use_ddp for b in books):
+        if not synced and packed is not None and any(b.use_ddp for b in books):
             allreduce_packed(packed)
         for q, book in enumerate(books):
-            if not do_update[q]:
+            if not do_update[q] or not stat_sizes[q]:   # nothing to do, or already applied inline
                 continue
             stats = packed[offs[q]:offs[q] + stat_sizes[q]]
             book.lerp_stats(stats, normalise=book.ema_update and not book.manual_ema_update)
+            if not self.shared_codebook and book.has_dead_code_replacement:
+                book.expire_codes_(book.transform_input(stage_inputs[q]).float())  # vqp:641 on the fp32 `flatten`
         if self.training and self.shared_codebook:
             shared = books[0]
             if self.vq_is_ema_updating and any(do_update):
                 shared.update_ema()
-            if shared.has_dead_code_replacement:
-                _unsupported("dead-code expiry over all residuals of a shared codebook")
+            if shared.has_dead_code_replacement and any(do_update):
+                # rvq:599-601 -> vqp:1051-1054 -> :573-574: the reference hands '(b) (n l) d' to Codebook.expire_codes_, whose
+                # 'h ... d -> h (...) d' reads the batch axis as the codebook axis, and `replace` zips it with the (1, K)
+                # mask: only batch element 0's rows (n-major, stage-minor) are sampled from.  Reproduced as is.
+                n0 = stage_inputs[0].shape[0] // shape[0] if len(shape) > 2 else stage_inputs[0].shape[0]
+                rows = torch.stack([r[:n0] for r in stage_inputs], dim=1).reshape(-1, stage_inputs[0].shape[-1])
+                shared.expire_codes_(shared.transform_input(rows))
 
     def _forward_layered(self, x, freeze_codebook, return_all_codes):
-        """Differentiable path: the reference's Python loop (rvq:469-568) over our VectorQuantize layers."""
-        x = self.project_in(x)
+        """Differentiable path: the reference's Python loop (rvq:469-568) over our VectorQuantize layers.
+        `x` is already projected (rvq:406)."""
         quantized_out = torch.zeros_like(x)
         residual = x
         all_idx, all_losses = [], []
@@ -267,13 +285,13 @@ class GroupedResidualVQ(nn.Module):
                 flat_all = torch.cat([p for _, p, *_ in sink])
                 allreduce_packed(flat_all)
                 pos = 0
-                for rvq, packed, offs, sizes, upd, flat in sink:
+                for rvq, packed, offs, sizes, upd, inputs in sink:
                     n = packed.numel()
-                    rvq._finish_update(flat_all[pos:pos + n], offs, sizes, upd, flat, synced=True)
+                    rvq._finish_update(flat_all[pos:pos + n], offs, sizes, upd, inputs, synced=True)
                     pos += n
             else:
-                for rvq, packed, offs, sizes, upd, flat in sink:
-                    rvq._finish_update(packed, offs, sizes, upd, flat, synced=True)
+                for rvq, packed, offs, sizes, upd, inputs in sink:
+                    rvq._finish_update(packed, offs, sizes, upd, inputs, synced=True)
         quantized = torch.cat([o[0] for o in outs], dim=-1)  # rvq:719-721
         all_indices = torch.stack([o[1] for o in outs])
         commit_losses = torch.stack([o[2] for o in outs])

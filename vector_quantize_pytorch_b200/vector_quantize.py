@@ -257,7 +257,9 @@ class VectorQuantize(nn.Module):
         kernels of chunk i and download of chunk i-1 overlap, so the call costs ~max(H2D, D2H) over PCIe instead
         of H2D + kernels + D2H.  Same arithmetic as forward(): every chunk searches the pre-update codebook, the
         chunks' EMA statistics are summed and the codebook is updated once at the end (vqp:586-617).
-        `out` = optional (quantize, indices, loss) host tensors to fill (pinned for full overlap)."""
+        `out` = optional (quantize, indices, loss) host tensors to fill (pinned for full overlap).
+        The device->host copies are ASYNCHRONOUS on an internal stream that the current stream waits for: synchronise
+        the current stream (or the device) before reading the returned host tensors."""
         if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last:
             _unsupported("forward_host with projections / feature-map layouts")
         cbk = self._codebook
@@ -326,6 +328,8 @@ class VectorQuantize(nn.Module):
         if do_update:
             cbk.sync_stats(st["stats"])
             cbk.lerp_stats(st["stats"], normalise=cbk.ema_update and not cbk.manual_ema_update)
+            if cbk.has_dead_code_replacement:   # vqp:641, over the whole batch (resident in st["x"])
+                cbk.expire_codes_(cbk.transform_input(st["x"]).float())
         if want_loss:
             w = torch.tensor(weights, dtype=torch.float32, device=dev)
             loss = (st["loss"][:n_chunks] * w).sum()
@@ -368,7 +372,7 @@ class VectorQuantize(nn.Module):
             fused = training and self.has_commitment_loss and not self.use_cosine_sim
             commit = torch.empty((), dtype=torch.float32, device=x.device) if fused else None
             cbk.quantize_rows(xc, update=do_update, q_out=qc, idx64_out=ic, loss_out=commit,
-                              loss_weight=self.commitment_weight)
+                              loss_weight=self.commitment_weight, ema_update=ema_update)
             quantize[rows] = qc
             embed_ind[rows] = ic
             if training and self.has_commitment_loss:
@@ -395,12 +399,11 @@ class VectorQuantize(nn.Module):
             mask = torch.arange(x.shape[1], device=lens.device) < lens[:, None]
         if mask is not None:
             return self._forward_masked(x, mask, freeze_codebook, ema_update, return_loss_breakdown)
-        if topk is not None or codebook_transform_fn is not None or ema_update_weight is not None or accum_ema_update:
-            _unsupported("topk / codebook_transform_fn / ema_update_weight / accum_ema_update")
+        if topk is not None or codebook_transform_fn is not None:
+            _unsupported("topk / codebook_transform_fn")
         if not x.is_cuda:
             raise RuntimeError("vqb200 has no CPU path: inputs must live on a CUDA (B200, sm_100) device")
 
-        input_requires_grad = x.requires_grad and torch.is_grad_enabled()
         freeze_codebook = self.freeze_codebook if freeze_codebook is None else freeze_codebook
         ema_update = self._codebook.ema_update if ema_update is None else ema_update
 
@@ -409,6 +412,9 @@ class VectorQuantize(nn.Module):
             x = x.unsqueeze(1)
         x, restore = self._to_rows_layout(x)
         x = self.project_in(x)  # vqp:1151
+        # decided AFTER project_in: with a projection the commitment loss must stay differentiable w.r.t. its weights
+        # even when the raw input carries no grad (vqp:1151, :1327)
+        input_requires_grad = x.requires_grad and torch.is_grad_enabled()
         shape, dtype = x.shape, x.dtype
         if dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"vqb200 supports float32 and bfloat16 inputs, got {dtype}")
@@ -425,16 +431,22 @@ class VectorQuantize(nn.Module):
         # the kernel returns weight * mse already rounded like F.mse_loss in x.dtype (vqp:1327-1329)
         # the loss lands in a persistent scalar (stable pointer for the graph cache) and is cloned out
         loss_buf = self._loss_scratch(flat.device) if fused_loss else None
+        # LossBreakdown.commitment is the UNweighted mse (vqp:1327-1329): ask the kernel for weight 1 then
+        split_weight = fused_loss and return_loss_breakdown and self.commitment_weight != 1.
         cbk.quantize_rows(flat, update=do_update, q_out=q, idx64_out=idx64, loss_out=loss_buf,
-                          loss_weight=self.commitment_weight)
+                          loss_weight=1. if split_weight else self.commitment_weight, ema_update=ema_update,
+                          ema_update_weight=ema_update_weight, accum_ema_update=accum_ema_update)
         commit_loss = loss_buf.clone().reshape(()) if fused_loss else self.zero
+        weighted = commit_loss
+        if split_weight:  # commit_loss * weight in the input dtype, promoted by the fp32 accumulator (vqp:1329, :1282)
+            weighted = (commit_loss.to(dtype) * self.commitment_weight).float()
 
         quantize = q.reshape(shape)
         embed_ind = idx64.reshape(shape[:-1])
 
         if training and fused_loss:
             # vqp:1282: `loss` is a fresh fp32 scalar that requires grad in training mode
-            loss = commit_loss.requires_grad_(torch.is_grad_enabled())
+            loss = weighted.requires_grad_(torch.is_grad_enabled())
         else:
             loss = torch.tensor(0., device=flat.device, requires_grad=training and torch.is_grad_enabled())  # vqp:1282
         if training:
