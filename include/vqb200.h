@@ -102,7 +102,8 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
  *   idx       i32 [N]            winner of the tensor-core pass (final for unflagged rows)
  *   flagged   [N] entries, flag_count i32[1] (caller zeroes it)  -> vqb_fix_flagged
  *   dbg_best  f32 [N] or NULL    best score per row (tests)
- * Supported: D % 8 == 0, 8 <= D, n_a * ceil(D/64) <= 8, 1 <= K, N >= 1, sm_100 device. */
+ * Supported: D % 8 == 0, 8 <= D <= 1024, 1 <= K, N >= 1, sm_100 device.  When n_a * ceil(D/64) > 8 (fp32 split input with
+ * D > 256) the A tile does not stay resident in shared memory: its k-blocks are streamed with the codebook's. */
 int vqb_assign(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, vqb_flag_entry* flagged,
                int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused /* NULL: search only */, void* stream);
@@ -169,6 +170,24 @@ int vqb_ema_apply_weighted(float* cluster_size, float* embed_avg, float* embed, 
                            double decay, double eps, int metric, int do_lerp, int do_normalise, const float* code_weight,
                            void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream);
 
+/* ---- multi-GPU: the all-reduce of the statistics (:603, :607) fused into the EMA kernels over NVLink peer memory ----
+ * Every rank keeps its packed statistics in SYMMETRIC memory (one allocation mapped into every peer's address space;
+ * the Python glue obtains the peer pointers from torch.distributed._symmetric_memory).  After vqb_peer_barrier the EMA
+ * kernels read all `world` copies with peer loads and add them in rank order 0..world-1 — identical fp32 additions on
+ * every rank, so the replicas stay bit-identical.  Both calls only enqueue kernels (graph-capturable).
+ *
+ * vqb_peer_barrier: cross-GPU barrier.  peer_flags_host[r] = rank r's flag array u32[world] (symmetric memory, zeroed
+ *   once), host array of `world` device pointers; epoch_dev u32[1] device memory owned by this rank (zeroed once).
+ *   Everything this rank wrote before the barrier is visible to every peer's reads after it (release / acquire, system
+ *   scope).  The caller double-buffers the statistics by step parity (a buffer may be rewritten two barriers later). */
+int vqb_peer_barrier(void* const* peer_flags_host, int rank, int world, uint32_t* epoch_dev, void* stream);
+/* vqb_ema_apply_weighted with `stats` replaced by the sum over ranks of peer_stats_host[r][slice_offset ...]
+ * (host array of `world` device pointers to the ranks' packed buffers; slice_offset in floats, multiple of 4). */
+int vqb_ema_apply_peers(float* cluster_size, float* embed_avg, float* embed, const void* const* peer_stats_host, int world,
+                        int64_t slice_offset, int K, int D, double decay, double eps, int metric, int do_normalise,
+                        const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2, float* cmax,
+                        float* scratch, void* stream);
+
 /* One-call composite of VectorQuantize.forward's arithmetic (or one ResidualVQ stage): input staging ->
  * vqb_assign (+ fused tail) -> vqb_fix_flagged -> vqb_loss_finalize -> vqb_ema_stats -> vqb_ema_apply, all
  * enqueued from C++ (the Python glue pays one FFI call instead of ~20).  Replaces vqp:1159-1178 + :674-791.
@@ -189,7 +208,8 @@ typedef struct vqb_vq_forward_args {
   float* loss_out; float loss_weight;       /* f32[1] = weight * mse (NULL to skip)                            */
   void* resid_out; void* qsum;              /* ResidualVQ recurrence (NULL to skip)                            */
   int32_t* idx32;           /* [N] int32 indices (always written; input of the statistics)                     */
-  int update;               /* 0: none; 1: statistics only (caller all-reduces, then vqb_ema_apply); 2: + apply */
+  int update;               /* 0: none; 1: statistics only (caller all-reduces, then vqb_ema_apply); 2: + apply;
+                               3: + peer barrier + apply over every rank's statistics (see peer_* below)             */
   int stats_mode;           /* 0: statistics accumulated by the search kernel's store warps (vector RED into L2);
                                1: separate counting-sort + segmented-sum kernels (vqb_ema_stats)                 */
   int stats_accumulate;     /* stats_mode 0: do not zero `stats` first (chunked batches sum their statistics)   */
@@ -199,6 +219,10 @@ typedef struct vqb_vq_forward_args {
   float margin_rel;
   void* workspace; size_t workspace_bytes;  /* >= vqb_vq_forward_workspace(...), 256-byte aligned              */
   void* ev_search_begin; void* ev_search_end; /* optional cudaEvent_t recorded around the search kernel (profiling) */
+  /* update == 3: statistics into `stats` (this rank's symmetric buffer slice) -> vqb_peer_barrier -> vqb_ema_apply_peers:
+   * the whole multi-GPU step is one chain / one CUDA graph.  Unused (NULL / 0) otherwise. */
+  const void* const* peer_stats; void* const* peer_flags; uint32_t* peer_epoch; int peer_rank, peer_world;
+  int64_t peer_slice_offset;
 } vqb_vq_forward_args;
 size_t vqb_vq_forward_workspace(int64_t N, int D, int K, int dtype, int metric, int update);
 int vqb_vq_forward(const vqb_vq_forward_args* args, void* stream);
@@ -208,6 +232,13 @@ int vqb_vq_forward(const vqb_vq_forward_args* args, void* stream);
  * (pass the same pointer stride 0 for a shared codebook via `embed_stride` in elements). */
 int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
                void* out, int dtype, void* stream);
+
+/* ResidualVQ's running sum rebuilt from the stage indices in one pass:
+ *   out = (((q_0) + q_1) + ... + q_{Q-1}),  q_j = embed_j[idx[row, j]].type(dtype), every partial sum rounded to dtype
+ * exactly like `quantized_out = quantized_out + quantized` (residual_vq.py:525, vector_quantize_pytorch.py:1178).
+ * idx i64 [N][Q] (no -1 entries), embeds as for vqb_decode.  Replaces Q read-modify-write passes over (N x D). */
+int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
+                       void* out, int dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,8 @@
+#!/bin/bash
+# round-2 GPU job: full GPU test suite, a bench line, the per-role cycle accounting.   usage: r2_job.sh <tag> [pytest args]
+TAG=${1:-x}; shift
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q "$@" > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
+grep -E "passed|failed|rc=|^FAILED|^ERROR" gpurun_out/pytest_gpu_$TAG.log | tail -30
+timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; tail -3 gpurun_out/bench_$TAG.err; python scripts/show_bench.py gpurun_out/bench_$TAG.json 2>/dev/null || cat gpurun_out/bench_$TAG.json
+bash scripts/roles_job.sh 2,0 > gpurun_out/roles_$TAG.txt 2>&1; cat gpurun_out/roles_$TAG.txt

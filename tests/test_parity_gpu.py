@@ -107,6 +107,10 @@ SEARCH_CASES = [
     (1500, 192, 700, "fp32", True),
     (1024, 512, 4096, "bf16", True),    # config-4 shape family
     (1, 64, 17, "fp32", False),         # single row
+    (1024, 512, 4096, "fp32", True),    # config 4 in fp32: A planes streamed through the ring (n_a * ceil(D/64) > 8)
+    (700, 384, 600, "fp32", False),     # streamed A, ragged K
+    (515, 1024, 300, "bf16", False),    # maximum D (16 k-blocks, streamed)
+    (333, 520, 96, "fp32", False),      # streamed A with a ragged last k-block (D % 64 != 0)
 ]
 
 
@@ -444,19 +448,20 @@ def test_config3_full_size_properties():
     assert not ((got0 != ref0) & ~tie).any()
 
 
-def test_config4_full_size_properties():
-    """cosine dim=512 K=16384, x=(16,4096,512) bf16."""
+@pytest.mark.parametrize("dt", ["bf16", "fp32"])
+def test_config4_full_size_properties(dt):
+    """cosine dim=512 K=16384, x=(16,4096,512), bf16 and fp32 (fp32 at D=512: the A planes are streamed, vq_assign.cu)."""
     m = vqb()
     torch.manual_seed(1234)
     vq = m.VectorQuantize(dim=512, codebook_size=16384, use_cosine_sim=True).to(DEV)
     _warm_codebook(vq, 512, 16384, cosine=True)
     pre = vq._codebook.embed[0].clone()
-    x = torch.randn(16, 4096, 512, device=DEV).bfloat16()
+    x = torch.randn(16, 4096, 512, device=DEV).to(TDT[dt])
     q, ind, loss = vq(x)
     torch.cuda.synchronize()
-    assert torch.equal(q, pre[ind].bfloat16())
+    assert torch.equal(q, pre[ind].to(TDT[dt]))
     sel = torch.randperm(16 * 4096, device=DEV)[:1024]
-    xs = O.l2norm(x.reshape(-1, 512)[sel].float().cpu().numpy(), "bf16")
+    xs = O.l2norm(x.reshape(-1, 512)[sel].float().cpu().numpy(), dt)
     ref = O.argmax_first(O.scores(xs, pre.cpu().numpy(), True))
     tie = near_tie_rows(xs, pre.cpu().numpy(), True)
     got = ind.reshape(-1)[sel].cpu().numpy()

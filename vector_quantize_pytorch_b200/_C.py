@@ -29,7 +29,9 @@ class VQForwardArgs(ctypes.Structure):
                 ("q_out", _vp), ("idx64_out", _vp), ("idx_stride", _i64), ("loss_out", _vp), ("loss_weight", _f32),
                 ("resid_out", _vp), ("qsum", _vp), ("idx32", _vp), ("update", _i32), ("stats_mode", _i32), ("stats_accumulate", _i32), ("do_normalise", _i32),
                 ("decay", _f64), ("eps", _f64), ("stats", _vp), ("margin_rel", _f32), ("workspace", _vp),
-                ("workspace_bytes", _sz), ("ev_search_begin", _vp), ("ev_search_end", _vp)]
+                ("workspace_bytes", _sz), ("ev_search_begin", _vp), ("ev_search_end", _vp),
+                ("peer_stats", _vp), ("peer_flags", _vp), ("peer_epoch", _vp), ("peer_rank", _i32), ("peer_world", _i32),
+                ("peer_slice_offset", _i64)]
 
 
 SIGNATURES = {
@@ -48,6 +50,8 @@ SIGNATURES = {
     "vqb_ema_stats_workspace": (_sz, [_i64, _i32]),
     "vqb_ema_stats": (_i32, [_vp, _i32, _i64, _i32, _vp, _i32, _vp, _vp, _sz, _vp]),
     "vqb_ema_apply": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vqb_peer_barrier": (_i32, [_vp, _i32, _i32, _vp, _vp]),
+    "vqb_ema_apply_peers": (_i32, [_vp, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _f64, _f64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqb_ema_apply_weighted": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _f64, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "vqb_vq_forward_workspace": (_sz, [_i64, _i32, _i32, _i32, _i32, _i32]),
     "vqb_vq_forward": (_i32, [_vp, _vp]),
@@ -56,6 +60,7 @@ SIGNATURES = {
     "vqb_debug_active": (_i32, []),
     "vqb_debug_graph_stats": (_i32, [_vp]),
     "vqb_decode": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
+    "vqb_rvq_accumulate": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
 }
 
 

@@ -11,8 +11,8 @@ import sys
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "libvqb200.so")
-SOURCES = ["vq_assign.cu", "vq_aux.cu", "vq_ema.cu", "vq_forward.cu"]
-HEADERS = ["ptx.cuh", "vqb_common.cuh", "code_operands.cuh", "gather_row.cuh", os.path.join("..", "..", "include", "vqb200.h")]
+SOURCES = ["vq_assign.cu", "vq_aux.cu", "vq_ema.cu", "vq_forward.cu", "vq_peer.cu"]
+HEADERS = ["ptx.cuh", "vqb_common.cuh", "code_operands.cuh", "gather_row.cuh", "epilogue.cuh", os.path.join("..", "..", "include", "vqb200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import ops
-from .dist import allreduce_packed
+from .dist import allreduce_packed, PeerReducer
 
 
 def _uniform_init(*shape):
@@ -96,6 +96,8 @@ class Codebook(nn.Module):
 
         self._operands: ops.CodebookOperands | None = None
         self._operands_key = None
+        self._peer = None          # dist.PeerReducer of this codebook's packed statistics (use_ddp, created on first use)
+        self._peer_tried = False
 
     # ------------------------------------------------------------------ operand cache
     def _state2d(self):
@@ -124,6 +126,23 @@ class Codebook(nn.Module):
     # ------------------------------------------------------------------ reference surface
     def transform_input(self, t):  # vqp:376
         return F.normalize(t, p=2, dim=-1, eps=1e-6) if self.use_cosine_sim else t
+
+    def peer_reducer(self):
+        """Symmetric-memory statistics buffers for the fused multi-GPU EMA (csrc/vq_peer.cu); None -> NCCL all-reduce.
+        Created on the first training forward (a collective rendezvous: every rank gets here in the same call)."""
+        if not self._peer_tried:
+            self._peer_tried = True
+            if self.use_ddp and self.embed.is_cuda:
+                self._peer = PeerReducer.create(ops.stats_floats(self.codebook_size, self.dim), self.embed.device)
+        return self._peer
+
+    def lerp_stats_peers(self, peer, peer_ptrs, slice_offset: int, normalise: bool):
+        """`lerp_stats` with the sum over ranks taken inside the EMA kernels (call `peer.barrier()` first)."""
+        cs, ea, emb = self._state2d()
+        cb = self.operands()
+        ops.ema_apply_peers(cs, ea, emb, peer, peer_ptrs, slice_offset, cb, decay=self.decay, eps=self.eps, do_normalise=normalise)
+        if normalise:
+            self._mark_operands_fresh()
 
     def sync_stats(self, stats: torch.Tensor) -> torch.Tensor:
         """The reference all-reduces cluster_size and embed_sum separately (vqp:603, :607); the packed
@@ -263,11 +282,18 @@ class Codebook(nn.Module):
         apply_here = update and not defer_ema and not self.use_ddp and not custom
         mode = 0 if not update else (2 if apply_here else 1)
         normalise = ema_update and not self.manual_ema_update
+        peer = peer_ptrs = None
+        if update and not defer_ema and self.use_ddp and not custom and stats_out is None:
+            peer = self.peer_reducer()
+            if peer is not None:   # multi-GPU step in ONE chain: statistics -> peer barrier -> reduce + EMA (vq_peer.cu)
+                mode = 3
+                stats_out, peer_ptrs = peer.next_buffer()
         idx32, stats = ops.vq_forward(
             x, cb, self._state2d(), update=mode, do_normalise=normalise, decay=self.decay, eps=self.eps, q_out=q_out,
             idx64_out=idx64_out, idx_stride=idx_stride, loss_out=loss_out, loss_weight=loss_weight, resid_out=resid_out,
-            qsum=qsum, stats=stats_out, margin=margin, ws_key=id(self), stats_accumulate=stats_accumulate)
-        if mode == 2 and normalise:
+            qsum=qsum, stats=stats_out, margin=margin, ws_key=id(self), stats_accumulate=stats_accumulate,
+            peer=peer, peer_ptrs=peer_ptrs)
+        if mode >= 2 and normalise:
             self._mark_operands_fresh()
         if update and not defer_ema:
             applied = True

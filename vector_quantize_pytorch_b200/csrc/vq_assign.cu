@@ -69,6 +69,9 @@ struct AssignParams {
   int n_a, n_passes;   // passes: 0:(a0,hi) 1:(a0,lo) 2:(a1,hi)
   int KB;              // ceil(D / 64)
   int n_stages, n_xstages;
+  int stream_a;        // A does not fit in smem next to a useful B ring (fp32 split input with D > 256): its k-blocks travel
+                       // through the ring together with the codebook k-blocks (re-read from L2 for every code tile)
+  const uint16_t* a_global;   // [n_a][N][D] bf16: the A planes in global memory (row norms in stream_a mode)
   int num_row_tiles, num_code_tiles;
   float margin_rel;
   const float* cmax;   // [1]
@@ -137,12 +140,15 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = (smem_base + SMEM_CTRL_BYTES + 1023u) & ~1023u;    // swizzled tiles need 1024 B alignment
   const uint8_t* a_gen = smem + (a_base - smem_base);                         // same place, generic address
-  const int n_sub = p.n_a * p.KB;
+  const int n_sub = p.stream_a ? 0 : p.n_a * p.KB;                            // stationary A sub-tiles
   const uint32_t aext_base = a_base + n_sub * A_SUB_BYTES;                    // 4 KiB
   const uint32_t b_stage_bytes = (p.BN / 2) * BK * 2;   // this CTA's half of a codebook tile
   const uint32_t x_stage_bytes = (p.BN / 2) * 32;
   const uint32_t xb_base = aext_base + AEXT_BYTES;                            // n_xstages * BN*32
   const uint32_t b_base = (xb_base + p.n_xstages * x_stage_bytes + 1023u) & ~1023u;
+  // ring stage = [A k-block (stream_a only) | this CTA's half of the codebook k-block]
+  const uint32_t a_stage_bytes = p.stream_a ? A_SUB_BYTES : 0;
+  const uint32_t stage_stride = a_stage_bytes + b_stage_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -216,7 +222,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
         const int row0 = tile * BM;  // may lie beyond N for the odd last pair: TMA zero-fills, nothing is written back
-        if (t > 0) mbar_wait(smem_u32(&ctrl->a_read), (t - 1) & 1);  // norms of the previous tile were read
+        if (t > 0 && !p.stream_a) mbar_wait(smem_u32(&ctrl->a_read), (t - 1) & 1);  // norms of the previous tile were read
         for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
           {  // bias block of this code tile (this CTA's half of the codes)
             const uint32_t xs = p.n_xstages == 2 ? (it & 1) : 0;
@@ -226,11 +232,13 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_3d_2sm(xb_base + xs * x_stage_bytes, &tmX, smem_u32(&ctrl->x_full[xs]) & kPeerBitMask, 0,
                             ct * p.BN + code_half, 0);
           }
-          for (int ps = 0; ps < p.n_passes; ++ps) {
-            const int bplane = (ps == 1) ? 1 : 0;
-            const int aplane = (ps == 2) ? 1 : 0;
-            const bool first_use = (ct == 0) && (ps == 0 || ps == 2);
-            for (int kb = 0; kb < p.KB; ++kb) {
+          // k-block-major: all passes of a k-block back to back, so that in the LAST code tile of a row tile an A sub-tile
+          // is released (and refilled for the next row tile) a whole code tile ahead of its next use instead of 3 k-blocks
+          for (int kb = 0; kb < p.KB; ++kb) {
+            for (int ps = 0; ps < p.n_passes; ++ps) {
+              const int bplane = (ps == 1) ? 1 : 0;
+              const int aplane = (ps == 2) ? 1 : 0;
+              const bool first_use = !p.stream_a && (ct == 0) && (ps == 0 || ps == 2);
               if (first_use) {  // refill this A sub-tile as soon as the previous row tile released it
                 const int sub = aplane * p.KB + kb;
                 mbar_wait(smem_u32(&ctrl->a_empty[sub]), (t & 1) ^ 1);
@@ -242,9 +250,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (p.dbg_mode & 4) {  // timing experiment: no codebook traffic, the MMAs run on stale smem
                 if (leader) mbar_arrive(smem_u32(&ctrl->b_full[stage]));
               } else {
-                if (leader) mbar_arrive_expect_tx(smem_u32(&ctrl->b_full[stage]), 2 * b_stage_bytes);
-                tma_load_3d_2sm(b_base + stage * b_stage_bytes, &tmB, smem_u32(&ctrl->b_full[stage]) & kPeerBitMask, kb * BK,
-                                ct * p.BN + code_half, bplane);
+                if (leader) mbar_arrive_expect_tx(smem_u32(&ctrl->b_full[stage]), 2 * stage_stride);
+                if (p.stream_a)
+                  tma_load_3d_2sm(b_base + stage * stage_stride, &tmA, smem_u32(&ctrl->b_full[stage]) & kPeerBitMask, kb * BK, row0,
+                                  aplane);
+                tma_load_3d_2sm(b_base + stage * stage_stride + a_stage_bytes, &tmB, smem_u32(&ctrl->b_full[stage]) & kPeerBitMask,
+                                kb * BK, ct * p.BN + code_half, bplane);
               }
               if (++stage == p.n_stages) { stage = 0; ph ^= 1; }
             }
@@ -268,8 +279,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint64_t d0 = umma_smem_desc_sw128(a_base);
       const uint32_t desc_hi = static_cast<uint32_t>(d0 >> 32);
       const uint32_t a_desc_lo0 = static_cast<uint32_t>(d0);
-      const uint32_t b_desc_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(b_base));
-      const uint32_t b_stage_units = b_stage_bytes >> 4;
+      const uint32_t b_desc_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(b_base + a_stage_bytes));
+      const uint32_t as_desc_lo0 = static_cast<uint32_t>(umma_smem_desc_sw128(b_base));   // stream_a: A block of stage 0
+      const uint32_t b_stage_units = stage_stride >> 4;
       const bool full_k = (p.D & (BK - 1)) == 0;
       const int ksteps_last = full_k ? 4 : ((p.D & (BK - 1)) + UMMA_K - 1) / UMMA_K;
       // a group never spans more than half of the B ring (the producer must be able to run ahead of it)
@@ -293,54 +305,61 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             __syncwarp();
           }
-          for (int ps = 0; ps < p.n_passes; ++ps) {
-            const int aplane = (ps == 2) ? 1 : 0;
-            const bool last_use = (ct == p.num_code_tiles - 1) && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
-            // Groups of up to MMA_GROUP k-blocks: wait for all their operands, then ONE elected region issues their
-            // MMAs back to back.  The issuing warp shares its scheduler with two always-ready epilogue warps; every
-            // instruction it does not execute (loop control, waits, elect, fences per k-block) is issue latency the
-            // tensor pipe does not see (measured: 103 -> see DESIGN.md section 8 clk per MMA).
-            for (int kb0 = 0; kb0 < p.KB; kb0 += mma_group) {
-              const int cnt = min(mma_group, p.KB - kb0);
-              int st_w = stage;
-              uint32_t ph_w = ph;
+          // Items of a code tile in k-block-major order (kb, ps) — the order the producer stages them in.  Groups of up to
+          // MMA_GROUP items: wait for all their operands, then ONE elected region issues their MMAs back to back.  The
+          // issuing warp shares its scheduler with two always-ready epilogue warps; every instruction it does not
+          // execute (loop control, waits, elect, fences per item) is issue latency the tensor pipe does not see.
+          const int n_items = p.KB * p.n_passes;
+          const bool last_ct = ct == p.num_code_tiles - 1;
+          int kb_w = 0, ps_w = 0;   // (kb, ps) of the next item to wait for / issue
+          for (int i0 = 0; i0 < n_items; i0 += mma_group) {
+            const int cnt = min(mma_group, n_items - i0);
+            int st_w = stage;
+            uint32_t ph_w = ph;
+            int kb_g = kb_w, ps_g = ps_w;
+#pragma unroll
+            for (int g = 0; g < MMA_GROUP; ++g) {
+              if (g < cnt) {
+                if (ct == 0 && !p.stream_a) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[(ps_g == 2 ? p.KB : 0) + kb_g]), t & 1); w_afull += PROF_CLOCK() - c0; }
+                { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[st_w]), ph_w); w_bfull += PROF_CLOCK() - c0; }
+                if (++st_w == p.n_stages) { st_w = 0; ph_w ^= 1; }
+                if (++ps_g == p.n_passes) { ps_g = 0; ++kb_g; }
+              }
+            }
+            tc_fence_after();
+            if (elect_one_sync()) {
+              int st_i = stage;
+              int kb = kb_w, ps = ps_w;
 #pragma unroll
               for (int g = 0; g < MMA_GROUP; ++g) {
                 if (g < cnt) {
-                  if (ct == 0) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[aplane * p.KB + kb0 + g]), t & 1); w_afull += PROF_CLOCK() - c0; }
-                  { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[st_w]), ph_w); w_bfull += PROF_CLOCK() - c0; }
-                  if (++st_w == p.n_stages) { st_w = 0; ph_w ^= 1; }
-                }
-              }
-              tc_fence_after();
-              if (elect_one_sync()) {
-                int st_i = stage;
-#pragma unroll
-                for (int g = 0; g < MMA_GROUP; ++g) {
-                  if (g < cnt) {
-                    const int kb = kb0 + g;
-                    const int sub = aplane * p.KB + kb;
-                    const uint32_t a_lo = a_desc_lo0 + static_cast<uint32_t>(sub) * (A_SUB_BYTES >> 4);
-                    const uint32_t b_lo = b_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units;
-                    if (full_k || kb + 1 < p.KB) {  // full k-block: four K=16 steps, descriptors advance by 32 B
-                      umma_bf16_ss_2sm_acc(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc_pass);
-                      umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc_pass);
-                      umma_bf16_ss_2sm_acc(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc_pass);
-                      umma_bf16_ss_2sm_acc(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc_pass);
-                    } else {  // ragged last k-block (D % 64 != 0): only the K steps that hold data (the rest is TMA zero fill)
-                      for (int k = 0; k < ksteps_last; ++k)
-                        umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc_pass);
-                    }
-                    umma_commit_2sm(smem_u32(&ctrl->b_empty[st_i]), kBoth);              // B stage reusable once these MMAs retire
-                    if (last_use) umma_commit_2sm(smem_u32(&ctrl->a_empty[sub]), kBoth); // ... and this A sub-tile too
-                    if (++st_i == p.n_stages) st_i = 0;
+                  const int aplane = (ps == 2) ? 1 : 0;
+                  const int sub = aplane * p.KB + kb;
+                  const bool last_use = last_ct && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
+                  const uint32_t a_lo = p.stream_a ? as_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units
+                                                   : a_desc_lo0 + static_cast<uint32_t>(sub) * (A_SUB_BYTES >> 4);
+                  const uint32_t b_lo = b_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units;
+                  if (full_k || kb + 1 < p.KB) {  // full k-block: four K=16 steps, descriptors advance by 32 B
+                    umma_bf16_ss_2sm_acc(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc_pass);
+                    umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc_pass);
+                    umma_bf16_ss_2sm_acc(d_tmem, a_lo + 4, desc_hi, b_lo + 4, desc_hi, idesc_pass);
+                    umma_bf16_ss_2sm_acc(d_tmem, a_lo + 6, desc_hi, b_lo + 6, desc_hi, idesc_pass);
+                  } else {  // ragged last k-block (D % 64 != 0): only the K steps that hold data (the rest is TMA zero fill)
+                    for (int k = 0; k < ksteps_last; ++k)
+                      umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2 * k, desc_hi, b_lo + 2 * k, desc_hi, idesc_pass);
                   }
+                  umma_commit_2sm(smem_u32(&ctrl->b_empty[st_i]), kBoth);              // ring stage reusable once these MMAs retire
+                  if (last_use && !p.stream_a) umma_commit_2sm(smem_u32(&ctrl->a_empty[sub]), kBoth); // ... and this A sub-tile too
+                  if (++st_i == p.n_stages) st_i = 0;
+                  if (++ps == p.n_passes) { ps = 0; ++kb; }
                 }
               }
-              __syncwarp();
-              stage = st_w;
-              ph = ph_w;
             }
+            __syncwarp();
+            stage = st_w;
+            ph = ph_w;
+            kb_w = kb_g;
+            ps_w = ps_g;
           }
           if (elect_one_sync()) umma_commit_2sm(smem_u32(&ctrl->t_full[as]), kBoth);  // accumulator complete -> both epilogues
           __syncwarp();
@@ -410,7 +429,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #ifdef VQB_PROFILE
           if (p.dbg_mode & 16) { sc.t1 = fmaxf(sc.t1, max16(r)); return; }  // timing experiment: TMEM loads + max tree only
 #endif
-          sc.scan16<true, true>(sq, r, cbase, p.mul1);
+          sc.scan16<true, false>(sq, r, cbase, p.mul1);
         };
         // The accumulator stage goes back to the MMA issuer as soon as this warp's LAST tcgen05.ld has completed (the
         // final piece is scanned from registers afterwards): the release -> MMA -> t_full loop is the critical path.
@@ -527,6 +546,38 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // fp32 accumulation: the norm scales the certification band AND carries the commitment loss
     // (sum ||q - x||^2 = sum ||x||^2 - 2 score), so it must be as exact as the scores.
     auto row_norms = [&](int t) {
+      if (p.stream_a) {  // A is not resident: the norms come from the planes in global memory (L2: the TMA reads them next)
+        const int64_t row_t0 = static_cast<int64_t>((cluster_id + t * num_clusters) * 2 + static_cast<int>(rank)) * BM;
+        for (int i = 0; i < 32; ++i) {
+          const int64_t row = row_t0 + sw * 32 + i;
+          float acc = 0.f;
+          if (row < p.N) {
+            const uint16_t* h = p.a_global + row * p.D;
+            for (int c = lane * 8; c < p.D; c += 256) {
+              const uint4 u = __ldg(reinterpret_cast<const uint4*>(h + c));
+              uint4 l = make_uint4(0u, 0u, 0u, 0u);
+              if (p.n_a == 2) l = __ldg(reinterpret_cast<const uint4*>(h + p.N * p.D + c));
+              const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+              const uint32_t wl[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float v0 = __uint_as_float(w[e] << 16) + __uint_as_float(wl[e] << 16);
+                const float v1 = __uint_as_float(w[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
+                acc = fmaf(v0, v0, acc);
+                acc = fmaf(v1, v1, acc);
+              }
+            }
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) ctrl->xn2[t & 1][sw * 32 + i] = acc;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(smem_u32(&ctrl->a_read));
+          mbar_arrive(smem_u32(&ctrl->n_full[t & 1]));
+        }
+        return;
+      }
       if (leader) {
         for (int s2 = 0; s2 < n_sub; ++s2) mbar_wait(smem_u32(&ctrl->a_full[s2]), t & 1);
         if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready), 1));
@@ -735,7 +786,6 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   if (n_passes < 1 || n_passes > 3 || (n_passes == 3 && n_a != 2)) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   const int KB = (D + BK - 1) / BK;
-  if (n_a * KB > MAX_A_SUB) return VQB_E_UNSUPPORTED;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(a_planes) | reinterpret_cast<uintptr_t>(b_planes) | reinterpret_cast<uintptr_t>(bext)) & 15)
     return VQB_E_ALIGN;
@@ -763,8 +813,12 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   // pure-copy tail: nothing needs x again (no residual / running sum / fused statistics); the cosine loss needs ||c||^2
   p.copy_mode = p.fo.enabled && !p.fo.resid_out && !p.fo.qsum && !p.fo.stats_sum &&
                 !(metric == VQB_METRIC_COSINE && p.fo.loss_sum && !cnorm2);
-  const int a_bytes = n_a * KB * A_SUB_BYTES;
-  const int b_stage = (p.BN / 2) * BK * 2;
+  // A stationary in smem when it leaves room for >= 3 ring stages; else (fp32 split input with D > 256) its k-blocks are
+  // streamed through the ring next to the codebook's (re-read from L2 for every code tile)
+  p.stream_a = n_a * KB > MAX_A_SUB ? 1 : 0;
+  p.a_global = static_cast<const uint16_t*>(a_planes);
+  const int a_bytes = p.stream_a ? 0 : n_a * KB * A_SUB_BYTES;
+  const int b_stage = (p.BN / 2) * BK * 2 + (p.stream_a ? A_SUB_BYTES : 0);
   const int x_stage = (p.BN / 2) * 32;
   const int fixed = SMEM_CTRL_BYTES + 1024 /*align*/ + a_bytes + AEXT_BYTES + 1024 /*align of B ring*/;
   int xstages = 2;

@@ -312,6 +312,34 @@ __global__ void decode_kernel(const float* __restrict__ embeds, int64_t embed_st
   }
 }
 
+// quantized_out of ResidualVQ.forward rebuilt from the stage indices:  out = (((q_0) + q_1) + ...), q_j = embed_j[idx_j].type(dtype),
+// every partial sum rounded to dtype exactly where the reference's `quantized_out = quantized_out + quantized` rounds
+// (rvq:525, vqp:1178).  One pass over the indices, code rows from L2, ONE write of (N x D) instead of a read-modify-write
+// of the running sum in every stage.
+template <int DT>
+__global__ void rvq_accumulate_kernel(const float* __restrict__ embeds, int64_t embed_stride, int Q, int D,
+                                      const int64_t* __restrict__ idx, int64_t N, void* out) {
+  using E = Elem<DT>;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
+       row += static_cast<int64_t>(gridDim.x) * wpb) {
+    for (int i = lane * 4; i < D; i += 128) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < Q; ++q) {
+        const int64_t k = idx[row * Q + q];
+        const float4 c = __ldg(reinterpret_cast<const float4*>(embeds + q * embed_stride + k * D + i));
+        acc.x = E::round(acc.x + E::round(c.x)); acc.y = E::round(acc.y + E::round(c.y));
+        acc.z = E::round(acc.z + E::round(c.z)); acc.w = E::round(acc.w + E::round(c.w));
+      }
+      E::store(out, row * D + i, acc.x);
+      E::store(out, row * D + i + 1, acc.y);
+      E::store(out, row * D + i + 2, acc.z);
+      E::store(out, row * D + i + 3, acc.w);
+    }
+  }
+}
+
 static inline int row_grid(int64_t rows, int wpb) {
   int64_t g = (rows + wpb - 1) / wpb;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
@@ -330,7 +358,7 @@ extern "C" const char* vqb_strerror(int code) {
   switch (code) {
     case VQB_OK: return "ok";
     case VQB_E_INVALID: return "vqb200: invalid argument (null pointer, non-positive size or bad enum)";
-    case VQB_E_UNSUPPORTED: return "vqb200: shape not supported by the sm_100a kernels (need D % 8 == 0 and n_a*ceil(D/64) <= 8)";
+    case VQB_E_UNSUPPORTED: return "vqb200: shape not supported by the sm_100a kernels (need D % 8 == 0, D <= 1024)";
     case VQB_E_ALIGN: return "vqb200: pointer is not 16-byte aligned";
     case VQB_E_NO_DEVICE: return "vqb200: no CUDA device or device is not compute capability 10.x (B200)";
     case VQB_E_DRIVER: return "vqb200: cuTensorMapEncodeTiled unavailable or failed";
@@ -433,5 +461,19 @@ extern "C" int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int 
     decode_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, K, D, idx, N, out);
   else
     decode_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, K, D, idx, N, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
+                                  void* out, int dtype, void* stream) {
+  if (!embeds || !idx || !out || Q <= 0 || K <= 0 || D <= 0 || N <= 0) return VQB_E_INVALID;
+  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
+  if (D % 4 != 0) return VQB_E_UNSUPPORTED;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = row_grid(N, ROW_THREADS / 32);
+  if (dtype == VQB_DTYPE_F32)
+    rvq_accumulate_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
+  else
+    rvq_accumulate_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
   return static_cast<int>(cudaGetLastError());
 }

@@ -63,7 +63,7 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream);
 // (then the launches simply become part of the caller's graph).
 // ---------------------------------------------------------------------------------------------
 namespace {
-constexpr int kKeyWords = 24;
+constexpr int kKeyWords = 64;
 constexpr int kVariants = 32;     // executable graphs per structural key
 constexpr int kMaxStruct = 16;    // structural keys (LRU)
 constexpr int kCaptureFailed = -2147483647;
@@ -104,9 +104,12 @@ void make_keys(const vqb_vq_forward_args* a, void* stream, uint64_t* sk, uint64_
   P(a->x); P(a->cluster_size); P(a->embed_avg); P(a->embed); P(a->planes); P(a->bext); P(a->bias); P(a->cnorm2); P(a->cmax);
   P(a->scratch); P(a->q_out); P(a->idx64_out); P(a->loss_out); P(a->resid_out); P(a->qsum); P(a->idx32); P(a->stats);
   P(a->workspace);
+  P(a->peer_epoch);
+  for (int r = 0; r < a->peer_world && r < 16; ++r) { P(a->peer_stats ? a->peer_stats[r] : nullptr); P(a->peer_flags ? a->peer_flags[r] : nullptr); }
   I(a->dtype); I(a->metric); I(a->N); I(a->D); I(a->K); I(a->already_normalised); I(a->idx_stride); F(a->loss_weight);
   I(a->update); I(a->stats_mode); I(a->stats_accumulate); I(a->do_normalise); F(a->decay); F(a->eps); F(a->margin_rel);
   I(static_cast<long long>(a->workspace_bytes)); I(reinterpret_cast<long long>(stream)); I(static_cast<long long>(present));
+  I(a->peer_rank); I(a->peer_world); I(a->peer_slice_offset);
   while (si < kKeyWords) sk[si++] = 0;
   while (pi < kKeyWords) pk[pi++] = 0;
 }
@@ -299,7 +302,10 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   if (a->N <= 0 || a->D <= 0 || a->K <= 0) return VQB_E_INVALID;
   if (a->dtype != VQB_DTYPE_F32 && a->dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
   if (a->update && (!a->stats)) return VQB_E_INVALID;
-  if (a->update == 2 && (!a->cluster_size || !a->embed_avg || !a->bias || !a->scratch)) return VQB_E_INVALID;
+  if (a->update >= 2 && (!a->cluster_size || !a->embed_avg || !a->bias || !a->scratch)) return VQB_E_INVALID;
+  if (a->update == 3 && (!a->peer_stats || !a->peer_flags || !a->peer_epoch || a->peer_world < 1 || a->peer_world > 16))
+    return VQB_E_INVALID;
+  if (a->update < 0 || a->update > 3) return VQB_E_INVALID;
   const FwdWs w = carve_fwd(a->N, a->D, a->K, a->dtype, a->metric, a->update);
   if (w.total > a->workspace_bytes) return VQB_E_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(a->workspace) & 255) return VQB_E_ALIGN;
@@ -348,10 +354,12 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
     f.stats_cnt = a->stats;
     f.stats_sum = a->stats + vqb_stats_offset(a->K);
   }
-  // ResidualVQ stages need x again (residual, running sum): that generic tail is HBM-heavy and throttles the search
-  // kernel when run by its four store warps (measured +0.3 ms per stage at config 3), so it runs as the stand-alone
-  // gather kernel after the re-score instead.  The VectorQuantize tail (row copy + loss from the scores) stays fused.
-  const bool split_tail = (a->resid_out || a->qsum) && !fused_stats;
+  // A ResidualVQ stage that also keeps the running sum (qsum: read-modify-write of one more (N x D) tensor from HBM)
+  // throttles the search kernel when its four store warps run that tail (measured +0.3 ms per stage at config 3), so
+  // it runs as the stand-alone gather kernel after the re-score.  The residual-only tail (x row from L2 — the TMA just
+  // read it —, code row from L2, one (N x D) write) stays fused: ResidualVQ rebuilds the running sum from the indices
+  // at the end (vqb_rvq_accumulate).  The VectorQuantize tail (row copy + loss from the scores) is always fused.
+  const bool split_tail = a->qsum && !fused_stats;
   const bool want_tail = !split_tail && (a->q_out || a->idx64_out || a->loss_out || fused_stats);
   vqb_flag_entry* flagged = reinterpret_cast<vqb_flag_entry*>(ws + w.flagged);
   // The EMA sort (histogram -> scans -> scatter -> segmented sums) only needs the indices, and all but ~0.3 % of them
@@ -402,6 +410,13 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
     if (a->update == 2) {
       rc = vqb_ema_apply(a->cluster_size, a->embed_avg, a->embed, a->stats, a->K, a->D, a->decay, a->eps, a->metric, 1,
                          a->do_normalise, a->planes, a->bext, a->bias, a->cnorm2, a->cmax, a->scratch, stream);
+      if (rc) return rc;
+    } else if (a->update == 3) {  // multi-GPU: barrier, then every rank sums all ranks' statistics inside its EMA kernels
+      rc = vqb_peer_barrier(a->peer_flags, a->peer_rank, a->peer_world, a->peer_epoch, stream);
+      if (rc) return rc;
+      rc = vqb_ema_apply_peers(a->cluster_size, a->embed_avg, a->embed, a->peer_stats, a->peer_world, a->peer_slice_offset,
+                               a->K, a->D, a->decay, a->eps, a->metric, a->do_normalise, nullptr, a->planes, a->bext, a->bias,
+                               a->cnorm2, a->cmax, a->scratch, stream);
       if (rc) return rc;
     }
   }

@@ -183,7 +183,8 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
 def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: int, do_normalise: bool, decay: float,
                eps: float, q_out=None, idx64_out=None, idx_stride: int = 1, loss_out=None, loss_weight: float = 1.0,
                resid_out=None, qsum=None, stats=None, margin: float | None = None, already_normalised: bool = False,
-               ws_key=None, stats_accumulate: bool = False) -> tuple[torch.Tensor, torch.Tensor | None]:
+               ws_key=None, stats_accumulate: bool = False, peer=None, peer_ptrs=None,
+               peer_slice_offset: int = 0) -> tuple[torch.Tensor, torch.Tensor | None]:
     """ONE C call for the arithmetic of VectorQuantize.forward / one ResidualVQ stage (vqb_vq_forward).
 
     state = (cluster_size (K,), embed_avg (K, D), embed (K, D)).  update: 0 none, 1 statistics only (returned
@@ -209,6 +210,11 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
         qsum=_p(qsum), idx32=_p(idx32), update=int(update), stats_mode=STATS_MODE, stats_accumulate=int(stats_accumulate), do_normalise=int(do_normalise), decay=float(decay),
         eps=float(eps), stats=_p(stats), margin_rel=float(DEFAULT_MARGIN if margin is None else margin),
         workspace=_p(ws), workspace_bytes=nbytes, ev_search_begin=None, ev_search_end=None)
+    if update == 3:  # multi-GPU: statistics -> peer barrier -> EMA kernels summing every rank's statistics (vq_peer.cu)
+        a.peer_stats = ctypes.cast(peer_ptrs, ctypes.c_void_p)
+        a.peer_flags = ctypes.cast(peer.flag_ptrs, ctypes.c_void_p)
+        a.peer_epoch = peer.epoch.data_ptr()
+        a.peer_rank, a.peer_world, a.peer_slice_offset = peer.rank, peer.world, int(peer_slice_offset)
     with torch.cuda.device(dev):
         prof = PROFILE_EVENTS
         if prof is not None:  # bench instrumentation: CUDA events around the search kernel, recorded from C
@@ -218,7 +224,7 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
             prof.append((ev0, ev1))
         check(lib.vqb_vq_forward(ctypes.byref(a), _stream()), "vqb_vq_forward")
     _count(4 + (1 if dt == _C.DTYPE_F32 or ops.cosine else 0) + (1 if loss_out is not None else 0) + (5 if update else 0)
-           + (2 if update == 2 else 0))
+           + (2 if update == 2 else 0) + (3 if update == 3 else 0))
     return idx32, stats
 
 
@@ -298,3 +304,47 @@ def decode(embeds: torch.Tensor, indices: torch.Tensor, out_dtype: torch.dtype =
         check(lib.vqb_decode(_p(embeds), K * D, Q, K, D, _p(flat), N, _p(out), _DT[out_dtype], _stream()), "vqb_decode")
     _count(1)
     return out.reshape(*indices.shape[:-1], D)
+
+
+def rvq_accumulate(embeds: torch.Tensor, indices: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    """ResidualVQ's `quantized_out` from the stage indices (N, Q): the rounded running sum of rvq:525 in ONE pass.
+    embeds (Q, K, D) fp32 — the codebooks the stages SEARCHED (pre-update), or (K, D) for a shared codebook."""
+    _require_cuda(embeds, indices)
+    assert indices.dim() == 2 and indices.dtype == torch.int64 and indices.is_contiguous()
+    N, Q = indices.shape
+    if embeds.dim() == 2:
+        K, D = embeds.shape
+        stride = 0
+    else:
+        assert embeds.shape[0] == Q
+        _, K, D = embeds.shape
+        stride = K * D
+    embeds = embeds.contiguous()
+    out = torch.empty((N, D), dtype=out_dtype, device=embeds.device)
+    with torch.cuda.device(embeds.device):
+        check(lib.vqb_rvq_accumulate(_p(embeds), stride, Q, K, D, _p(indices), N, _p(out), _DT[out_dtype], _stream()),
+              "vqb_rvq_accumulate")
+    _count(1)
+    return out
+
+
+def peer_barrier(peer) -> None:
+    """Cross-GPU barrier kernel on the current stream (dist.PeerReducer; csrc/vq_peer.cu)."""
+    with torch.cuda.device(peer.device):
+        check(lib.vqb_peer_barrier(ctypes.cast(peer.flag_ptrs, ctypes.c_void_p), peer.rank, peer.world, peer.epoch.data_ptr(),
+                                   _stream()), "vqb_peer_barrier")
+    _count(1)
+
+
+def ema_apply_peers(cluster_size: torch.Tensor, embed_avg: torch.Tensor, embed: torch.Tensor, peer, peer_ptrs, slice_offset: int,
+                    ops: CodebookOperands, *, decay: float, eps: float, do_normalise: bool,
+                    code_weight: torch.Tensor | None = None) -> None:
+    """`ema_apply` with the statistics summed over every rank's symmetric buffer inside the kernels (after `peer_barrier`)."""
+    _require_cuda(cluster_size, embed_avg, embed, code_weight)
+    K, D = embed.shape
+    with torch.cuda.device(embed.device):
+        check(lib.vqb_ema_apply_peers(_p(cluster_size), _p(embed_avg), _p(embed), ctypes.cast(peer_ptrs, ctypes.c_void_p), peer.world,
+                                      int(slice_offset), K, D, float(decay), float(eps), int(ops.cosine), int(do_normalise),
+                                      _p(code_weight), _p(ops.planes), _p(ops.bext), _p(ops.bias), _p(ops.cnorm2), _p(ops.cmax),
+                                      _p(ops.scratch), _stream()), "vqb_ema_apply_peers")
+    _count(2)

@@ -15,7 +15,7 @@ from torch import nn
 
 from . import ops
 from .codebook import _unsupported
-from .dist import allreduce_packed
+from .dist import allreduce_packed, PeerReducer
 from .vector_quantize import VectorQuantize
 
 
@@ -121,6 +121,13 @@ class ResidualVQ(nn.Module):
     def _stage_plan(self):
         return [vq._codebook for vq in self.layers]
 
+    def _peer_reducer(self, numel, device):
+        """One symmetric-memory buffer for the statistics of ALL stages (dist.PeerReducer); None -> NCCL all-reduce."""
+        if not getattr(self, "_peer_tried", False) or (self._peer is not None and self._peer.numel < numel):
+            self._peer_tried = True
+            self._peer = PeerReducer.create(numel, device)
+        return self._peer
+
     def forward(self, x, mask=None, indices=None, return_all_codes=False, sample_codebook_temp=None,
                 freeze_codebook=False, beam_size=None, rand_quantize_dropout_fixed_seed=None,
                 _stats_sink=None):
@@ -145,7 +152,6 @@ class ResidualVQ(nn.Module):
         training = self.training
         books = self._stage_plan()
 
-        quantized_out = torch.zeros_like(flat)  # rvq:410
         all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)
         loss_buf = getattr(self, "_loss_buf", None)  # persistent (stable pointers for the graph cache), cloned out below
         if loss_buf is None or loss_buf.device != dev or loss_buf.numel() != Q:
@@ -165,7 +171,15 @@ class ResidualVQ(nn.Module):
         # update_codebook ends with expire_codes_, vqp:641, on the one aliased Codebook): such stages cannot be deferred.
         inline = [u and self.shared_codebook and b.has_dead_code_replacement for b, u in zip(books, do_update)]
         stat_sizes = [ops.stats_floats(b.codebook_size, D) if (u and not i) else 0 for b, u, i in zip(books, do_update, inline)]
-        packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
+        running_sum = torch.zeros_like(flat) if (any(inline) or not self.uniform_codebook_size) else None  # rvq:410
+        packed, peer_ptrs = None, None
+        if sum(stat_sizes):
+            peer = self._peer_reducer(sum(stat_sizes), dev) if any(b.use_ddp for b in books) else None
+            if peer is not None:   # statistics straight into symmetric memory: summed over the ranks inside the EMA kernels
+                buf, peer_ptrs = peer.next_buffer()
+                packed = buf[:sum(stat_sizes)]
+            else:
+                packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev)
         offs = [sum(stat_sizes[:i]) for i in range(Q)]
 
         for q, book in enumerate(books):  # rvq:469
@@ -176,15 +190,24 @@ class ResidualVQ(nn.Module):
             book.quantize_rows(
                 residual, update=do_update[q], idx64_out=all_idx[:, q], idx_stride=Q,
                 loss_out=losses[q:q + 1] if want_loss else None, loss_weight=self.layers[q].commitment_weight,
-                resid_out=nxt, qsum=quantized_out,
+                resid_out=nxt, qsum=running_sum,
                 stats_out=packed[offs[q]:offs[q] + stat_sizes[q]] if stat_sizes[q] else None, defer_ema=not inline[q])
             residual = nxt
 
+        # quantized_out (rvq:410, :525): rebuilt from the indices in one pass over the codebooks the stages searched (their
+        # update is deferred to _finish_update below) instead of a read-modify-write of (N x D) in every stage.  Only when
+        # the codebooks cannot be stacked, or a shared codebook is modified between stages, the stages keep the sum.
+        if running_sum is None:
+            embeds = books[0].embed[0] if self.shared_codebook else torch.stack([b.embed[0] for b in books])
+            quantized_out = ops.rvq_accumulate(embeds, all_idx, dtype)
+        else:
+            quantized_out = running_sum
+
         if packed is not None or any(inline):
             if _stats_sink is not None:  # GroupedResidualVQ gathers every group's statistics into one collective
-                _stats_sink.append((self, packed, offs, stat_sizes, do_update, (stage_inputs, shape)))
+                _stats_sink.append((self, packed, offs, stat_sizes, do_update, (stage_inputs, shape, peer_ptrs)))
             else:
-                self._finish_update(packed, offs, stat_sizes, do_update, (stage_inputs, shape), synced=False)
+                self._finish_update(packed, offs, stat_sizes, do_update, (stage_inputs, shape, peer_ptrs), synced=False)
 
         quantized_out = self.project_out(quantized_out.reshape(shape))  # rvq:610
         ret = (quantized_out, all_idx.reshape(*shape[:-1], Q), losses.clone())
@@ -197,15 +220,21 @@ class ResidualVQ(nn.Module):
         order (vqp:616-617) and update_ema — once at the end for a shared codebook (rvq:593-597) — and the dead-code
         expiry: per stage from that stage's input (vqp:641), for a shared codebook once over all residuals (rvq:599-601).
         stage_inputs: (the Q stage inputs (N, D) — kept only when some codebook replaces dead codes —, input shape)."""
-        stage_inputs, shape = stage_inputs
+        stage_inputs, shape, peer_ptrs = stage_inputs
         books = self._stage_plan()
-        if not synced and packed is not None and any(b.use_ddp for b in books):
+        peer = self._peer if peer_ptrs is not None else None
+        if peer is not None:
+            peer.barrier()       # every rank's statistics of this forward are in place
+        elif not synced and packed is not None and any(b.use_ddp for b in books):
             allreduce_packed(packed)
         for q, book in enumerate(books):
             if not do_update[q] or not stat_sizes[q]:   # nothing to do, or already applied inline
                 continue
-            stats = packed[offs[q]:offs[q] + stat_sizes[q]]
-            book.lerp_stats(stats, normalise=book.ema_update and not book.manual_ema_update)
+            normalise = book.ema_update and not book.manual_ema_update
+            if peer is not None:
+                book.lerp_stats_peers(peer, peer_ptrs, offs[q], normalise)
+            else:
+                book.lerp_stats(packed[offs[q]:offs[q] + stat_sizes[q]], normalise=normalise)
             if not self.shared_codebook and book.has_dead_code_replacement:
                 book.expire_codes_(book.transform_input(stage_inputs[q]).float())  # vqp:641 on the fp32 `flatten`
         if self.training and self.shared_codebook:
@@ -280,8 +309,8 @@ class GroupedResidualVQ(nn.Module):
         outs = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _stats_sink=sink)
                 for rvq, c in zip(self.rvqs, chunks)]  # rvq:706
         if sink:
-            need_sync = any(b.use_ddp for rvq, *_ in sink for b in rvq._stage_plan())
-            if need_sync:  # ONE collective for every codebook of every group
+            need_sync = any(b.use_ddp for rvq, *_ in sink for b in rvq._stage_plan()) and all(e[5][2] is None for e in sink)
+            if need_sync:  # no peer memory: ONE NCCL collective for every codebook of every group
                 flat_all = torch.cat([p for _, p, *_ in sink])
                 allreduce_packed(flat_all)
                 pos = 0
