@@ -63,7 +63,9 @@ def cpu_reference_step_factory(threads=None):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import ref_loader
         ref = ref_loader.load_reference()
-        vq = ref.VectorQuantize(dim=D, codebook_size=K)
+        # sync_codebook=False: under torchrun the reference would otherwise all-reduce its CPU statistics over NCCL
+        # (vqp:925-926); a single process owns this arm (rank 0), the arithmetic is the same
+        vq = ref.VectorQuantize(dim=D, codebook_size=K, sync_codebook=False)
         with torch.no_grad():
             vq._codebook.embed.copy_(e[None]); vq._codebook.embed_avg.copy_(e[None])
         vq.train()

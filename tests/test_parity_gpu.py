@@ -158,19 +158,64 @@ def test_search_gather_stats_match_oracle(N, D, K, dt, cosine):
     np.testing.assert_allclose(st[off:].view(K, D).cpu().numpy(), es_ref, rtol=1e-5, atol=1e-5)
 
 
-def test_score_error_inside_margin():
-    """The certification margin (2^-17 |x| max|c|) must bound the real tensor-core error with room to spare."""
+SCORE_CASES = [
+    # dtype, D, K, distribution
+    ("bf16", 256, 1024, "randn"), ("fp32", 256, 1024, "randn"), ("bf16", 512, 512, "randn"), ("fp32", 64, 4096, "randn"),
+    ("bf16", 256, 1024, "heavy"),     # heavy-tailed rows: one coordinate 1e3 x the rest
+    ("fp32", 256, 1024, "heavy"),
+    ("bf16", 200, 777, "randn"),      # D not a multiple of 64 (zero-filled last k-block), ragged K
+    ("fp32", 520, 300, "randn"),      # streamed A planes, ragged last k-block
+    ("bf16", 512, 16384, "unit"),     # config-4 shape family: unit-norm rows and codes
+    ("fp32", 512, 16384, "unit"),
+    ("bf16", 256, 1024, "tiny"),      # |x| ~ 1e-6: below the fp16 normal range (the 2^-25 per-element term of the band)
+    ("bf16", 256, 1024, "cold"),      # default-init codebook: |c| ~ 5e-3
+]
+
+
+@pytest.mark.parametrize("dt,D,K,dist", SCORE_CASES)
+@pytest.mark.parametrize("extra_pass", [False, True])
+def test_score_error_inside_margin(dt, D, K, dist, extra_pass):
+    """The band that certifies a row must bound the real tensor-core error of EVERY pass scheme with room to spare:
+    |score_mma - score_exact| <= ||x|| * cres + margin * ||x|| * max||c|| + 2^-25 * sqrt(D) * max||c||, cres = the exact
+    norm of what the scheme leaves out of the fp16 codebook operands (ops.CodebookOperands.cmax[1 / 2])."""
     from vector_quantize_pytorch_b200 import ops
     torch.manual_seed(5)
-    for dt, D, K in (("bf16", 256, 1024), ("fp32", 256, 1024), ("bf16", 512, 512), ("fp32", 64, 4096)):
-        x = (torch.randn(8192, D) * 3).to(TDT[dt]).to(DEV)
-        c = (torch.randn(K, D) * 2).to(DEV)
-        cb = ops.prepare_codebook(c, False)
-        res = ops.search(x, cb, c, debug_best=True, fix=False)
-        s = x.double() @ c.double().T - 0.5 * (c.double() ** 2).sum(-1)[None]
-        got = s.gather(1, res.idx.long()[:, None])[:, 0]
-        rel = (res.best.double() - got).abs() / (x.double().norm(dim=-1) * c.double().norm(dim=-1).max())
-        assert rel.max().item() < 0.5 * 2.0 ** -17, (dt, D, K, rel.max().item())
+    N = 8192 if K <= 4096 else 2048
+    x = torch.randn(N, D)
+    c = torch.randn(K, D) * 2
+    if dist == "heavy":
+        x[:, 3] *= 1e3
+        c[:, 3] *= 30
+    elif dist == "unit":
+        x, c = torch.nn.functional.normalize(x, dim=-1), torch.nn.functional.normalize(c, dim=-1)
+    elif dist == "tiny":
+        x = x * 1e-6
+    elif dist == "cold":
+        c = (torch.rand(K, D) * 2 - 1) * (6.0 / (K * D)) ** 0.5
+    x = (x * (1 if dist != "randn" else 3)).to(TDT[dt]).to(DEV)
+    c = c.to(DEV).contiguous()
+    cb = ops.prepare_codebook(c, False)
+    base = 1 if dt == "bf16" else 2
+    n_passes = base + int(extra_pass)
+    res = ops.search(x, cb, c, debug_best=True, fix=False, n_passes=n_passes)
+    torch.cuda.synchronize()
+    s = x.double() @ c.double().T - 0.5 * (c.double() ** 2).sum(-1)[None]
+    got = s.gather(1, res.idx.long()[:, None])[:, 0]
+    err = (res.best.double() - got).abs()
+    xn = x.double().norm(dim=-1)
+    cmax = c.double().norm(dim=-1).max()
+    cres = cb.cmax[2 if extra_pass else 1].item() + (2.0 ** -10 * cb.cmax[1].item() if n_passes == 3 else 0.0)
+    # the residual norms are what the kernel believes: they must be true upper bounds
+    hi = cb.planes[0, :K].float().double()
+    lo = cb.planes[1, :K].float().double()
+    assert (c.double() - hi).norm(dim=-1).max().item() <= cb.cmax[1].item()
+    assert (c.double() - hi - lo).norm(dim=-1).max().item() <= cb.cmax[2].item()
+    bound = xn * cres + 0.5 * 2.0 ** -17 * xn * cmax + 2.0 ** -25 * (D ** 0.5) * cmax
+    worst = (err / bound).max().item()
+    assert worst < 1.0, (dt, D, K, dist, n_passes, worst)
+    # and the measured error of the residual-free part alone stays below half the margin
+    if extra_pass:
+        assert (err / (xn * cmax)).max().item() < 0.5 * 2.0 ** -17 + cres / cmax.item(), (dt, D, K, dist)
 
 
 def test_flagged_rows_are_rescored_exactly():

@@ -35,6 +35,7 @@
 #include "vqb_common.cuh"
 #include "gather_row.cuh"
 #include "epilogue.cuh"
+#include <cuda_fp16.h>
 
 // Per-role cycle accounting (scripts/gpu_roles.py): compile with -DVQB_PROFILE.  Off by default: the counters cost
 // registers in a kernel that runs at the 128-register cap.
@@ -60,13 +61,16 @@ constexpr int MMA_GROUP = 4;      // k-blocks issued per elected region of the M
 constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
 constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 11264;    // barriers + tmem ptr + row norms + merge area + threshold exchange
+constexpr int SMEM_CTRL_BYTES = 12288;    // barriers + tmem ptr + row norms + merge area + threshold exchange
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
   int64_t N;
   int D, K, Kpad, BN;
-  int n_a, n_passes;   // passes: 0:(a0,hi) 1:(a0,lo) 2:(a1,hi)
+  int n_a, n_passes;   // pass ps multiplies A plane pass_a[ps] with codebook plane pass_b[ps] (fp16 operands: 0 = hi, 1 = lo)
+  int pass_a[3], pass_b[3];
+  int a_fp16;          // A planes already hold fp16 (vqb_input_prepare: fp32 inputs); 0: bf16 rows, converted in smem
+  int cres_index;      // which residual norm of the codebook the passes leave out: cmax[1] (no c_lo pass) or cmax[2]
   int KB;              // ceil(D / 64)
   int n_stages, n_xstages;
   int stream_a;        // A does not fit in smem next to a useful B ring (fp32 split input with D > 256): its k-blocks travel
@@ -93,7 +97,8 @@ struct AssignParams {
 struct Ctrl {  // lives at the start of dynamic smem
   uint64_t a_full[MAX_A_SUB], a_empty[MAX_A_SUB];
   uint64_t a_read;                       // store warps finished reading A (row norms)
-  uint64_t a_ready;                      // follower CTA: its A tile has landed (forwarded by the leader's store warp 0)
+  uint64_t a_ready[MAX_A_SUB];           // follower CTA: this A sub-tile has landed (forwarded by the leader's store warp 0)
+  uint64_t a_conv[MAX_A_SUB];            // (bf16 inputs) this A sub-tile has been converted to fp16 in BOTH CTAs
   uint64_t n_full[2];                    // row norms of a tile are in xn2[tile parity]
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
   uint64_t x_full[2], x_empty[2];        // bias blocks
@@ -104,6 +109,7 @@ struct Ctrl {  // lives at the start of dynamic smem
   float xn2[2][BM];                      // row norms, double buffered by row-tile parity
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
   int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
+  int xflag[2][BM];                      // the row holds values beyond the fp16 range: hand it to the exact re-score
   float share[2][2][BM];                 // [row-tile parity][column half][row]: running maximum of each slice, read by the
                                          // partner warp to raise its skip threshold (stale values are merely conservative)
 };
@@ -163,7 +169,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&ctrl->a_empty[s]), 1);
     }
     mbar_init(smem_u32(&ctrl->a_read), NUM_STORE_WARPS);
-    mbar_init(smem_u32(&ctrl->a_ready), 1);
+    for (int s = 0; s < n_sub; ++s) {
+      mbar_init(smem_u32(&ctrl->a_ready[s]), 1);
+      mbar_init(smem_u32(&ctrl->a_conv[s]), NUM_STORE_WARPS + 1);   // the leader's store warps + one forwarded arrive of the follower
+    }
     mbar_init(smem_u32(&ctrl->n_full[0]), NUM_STORE_WARPS);
     mbar_init(smem_u32(&ctrl->n_full[1]), NUM_STORE_WARPS);
     for (int s = 0; s < p.n_stages; ++s) {
@@ -207,8 +216,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_clusters = gridDim.x >> 1;
   const int num_pairs = (p.num_row_tiles + 1) >> 1;  // a pair of CTAs quantizes two adjacent row tiles
   const int my_tiles = (num_pairs - cluster_id + num_clusters - 1) / num_clusters;
-  // plane used by pass ps: A plane = (ps == 2), B plane = (ps == 1)
-  const int last_pass_a0 = p.n_passes >= 2 ? 1 : 0;  // last pass that reads A plane 0
+  // last pass (of a k-block's passes) that reads A plane 0 / 1
+  int last_pass_of_plane[2] = {-1, -1};
+  for (int ps = 0; ps < p.n_passes; ++ps) last_pass_of_plane[p.pass_a[ps]] = ps;
 
   if (warp == WARP_PROD) {
     // ================================================================ TMA producer
@@ -236,9 +246,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // is released (and refilled for the next row tile) a whole code tile ahead of its next use instead of 3 k-blocks
           for (int kb = 0; kb < p.KB; ++kb) {
             for (int ps = 0; ps < p.n_passes; ++ps) {
-              const int bplane = (ps == 1) ? 1 : 0;
-              const int aplane = (ps == 2) ? 1 : 0;
-              const bool first_use = !p.stream_a && (ct == 0) && (ps == 0 || ps == 2);
+              const int bplane = p.pass_b[ps];
+              const int aplane = p.pass_a[ps];
+              const bool first_use = !p.stream_a && (ct == 0) && (ps == 0 || p.pass_a[ps] != p.pass_a[ps - 1]);
               if (first_use) {  // refill this A sub-tile as soon as the previous row tile released it
                 const int sub = aplane * p.KB + kb;
                 mbar_wait(smem_u32(&ctrl->a_empty[sub]), (t & 1) ^ 1);
@@ -267,9 +277,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp == WARP_MMA) {
     // ================================================================ MMA issuer
     if (leader) {  // the whole warp runs the loop (warp-uniform); one elected lane issues
-      const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);
+      const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);                 // bias MMA: bf16 x bf16
+      // the passes multiply fp16 operands (same tensor-core rate, 3 more mantissa bits per operand than bf16)
       // timing experiment (results invalid): issue the pass MMAs with half the N extent
-      const uint32_t idesc_pass = (p.dbg_mode & 8) ? umma_idesc_bf16(2 * BM, p.BN / 2) : idesc;
+      const uint32_t idesc_pass = umma_idesc_f16(2 * BM, (p.dbg_mode & 8) ? p.BN / 2 : p.BN);
       constexpr uint16_t kBoth = 0x3;
       long long w_tempty = 0, w_bfull = 0, w_xfull = 0, w_afull = 0;
       const long long mstart = PROF_CLOCK();
@@ -320,7 +331,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int g = 0; g < MMA_GROUP; ++g) {
               if (g < cnt) {
-                if (ct == 0 && !p.stream_a) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[(ps_g == 2 ? p.KB : 0) + kb_g]), t & 1); w_afull += PROF_CLOCK() - c0; }
+                if (ct == 0 && !p.stream_a) {  // the A sub-tile has landed (fp16 planes) / has been converted to fp16 (bf16 rows)
+                  const int sub_g = p.pass_a[ps_g] * p.KB + kb_g;
+                  const long long c0 = PROF_CLOCK();
+                  mbar_wait(smem_u32(p.a_fp16 ? &ctrl->a_full[sub_g] : &ctrl->a_conv[sub_g]), t & 1);
+                  w_afull += PROF_CLOCK() - c0;
+                }
                 { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[st_w]), ph_w); w_bfull += PROF_CLOCK() - c0; }
                 if (++st_w == p.n_stages) { st_w = 0; ph_w ^= 1; }
                 if (++ps_g == p.n_passes) { ps_g = 0; ++kb_g; }
@@ -333,9 +349,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int g = 0; g < MMA_GROUP; ++g) {
                 if (g < cnt) {
-                  const int aplane = (ps == 2) ? 1 : 0;
+                  const int aplane = p.pass_a[ps];
                   const int sub = aplane * p.KB + kb;
-                  const bool last_use = last_ct && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
+                  const bool last_use = last_ct && ps == last_pass_of_plane[aplane];
                   const uint32_t a_lo = p.stream_a ? as_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units
                                                    : a_desc_lo0 + static_cast<uint32_t>(sub) * (A_SUB_BYTES >> 4);
                   const uint32_t b_lo = b_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units;
@@ -378,6 +394,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
     const int pair_bar = 1 + lg;             // named barrier shared by the two warps of a lane group
     const float cmax = __ldg(p.cmax);
+    // residual of the codebook operands under this pass scheme (+ the x_lo . c_lo term a 3-pass scheme still omits)
+    const float cres = __ldg(p.cmax + p.cres_index) + (p.n_passes == 3 ? 0x1p-10f * __ldg(p.cmax + 1) : 0.f);
     const uint32_t te_remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
     const uint32_t te_remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
     // number of 16-column pieces of a code tile owned by this warp (pieces 4q + 2*half + {0,1} below BN/16)
@@ -409,9 +427,14 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // (the default init) that exceeds the MMA band.  Rows inside it go to the exact re-score, which evaluates the
           // reference formula including the sqrt.  In score units (d^2 / 2), with a 2x safety factor:
           const float x2 = ctrl->xn2[t & 1][row_in_tile];
-          const float xc = sqrtf(x2) * cmax;
+          const float xn = sqrtf(x2);
+          const float xc = xn * cmax;
           const bool euclid = p.metric != VQB_METRIC_COSINE;
-          sc.init(2.f * p.margin_rel * xc + 0x1p-18f * (xc + (euclid ? 0.5f * cmax * cmax : 0.f)) +
+          // 2 * |score error|: what the passes leave out of the codebook (||x|| * cres, Cauchy-Schwarz on the exact fp16
+          // residual norms), fp32 accumulation + everything second order (margin_rel), bf16 -> fp16 rounding of |x_j| < 2^-14
+          // (<= 2^-25 per element), then the tag slack and the sqrt-collapse width.
+          sc.init(2.f * (xn * cres + p.margin_rel * xc + 0x1p-25f * 32.f * cmax) +
+                  0x1p-18f * (xc + (euclid ? 0.5f * cmax * cmax : 0.f)) +
                   (euclid ? 0x1p-22f * (x2 + cmax * cmax) : 0.f) + 1e-30f);
           // the slot of the NEXT row tile (same parity as the previous one) was last read before the pair barrier of
           // that tile's merge, which both warps of the pair have passed
@@ -490,7 +513,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // candidates = tagged scores inside the band below the tagged maximum, over both slices
         const float tb = fmaxf(st.t1, b1);
         const float band = tb - st.W;
-        const int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (b1 > band) + (b2 > band) + (b3 > band);
+        const int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (b1 > band) + (b2 > band) + (b3 > band) +
+                      3 * ctrl->xflag[t & 1][row_in_tile];   // values beyond the fp16 range: whole-row exact re-scan
         int i0, i1;
         if (st.t1 > b1 || (st.t1 == b1 && ia0 < ib0)) { i0 = ia0; i1 = (st.t2 > b1) ? ia1 : ib0; }
         else { i0 = ib0; i1 = (b2 > st.t1) ? ib1 : ia0; }
@@ -545,12 +569,22 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Only the leader's barriers see the TMA bytes; its store warp 0 forwards "landed" to the follower.
     // fp32 accumulation: the norm scales the certification band AND carries the commitment loss
     // (sum ||q - x||^2 = sum ||x||^2 - 2 score), so it must be as exact as the scores.
+    // |v| >= 65504 (or NaN): outside the fp16 range of the MMA operands -> the row is handed to the exact re-score
+    auto sq2 = [](uint32_t w, bool fp16, float& a0, float& a1, bool& big) {
+      float v0, v1;
+      if (fp16) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w)); v0 = f.x; v1 = f.y; }
+      else { v0 = __uint_as_float(w << 16); v1 = __uint_as_float(w & 0xFFFF0000u); }
+      big |= !(fabsf(v0) < 65504.f) | !(fabsf(v1) < 65504.f);
+      a0 = v0; a1 = v1;
+    };
     auto row_norms = [&](int t) {
-      if (p.stream_a) {  // A is not resident: the norms come from the planes in global memory (L2: the TMA reads them next)
+      int* xflag = ctrl->xflag[t & 1];
+      if (p.stream_a) {  // A is not resident: the norms come from the fp16 planes in global memory (L2: the TMA reads them next)
         const int64_t row_t0 = static_cast<int64_t>((cluster_id + t * num_clusters) * 2 + static_cast<int>(rank)) * BM;
         for (int i = 0; i < 32; ++i) {
           const int64_t row = row_t0 + sw * 32 + i;
           float acc = 0.f;
+          bool big = false;
           if (row < p.N) {
             const uint16_t* h = p.a_global + row * p.D;
             for (int c = lane * 8; c < p.D; c += 256) {
@@ -561,15 +595,18 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const uint32_t wl[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const float v0 = __uint_as_float(w[e] << 16) + __uint_as_float(wl[e] << 16);
-                const float v1 = __uint_as_float(w[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
-                acc = fmaf(v0, v0, acc);
-                acc = fmaf(v1, v1, acc);
+                float h0, h1, l0, l1;
+                bool dummy = false;
+                sq2(w[e], true, h0, h1, big);
+                sq2(wl[e], true, l0, l1, dummy);
+                acc = fmaf(h0 + l0, h0 + l0, acc);
+                acc = fmaf(h1 + l1, h1 + l1, acc);
               }
             }
           }
           acc = warp_sum(acc);
-          if (lane == 0) ctrl->xn2[t & 1][sw * 32 + i] = acc;
+          big = __any_sync(0xffffffffu, big);
+          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xflag[sw * 32 + i] = big ? 1 : 0; }
         }
         __syncwarp();
         if (lane == 0) {
@@ -578,50 +615,112 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         return;
       }
-      if (leader) {
-        for (int s2 = 0; s2 < n_sub; ++s2) mbar_wait(smem_u32(&ctrl->a_full[s2]), t & 1);
-        if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready), 1));
-      } else {
-        mbar_wait_cluster(smem_u32(&ctrl->a_ready), t & 1);
-      }
       const int sub = lane >> 3, chunk = lane & 7;  // conflict-free: a warp reads 4 full 128 B rows per request
-      // two rows per lane in flight, two partial sums per row: the dependent-FMA chain, not smem, bounds this loop
-      for (int i = 0; i < 8; i += 2) {
-        const int r0 = sw * 32 + i * 4 + sub, r1 = r0 + 4;
-        const uint32_t off0 = (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4);
-        const uint32_t off1 = (r1 >> 3) * 1024 + (r1 & 7) * 128 + ((chunk ^ (r1 & 7)) << 4);
-        float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-#pragma unroll 4
+      if (!p.a_fp16) {
+        // bf16 rows (the caller's tensor, read in place by the TMA): converted to fp16 IN the A tile, k-block by k-block as
+        // they land — exact for 2^-14 <= |v| < 65504 (bf16 has fewer mantissa bits), |error| <= 2^-25 below (in the band).
+        // The same sweep accumulates ||x||^2 from the original values.
+        uint8_t* a_mut = const_cast<uint8_t*>(a_gen);
+        float acc[8];
+        bool big[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i] = 0.f; big[i] = false; }
         for (int kb = 0; kb < p.KB; ++kb) {
-          uint4 u[2], l[2];
-          u[0] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off0);
-          u[1] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off1);
-          if (p.n_a == 2) {
-            l[0] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off0);
-            l[1] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off1);
+          if (leader) {
+            mbar_wait(smem_u32(&ctrl->a_full[kb]), t & 1);
+            if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready[kb]), 1));
           } else {
-            l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
+            mbar_wait_cluster(smem_u32(&ctrl->a_ready[kb]), t & 1);
           }
 #pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const uint32_t w[4] = {u[b].x, u[b].y, u[b].z, u[b].w};
-            const uint32_t wl[4] = {l[b].x, l[b].y, l[b].z, l[b].w};
+          for (int i = 0; i < 8; ++i) {
+            const int r = sw * 32 + i * 4 + sub;
+            uint4* ptr = reinterpret_cast<uint4*>(a_mut + kb * A_SUB_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
+            const uint4 u = *ptr;
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float v0 = __uint_as_float(w[e] << 16) + __uint_as_float(wl[e] << 16);
-              const float v1 = __uint_as_float(w[e] & 0xFFFF0000u) + __uint_as_float(wl[e] & 0xFFFF0000u);
-              acc[b][0] = fmaf(v0, v0, acc[b][0]);
-              acc[b][1] = fmaf(v1, v1, acc[b][1]);
+              float v0, v1;
+              sq2(w[e], false, v0, v1, big[i]);
+              acc[i] = fmaf(v0, v0, acc[i]);
+              acc[i] = fmaf(v1, v1, acc[i]);
+              const __half2 h = __floats2half2_rn(fminf(fmaxf(v0, -65504.f), 65504.f), fminf(fmaxf(v1, -65504.f), 65504.f));
+              o[e] = *reinterpret_cast<const uint32_t*>(&h);
             }
+            *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (leader) {
+            if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_conv[kb]));
+          } else {   // one forwarded arrive per sub-tile: the follower's four store warps meet, one lane posts to the leader
+            named_bar_sync(6, NUM_STORE_WARPS * 32);
+            if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_conv[kb]), 0));
           }
         }
-        float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1];
 #pragma unroll
-        for (int m = 1; m <= 4; m <<= 1) {
-          a0 += __shfl_xor_sync(0xffffffffu, a0, m);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+        for (int i = 0; i < 8; ++i) {
+          float a0 = acc[i];
+          int bg = big[i] ? 1 : 0;
+#pragma unroll
+          for (int m = 1; m <= 4; m <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, m);
+            bg |= __shfl_xor_sync(0xffffffffu, bg, m);
+          }
+          if (chunk == 0) { ctrl->xn2[t & 1][sw * 32 + i * 4 + sub] = a0; xflag[sw * 32 + i * 4 + sub] = bg; }
         }
-        if (chunk == 0) { ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1; }
+      } else {
+        if (leader) {
+          for (int s2 = 0; s2 < n_sub; ++s2) mbar_wait(smem_u32(&ctrl->a_full[s2]), t & 1);
+          if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready[0]), 1));
+        } else {
+          mbar_wait_cluster(smem_u32(&ctrl->a_ready[0]), t & 1);
+        }
+        // two rows per lane in flight: the dependent-FMA chain, not smem, bounds this loop
+        for (int i = 0; i < 8; i += 2) {
+          const int r0 = sw * 32 + i * 4 + sub, r1 = r0 + 4;
+          const uint32_t off0 = (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4);
+          const uint32_t off1 = (r1 >> 3) * 1024 + (r1 & 7) * 128 + ((chunk ^ (r1 & 7)) << 4);
+          float acc[2] = {0.f, 0.f};
+          bool big[2] = {false, false};
+#pragma unroll 4
+          for (int kb = 0; kb < p.KB; ++kb) {
+            uint4 u[2], l[2];
+            u[0] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off0);
+            u[1] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off1);
+            if (p.n_a == 2) {
+              l[0] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off0);
+              l[1] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off1);
+            } else {
+              l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const uint32_t w[4] = {u[b].x, u[b].y, u[b].z, u[b].w};
+              const uint32_t wl[4] = {l[b].x, l[b].y, l[b].z, l[b].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float h0, h1, l0, l1;
+                bool dummy = false;
+                sq2(w[e], true, h0, h1, big[b]);
+                sq2(wl[e], true, l0, l1, dummy);
+                acc[b] = fmaf(h0 + l0, h0 + l0, acc[b]);
+                acc[b] = fmaf(h1 + l1, h1 + l1, acc[b]);
+              }
+            }
+          }
+          float a0 = acc[0], a1 = acc[1];
+          int b0 = big[0] ? 1 : 0, b1 = big[1] ? 1 : 0;
+#pragma unroll
+          for (int m = 1; m <= 4; m <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, m);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+            b0 |= __shfl_xor_sync(0xffffffffu, b0, m);
+            b1 |= __shfl_xor_sync(0xffffffffu, b1, m);
+          }
+          if (chunk == 0) { ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1; xflag[r0] = b0; xflag[r1] = b1; }
+        }
       }
       __syncwarp();
       if (lane == 0) {
@@ -782,8 +881,14 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
                        int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
-  if (n_passes == 0) n_passes = (n_a == 2) ? 3 : 2;
-  if (n_passes < 1 || n_passes > 3 || (n_passes == 3 && n_a != 2)) return VQB_E_INVALID;
+  // Pass schemes (fp16 operands; hi carries 11 mantissa bits, hi + lo 22):
+  //   bf16 rows  (n_a = 1, exact in fp16):  1: (x, c_hi)                     2: + (x, c_lo)
+  //   fp16 split (n_a = 2, fp32 inputs):     2: (x_hi, c_hi) + (x_lo, c_hi)  3: + (x_hi, c_lo)
+  // The cheaper scheme leaves ||x|| * max||c - fp16(c)|| (~2^-12 ||x|| ||c||) in the band: the share of rows sent to the
+  // exact re-score grows with the codebook size (top-2 gaps shrink ~ 1/K), so large codebooks take the extra pass.
+  const bool a_fp16 = n_a == 2;
+  if (n_passes == 0) n_passes = (a_fp16 ? 2 : 1) + (K > 4096 ? 1 : 0);
+  if (n_passes < 1 || n_passes > 3 || (a_fp16 ? n_passes < 2 : n_passes > 2)) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   const int KB = (D + BK - 1) / BK;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;
@@ -796,8 +901,12 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   p.N = N; p.D = D; p.K = K;
   p.BN = code_tile(K);
   p.Kpad = vqb_padded_codes(K);
-  if (n_passes < 3) n_a = 1;  // plane 1 of A is only read by pass 2
   p.n_a = n_a; p.n_passes = n_passes; p.KB = KB;
+  p.a_fp16 = a_fp16 ? 1 : 0;
+  for (int i = 0; i < 3; ++i) { p.pass_a[i] = 0; p.pass_b[i] = 0; }
+  if (a_fp16) { p.pass_a[1] = 1; p.pass_b[2] = 1; }   // (a0,hi) (a1,hi) [(a0,lo)]
+  else p.pass_b[1] = 1;                                // (a0,hi) [(a0,lo)]
+  p.cres_index = (a_fp16 ? n_passes == 3 : n_passes == 2) ? 2 : 1;
   p.num_row_tiles = static_cast<int>((N + BM - 1) / BM);
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
@@ -809,7 +918,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   if (rc) return rc;
   p.metric = metric;
   p.cnorm2 = cnorm2;
-  p.b_hi = static_cast<const uint16_t*>(b_planes);
+  p.b_hi = static_cast<const uint16_t*>(b_planes) + static_cast<size_t>(2) * p.Kpad * D;   // plane 2: bf16(c), the quantized rows
   // pure-copy tail: nothing needs x again (no residual / running sum / fused statistics); the cosine loss needs ||c||^2
   p.copy_mode = p.fo.enabled && !p.fo.resid_out && !p.fo.qsum && !p.fo.stats_sum &&
                 !(metric == VQB_METRIC_COSINE && p.fo.loss_sum && !cnorm2);
@@ -836,7 +945,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   CUtensorMap tmA, tmB, tmX;
   rc = make_map(&tmA, a_planes, D, N, n_a, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);  // plane stride = N*D either way
   if (rc) return rc;
-  rc = make_map(&tmB, b_planes, D, p.Kpad, 2, BK, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);
+  rc = make_map(&tmB, b_planes, D, p.Kpad, 3, BK, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);   // planes: fp16 hi, fp16 lo, bf16 rows
   if (rc) return rc;
   rc = make_map(&tmX, bext, 16, p.Kpad, 1, 16, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;

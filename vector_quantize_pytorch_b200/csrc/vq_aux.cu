@@ -4,6 +4,7 @@
 #include "vqb_common.cuh"
 #include "code_operands.cuh"
 #include "gather_row.cuh"
+#include <cuda_fp16.h>
 
 namespace vqb {
 
@@ -48,10 +49,11 @@ __global__ void input_prepare_kernel(const void* __restrict__ x, int64_t N, int 
       float v = E::load(x, base + i);
       if (cosine) v = E::round(__fdiv_rn(v, nrm));  // ... x / norm, rounded to the dtype
       if (x_eff) E::store(x_eff, base + i, v);
-      if (planes) {
-        const uint16_t h = float_to_bf16_bits(v);
-        planes[base + i] = h;
-        if (n_planes == 2) planes[N * D + base + i] = float_to_bf16_bits(v - bf16_bits_to_float(h));
+      if (planes) {  // fp16 split (hi carries 11 mantissa bits, hi + lo 22); beyond the fp16 range: clamped, and the search
+                     // kernel hands such rows to the exact re-score (it sees |hi| = 65504)
+        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+        planes[base + i] = __half_as_ushort(h);
+        if (n_planes == 2) planes[N * D + base + i] = __half_as_ushort(__float2half_rn(v - __half2float(h)));
       }
     }
   }
@@ -376,7 +378,7 @@ extern "C" int vqb_codebook_prepare(const float* embed, int K, int D, int metric
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(planes)) & 15) return VQB_E_ALIGN;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaError_t e = cudaMemsetAsync(cmax, 0, sizeof(float), s);
+  cudaError_t e = cudaMemsetAsync(cmax, 0, 4 * sizeof(float), s);
   if (e != cudaSuccess) return static_cast<int>(e);
   const int Kpad = vqb_padded_codes(K);
   const int wpb = ROW_THREADS / 32;

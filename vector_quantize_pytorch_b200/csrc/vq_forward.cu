@@ -8,6 +8,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 
 using namespace vqb;
 
@@ -79,6 +80,9 @@ struct StructEntry {
   unsigned long long last_use;
   bool used;
 };
+// ctypes releases the GIL around every call: two Python threads may enter vqb_vq_forward at once.  The cache (and the lazily
+// created internal streams) are process-global, so one mutex serialises the cache lookup / capture / launch.
+std::mutex g_cache_mutex;
 StructEntry* g_struct = nullptr;  // [kMaxStruct], allocated on first use
 unsigned long long g_tick = 0;
 int g_graph_failures = 0;         // capture / instantiate / update failures: give up after a few
@@ -186,6 +190,7 @@ int capture_chain(const vqb_vq_forward_args* a, cudaStream_t s, cudaGraph_t* out
 
 extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   if (!a) return VQB_E_INVALID;
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   if (!graph_mode() || g_graph_disabled || a->ev_search_begin || a->ev_search_end || vqb_debug_active() ||

@@ -12,10 +12,12 @@ import torch
 from . import _C
 from ._C import lib, check
 
-# A row is certified by the tensor-core pass when its best score leads all others by more than
-# 2*margin*||x||*max||c||.  The split-bf16 passes were measured at <= 1.5e-6 * ||x|| max||c|| (2^-19.3) on B200
-# (tests/test_parity_gpu.py::test_score_error_inside_margin asserts < 2^-18); 2^-17 keeps a 5x margin over the
-# measurement while halving the flagged rows of the earlier 2^-16 setting.  See DESIGN.md 4.1.
+# A row is certified by the tensor-core passes when its best score leads all others by more than the band
+#   2 * (||x|| * cres + margin * ||x|| * max||c||) + (tag slack, sqrt-collapse width),
+# cres = exact norm of what the pass scheme leaves out of the fp16 codebook operands (max_k ||c - hi|| or ||c - hi - lo||,
+# csrc/code_operands.cuh).  `margin` covers the fp32 accumulation in the tensor core and all second-order terms: measured
+# <= 1.5e-6 * ||x|| max||c|| (2^-19.3) on B200 (tests/test_parity_gpu.py::test_score_error_inside_margin asserts the whole
+# bound); 2^-17 keeps a 5x margin over the measurement.  See DESIGN.md 4.1.
 DEFAULT_MARGIN = 2.0 ** -17
 
 _DT = {torch.float32: _C.DTYPE_F32, torch.bfloat16: _C.DTYPE_BF16}
@@ -59,11 +61,11 @@ def padded_codes(K: int) -> int:
 @dataclass
 class CodebookOperands:
     """Tensor-core view of one codebook (see vqb_codebook_prepare in include/vqb200.h)."""
-    planes: torch.Tensor  # bf16 (2, Kpad, D)
+    planes: torch.Tensor  # 2-byte (3, Kpad, D): fp16 hi, fp16 lo, bf16 rows (csrc/code_operands.cuh)
     bext: torch.Tensor  # bf16 (Kpad, 16): -bias as three bf16 terms (the operand of the "bias MMA")
     bias: torch.Tensor  # f32 (Kpad,)
     cnorm2: torch.Tensor  # f32 (K,)
-    cmax: torch.Tensor  # f32 (1,)
+    cmax: torch.Tensor  # f32 (4,): max||c||, max||c - hi||, max||c - hi - lo||, unused
     scratch: torch.Tensor  # f32 (2,)
     K: int
     D: int
@@ -73,11 +75,11 @@ class CodebookOperands:
     def allocate(K: int, D: int, cosine: bool, device) -> "CodebookOperands":
         Kpad = padded_codes(K)
         return CodebookOperands(
-            planes=torch.empty((2, Kpad, D), dtype=torch.bfloat16, device=device),
+            planes=torch.empty((3, Kpad, D), dtype=torch.float16, device=device),
             bext=torch.empty((Kpad, 16), dtype=torch.bfloat16, device=device),
             bias=torch.empty((Kpad,), dtype=torch.float32, device=device),
             cnorm2=torch.empty((K,), dtype=torch.float32, device=device),
-            cmax=torch.zeros((1,), dtype=torch.float32, device=device),
+            cmax=torch.zeros((4,), dtype=torch.float32, device=device),
             scratch=torch.zeros((2,), dtype=torch.float32, device=device),
             K=K, D=D, cosine=cosine)
 
@@ -131,7 +133,7 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
                 x_eff = x
             a_planes, n_a = x_eff, 1
         else:
-            a_planes = torch.empty((2, N, D), dtype=torch.bfloat16, device=dev)
+            a_planes = torch.empty((2, N, D), dtype=torch.float16, device=dev)   # fp16 hi / lo split of the fp32 input
             x_eff = torch.empty_like(x) if l2 else x
             check(lib.vqb_input_prepare(_p(x), dt, N, D, int(l2), _p(x_eff) if l2 else None, _p(a_planes), 2, st),
                   "vqb_input_prepare")
