@@ -74,13 +74,14 @@ const char* vqb_strerror(int code);
 int vqb_padded_codes(int K);
 
 /* Derive the tensor-core operands of a codebook from its fp32 rows (embed, K x D):
- *   planes  2-byte [3][Kpad][D] : [0] fp16 hi = fp16(c), [1] fp16 lo = fp16(c - hi), [2] bf16(c) (rows >= K are zero)
+ *   planes  2-byte [3][Kpad][D] : [0] bf16 hi = bf16(c), [1] bf16 lo = bf16(c - hi), [2] fp16(c) with |c| < 2^-14 flushed to 0
+ *                               and |c| clamped to 65504 (rows >= K are zero)
  *   bext    bf16 [Kpad][16]   : -bias as three bf16 terms in columns 0..2 (rest 0); rows >= K hold -3e38.
  *                               A K=16 MMA against [1 1 1 0..] seeds the accumulator with -bias.
  *   bias    f32  [Kpad]       : euclid 0.5*||c||^2, cosine 0, rows >= K +inf (informational)
  *   cnorm2  f32  [K]          : ||c||^2 (f64-accumulated), used by the exact re-score
- *   cmax    f32  [4]          : [0] max_k ||c||, [1] max_k ||c - hi||, [2] max_k ||c - hi - lo|| (exact residual norms
- *                               of the fp16 operands: they size the certification band of the search), [3] unused
+ *   cmax    f32  [4]          : [0] max_k ||c||, [1] max_k ||c - fp16 plane|| (exact residual norm: it sizes the certification
+ *                               band of the single-pass scheme), [2..3] unused
  * Replaces nothing in the reference (it searches the fp32 rows directly, :710-712, :743); this is
  * the layout change that lets the search run on tcgen05.  Also done by vqb_ema_apply. */
 int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, void* bext, float* bias,
@@ -88,8 +89,8 @@ int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* pla
 
 /* Input staging (only needed for fp32 inputs and/or the cosine metric):
  *   x_eff    [N][D] in `dtype`: l2norm(x) evaluated in the input dtype (:1159 -> :376); may be NULL for euclid
- *   a_planes fp16 [n_planes][N][D]: fp16 hi / lo split of the (normalised) input — fp32 inputs, n_planes = 2.
- *            (bf16 inputs need no planes: vqb_assign reads the bf16 rows and converts them to fp16 in shared memory)
+ *   a_planes bf16 [n_planes][N][D]: bf16 hi / lo split of the (normalised) input — fp32 inputs, n_planes = 2.
+ *            (bf16 inputs need no planes: vqb_assign reads the bf16 rows in place)
  * For a bf16 euclid input nothing is needed: x itself is the single A plane. */
 int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, void* x_eff, void* a_planes,
                       int n_planes, void* stream);
@@ -97,9 +98,10 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
 /* Nearest-code search: replaces cdist/einsum + argmax (:58-62, :741-747, :130-145) without ever
  * materialising the (N x K) distance matrix.  tcgen05 MMA over TMA-staged tiles, fp32 accumulate in
  * TMEM, fused running arg-max.  Scores are x.c - 0.5||c||^2 (euclid) or x.c (cosine).
- *   a_planes  n_a = 1: bf16 rows [N][D] (the input itself; exact in fp16)  — n_passes 1: (x,c_hi), 2: + (x,c_lo)
- *             n_a = 2: fp16 hi/lo planes [2][N][D] from vqb_input_prepare — n_passes 2: (x_hi,c_hi)+(x_lo,c_hi), 3: + (x_hi,c_lo)
- *             n_passes 0 = automatic (the extra c_lo pass for K > 4096)
+ *   a_planes  n_a = 1: bf16 rows [N][D] (the input itself) — n_passes 1: ONE fp16 pass (rows converted to fp16 in shared
+ *                      memory, fp16 codebook plane; needs ceil(D/64) <= 8), 2: bf16 (x,c_hi) + (x,c_lo)
+ *             n_a = 2: bf16 hi/lo planes [2][N][D] from vqb_input_prepare — n_passes 3: (x_hi,c_hi)+(x_hi,c_lo)+(x_lo,c_hi)
+ *             n_passes 0 = automatic: n_a = 2 -> 3;  n_a = 1 -> 1 if K <= 4096 and ceil(D/64) <= 8, else 2
  *   b_planes/bext/cmax           from vqb_codebook_prepare / vqb_ema_apply
  *   margin_rel                   a row is certified when its best score leads every other code by more
  *                                than 2*margin_rel*||x||*cmax; otherwise it is appended to `flagged`

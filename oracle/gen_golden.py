@@ -112,9 +112,22 @@ def expire_cases():
              clustered=True, seed_steps=True)
 
 
+def kmeans_cases():
+    """kmeans_init=True (vqp:238-278, :451-473): the first training batch initialises the codebook with Lloyd iterations;
+    `initted` starts False, so `randomize=False` (the zero codebook of vqp:383) and the RNG is re-seeded per step."""
+    T = "train"
+    run_case("kmeans_vq_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=24, kmeans_init=True, kmeans_iters=4), (4, 128, 32), "fp32",
+             [T, T], dict(kind="vq", dim=32, codebook_size=24, kmeans_init=True, kmeans_iters=4), randomize=False, seed_steps=True)
+    run_case("kmeans_vq_cosine_bf16", lambda r: r.VectorQuantize(dim=32, codebook_size=24, kmeans_init=True, kmeans_iters=3, use_cosine_sim=True),
+             (4, 128, 32), "bf16", [T, T], dict(kind="vq", dim=32, codebook_size=24, kmeans_init=True, kmeans_iters=3, use_cosine_sim=True),
+             randomize=False, seed_steps=True)
+
+
 def main():
     if "--expire" in sys.argv:
         return expire_cases()
+    if "--kmeans" in sys.argv:
+        return kmeans_cases()
     T, E = "train", "eval"
     # --- VectorQuantize (vqp.py:802) ---
     run_case("vq_euclid_fp32", lambda r: r.VectorQuantize(dim=64, codebook_size=96), (2, 80, 64), "fp32",

@@ -208,17 +208,52 @@ def expire_codes(state: CodebookState, samples: np.ndarray, threshold: float, re
     return num
 
 
+def kmeans(samples: np.ndarray, num_clusters: int, num_iters: int, cosine: bool, pick_fn):
+    """vqp:238-278 for one codebook: Lloyd iterations from `sample_vectors(samples, K)` (vqp:156-163; `pick_fn(n, K)`
+    supplies the sampled row ids).  Empty clusters keep their previous mean (vqp:271-275).  Returns (means, bins)."""
+    samples = np.asarray(samples, dtype=F32)
+    means = samples[np.asarray(pick_fn(samples.shape[0], num_clusters)).astype(np.int64)].copy()
+    bins = np.zeros(num_clusters, dtype=np.int64)
+    for _ in range(num_iters):
+        dists = (samples @ means.T).astype(F32) if cosine else neg_cdist(samples, means)  # vqp:251-254
+        buckets = argmax_first(dists)  # vqp:256
+        bins = np.bincount(buckets, minlength=num_clusters)  # vqp:257
+        zero = bins == 0
+        new = np.zeros((num_clusters, samples.shape[1]), dtype=np.float64)
+        np.add.at(new, buckets, samples.astype(np.float64))  # vqp:265
+        new = (new / np.maximum(bins, 1)[:, None]).astype(F32)  # vqp:266
+        if cosine:
+            new = l2norm(new)  # vqp:269-270
+        means = np.where(zero[:, None], means, new)  # vqp:272-276
+    return means.astype(F32), bins
+
+
+def init_embed(state: CodebookState, data: np.ndarray, *, kmeans_iters: int, cosine: bool, eps: float, pick_fn) -> None:
+    """vqp:451-473: k-means initialisation on the first batch, then update_ema."""
+    if state.initted:
+        return
+    K = state.cluster_size.shape[0]
+    embed, bins = kmeans(data, K, kmeans_iters, cosine, pick_fn)
+    cluster_size = bins.astype(F32)
+    state.embed_avg[...] = embed * cluster_size[:, None]  # vqp:467-469
+    state.cluster_size[...] = cluster_size  # vqp:470
+    update_ema(state, eps, cosine)  # vqp:471
+    state.initted = True
+
+
 def codebook_forward(x: np.ndarray, state: CodebookState, *, cosine: bool = False, training: bool = True,
                      decay: float = 0.8, eps: float = 1e-5, ema_update: bool = True,
                      manual_ema_update: bool = False, freeze_codebook: bool = False, all_reduce=None,
                      ema_update_weight=None, faithful: bool = False, threshold_ema_dead_code: float = 0,
-                     pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False):
+                     pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False, kmeans_iters: int = 10):
     """x: (N, D) fp32 (already upcast, vqp:692; already l2-normalised if cosine, vqp:1159).
 
     Returns (quantize (N, D) fp32, embed_ind (N,) int64).  Mutates `state` like the reference:
     the search and the returned quantize use the PRE-update codebook (vqp:766 precedes :783-784).
     """
     x = np.asarray(x, dtype=F32)
+    if not state.initted:  # vqp:703
+        init_embed(state, x, kmeans_iters=kmeans_iters, cosine=cosine, eps=eps, pick_fn=pick_fn)
     embed = state.embed  # vqp:710-712
     dist = scores(x, embed, cosine)  # vqp:741 / :743
     ind = argmax_first(dist)  # vqp:747 -> :140
@@ -288,6 +323,7 @@ class VQConfig:
     manual_ema_update: bool = False
     ema_update: bool = True
     threshold_ema_dead_code: float = 0  # vqp:818
+    kmeans_iters: int = 10  # vqp:816
 
 
 def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *, training: bool = True,
@@ -305,7 +341,8 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
         x, state, cosine=cfg.use_cosine_sim, training=training, decay=cfg.decay, eps=cfg.eps,
         ema_update=cfg.ema_update, manual_ema_update=cfg.manual_ema_update, freeze_codebook=freeze_codebook,
         all_reduce=all_reduce, faithful=faithful, ema_update_weight=ema_update_weight,
-        threshold_ema_dead_code=cfg.threshold_ema_dead_code, pick_fn=pick_fn, accum=accum, accum_ema_update=accum_ema_update)
+        threshold_ema_dead_code=cfg.threshold_ema_dead_code, pick_fn=pick_fn, accum=accum, accum_ema_update=accum_ema_update,
+        kmeans_iters=cfg.kmeans_iters)
     quantize = cast_like(quantize, dtype)  # vqp:1178
     loss = F32(0.0)
     loss_f32 = F32(0.0)

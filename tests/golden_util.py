@@ -18,7 +18,7 @@ def golden_names():
 
 def replayable_on_gpu(names):
     """Fixtures whose outputs do not depend on the CPU RNG (dead-code expiry draws torch.randperm on the tensor's device)."""
-    return [n for n in names if not n.startswith("expire")]
+    return [n for n in names if not n.startswith(("expire", "kmeans"))]
 
 
 def cpu_pick_fn(n, num):
@@ -43,11 +43,12 @@ class Golden:
         return O.VQConfig(dim=dim, codebook_size=m["codebook_size"], use_cosine_sim=m.get("use_cosine_sim", False),
                           decay=m.get("decay", 0.8), eps=m.get("eps", 1e-5),
                           commitment_weight=m.get("commitment_weight", 1.0),
-                          threshold_ema_dead_code=m.get("threshold_ema_dead_code", 0))
+                          threshold_ema_dead_code=m.get("threshold_ema_dead_code", 0), kmeans_iters=m.get("kmeans_iters", 10))
 
     def state(self, tag, i):
         return O.CodebookState(self.z[f"{tag}_cb{i}_embed"].copy(), self.z[f"{tag}_cb{i}_embed_avg"].copy(),
-                               self.z[f"{tag}_cb{i}_cluster_size"].copy())
+                               self.z[f"{tag}_cb{i}_cluster_size"].copy(),
+                               initted=not (self.meta.get("kmeans_init", False) and tag == "s0_pre"))
 
     def states(self, tag):
         """Codebook states arranged as the oracle entry points expect them."""

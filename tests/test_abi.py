@@ -112,10 +112,12 @@ def test_reference_state_dict_loads(tmp_path):
 
 def test_unsupported_options_raise():
     import vector_quantize_pytorch_b200 as m
-    for kw in (dict(heads=2), dict(kmeans_init=True), dict(learnable_codebook=True), dict(stochastic_sample_codes=True),
+    for kw in (dict(heads=2), dict(learnable_codebook=True), dict(stochastic_sample_codes=True),
                dict(orthogonal_reg_weight=1.0), dict(affine_param=True)):
         with pytest.raises(NotImplementedError):
             m.VectorQuantize(dim=64, codebook_size=32, **kw)
+    vq = m.VectorQuantize(dim=64, codebook_size=32, kmeans_init=True, kmeans_iters=3)   # supported since round 2
+    assert not bool(vq._codebook.initted) and float(vq._codebook.embed.abs().sum()) == 0.0   # vqp:383, :415
     with pytest.raises(NotImplementedError):
         m.ResidualVQ(dim=32, num_quantizers=2, codebook_size=16, quantize_dropout=True)
     with pytest.raises(NotImplementedError):

@@ -186,6 +186,34 @@ def test_dead_code_expiry_matches_oracle(name):
     assert replaced_total > 0, "the fixture is meant to replace dead codes"
 
 
+@pytest.mark.parametrize("name", ["kmeans_vq_fp32", "kmeans_vq_cosine_bf16"])
+def test_kmeans_init_matches_oracle(name):
+    """kmeans_init=True (vqp:238-278, :451-473): every Lloyd iteration runs the search + statistics kernels.  Inputs as in
+    the reference-generated `kmeans_*` goldens (which pin the oracle); sampled seeds replayed from the CUDA generator."""
+    m = vqb()
+    g = Golden(name)
+    meta = g.meta
+    kw = dict(dim=meta["dim"], codebook_size=meta["codebook_size"], kmeans_init=True, kmeans_iters=meta["kmeans_iters"])
+    if meta.get("use_cosine_sim"):
+        kw["use_cosine_sim"] = True
+    module = m.VectorQuantize(**kw).to(DEV)
+    state = g.states("s0_pre")
+    assert not state.initted and not bool(module._codebook.initted)
+    dt = meta["dtype"]
+    module.train()
+    for step in range(len(meta["steps"])):
+        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(torch.bfloat16 if dt == "bf16" else torch.float32)
+        torch.manual_seed(9100 + step)
+        q, ind, loss = module(x)
+        torch.cuda.synchronize()
+        torch.manual_seed(9100 + step)
+        qo, io, lo, _ = O.vq_forward(g[f"s{step}_x"], dt, state, g.cfg, pick_fn=cuda_pick_fn)
+        assert bool(module._codebook.initted)
+        assert np.array_equal(ind.cpu().numpy(), io), f"{name} step {step}"
+        np.testing.assert_allclose(loss.item(), float(lo), rtol=1e-5 if dt == "fp32" else 8e-3)
+        assert_state(module._codebook, state, 3e-5)
+
+
 def test_forward_host_expires_dead_codes():
     torch.manual_seed(15)
     vq = vqb().VectorQuantize(dim=64, codebook_size=64, threshold_ema_dead_code=2).to(DEV)

@@ -14,7 +14,7 @@ def run_oracle(g, step, states, faithful=False):
     m, cfg = g.meta, g.cfg
     x = g[f"s{step}_x"]
     training = m["steps"][step] == "train"
-    if m.get("threshold_ema_dead_code", 0) > 0:  # replay the reference's RNG stream (oracle/gen_golden.py seeds every step)
+    if m.get("threshold_ema_dead_code", 0) > 0 or m.get("kmeans_init"):  # replay the reference's RNG stream (gen_golden.py seeds every step)
         import torch
         torch.manual_seed(5000 + step)
     if m["kind"] == "vq":

@@ -56,8 +56,8 @@ class Codebook(nn.Module):
         super().__init__()
         if num_codebooks != 1:
             _unsupported("num_codebooks > 1 (multi-head codebooks)")
-        if kmeans_init:
-            _unsupported("kmeans_init")
+        if kmeans_init and use_ddp and sync_kmeans:
+            _unsupported("kmeans_init with distributed sampling (use_ddp + sync_kmeans, vqp:211-229)")
         if learnable_codebook:
             _unsupported("learnable_codebook")
         if affine_param:
@@ -85,11 +85,16 @@ class Codebook(nn.Module):
         self.learnable_codebook = False
         self.use_cosine_sim = use_cosine_sim
 
-        embed = _uniform_init(num_codebooks, codebook_size, dim)  # vqp:385
-        if use_cosine_sim:
-            embed = F.normalize(embed, p=2, dim=-1, eps=1e-6)  # vqp:387-388
+        self.kmeans_iters = kmeans_iters
+        if kmeans_init:
+            embed = torch.zeros(num_codebooks, codebook_size, dim)  # vqp:383
+        else:
+            embed = _uniform_init(num_codebooks, codebook_size, dim)  # vqp:385
+            if use_cosine_sim:
+                embed = F.normalize(embed, p=2, dim=-1, eps=1e-6)  # vqp:387-388
+        self._initted_host = not kmeans_init   # host-side copy of `initted`: no device sync per forward once True
 
-        self.register_buffer("initted", torch.tensor(True))  # vqp:415 (not kmeans_init)
+        self.register_buffer("initted", torch.tensor(not kmeans_init))  # vqp:415
         self.register_buffer("cluster_size", torch.ones(num_codebooks, codebook_size))  # vqp:416
         self.register_buffer("embed_avg", embed.clone())  # vqp:417
         self.register_buffer("embed", embed)  # vqp:423
@@ -199,6 +204,42 @@ class Codebook(nn.Module):
         self._mark_operands_fresh()
 
     @torch.no_grad()
+    def init_embed_(self, data):
+        """vqp:451-473 + :238-278: k-means initialisation from the first batch (`data`: the fp32 `flatten` of vqp:692-698,
+        already l2-normalised for cosine).  Every Lloyd iteration is the hot path itself — tensor-core search with the
+        exact re-score, then the counting-sort statistics — so the bucket of every sample follows the reference's
+        argmax(-cdist) / argmax(dot) rule exactly; only the K x D mean update is torch glue."""
+        if self._initted_host:
+            return
+        if bool(self.initted):  # e.g. a loaded checkpoint: one host sync, then never again
+            self._initted_host = True
+            return
+        samples = data.reshape(-1, data.shape[-1]).float().contiguous()
+        n, K = samples.shape[0], self.codebook_size
+        # sample_vectors (vqp:156-163)
+        picks = torch.randperm(n, device=samples.device)[:K] if n >= K else torch.randint(0, n, (K,), device=samples.device)
+        means = samples[picks].contiguous()
+        off = ops.stats_offset(K)
+        bins = torch.zeros((K,), dtype=torch.float32, device=samples.device)
+        cb = None
+        for _ in range(self.kmeans_iters):
+            cb = ops.prepare_codebook(means, self.use_cosine_sim, out=cb)
+            res = ops.search(samples, cb, means, normalise=False)           # vqp:251-256
+            stats = ops.ema_stats(samples, res.idx, K)                      # vqp:257, :265
+            bins = stats[:K]
+            sums = stats[off:off + K * samples.shape[1]].view(K, -1)
+            new = sums / bins.clamp(min=1.)[:, None]                        # vqp:260-266
+            if self.use_cosine_sim:
+                new = F.normalize(new, p=2, dim=-1, eps=1e-6)               # vqp:269-270
+            means = torch.where((bins == 0)[:, None], means, new).contiguous()  # vqp:272-276
+        self.embed_avg.data.copy_((means * bins[:, None])[None])            # vqp:467-469
+        self.cluster_size.data.copy_(bins[None])                            # vqp:470
+        self._operands_key = None
+        self.update_ema()                                                   # vqp:471
+        self.initted.data.copy_(torch.tensor(True))
+        self._initted_host = True
+
+    @torch.no_grad()
     def expire_codes_(self, batch_samples):  # vqp:544-574 (PyTorch glue: RNG-bound, cold, off by default)
         """`batch_samples` as the reference's call site passes them: the fp32 `flatten` from Codebook.forward (vqp:641),
         tensors in the input dtype from ResidualVQ's final expiry (rvq:601) — `replace` re-normalises in THAT dtype."""
@@ -275,6 +316,8 @@ class Codebook(nn.Module):
         With defer_ema (or when the statistics must be all-reduced first) the EMA apply is left to the caller.
         Returns (idx32, stats or None).
         """
+        if not self._initted_host:
+            self.init_embed_(self.transform_input(x).float())   # vqp:703 (every mode, like the reference)
         cb = self.operands()
         ema_update = self.ema_update if ema_update is None else ema_update   # per-call override (vqp:628)
         custom = ema_update_weight is not None or accum_ema_update or any(
@@ -324,6 +367,8 @@ class Codebook(nn.Module):
         if flat.dtype not in (torch.float32, torch.bfloat16):
             flat = flat.float()
         flat = flat.contiguous()
+        if not self._initted_host:
+            self.init_embed_(flat.float())   # vqp:703
         cb = self.operands()
         embed2d = self.embed[0]
         with torch.no_grad():

@@ -10,19 +10,19 @@ namespace vqb {
 // One warp owns one (padded) code row.  `vals(i)` yields c[i] in fp32.
 // ---------------------------------------------------------------------------------------------
 // planes (three 2-byte planes of [Kpad][D]):
-//   [0] fp16 hi = fp16(c)            B operand of the (x, c_hi) passes
-//   [1] fp16 lo = fp16(c - hi)       B operand of the optional (x, c_lo) pass (hi + lo carries 22 mantissa bits)
-//   [2] bf16(c)                      the row `quantize = embed[ind].type(bf16)` copies for bf16 inputs (vqp:1178)
-// fp16 instead of bf16 halves: 11 instead of 8 mantissa bits per MMA operand at the same tensor-core rate, so ONE pass
-// already has a residual of 2^-12 ||c|| (bf16: 2^-9) — small enough to certify ~97 % of the rows at K ~ 1e3 — and the
-// exact norms of what each pass scheme leaves out, cmax[1] = max_k ||c - hi||, cmax[2] = max_k ||c - hi - lo||, feed the
-// certification band of the search (vq_assign.cu).  Values beyond the fp16 range are clamped; the clamp error is part
-// of those norms, i.e. such a codebook is searched correctly, just through the exact re-score.
+//   [0] bf16 hi = bf16(c)        B operand of the bf16 pass schemes; ALSO the row `quantize = embed[ind].type(bf16)` copies
+//   [1] bf16 lo = bf16(c - hi)   B operand of the (x, c_lo) pass of the bf16 schemes (hi + lo carries 16 mantissa bits)
+//   [2] fp16(c)                  B operand of the SINGLE-pass scheme for bf16 inputs: 11 instead of 8 mantissa bits at the
+//                                same tensor-core rate, i.e. a residual of 2^-12 ||c|| that certifies ~97 % of the rows at
+//                                K ~ 1e3 with one pass instead of two.  The tensor core flushes fp16 subnormals (measured:
+//                                |x| ~ 1e-6 rows scored as zero), so |c| < 2^-14 is flushed to zero HERE and values beyond
+//                                +-65504 are clamped; cmax[1] = max_k ||c - fp16 plane|| is the exact norm of everything the
+//                                plane leaves out and sizes the certification band of that scheme (vq_assign.cu).
 __device__ __forceinline__ void write_code_operands(const float* crow /*K x D row or nullptr for padding*/, int k, int K, int Kpad, int D,
                                     int metric, uint16_t* planes, uint16_t* bext, float* bias, float* cnorm2, float* cmax, int lane) {
   uint16_t* hi = planes + static_cast<int64_t>(k) * D;
   uint16_t* lo = planes + (static_cast<int64_t>(Kpad) + k) * D;
-  uint16_t* qr = planes + (static_cast<int64_t>(2) * Kpad + k) * D;
+  uint16_t* qr = planes + (static_cast<int64_t>(2) * Kpad + k) * D;   // the fp16 plane
   if (crow == nullptr) {  // padding row: never wins (bias = +inf), contributes zeros to the MMA
     for (int i = lane; i < D; i += 32) { hi[i] = 0; lo[i] = 0; qr[i] = 0; }
     if (lane == 0) bias[k] = INFINITY;
@@ -30,22 +30,19 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
     return;
   }
   double n2 = 0.0;
-  float r1 = 0.f, r2 = 0.f;
+  float r1 = 0.f;
   for (int i = lane * 4; i < D; i += 128) {
     const float4 c = *reinterpret_cast<const float4*>(crow + i);
     const float v[4] = {c.x, c.y, c.z, c.w};
     uint16_t h[4], l[4], q[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const __half hh = __float2half_rn(fminf(fmaxf(v[e], -65504.f), 65504.f));
+      h[e] = float_to_bf16_bits(v[e]);
+      l[e] = float_to_bf16_bits(v[e] - bf16_bits_to_float(h[e]));
+      const __half hh = fabsf(v[e]) < 0x1p-14f ? __float2half_rn(0.f) : __float2half_rn(fminf(fmaxf(v[e], -65504.f), 65504.f));
       const float d1 = v[e] - __half2float(hh);
-      const __half ll = __float2half_rn(fminf(fmaxf(d1, -65504.f), 65504.f));
-      const float d2 = d1 - __half2float(ll);
-      h[e] = __half_as_ushort(hh);
-      l[e] = __half_as_ushort(ll);
-      q[e] = float_to_bf16_bits(v[e]);
+      q[e] = __half_as_ushort(hh);
       r1 = fmaf(d1, d1, r1);
-      r2 = fmaf(d2, d2, r2);
       n2 += static_cast<double>(v[e]) * static_cast<double>(v[e]);
     }
     *reinterpret_cast<uint2*>(hi + i) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
@@ -54,7 +51,6 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
   }
   n2 = warp_sum(n2);
   r1 = warp_sum(r1);
-  r2 = warp_sum(r2);
   if (lane == 0) {
     const float n2f = static_cast<float>(n2);
     cnorm2[k] = n2f;
@@ -73,7 +69,6 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
     // valid as unsigned-int maxima: the values are >= 0.  The residual norms are rounded UP (they are error bounds).
     atomicMax(reinterpret_cast<unsigned int*>(cmax), __float_as_uint(sqrtf(n2f)));
     atomicMax(reinterpret_cast<unsigned int*>(cmax + 1), __float_as_uint(__fsqrt_ru(r1) * 1.0001f));
-    atomicMax(reinterpret_cast<unsigned int*>(cmax + 2), __float_as_uint(__fsqrt_ru(r2) * 1.0001f));
   }
 }
 

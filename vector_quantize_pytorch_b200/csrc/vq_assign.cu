@@ -61,16 +61,16 @@ constexpr int MMA_GROUP = 4;      // k-blocks issued per elected region of the M
 constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
 constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 12288;    // barriers + tmem ptr + row norms + merge area + threshold exchange
+constexpr int SMEM_CTRL_BYTES = 13312;    // barriers + tmem ptr + row norms + merge area + threshold exchange
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
   int64_t N;
   int D, K, Kpad, BN;
-  int n_a, n_passes;   // pass ps multiplies A plane pass_a[ps] with codebook plane pass_b[ps] (fp16 operands: 0 = hi, 1 = lo)
+  int n_a, n_passes;   // pass ps multiplies A plane pass_a[ps] with codebook plane pass_b[ps] (0 = bf16 hi, 1 = bf16 lo, 2 = fp16)
   int pass_a[3], pass_b[3];
-  int a_fp16;          // A planes already hold fp16 (vqb_input_prepare: fp32 inputs); 0: bf16 rows, converted in smem
-  int cres_index;      // which residual norm of the codebook the passes leave out: cmax[1] (no c_lo pass) or cmax[2]
+  int fp16_single;     // ONE pass with fp16 operands: the bf16 rows are converted to fp16 in the A tile, B = the fp16 plane; the
+                       // band carries the exact residual norm cmax[1].  0: the bf16 split schemes (2 / 3 passes, residual-free band)
   int KB;              // ceil(D / 64)
   int n_stages, n_xstages;
   int stream_a;        // A does not fit in smem next to a useful B ring (fp32 split input with D > 256): its k-blocks travel
@@ -110,6 +110,7 @@ struct Ctrl {  // lives at the start of dynamic smem
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
   int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
   int xflag[2][BM];                      // the row holds values beyond the fp16 range: hand it to the exact re-score
+  float xtiny[2][BM];                    // norm of the row's elements below the fp16 normal range (flushed to zero)
   float share[2][2][BM];                 // [row-tile parity][column half][row]: running maximum of each slice, read by the
                                          // partner warp to raise its skip threshold (stale values are merely conservative)
 };
@@ -280,7 +281,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);                 // bias MMA: bf16 x bf16
       // the passes multiply fp16 operands (same tensor-core rate, 3 more mantissa bits per operand than bf16)
       // timing experiment (results invalid): issue the pass MMAs with half the N extent
-      const uint32_t idesc_pass = umma_idesc_f16(2 * BM, (p.dbg_mode & 8) ? p.BN / 2 : p.BN);
+      const uint32_t n_pass = (p.dbg_mode & 8) ? p.BN / 2 : p.BN;
+      const uint32_t idesc_pass = p.fp16_single ? umma_idesc_f16(2 * BM, n_pass) : umma_idesc_bf16(2 * BM, n_pass);
       constexpr uint16_t kBoth = 0x3;
       long long w_tempty = 0, w_bfull = 0, w_xfull = 0, w_afull = 0;
       const long long mstart = PROF_CLOCK();
@@ -334,7 +336,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (ct == 0 && !p.stream_a) {  // the A sub-tile has landed (fp16 planes) / has been converted to fp16 (bf16 rows)
                   const int sub_g = p.pass_a[ps_g] * p.KB + kb_g;
                   const long long c0 = PROF_CLOCK();
-                  mbar_wait(smem_u32(p.a_fp16 ? &ctrl->a_full[sub_g] : &ctrl->a_conv[sub_g]), t & 1);
+                  mbar_wait(smem_u32(p.fp16_single ? &ctrl->a_conv[sub_g] : &ctrl->a_full[sub_g]), t & 1);
                   w_afull += PROF_CLOCK() - c0;
                 }
                 { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[st_w]), ph_w); w_bfull += PROF_CLOCK() - c0; }
@@ -394,8 +396,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
     const int pair_bar = 1 + lg;             // named barrier shared by the two warps of a lane group
     const float cmax = __ldg(p.cmax);
-    // residual of the codebook operands under this pass scheme (+ the x_lo . c_lo term a 3-pass scheme still omits)
-    const float cres = __ldg(p.cmax + p.cres_index) + (p.n_passes == 3 ? 0x1p-10f * __ldg(p.cmax + 1) : 0.f);
+    // fp16 single pass: the exact norm of what the fp16 codebook plane leaves out (code_operands.cuh); the bf16 split
+    // schemes leave nothing first-order out (margin_rel covers them, validated in round 1)
+    const float cres = p.fp16_single ? __ldg(p.cmax + 1) : 0.f;
     const uint32_t te_remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
     const uint32_t te_remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
     // number of 16-column pieces of a code tile owned by this warp (pieces 4q + 2*half + {0,1} below BN/16)
@@ -430,10 +433,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float xn = sqrtf(x2);
           const float xc = xn * cmax;
           const bool euclid = p.metric != VQB_METRIC_COSINE;
-          // 2 * |score error|: what the passes leave out of the codebook (||x|| * cres, Cauchy-Schwarz on the exact fp16
-          // residual norms), fp32 accumulation + everything second order (margin_rel), bf16 -> fp16 rounding of |x_j| < 2^-14
-          // (<= 2^-25 per element), then the tag slack and the sqrt-collapse width.
-          sc.init(2.f * (xn * cres + p.margin_rel * xc + 0x1p-25f * 32.f * cmax) +
+          // 2 * |score error|: what the pass leaves out of the codebook (||x|| * cres) and of the row (the elements below the
+          // fp16 normal range are flushed: their exact norm, xtiny), both by Cauchy-Schwarz; fp32 accumulation + everything
+          // second order (margin_rel); then the tag slack and the sqrt-collapse width.
+          sc.init(2.f * (xn * cres + p.margin_rel * xc + ctrl->xtiny[t & 1][row_in_tile] * cmax) +
                   0x1p-18f * (xc + (euclid ? 0.5f * cmax * cmax : 0.f)) +
                   (euclid ? 0x1p-22f * (x2 + cmax * cmax) : 0.f) + 1e-30f);
           // the slot of the NEXT row tile (same parity as the previous one) was last read before the pair barrier of
@@ -569,22 +572,15 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Only the leader's barriers see the TMA bytes; its store warp 0 forwards "landed" to the follower.
     // fp32 accumulation: the norm scales the certification band AND carries the commitment loss
     // (sum ||q - x||^2 = sum ||x||^2 - 2 score), so it must be as exact as the scores.
-    // |v| >= 65504 (or NaN): outside the fp16 range of the MMA operands -> the row is handed to the exact re-score
-    auto sq2 = [](uint32_t w, bool fp16, float& a0, float& a1, bool& big) {
-      float v0, v1;
-      if (fp16) { const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w)); v0 = f.x; v1 = f.y; }
-      else { v0 = __uint_as_float(w << 16); v1 = __uint_as_float(w & 0xFFFF0000u); }
-      big |= !(fabsf(v0) < 65504.f) | !(fabsf(v1) < 65504.f);
-      a0 = v0; a1 = v1;
-    };
+    auto bf16x2 = [](uint32_t w, float& v0, float& v1) { v0 = __uint_as_float(w << 16); v1 = __uint_as_float(w & 0xFFFF0000u); };
     auto row_norms = [&](int t) {
       int* xflag = ctrl->xflag[t & 1];
-      if (p.stream_a) {  // A is not resident: the norms come from the fp16 planes in global memory (L2: the TMA reads them next)
+      float* xtiny = ctrl->xtiny[t & 1];
+      if (p.stream_a) {  // A is not resident: the norms come from the bf16 planes in global memory (L2: the TMA reads them next)
         const int64_t row_t0 = static_cast<int64_t>((cluster_id + t * num_clusters) * 2 + static_cast<int>(rank)) * BM;
         for (int i = 0; i < 32; ++i) {
           const int64_t row = row_t0 + sw * 32 + i;
           float acc = 0.f;
-          bool big = false;
           if (row < p.N) {
             const uint16_t* h = p.a_global + row * p.D;
             for (int c = lane * 8; c < p.D; c += 256) {
@@ -596,17 +592,15 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float h0, h1, l0, l1;
-                bool dummy = false;
-                sq2(w[e], true, h0, h1, big);
-                sq2(wl[e], true, l0, l1, dummy);
+                bf16x2(w[e], h0, h1);
+                bf16x2(wl[e], l0, l1);
                 acc = fmaf(h0 + l0, h0 + l0, acc);
                 acc = fmaf(h1 + l1, h1 + l1, acc);
               }
             }
           }
           acc = warp_sum(acc);
-          big = __any_sync(0xffffffffu, big);
-          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xflag[sw * 32 + i] = big ? 1 : 0; }
+          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xflag[sw * 32 + i] = 0; xtiny[sw * 32 + i] = 0.f; }
         }
         __syncwarp();
         if (lane == 0) {
@@ -616,15 +610,17 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         return;
       }
       const int sub = lane >> 3, chunk = lane & 7;  // conflict-free: a warp reads 4 full 128 B rows per request
-      if (!p.a_fp16) {
-        // bf16 rows (the caller's tensor, read in place by the TMA): converted to fp16 IN the A tile, k-block by k-block as
-        // they land — exact for 2^-14 <= |v| < 65504 (bf16 has fewer mantissa bits), |error| <= 2^-25 below (in the band).
-        // The same sweep accumulates ||x||^2 from the original values.
+      if (p.fp16_single) {
+        // bf16 rows (the caller's tensor, read in place by the TMA) are converted to fp16 IN the A tile, k-block by k-block
+        // as they land: exact for 2^-14 <= |v| < 65504 (bf16 has fewer mantissa bits than fp16).  The tensor core flushes
+        // fp16 subnormals, so smaller elements are flushed HERE and their exact norm goes into the band (xtiny); a row
+        // with |v| >= 65504 (or NaN) is handed to the exact re-score (xflag).  The same sweep accumulates ||x||^2.
         uint8_t* a_mut = const_cast<uint8_t*>(a_gen);
-        float acc[8];
-        bool big[8];
+        float* xn2 = ctrl->xn2[t & 1];
+        if (chunk == 0) {   // the per-row sums are accumulated in smem k-block by k-block (keeps the sweep out of registers)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i] = 0.f; big[i] = false; }
+          for (int i = 0; i < 8; ++i) { const int r = sw * 32 + i * 4 + sub; xn2[r] = 0.f; xtiny[r] = 0.f; xflag[r] = 0; }
+        }
         for (int kb = 0; kb < p.KB; ++kb) {
           if (leader) {
             mbar_wait(smem_u32(&ctrl->a_full[kb]), t & 1);
@@ -632,23 +628,37 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           } else {
             mbar_wait_cluster(smem_u32(&ctrl->a_ready[kb]), t & 1);
           }
-#pragma unroll
+#pragma unroll 2
           for (int i = 0; i < 8; ++i) {
             const int r = sw * 32 + i * 4 + sub;
             uint4* ptr = reinterpret_cast<uint4*>(a_mut + kb * A_SUB_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
             const uint4 u = *ptr;
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
             uint32_t o[4];
+            float acc = 0.f, tiny = 0.f;
+            int big = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float v0, v1;
-              sq2(w[e], false, v0, v1, big[i]);
-              acc[i] = fmaf(v0, v0, acc[i]);
-              acc[i] = fmaf(v1, v1, acc[i]);
-              const __half2 h = __floats2half2_rn(fminf(fmaxf(v0, -65504.f), 65504.f), fminf(fmaxf(v1, -65504.f), 65504.f));
+              bf16x2(w[e], v0, v1);
+              acc = fmaf(v0, v0, acc);
+              acc = fmaf(v1, v1, acc);
+              big |= static_cast<int>(!(fabsf(v0) < 65504.f)) | static_cast<int>(!(fabsf(v1) < 65504.f));
+              const bool t0 = fabsf(v0) < 0x1p-14f, t1 = fabsf(v1) < 0x1p-14f;
+              tiny = fmaf(t0 ? v0 : 0.f, v0, tiny);
+              tiny = fmaf(t1 ? v1 : 0.f, v1, tiny);
+              const __half2 h = __floats2half2_rn(t0 ? 0.f : fminf(fmaxf(v0, -65504.f), 65504.f),
+                                                  t1 ? 0.f : fminf(fmaxf(v1, -65504.f), 65504.f));
               o[e] = *reinterpret_cast<const uint32_t*>(&h);
             }
             *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+#pragma unroll
+            for (int m = 1; m <= 4; m <<= 1) {
+              acc += __shfl_xor_sync(0xffffffffu, acc, m);
+              tiny += __shfl_xor_sync(0xffffffffu, tiny, m);
+              big |= __shfl_xor_sync(0xffffffffu, big, m);
+            }
+            if (chunk == 0) { xn2[r] += acc; xtiny[r] += tiny; xflag[r] |= big; }
           }
           fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
@@ -659,16 +669,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_conv[kb]), 0));
           }
         }
+        if (chunk == 0) {   // xtiny held the squared norm so far
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float a0 = acc[i];
-          int bg = big[i] ? 1 : 0;
-#pragma unroll
-          for (int m = 1; m <= 4; m <<= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, m);
-            bg |= __shfl_xor_sync(0xffffffffu, bg, m);
-          }
-          if (chunk == 0) { ctrl->xn2[t & 1][sw * 32 + i * 4 + sub] = a0; xflag[sw * 32 + i * 4 + sub] = bg; }
+          for (int i = 0; i < 8; ++i) { const int r = sw * 32 + i * 4 + sub; xtiny[r] = sqrtf(xtiny[r]) * 1.0001f; }
         }
       } else {
         if (leader) {
@@ -677,13 +680,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           mbar_wait_cluster(smem_u32(&ctrl->a_ready[0]), t & 1);
         }
-        // two rows per lane in flight: the dependent-FMA chain, not smem, bounds this loop
+        // two rows per lane in flight, two partial sums per row: the dependent-FMA chain, not smem, bounds this loop
         for (int i = 0; i < 8; i += 2) {
           const int r0 = sw * 32 + i * 4 + sub, r1 = r0 + 4;
           const uint32_t off0 = (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4);
           const uint32_t off1 = (r1 >> 3) * 1024 + (r1 & 7) * 128 + ((chunk ^ (r1 & 7)) << 4);
-          float acc[2] = {0.f, 0.f};
-          bool big[2] = {false, false};
+          float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll 4
           for (int kb = 0; kb < p.KB; ++kb) {
             uint4 u[2], l[2];
@@ -702,24 +704,23 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 float h0, h1, l0, l1;
-                bool dummy = false;
-                sq2(w[e], true, h0, h1, big[b]);
-                sq2(wl[e], true, l0, l1, dummy);
-                acc[b] = fmaf(h0 + l0, h0 + l0, acc[b]);
-                acc[b] = fmaf(h1 + l1, h1 + l1, acc[b]);
+                bf16x2(w[e], h0, h1);
+                bf16x2(wl[e], l0, l1);
+                acc[b][0] = fmaf(h0 + l0, h0 + l0, acc[b][0]);
+                acc[b][1] = fmaf(h1 + l1, h1 + l1, acc[b][1]);
               }
             }
           }
-          float a0 = acc[0], a1 = acc[1];
-          int b0 = big[0] ? 1 : 0, b1 = big[1] ? 1 : 0;
+          float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1];
 #pragma unroll
           for (int m = 1; m <= 4; m <<= 1) {
             a0 += __shfl_xor_sync(0xffffffffu, a0, m);
             a1 += __shfl_xor_sync(0xffffffffu, a1, m);
-            b0 |= __shfl_xor_sync(0xffffffffu, b0, m);
-            b1 |= __shfl_xor_sync(0xffffffffu, b1, m);
           }
-          if (chunk == 0) { ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1; xflag[r0] = b0; xflag[r1] = b1; }
+          if (chunk == 0) {
+            ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1;
+            xflag[r0] = 0; xflag[r1] = 0; xtiny[r0] = 0.f; xtiny[r1] = 0.f;
+          }
         }
       }
       __syncwarp();
@@ -881,14 +882,15 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
                        int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
-  // Pass schemes (fp16 operands; hi carries 11 mantissa bits, hi + lo 22):
-  //   bf16 rows  (n_a = 1, exact in fp16):  1: (x, c_hi)                     2: + (x, c_lo)
-  //   fp16 split (n_a = 2, fp32 inputs):     2: (x_hi, c_hi) + (x_lo, c_hi)  3: + (x_hi, c_lo)
-  // The cheaper scheme leaves ||x|| * max||c - fp16(c)|| (~2^-12 ||x|| ||c||) in the band: the share of rows sent to the
-  // exact re-score grows with the codebook size (top-2 gaps shrink ~ 1/K), so large codebooks take the extra pass.
-  const bool a_fp16 = n_a == 2;
-  if (n_passes == 0) n_passes = (a_fp16 ? 2 : 1) + (K > 4096 ? 1 : 0);
-  if (n_passes < 1 || n_passes > 3 || (a_fp16 ? n_passes < 2 : n_passes > 2)) return VQB_E_INVALID;
+  // Pass schemes:
+  //   n_a = 1 (bf16 rows, read in place)   1: (x -> fp16, fp16 plane): ONE pass, residual 2^-12 ||c|| carried by the band
+  //                                        2: (x, c_hi) + (x, c_lo), bf16: residual-free band (round 1)
+  //   n_a = 2 (bf16 hi/lo planes of an fp32 input, vqb_input_prepare)    3: (x_hi, c_hi) + (x_hi, c_lo) + (x_lo, c_hi)
+  // The single pass sends ~18x more rows to the exact re-score (top-2 gaps shrink ~ 1/K): it pays up to K ~ 4096.
+  const int KB0 = (D + BK - 1) / BK;
+  const bool can_single = n_a == 1 && KB0 <= MAX_A_SUB;     // the conversion needs the A tile resident in smem
+  if (n_passes == 0) n_passes = n_a == 2 ? 3 : ((can_single && K <= 4096) ? 1 : 2);
+  if (n_passes < 1 || n_passes > 3 || (n_passes == 3 && n_a != 2) || (n_passes == 1 && !can_single)) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   const int KB = (D + BK - 1) / BK;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;
@@ -901,12 +903,12 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   p.N = N; p.D = D; p.K = K;
   p.BN = code_tile(K);
   p.Kpad = vqb_padded_codes(K);
+  if (n_passes < 3) n_a = 1;  // plane 1 of A is only read by the third pass
   p.n_a = n_a; p.n_passes = n_passes; p.KB = KB;
-  p.a_fp16 = a_fp16 ? 1 : 0;
+  p.fp16_single = n_passes == 1 ? 1 : 0;
   for (int i = 0; i < 3; ++i) { p.pass_a[i] = 0; p.pass_b[i] = 0; }
-  if (a_fp16) { p.pass_a[1] = 1; p.pass_b[2] = 1; }   // (a0,hi) (a1,hi) [(a0,lo)]
-  else p.pass_b[1] = 1;                                // (a0,hi) [(a0,lo)]
-  p.cres_index = (a_fp16 ? n_passes == 3 : n_passes == 2) ? 2 : 1;
+  if (p.fp16_single) p.pass_b[0] = 2;                  // (x fp16, fp16 plane)
+  else { p.pass_b[1] = 1; p.pass_a[2] = 1; }           // (a0,hi) (a0,lo) (a1,hi)
   p.num_row_tiles = static_cast<int>((N + BM - 1) / BM);
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
@@ -918,7 +920,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   if (rc) return rc;
   p.metric = metric;
   p.cnorm2 = cnorm2;
-  p.b_hi = static_cast<const uint16_t*>(b_planes) + static_cast<size_t>(2) * p.Kpad * D;   // plane 2: bf16(c), the quantized rows
+  p.b_hi = static_cast<const uint16_t*>(b_planes);   // plane 0: bf16(c) == the quantized row for bf16 inputs
   // pure-copy tail: nothing needs x again (no residual / running sum / fused statistics); the cosine loss needs ||c||^2
   p.copy_mode = p.fo.enabled && !p.fo.resid_out && !p.fo.qsum && !p.fo.stats_sum &&
                 !(metric == VQB_METRIC_COSINE && p.fo.loss_sum && !cnorm2);
@@ -945,7 +947,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   CUtensorMap tmA, tmB, tmX;
   rc = make_map(&tmA, a_planes, D, N, n_a, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);  // plane stride = N*D either way
   if (rc) return rc;
-  rc = make_map(&tmB, b_planes, D, p.Kpad, 3, BK, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);   // planes: fp16 hi, fp16 lo, bf16 rows
+  rc = make_map(&tmB, b_planes, D, p.Kpad, 3, BK, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_128B);   // planes: bf16 hi, bf16 lo, fp16
   if (rc) return rc;
   rc = make_map(&tmX, bext, 16, p.Kpad, 1, 16, p.BN / 2, CU_TENSOR_MAP_SWIZZLE_32B);
   if (rc) return rc;

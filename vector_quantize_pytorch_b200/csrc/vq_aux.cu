@@ -49,11 +49,10 @@ __global__ void input_prepare_kernel(const void* __restrict__ x, int64_t N, int 
       float v = E::load(x, base + i);
       if (cosine) v = E::round(__fdiv_rn(v, nrm));  // ... x / norm, rounded to the dtype
       if (x_eff) E::store(x_eff, base + i, v);
-      if (planes) {  // fp16 split (hi carries 11 mantissa bits, hi + lo 22); beyond the fp16 range: clamped, and the search
-                     // kernel hands such rows to the exact re-score (it sees |hi| = 65504)
-        const __half h = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
-        planes[base + i] = __half_as_ushort(h);
-        if (n_planes == 2) planes[N * D + base + i] = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+      if (planes) {
+        const uint16_t h = float_to_bf16_bits(v);
+        planes[base + i] = h;
+        if (n_planes == 2) planes[N * D + base + i] = float_to_bf16_bits(v - bf16_bits_to_float(h));
       }
     }
   }

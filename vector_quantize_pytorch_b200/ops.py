@@ -13,11 +13,12 @@ from . import _C
 from ._C import lib, check
 
 # A row is certified by the tensor-core passes when its best score leads all others by more than the band
-#   2 * (||x|| * cres + margin * ||x|| * max||c||) + (tag slack, sqrt-collapse width),
-# cres = exact norm of what the pass scheme leaves out of the fp16 codebook operands (max_k ||c - hi|| or ||c - hi - lo||,
-# csrc/code_operands.cuh).  `margin` covers the fp32 accumulation in the tensor core and all second-order terms: measured
-# <= 1.5e-6 * ||x|| max||c|| (2^-19.3) on B200 (tests/test_parity_gpu.py::test_score_error_inside_margin asserts the whole
-# bound); 2^-17 keeps a 5x margin over the measurement.  See DESIGN.md 4.1.
+#   2 * (||x|| * cres + xtiny * max||c|| + margin * ||x|| * max||c||) + (tag slack, sqrt-collapse width).
+# Single fp16 pass (bf16 inputs, K <= 4096): cres = max_k ||c - fp16 plane|| exactly (csrc/code_operands.cuh), xtiny = norm
+# of the row's elements below the fp16 normal range (flushed).  bf16 split schemes: cres = xtiny = 0.  `margin` covers the
+# fp32 accumulation in the tensor core and all second-order terms: measured <= 1.5e-6 * ||x|| max||c|| (2^-19.3) on B200
+# (tests/test_parity_gpu.py::test_score_error_inside_margin asserts the whole bound for every scheme); 2^-17 keeps a 5x
+# margin over the measurement.  See DESIGN.md 4.1.
 DEFAULT_MARGIN = 2.0 ** -17
 
 _DT = {torch.float32: _C.DTYPE_F32, torch.bfloat16: _C.DTYPE_BF16}
@@ -61,11 +62,11 @@ def padded_codes(K: int) -> int:
 @dataclass
 class CodebookOperands:
     """Tensor-core view of one codebook (see vqb_codebook_prepare in include/vqb200.h)."""
-    planes: torch.Tensor  # 2-byte (3, Kpad, D): fp16 hi, fp16 lo, bf16 rows (csrc/code_operands.cuh)
+    planes: torch.Tensor  # 2-byte (3, Kpad, D): bf16 hi, bf16 lo (bit patterns), fp16(c) (csrc/code_operands.cuh)
     bext: torch.Tensor  # bf16 (Kpad, 16): -bias as three bf16 terms (the operand of the "bias MMA")
     bias: torch.Tensor  # f32 (Kpad,)
     cnorm2: torch.Tensor  # f32 (K,)
-    cmax: torch.Tensor  # f32 (4,): max||c||, max||c - hi||, max||c - hi - lo||, unused
+    cmax: torch.Tensor  # f32 (4,): max||c||, max||c - fp16 plane||, unused, unused
     scratch: torch.Tensor  # f32 (2,)
     K: int
     D: int
@@ -133,7 +134,7 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
                 x_eff = x
             a_planes, n_a = x_eff, 1
         else:
-            a_planes = torch.empty((2, N, D), dtype=torch.float16, device=dev)   # fp16 hi / lo split of the fp32 input
+            a_planes = torch.empty((2, N, D), dtype=torch.bfloat16, device=dev)   # bf16 hi / lo split of the fp32 input
             x_eff = torch.empty_like(x) if l2 else x
             check(lib.vqb_input_prepare(_p(x), dt, N, D, int(l2), _p(x_eff) if l2 else None, _p(a_planes), 2, st),
                   "vqb_input_prepare")

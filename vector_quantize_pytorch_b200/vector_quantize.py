@@ -131,9 +131,6 @@ class VectorQuantize(nn.Module):
             _unsupported("cross-entropy / orthogonal / diversity losses (they need the N x K distance matrix)")
         if sync_update_v > 0:
             _unsupported("sync_update_v")
-        if kmeans_init:
-            _unsupported("kmeans_init")
-
         ema_update = True if ema_update is None else ema_update  # vqp:854
         if not ema_update:
             # a frozen, non-learnable codebook is still a valid use of the search kernels
@@ -175,6 +172,8 @@ class VectorQuantize(nn.Module):
             decay=decay,
             eps=eps,
             threshold_ema_dead_code=threshold_ema_dead_code,
+            kmeans_init=kmeans_init,
+            kmeans_iters=kmeans_iters,
             use_ddp=sync_codebook,
             sync_kmeans=sync_kmeans,
             sample_codebook_temp=sample_codebook_temp,
