@@ -18,6 +18,8 @@ namespace vqb {
 //                                |x| ~ 1e-6 rows scored as zero), so |c| < 2^-14 is flushed to zero HERE and values beyond
 //                                +-65504 are clamped; cmax[1] = max_k ||c - fp16 plane|| is the exact norm of everything the
 //                                plane leaves out and sizes the certification band of that scheme (vq_assign.cu).
+// cmax[2] = max_k ||c - hi - lo|| and cmax[3] = max_k ||lo|| do the same for the bf16 split schemes: the band is a
+// Cauchy-Schwarz bound on exact norms, not an empirical constant (a single heavy coordinate reaches it).
 __device__ __forceinline__ void write_code_operands(const float* crow /*K x D row or nullptr for padding*/, int k, int K, int Kpad, int D,
                                     int metric, uint16_t* planes, uint16_t* bext, float* bias, float* cnorm2, float* cmax, int lane) {
   uint16_t* hi = planes + static_cast<int64_t>(k) * D;
@@ -30,7 +32,7 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
     return;
   }
   double n2 = 0.0;
-  float r1 = 0.f;
+  float r1 = 0.f, r2 = 0.f, l2 = 0.f;
   for (int i = lane * 4; i < D; i += 128) {
     const float4 c = *reinterpret_cast<const float4*>(crow + i);
     const float v[4] = {c.x, c.y, c.z, c.w};
@@ -38,7 +40,11 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       h[e] = float_to_bf16_bits(v[e]);
-      l[e] = float_to_bf16_bits(v[e] - bf16_bits_to_float(h[e]));
+      const float dl = v[e] - bf16_bits_to_float(h[e]);
+      l[e] = float_to_bf16_bits(dl);
+      const float d2 = dl - bf16_bits_to_float(l[e]);
+      r2 = fmaf(d2, d2, r2);
+      l2 = fmaf(bf16_bits_to_float(l[e]), bf16_bits_to_float(l[e]), l2);
       const __half hh = fabsf(v[e]) < 0x1p-14f ? __float2half_rn(0.f) : __float2half_rn(fminf(fmaxf(v[e], -65504.f), 65504.f));
       const float d1 = v[e] - __half2float(hh);
       q[e] = __half_as_ushort(hh);
@@ -51,6 +57,8 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
   }
   n2 = warp_sum(n2);
   r1 = warp_sum(r1);
+  r2 = warp_sum(r2);
+  l2 = warp_sum(l2);
   if (lane == 0) {
     const float n2f = static_cast<float>(n2);
     cnorm2[k] = n2f;
@@ -68,7 +76,9 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
     for (int j = 3; j < 16; ++j) row[j] = 0;
     // valid as unsigned-int maxima: the values are >= 0.  The residual norms are rounded UP (they are error bounds).
     atomicMax(reinterpret_cast<unsigned int*>(cmax), __float_as_uint(sqrtf(n2f)));
-    atomicMax(reinterpret_cast<unsigned int*>(cmax + 1), __float_as_uint(__fsqrt_ru(r1) * 1.0001f));
+    atomicMax(reinterpret_cast<unsigned int*>(cmax + 1), __float_as_uint(__fsqrt_ru(r1) * 1.0001f));   // ||c - fp16 plane||
+    atomicMax(reinterpret_cast<unsigned int*>(cmax + 2), __float_as_uint(__fsqrt_ru(r2) * 1.0001f));   // ||c - bf16 hi - bf16 lo||
+    atomicMax(reinterpret_cast<unsigned int*>(cmax + 3), __float_as_uint(__fsqrt_ru(l2) * 1.0001f));   // ||bf16 lo||
   }
 }
 

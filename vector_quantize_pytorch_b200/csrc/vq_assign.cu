@@ -110,7 +110,8 @@ struct Ctrl {  // lives at the start of dynamic smem
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
   int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
   int xflag[2][BM];                      // the row holds values beyond the fp16 range: hand it to the exact re-score
-  float xtiny[2][BM];                    // norm of the row's elements below the fp16 normal range (flushed to zero)
+  float xtiny[2][BM];                    // single pass: norm of the row's elements below the fp16 normal range (flushed);
+                                         // bf16 split schemes: ||x_lo|| (0 for bf16 inputs)
   float share[2][2][BM];                 // [row-tile parity][column half][row]: running maximum of each slice, read by the
                                          // partner warp to raise its skip threshold (stale values are merely conservative)
 };
@@ -396,9 +397,11 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
     const int pair_bar = 1 + lg;             // named barrier shared by the two warps of a lane group
     const float cmax = __ldg(p.cmax);
-    // fp16 single pass: the exact norm of what the fp16 codebook plane leaves out (code_operands.cuh); the bf16 split
-    // schemes leave nothing first-order out (margin_rel covers them, validated in round 1)
-    const float cres = p.fp16_single ? __ldg(p.cmax + 1) : 0.f;
+    // Exact norms of what the pass scheme leaves out of the codebook operands (code_operands.cuh): the fp16 plane's residual
+    // for the single pass; ||c - hi - lo|| for the bf16 split schemes, whose three-pass form (fp32 inputs) also omits
+    // x_res . c  (|x - hi - lo| <= 2^-8 |lo| per element) and x_lo . c_lo:  xaux = ||x_lo|| there, the flushed norm otherwise.
+    const float cres = __ldg(p.cmax + (p.fp16_single ? 1 : 2));
+    const float caux = p.fp16_single ? cmax : (p.n_a == 2 ? 0x1.02p-8f * cmax + __ldg(p.cmax + 3) : 0.f);
     const uint32_t te_remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
     const uint32_t te_remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
     // number of 16-column pieces of a code tile owned by this warp (pieces 4q + 2*half + {0,1} below BN/16)
@@ -433,10 +436,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const float xn = sqrtf(x2);
           const float xc = xn * cmax;
           const bool euclid = p.metric != VQB_METRIC_COSINE;
-          // 2 * |score error|: what the pass leaves out of the codebook (||x|| * cres) and of the row (the elements below the
-          // fp16 normal range are flushed: their exact norm, xtiny), both by Cauchy-Schwarz; fp32 accumulation + everything
-          // second order (margin_rel); then the tag slack and the sqrt-collapse width.
-          sc.init(2.f * (xn * cres + p.margin_rel * xc + ctrl->xtiny[t & 1][row_in_tile] * cmax) +
+          // 2 * |score error|: what the passes leave out of the codebook (||x|| * cres) and of the row (xaux * caux), both by
+          // Cauchy-Schwarz on exact norms; the fp32 accumulation in the tensor core (margin_rel relative to ||x|| max||c||,
+          // 2^-20 relative to the bias it starts from); then the tag slack and the sqrt-collapse width.
+          sc.init(2.f * (xn * cres + ctrl->xtiny[t & 1][row_in_tile] * caux + p.margin_rel * xc + (euclid ? 0x1p-21f * cmax * cmax : 0.f)) +
                   0x1p-18f * (xc + (euclid ? 0.5f * cmax * cmax : 0.f)) +
                   (euclid ? 0x1p-22f * (x2 + cmax * cmax) : 0.f) + 1e-30f);
           // the slot of the NEXT row tile (same parity as the previous one) was last read before the pair barrier of
@@ -580,7 +583,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int64_t row_t0 = static_cast<int64_t>((cluster_id + t * num_clusters) * 2 + static_cast<int>(rank)) * BM;
         for (int i = 0; i < 32; ++i) {
           const int64_t row = row_t0 + sw * 32 + i;
-          float acc = 0.f;
+          float acc = 0.f, alo = 0.f;
           if (row < p.N) {
             const uint16_t* h = p.a_global + row * p.D;
             for (int c = lane * 8; c < p.D; c += 256) {
@@ -596,11 +599,14 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 bf16x2(wl[e], l0, l1);
                 acc = fmaf(h0 + l0, h0 + l0, acc);
                 acc = fmaf(h1 + l1, h1 + l1, acc);
+                alo = fmaf(l0, l0, alo);
+                alo = fmaf(l1, l1, alo);
               }
             }
           }
           acc = warp_sum(acc);
-          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xflag[sw * 32 + i] = 0; xtiny[sw * 32 + i] = 0.f; }
+          alo = warp_sum(alo);
+          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xflag[sw * 32 + i] = 0; xtiny[sw * 32 + i] = sqrtf(alo) * 1.0001f; }
         }
         __syncwarp();
         if (lane == 0) {
@@ -635,30 +641,32 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint4 u = *ptr;
             const uint32_t w[4] = {u.x, u.y, u.z, u.w};
             uint32_t o[4];
-            float acc = 0.f, tiny = 0.f;
-            int big = 0;
+            float sq[8];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               float v0, v1;
               bf16x2(w[e], v0, v1);
-              acc = fmaf(v0, v0, acc);
-              acc = fmaf(v1, v1, acc);
-              big |= static_cast<int>(!(fabsf(v0) < 65504.f)) | static_cast<int>(!(fabsf(v1) < 65504.f));
-              const bool t0 = fabsf(v0) < 0x1p-14f, t1 = fabsf(v1) < 0x1p-14f;
-              tiny = fmaf(t0 ? v0 : 0.f, v0, tiny);
-              tiny = fmaf(t1 ? v1 : 0.f, v1, tiny);
-              const __half2 h = __floats2half2_rn(t0 ? 0.f : fminf(fmaxf(v0, -65504.f), 65504.f),
-                                                  t1 ? 0.f : fminf(fmaxf(v1, -65504.f), 65504.f));
+              sq[2 * e] = v0 * v0;
+              sq[2 * e + 1] = v1 * v1;
+              // no clamp, no explicit flush: a value beyond +-65504 becomes inf (its row is re-scanned exactly, xflag below),
+              // one below 2^-14 an fp16 subnormal that the tensor core reads as zero (its exact norm is in xtiny)
+              const __half2 h = __floats2half2_rn(v0, v1);
               o[e] = *reinterpret_cast<const uint32_t*>(&h);
             }
             *ptr = make_uint4(o[0], o[1], o[2], o[3]);
+            float acc = ((sq[0] + sq[1]) + (sq[2] + sq[3])) + ((sq[4] + sq[5]) + (sq[6] + sq[7]));
+            float tiny = 0.f;
+            const float smin = fminf(fmin3(sq[0], sq[1], sq[2]), fmin3(fmin3(sq[3], sq[4], sq[5]), sq[6], sq[7]));
+            if (__any_sync(0xffffffffu, smin < 0x1p-28f)) {   // some element below the fp16 normal range (or an exact zero)
+#pragma unroll
+              for (int e = 0; e < 8; ++e) tiny += sq[e] < 0x1p-28f ? sq[e] : 0.f;
+            }
 #pragma unroll
             for (int m = 1; m <= 4; m <<= 1) {
               acc += __shfl_xor_sync(0xffffffffu, acc, m);
               tiny += __shfl_xor_sync(0xffffffffu, tiny, m);
-              big |= __shfl_xor_sync(0xffffffffu, big, m);
             }
-            if (chunk == 0) { xn2[r] += acc; xtiny[r] += tiny; xflag[r] |= big; }
+            if (chunk == 0) { xn2[r] += acc; xtiny[r] += tiny; }
           }
           fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
           __syncwarp();
@@ -669,9 +677,13 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_conv[kb]), 0));
           }
         }
-        if (chunk == 0) {   // xtiny held the squared norm so far
+        if (chunk == 0) {   // xtiny held the squared norm so far; an element >= 65504 (or NaN / inf) shows in the row norm
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { const int r = sw * 32 + i * 4 + sub; xtiny[r] = sqrtf(xtiny[r]) * 1.0001f; }
+          for (int i = 0; i < 8; ++i) {
+            const int r = sw * 32 + i * 4 + sub;
+            xtiny[r] = sqrtf(xtiny[r]) * 1.0001f;
+            xflag[r] = !(xn2[r] < 65504.f * 65504.f) ? 1 : 0;
+          }
         }
       } else {
         if (leader) {
@@ -686,6 +698,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t off0 = (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4);
           const uint32_t off1 = (r1 >> 3) * 1024 + (r1 & 7) * 128 + ((chunk ^ (r1 & 7)) << 4);
           float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+          float alo[2] = {0.f, 0.f};   // ||x_lo||^2 (fp32 inputs): sizes the x-side residual of the band
 #pragma unroll 4
           for (int kb = 0; kb < p.KB; ++kb) {
             uint4 u[2], l[2];
@@ -708,6 +721,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 bf16x2(wl[e], l0, l1);
                 acc[b][0] = fmaf(h0 + l0, h0 + l0, acc[b][0]);
                 acc[b][1] = fmaf(h1 + l1, h1 + l1, acc[b][1]);
+                alo[b] = fmaf(l0, l0, alo[b]);
+                alo[b] = fmaf(l1, l1, alo[b]);
               }
             }
           }
@@ -716,10 +731,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int m = 1; m <= 4; m <<= 1) {
             a0 += __shfl_xor_sync(0xffffffffu, a0, m);
             a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+            alo[0] += __shfl_xor_sync(0xffffffffu, alo[0], m);
+            alo[1] += __shfl_xor_sync(0xffffffffu, alo[1], m);
           }
           if (chunk == 0) {
             ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1;
-            xflag[r0] = 0; xflag[r1] = 0; xtiny[r0] = 0.f; xtiny[r1] = 0.f;
+            xflag[r0] = 0; xflag[r1] = 0; xtiny[r0] = sqrtf(alo[0]) * 1.0001f; xtiny[r1] = sqrtf(alo[1]) * 1.0001f;
           }
         }
       }

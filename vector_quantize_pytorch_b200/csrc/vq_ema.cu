@@ -321,7 +321,7 @@ __global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K,
     double t = 0.0;
     for (int i = 0; i < (blockDim.x >> 5); ++i) t += part[i];
     scratch[0] = static_cast<float>(t);
-    if (cmax) { cmax[0] = 0.f; cmax[1] = 0.f; cmax[2] = 0.f; }
+    if (cmax) { cmax[0] = 0.f; cmax[1] = 0.f; cmax[2] = 0.f; cmax[3] = 0.f; }
   }
 }
 

@@ -13,13 +13,14 @@ from . import _C
 from ._C import lib, check
 
 # A row is certified by the tensor-core passes when its best score leads all others by more than the band
-#   2 * (||x|| * cres + xtiny * max||c|| + margin * ||x|| * max||c||) + (tag slack, sqrt-collapse width).
-# Single fp16 pass (bf16 inputs, K <= 4096): cres = max_k ||c - fp16 plane|| exactly (csrc/code_operands.cuh), xtiny = norm
-# of the row's elements below the fp16 normal range (flushed).  bf16 split schemes: cres = xtiny = 0.  `margin` covers the
-# fp32 accumulation in the tensor core and all second-order terms: measured <= 1.5e-6 * ||x|| max||c|| (2^-19.3) on B200
-# (tests/test_parity_gpu.py::test_score_error_inside_margin asserts the whole bound for every scheme); 2^-17 keeps a 5x
-# margin over the measurement.  See DESIGN.md 4.1.
-DEFAULT_MARGIN = 2.0 ** -17
+#   2 * (||x|| * cres + xaux * caux + margin * ||x|| * max||c|| [+ 2^-21 max||c||^2]) + (tag slack, sqrt-collapse width):
+# Cauchy-Schwarz on the EXACT norms of what the pass scheme leaves out (csrc/code_operands.cuh, vq_assign.cu) — single fp16
+# pass: cres = max_k ||c - fp16 plane||, xaux = norm of the row's flushed elements; bf16 split: cres = max_k ||c - hi - lo||,
+# and for fp32 inputs xaux = ||x_lo|| with caux = 2^-8 max||c|| + max||c_lo|| — plus `margin` for the fp32 accumulation in the
+# tensor core alone: the TOTAL error of the bf16 split was measured at <= 2^-19.3 ||x|| max||c|| on B200, so 2^-18 for the
+# accumulation share keeps > 2.5x.  tests/test_parity_gpu.py::test_score_error_inside_margin asserts the bound for every
+# scheme on randn, heavy-tailed, tiny, unit-norm and default-init data.  See DESIGN.md 4.1.
+DEFAULT_MARGIN = 2.0 ** -18
 
 _DT = {torch.float32: _C.DTYPE_F32, torch.bfloat16: _C.DTYPE_BF16}
 
@@ -66,7 +67,7 @@ class CodebookOperands:
     bext: torch.Tensor  # bf16 (Kpad, 16): -bias as three bf16 terms (the operand of the "bias MMA")
     bias: torch.Tensor  # f32 (Kpad,)
     cnorm2: torch.Tensor  # f32 (K,)
-    cmax: torch.Tensor  # f32 (4,): max||c||, max||c - fp16 plane||, unused, unused
+    cmax: torch.Tensor  # f32 (4,): max||c||, max||c - fp16 plane||, max||c - bf16 hi - bf16 lo||, max||bf16 lo||
     scratch: torch.Tensor  # f32 (2,)
     K: int
     D: int
