@@ -74,14 +74,14 @@ const char* vqb_strerror(int code);
 int vqb_padded_codes(int K);
 
 /* Derive the tensor-core operands of a codebook from its fp32 rows (embed, K x D):
- *   planes  2-byte [3][Kpad][D] : [0] bf16 hi = bf16(c), [1] bf16 lo = bf16(c - hi), [2] fp16(c) with |c| < 2^-14 flushed to 0
- *                               and |c| clamped to 65504 (rows >= K are zero)
+ *   planes  2-byte [3][Kpad][D] : [0] bf16 hi = bf16(c), [1] bf16 lo = bf16(c - hi), [2] fp16(c), |c| clamped to 65504
+ *                               (rows >= K are zero)
  *   bext    bf16 [Kpad][16]   : -bias as three bf16 terms in columns 0..2 (rest 0); rows >= K hold -3e38.
  *                               A K=16 MMA against [1 1 1 0..] seeds the accumulator with -bias.
  *   bias    f32  [Kpad]       : euclid 0.5*||c||^2, cosine 0, rows >= K +inf (informational)
  *   cnorm2  f32  [K]          : ||c||^2 (f64-accumulated), used by the exact re-score
- *   cmax    f32  [4]          : [0] max_k ||c||, [1] max_k ||c - fp16 plane|| (exact residual norm: it sizes the certification
- *                               band of the single-pass scheme), [2..3] unused
+ *   cmax    f32  [4]          : [0] max_k ||c||, [1] max_k ||c - fp16 plane||, [2] max_k ||c - hi - lo||, [3] max_k ||lo||: the
+ *                               exact residual norms that size the certification band of each pass scheme
  * Replaces nothing in the reference (it searches the fp32 rows directly, :710-712, :743); this is
  * the layout change that lets the search run on tcgen05.  Also done by vqb_ema_apply. */
 int vqb_codebook_prepare(const float* embed, int K, int D, int metric, void* planes, void* bext, float* bias,
@@ -98,10 +98,12 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
 /* Nearest-code search: replaces cdist/einsum + argmax (:58-62, :741-747, :130-145) without ever
  * materialising the (N x K) distance matrix.  tcgen05 MMA over TMA-staged tiles, fp32 accumulate in
  * TMEM, fused running arg-max.  Scores are x.c - 0.5||c||^2 (euclid) or x.c (cosine).
- *   a_planes  n_a = 1: bf16 rows [N][D] (the input itself) — n_passes 1: ONE fp16 pass (rows converted to fp16 in shared
- *                      memory, fp16 codebook plane; needs ceil(D/64) <= 8), 2: bf16 (x,c_hi) + (x,c_lo)
- *             n_a = 2: bf16 hi/lo planes [2][N][D] from vqb_input_prepare — n_passes 3: (x_hi,c_hi)+(x_hi,c_lo)+(x_lo,c_hi)
- *             n_passes 0 = automatic: n_a = 2 -> 3;  n_a = 1 -> 1 if K <= 4096 and ceil(D/64) <= 8, else 2
+ *   a_planes  n_a = 1: bf16 rows [N][D] (the input itself, read in place); n_a = 2: bf16 hi/lo planes [2][N][D] of an fp32
+ *             input (vqb_input_prepare).
+ *   n_passes  n_a     : "mixed" scheme, one pass per A plane against the FP16 codebook plane (bf16 x fp16 -> fp32 MMA);
+ *             n_a + 1 : "split" scheme, bf16 hi / lo codebook planes: (x,c_hi)+(x,c_lo) [+ (x_lo,c_hi)];
+ *             0       : automatic — mixed for K <= 4096, split above (the mixed scheme's wider band sends ~18x more rows
+ *                       to the exact re-score, and top-2 gaps shrink ~ 1/K).
  *   b_planes/bext/cmax           from vqb_codebook_prepare / vqb_ema_apply
  *   margin_rel                   a row is certified when its best score leads every other code by more
  *                                than 2*margin_rel*||x||*cmax; otherwise it is appended to `flagged`
@@ -245,6 +247,12 @@ int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int K, int D, c
  * idx i64 [N][Q] (no -1 entries), embeds as for vqb_decode.  Replaces Q read-modify-write passes over (N x D). */
 int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
                        void* out, int dtype, void* stream);
+
+/* Rotation-trick gradient estimator (vector_quantize_pytorch.py:287-318, default when x.requires_grad, :856, :1225-1228).
+ *   grad_out == NULL: forward   out = rotate_to(src, tgt)        (numerically ~ tgt, carries d out / d src)
+ *   grad_out != NULL: backward  out = d loss / d src given d loss / d rotate_to(src, tgt)
+ * src, tgt, grad_out, out: [N][D] in `dtype` (arithmetic in fp32, rounded once on store). */
+int vqb_rotate(const void* src, const void* tgt, const void* grad_out, int64_t N, int D, int dtype, void* out, void* stream);
 
 #ifdef __cplusplus
 }

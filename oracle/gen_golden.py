@@ -123,7 +123,48 @@ def kmeans_cases():
              randomize=False, seed_steps=True)
 
 
+def grad_case(name, build, x_shape, dtype, meta, freeze=True):
+    """Gradient estimators (vqp:282-318, :1225-1233): the reference's d(sum(quantize * G) + loss)/dx for a seeded x, G.
+    `freeze_codebook=True`: the codebook (and so the quantized rows) is the same before and after the call."""
+    ref = load_reference()
+    torch.manual_seed(1234)
+    gen = torch.Generator().manual_seed(2468)
+    module = build(ref)
+    randomize_codebooks(module, gen, 1.0, bool(meta.get("use_cosine_sim", False)))
+    tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+    x = torch.randn(*x_shape, generator=gen).to(tdtype).requires_grad_(True)
+    G = torch.randn(*x_shape, generator=gen).to(tdtype)
+    module.train()
+    store = {}
+    snap(module, "s0_pre", store)
+    q, ind, loss = module(x, freeze_codebook=freeze)
+    ((q * G).sum() + loss.sum().to(q.dtype)).backward()
+    store.update(s0_x=f32(x), s0_G=f32(G), s0_quantize=f32(q), s0_indices=ind.cpu().numpy().astype(np.int64), s0_loss=f32(loss),
+                 s0_xgrad=f32(x.grad))
+    meta = dict(meta, name=name, dtype=dtype, steps=["train"], x_shape=list(x_shape), torch=torch.__version__,
+                n_codebooks=len(codebooks_of(module)))
+    store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **store)
+    print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def grad_cases():
+    grad_case("grad_vq_rotation_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=48), (2, 64, 32), "fp32",
+              dict(kind="vq", dim=32, codebook_size=48))
+    grad_case("grad_vq_ste_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=48, rotation_trick=False), (2, 64, 32), "fp32",
+              dict(kind="vq", dim=32, codebook_size=48, rotation_trick=False))
+    grad_case("grad_vq_rotation_cosine_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=48, use_cosine_sim=True), (2, 64, 32), "fp32",
+              dict(kind="vq", dim=32, codebook_size=48, use_cosine_sim=True))
+    grad_case("grad_vq_rotation_bf16", lambda r: r.VectorQuantize(dim=32, codebook_size=48), (2, 64, 32), "bf16",
+              dict(kind="vq", dim=32, codebook_size=48))
+    grad_case("grad_rvq_rotation_fp32", lambda r: r.ResidualVQ(dim=32, num_quantizers=3, codebook_size=48), (2, 64, 32), "fp32",
+              dict(kind="rvq", dim=32, codebook_size=48, num_quantizers=3, shared_codebook=False))
+
+
 def main():
+    if "--grad" in sys.argv:
+        return grad_cases()
     if "--expire" in sys.argv:
         return expire_cases()
     if "--kmeans" in sys.argv:

@@ -13,12 +13,17 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names():
     """Small fixtures that store their inputs (the `big*` ones are replayed by tests/test_big_golden.py)."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith("big"))
+                  if not n.startswith(("big", "grad")))
+
+
+def grad_golden_names():
+    """Gradient fixtures (oracle/gen_golden.py --grad): x, upstream gradient G, the reference's d/dx."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "grad_*.npz"))))
 
 
 def replayable_on_gpu(names):
     """Fixtures whose outputs do not depend on the CPU RNG (dead-code expiry draws torch.randperm on the tensor's device)."""
-    return [n for n in names if not n.startswith(("expire", "kmeans"))]
+    return [n for n in names if not n.startswith(("expire", "kmeans", "grad"))]
 
 
 def cpu_pick_fn(n, num):

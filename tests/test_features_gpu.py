@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from golden_util import Golden
+from golden_util import Golden, grad_golden_names
 from oracle import vq_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -272,3 +272,46 @@ def test_commit_loss_trains_project_in():
     _, _, losses = rvq(x)
     losses.sum().backward()
     assert rvq.project_in.weight.grad is not None and rvq.project_in.weight.grad.abs().sum() > 0
+
+
+# ------------------------------------------------------------------------------------------------ gradient estimators (f2)
+@pytest.mark.parametrize("name", grad_golden_names())
+def test_gradient_estimators_match_reference(name):
+    """Rotation trick (default) / straight-through (vqp:282-318, :1225-1233): d(sum(quantize * G) + loss)/dx against the
+    gradient the UNMODIFIED reference computed for the same x, G and codebook (oracle/gen_golden.py --grad).  The rotation
+    trick's forward and backward run in the vqb_rotate kernel."""
+    m = vqb()
+    g = Golden(name)
+    meta = g.meta
+    kw = dict(dim=meta["dim"], codebook_size=meta["codebook_size"])
+    for k in ("use_cosine_sim", "rotation_trick"):
+        if k in meta:
+            kw[k] = meta[k]
+    if meta["kind"] == "vq":
+        module = m.VectorQuantize(**kw).to(DEV)
+    else:
+        module = m.ResidualVQ(num_quantizers=meta["num_quantizers"], shared_codebook=meta["shared_codebook"], **kw).to(DEV)
+    books = []
+    for sub in module.modules():
+        if isinstance(sub, m.Codebook) and all(sub is not b for b in books):
+            books.append(sub)
+    for i, cb in enumerate(books):
+        st = g.state("s0_pre", i)
+        with torch.no_grad():
+            cb.embed.copy_(torch.from_numpy(st.embed)[None]); cb.embed_avg.copy_(torch.from_numpy(st.embed_avg)[None])
+            cb.cluster_size.copy_(torch.from_numpy(st.cluster_size)[None])
+    dt = torch.bfloat16 if meta["dtype"] == "bf16" else torch.float32
+    x = torch.from_numpy(g["s0_x"]).to(DEV).to(dt).requires_grad_(True)
+    G = torch.from_numpy(g["s0_G"]).to(DEV).to(dt)
+    module.train()
+    q, ind, loss = module(x, freeze_codebook=True)
+    ((q * G).sum() + loss.sum().to(q.dtype)).backward()
+    torch.cuda.synchronize()
+    assert np.array_equal(ind.cpu().numpy(), g["s0_indices"])
+    tol = 2e-5 if meta["dtype"] == "fp32" else 3e-2
+    np.testing.assert_allclose(q.detach().float().cpu().numpy(), g["s0_quantize"], rtol=tol, atol=tol)
+    np.testing.assert_allclose(loss.detach().float().cpu().numpy(), g["s0_loss"], rtol=1e-5 if meta["dtype"] == "fp32" else 8e-3, atol=1e-7)
+    ref = g["s0_xgrad"]
+    got = x.grad.float().cpu().numpy()
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(got, ref, rtol=tol, atol=tol * scale)

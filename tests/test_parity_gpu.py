@@ -173,12 +173,12 @@ SCORE_CASES = [
 
 
 @pytest.mark.parametrize("dt,D,K,dist", SCORE_CASES)
-@pytest.mark.parametrize("scheme", ["auto", "bf16_split"])
+@pytest.mark.parametrize("scheme", ["mixed", "split"])
 def test_score_error_inside_margin(dt, D, K, dist, scheme):
     """The band that certifies a row must bound the real tensor-core error of EVERY pass scheme with room to spare:
-    |score_mma - score_exact| <= ||x|| * cres + xtiny * max||c|| + margin * ||x|| * max||c||.  Single fp16 pass (bf16 inputs,
-    K <= 4096, A resident): cres = max_k ||c - fp16 plane|| (ops.CodebookOperands.cmax[1]) and xtiny = norm of the row's
-    elements below 2^-14; bf16 split schemes: both zero."""
+    |score_mma - score_exact| <= ||x|| * cres + ||x_lo|| * caux + margin * ||x|| * max||c|| + 2^-21 max||c||^2, by
+    Cauchy-Schwarz on the exact residual norms the operand-preparation kernel reports (ops.CodebookOperands.cmax).
+    mixed = bf16 rows x the fp16 codebook plane (one pass per A plane); split = bf16 hi / lo codebook planes."""
     from vector_quantize_pytorch_b200 import ops
     torch.manual_seed(5)
     N = 8192 if K <= 4096 else 2048
@@ -196,11 +196,9 @@ def test_score_error_inside_margin(dt, D, K, dist, scheme):
     x = (x * (1 if dist != "randn" else 3)).to(TDT[dt]).to(DEV)
     c = c.to(DEV).contiguous()
     cb = ops.prepare_codebook(c, False)
-    single_ok = dt == "bf16" and K <= 4096 and D <= 512
-    if scheme == "bf16_split" and dt == "fp32":
-        pytest.skip("fp32 inputs have one scheme (3 bf16 passes): covered by 'auto'")
-    n_passes = 0 if scheme == "auto" else 2
-    single = scheme == "auto" and single_ok
+    n_a = 1 if dt == "bf16" else 2
+    single = scheme == "mixed"
+    n_passes = n_a if single else n_a + 1
     res = ops.search(x, cb, c, debug_best=True, fix=False, n_passes=n_passes)
     torch.cuda.synchronize()
     s = x.double() @ c.double().T - 0.5 * (c.double() ** 2).sum(-1)[None]
@@ -218,15 +216,11 @@ def test_score_error_inside_margin(dt, D, K, dist, scheme):
     assert lo.norm(dim=-1).max().item() <= cm[3].item()
     # the kernel's per-score allowance (half of its band without the tag / sqrt terms), vq_assign.cu
     allow = ops.DEFAULT_MARGIN * xn * cmax + 2.0 ** -21 * cmax * cmax
-    if single:
-        xtiny = torch.where(xd.abs() < 2.0 ** -14, xd, torch.zeros_like(xd)).norm(dim=-1)
-        allow = allow + xn * cm[1] + xtiny * cmax
-    else:
-        allow = allow + xn * cm[2]
-        if dt == "fp32":
-            xhi = x.bfloat16().float()
-            xlo = (x - xhi).bfloat16().double().norm(dim=-1)
-            allow = allow + xlo * (2.0 ** -8 * 1.01 * cmax + cm[3])
+    allow = allow + xn * cm[1 if single else 2]
+    if dt == "fp32":
+        xhi = x.bfloat16().float()
+        xlo = (x - xhi).bfloat16().double().norm(dim=-1)
+        allow = allow + xlo * (2.0 ** -8 * 1.01 * cmax + (0.0 if single else cm[3]))
     worst = (err / allow.clamp_min(1e-300)).max().item()
     print(f"{dt} D={D} K={K} {dist} {scheme}: worst error / allowance = {worst:.3f}")
     assert worst < 1.0, (dt, D, K, dist, scheme, worst)

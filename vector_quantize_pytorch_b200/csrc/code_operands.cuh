@@ -12,12 +12,12 @@ namespace vqb {
 // planes (three 2-byte planes of [Kpad][D]):
 //   [0] bf16 hi = bf16(c)        B operand of the bf16 pass schemes; ALSO the row `quantize = embed[ind].type(bf16)` copies
 //   [1] bf16 lo = bf16(c - hi)   B operand of the (x, c_lo) pass of the bf16 schemes (hi + lo carries 16 mantissa bits)
-//   [2] fp16(c)                  B operand of the SINGLE-pass scheme for bf16 inputs: 11 instead of 8 mantissa bits at the
-//                                same tensor-core rate, i.e. a residual of 2^-12 ||c|| that certifies ~97 % of the rows at
-//                                K ~ 1e3 with one pass instead of two.  The tensor core flushes fp16 subnormals (measured:
-//                                |x| ~ 1e-6 rows scored as zero), so |c| < 2^-14 is flushed to zero HERE and values beyond
-//                                +-65504 are clamped; cmax[1] = max_k ||c - fp16 plane|| is the exact norm of everything the
-//                                plane leaves out and sizes the certification band of that scheme (vq_assign.cu).
+//   [2] fp16(c)                  B operand of the MIXED scheme (bf16 rows x fp16 codes, products exact in fp32): 11 instead of 8
+//                                mantissa bits at the same tensor-core rate, i.e. a residual of 2^-12 ||c|| that certifies ~97 %
+//                                of the rows at K ~ 1e3 with ONE pass per A plane.  The tensor core honours fp16 subnormals
+//                                (scripts/gpu_flush_probe.py: exact down to 2^-24); values beyond +-65504 are clamped.
+//                                cmax[1] = max_k ||c - fp16 plane|| is the exact norm of everything the plane leaves out
+//                                (clamp included) and sizes the certification band of that scheme (vq_assign.cu).
 // cmax[2] = max_k ||c - hi - lo|| and cmax[3] = max_k ||lo|| do the same for the bf16 split schemes: the band is a
 // Cauchy-Schwarz bound on exact norms, not an empirical constant (a single heavy coordinate reaches it).
 __device__ __forceinline__ void write_code_operands(const float* crow /*K x D row or nullptr for padding*/, int k, int K, int Kpad, int D,
@@ -45,7 +45,7 @@ __device__ __forceinline__ void write_code_operands(const float* crow /*K x D ro
       const float d2 = dl - bf16_bits_to_float(l[e]);
       r2 = fmaf(d2, d2, r2);
       l2 = fmaf(bf16_bits_to_float(l[e]), bf16_bits_to_float(l[e]), l2);
-      const __half hh = fabsf(v[e]) < 0x1p-14f ? __float2half_rn(0.f) : __float2half_rn(fminf(fmaxf(v[e], -65504.f), 65504.f));
+      const __half hh = __float2half_rn(fminf(fmaxf(v[e], -65504.f), 65504.f));
       const float d1 = v[e] - __half2float(hh);
       q[e] = __half_as_ushort(hh);
       r1 = fmaf(d1, d1, r1);

@@ -61,7 +61,7 @@ constexpr int MMA_GROUP = 4;      // k-blocks issued per elected region of the M
 constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
 constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 13312;    // barriers + tmem ptr + row norms + merge area + threshold exchange
+constexpr int SMEM_CTRL_BYTES = 12288;    // barriers + tmem ptr + row norms + merge area + threshold exchange
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
@@ -69,8 +69,8 @@ struct AssignParams {
   int D, K, Kpad, BN;
   int n_a, n_passes;   // pass ps multiplies A plane pass_a[ps] with codebook plane pass_b[ps] (0 = bf16 hi, 1 = bf16 lo, 2 = fp16)
   int pass_a[3], pass_b[3];
-  int fp16_single;     // ONE pass with fp16 operands: the bf16 rows are converted to fp16 in the A tile, B = the fp16 plane; the
-                       // band carries the exact residual norm cmax[1].  0: the bf16 split schemes (2 / 3 passes, residual-free band)
+  int mixed;           // the passes multiply the bf16 rows with the FP16 codebook plane (one pass per A plane); the band carries the
+                       // exact residual norm cmax[1].  0: the bf16 split schemes (one more pass, residual norm cmax[2])
   int KB;              // ceil(D / 64)
   int n_stages, n_xstages;
   int stream_a;        // A does not fit in smem next to a useful B ring (fp32 split input with D > 256): its k-blocks travel
@@ -97,8 +97,7 @@ struct AssignParams {
 struct Ctrl {  // lives at the start of dynamic smem
   uint64_t a_full[MAX_A_SUB], a_empty[MAX_A_SUB];
   uint64_t a_read;                       // store warps finished reading A (row norms)
-  uint64_t a_ready[MAX_A_SUB];           // follower CTA: this A sub-tile has landed (forwarded by the leader's store warp 0)
-  uint64_t a_conv[MAX_A_SUB];            // (bf16 inputs) this A sub-tile has been converted to fp16 in BOTH CTAs
+  uint64_t a_ready;                      // follower CTA: its A tile has landed (forwarded by the leader's store warp 0)
   uint64_t n_full[2];                    // row norms of a tile are in xn2[tile parity]
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
   uint64_t x_full[2], x_empty[2];        // bias blocks
@@ -109,9 +108,7 @@ struct Ctrl {  // lives at the start of dynamic smem
   float xn2[2][BM];                      // row norms, double buffered by row-tile parity
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
   int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
-  int xflag[2][BM];                      // the row holds values beyond the fp16 range: hand it to the exact re-score
-  float xtiny[2][BM];                    // single pass: norm of the row's elements below the fp16 normal range (flushed);
-                                         // bf16 split schemes: ||x_lo|| (0 for bf16 inputs)
+  float xlo[2][BM];                      // ||x_lo|| of the row (fp32 inputs: the x-side residual terms of the band); 0 for bf16 inputs
   float share[2][2][BM];                 // [row-tile parity][column half][row]: running maximum of each slice, read by the
                                          // partner warp to raise its skip threshold (stale values are merely conservative)
 };
@@ -171,10 +168,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&ctrl->a_empty[s]), 1);
     }
     mbar_init(smem_u32(&ctrl->a_read), NUM_STORE_WARPS);
-    for (int s = 0; s < n_sub; ++s) {
-      mbar_init(smem_u32(&ctrl->a_ready[s]), 1);
-      mbar_init(smem_u32(&ctrl->a_conv[s]), NUM_STORE_WARPS + 1);   // the leader's store warps + one forwarded arrive of the follower
-    }
+    mbar_init(smem_u32(&ctrl->a_ready), 1);
     mbar_init(smem_u32(&ctrl->n_full[0]), NUM_STORE_WARPS);
     mbar_init(smem_u32(&ctrl->n_full[1]), NUM_STORE_WARPS);
     for (int s = 0; s < p.n_stages; ++s) {
@@ -282,8 +276,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t idesc = umma_idesc_bf16(2 * BM, p.BN);                 // bias MMA: bf16 x bf16
       // the passes multiply fp16 operands (same tensor-core rate, 3 more mantissa bits per operand than bf16)
       // timing experiment (results invalid): issue the pass MMAs with half the N extent
+      // the passes: A is always bf16; B is a bf16 plane or the fp16 plane (mixed bf16 x fp16: products exact in fp32)
       const uint32_t n_pass = (p.dbg_mode & 8) ? p.BN / 2 : p.BN;
-      const uint32_t idesc_pass = p.fp16_single ? umma_idesc_f16(2 * BM, n_pass) : umma_idesc_bf16(2 * BM, n_pass);
+      const uint32_t idesc_bf = umma_idesc_bf16(2 * BM, n_pass), idesc_mx = umma_idesc_bf16_f16(2 * BM, n_pass);
       constexpr uint16_t kBoth = 0x3;
       long long w_tempty = 0, w_bfull = 0, w_xfull = 0, w_afull = 0;
       const long long mstart = PROF_CLOCK();
@@ -334,12 +329,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int g = 0; g < MMA_GROUP; ++g) {
               if (g < cnt) {
-                if (ct == 0 && !p.stream_a) {  // the A sub-tile has landed (fp16 planes) / has been converted to fp16 (bf16 rows)
-                  const int sub_g = p.pass_a[ps_g] * p.KB + kb_g;
-                  const long long c0 = PROF_CLOCK();
-                  mbar_wait(smem_u32(p.fp16_single ? &ctrl->a_conv[sub_g] : &ctrl->a_full[sub_g]), t & 1);
-                  w_afull += PROF_CLOCK() - c0;
-                }
+                if (ct == 0 && !p.stream_a) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[p.pass_a[ps_g] * p.KB + kb_g]), t & 1); w_afull += PROF_CLOCK() - c0; }
                 { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[st_w]), ph_w); w_bfull += PROF_CLOCK() - c0; }
                 if (++st_w == p.n_stages) { st_w = 0; ph_w ^= 1; }
                 if (++ps_g == p.n_passes) { ps_g = 0; ++kb_g; }
@@ -358,6 +348,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   const uint32_t a_lo = p.stream_a ? as_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units
                                                    : a_desc_lo0 + static_cast<uint32_t>(sub) * (A_SUB_BYTES >> 4);
                   const uint32_t b_lo = b_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units;
+                  const uint32_t idesc_pass = p.pass_b[ps] == 2 ? idesc_mx : idesc_bf;
                   if (full_k || kb + 1 < p.KB) {  // full k-block: four K=16 steps, descriptors advance by 32 B
                     umma_bf16_ss_2sm_acc(d_tmem, a_lo, desc_hi, b_lo, desc_hi, idesc_pass);
                     umma_bf16_ss_2sm_acc(d_tmem, a_lo + 2, desc_hi, b_lo + 2, desc_hi, idesc_pass);
@@ -397,11 +388,11 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row_in_tile = lg * 32 + lane;  // TMEM lane == row of the tile
     const int pair_bar = 1 + lg;             // named barrier shared by the two warps of a lane group
     const float cmax = __ldg(p.cmax);
-    // Exact norms of what the pass scheme leaves out of the codebook operands (code_operands.cuh): the fp16 plane's residual
-    // for the single pass; ||c - hi - lo|| for the bf16 split schemes, whose three-pass form (fp32 inputs) also omits
-    // x_res . c  (|x - hi - lo| <= 2^-8 |lo| per element) and x_lo . c_lo:  xaux = ||x_lo|| there, the flushed norm otherwise.
-    const float cres = __ldg(p.cmax + (p.fp16_single ? 1 : 2));
-    const float caux = p.fp16_single ? cmax : (p.n_a == 2 ? 0x1.02p-8f * cmax + __ldg(p.cmax + 3) : 0.f);
+    // Exact norms of what the pass scheme leaves out of the codebook operand (code_operands.cuh): ||c - fp16 plane|| for the
+    // mixed passes, ||c - hi - lo|| for the bf16 split.  fp32 inputs (x = hi + lo + res, |res| <= 2^-8 |lo| per element) add
+    // x_res . c and, in the split scheme, the omitted x_lo . c_lo:  ||x_lo|| * caux.
+    const float cres = __ldg(p.cmax + (p.mixed ? 1 : 2));
+    const float caux = p.n_a == 2 ? 0x1.02p-8f * cmax + (p.mixed ? 0.f : __ldg(p.cmax + 3)) : 0.f;
     const uint32_t te_remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
     const uint32_t te_remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
     // number of 16-column pieces of a code tile owned by this warp (pieces 4q + 2*half + {0,1} below BN/16)
@@ -439,7 +430,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // 2 * |score error|: what the passes leave out of the codebook (||x|| * cres) and of the row (xaux * caux), both by
           // Cauchy-Schwarz on exact norms; the fp32 accumulation in the tensor core (margin_rel relative to ||x|| max||c||,
           // 2^-20 relative to the bias it starts from); then the tag slack and the sqrt-collapse width.
-          sc.init(2.f * (xn * cres + ctrl->xtiny[t & 1][row_in_tile] * caux + p.margin_rel * xc + (euclid ? 0x1p-21f * cmax * cmax : 0.f)) +
+          sc.init(2.f * (xn * cres + ctrl->xlo[t & 1][row_in_tile] * caux + p.margin_rel * xc + (euclid ? 0x1p-21f * cmax * cmax : 0.f)) +
                   0x1p-18f * (xc + (euclid ? 0.5f * cmax * cmax : 0.f)) +
                   (euclid ? 0x1p-22f * (x2 + cmax * cmax) : 0.f) + 1e-30f);
           // the slot of the NEXT row tile (same parity as the previous one) was last read before the pair barrier of
@@ -519,8 +510,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // candidates = tagged scores inside the band below the tagged maximum, over both slices
         const float tb = fmaxf(st.t1, b1);
         const float band = tb - st.W;
-        const int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (b1 > band) + (b2 > band) + (b3 > band) +
-                      3 * ctrl->xflag[t & 1][row_in_tile];   // values beyond the fp16 range: whole-row exact re-scan
+        const int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (b1 > band) + (b2 > band) + (b3 > band);
         int i0, i1;
         if (st.t1 > b1 || (st.t1 == b1 && ia0 < ib0)) { i0 = ia0; i1 = (st.t2 > b1) ? ia1 : ib0; }
         else { i0 = ib0; i1 = (b2 > st.t1) ? ib1 : ia0; }
@@ -577,8 +567,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // (sum ||q - x||^2 = sum ||x||^2 - 2 score), so it must be as exact as the scores.
     auto bf16x2 = [](uint32_t w, float& v0, float& v1) { v0 = __uint_as_float(w << 16); v1 = __uint_as_float(w & 0xFFFF0000u); };
     auto row_norms = [&](int t) {
-      int* xflag = ctrl->xflag[t & 1];
-      float* xtiny = ctrl->xtiny[t & 1];
+      float* xlo = ctrl->xlo[t & 1];
       if (p.stream_a) {  // A is not resident: the norms come from the bf16 planes in global memory (L2: the TMA reads them next)
         const int64_t row_t0 = static_cast<int64_t>((cluster_id + t * num_clusters) * 2 + static_cast<int>(rank)) * BM;
         for (int i = 0; i < 32; ++i) {
@@ -606,7 +595,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           acc = warp_sum(acc);
           alo = warp_sum(alo);
-          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xflag[sw * 32 + i] = 0; xtiny[sw * 32 + i] = sqrtf(alo) * 1.0001f; }
+          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xlo[sw * 32 + i] = sqrtf(alo) * 1.0001f; }
         }
         __syncwarp();
         if (lane == 0) {
@@ -616,81 +605,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         return;
       }
       const int sub = lane >> 3, chunk = lane & 7;  // conflict-free: a warp reads 4 full 128 B rows per request
-      if (p.fp16_single) {
-        // bf16 rows (the caller's tensor, read in place by the TMA) are converted to fp16 IN the A tile, k-block by k-block
-        // as they land: exact for 2^-14 <= |v| < 65504 (bf16 has fewer mantissa bits than fp16).  The tensor core flushes
-        // fp16 subnormals, so smaller elements are flushed HERE and their exact norm goes into the band (xtiny); a row
-        // with |v| >= 65504 (or NaN) is handed to the exact re-score (xflag).  The same sweep accumulates ||x||^2.
-        uint8_t* a_mut = const_cast<uint8_t*>(a_gen);
-        float* xn2 = ctrl->xn2[t & 1];
-        if (chunk == 0) {   // the per-row sums are accumulated in smem k-block by k-block (keeps the sweep out of registers)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { const int r = sw * 32 + i * 4 + sub; xn2[r] = 0.f; xtiny[r] = 0.f; xflag[r] = 0; }
-        }
-        for (int kb = 0; kb < p.KB; ++kb) {
-          if (leader) {
-            mbar_wait(smem_u32(&ctrl->a_full[kb]), t & 1);
-            if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready[kb]), 1));
-          } else {
-            mbar_wait_cluster(smem_u32(&ctrl->a_ready[kb]), t & 1);
-          }
-#pragma unroll 2
-          for (int i = 0; i < 8; ++i) {
-            const int r = sw * 32 + i * 4 + sub;
-            uint4* ptr = reinterpret_cast<uint4*>(a_mut + kb * A_SUB_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-            const uint4 u = *ptr;
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-            uint32_t o[4];
-            float sq[8];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float v0, v1;
-              bf16x2(w[e], v0, v1);
-              sq[2 * e] = v0 * v0;
-              sq[2 * e + 1] = v1 * v1;
-              // no clamp, no explicit flush: a value beyond +-65504 becomes inf (its row is re-scanned exactly, xflag below),
-              // one below 2^-14 an fp16 subnormal that the tensor core reads as zero (its exact norm is in xtiny)
-              const __half2 h = __floats2half2_rn(v0, v1);
-              o[e] = *reinterpret_cast<const uint32_t*>(&h);
-            }
-            *ptr = make_uint4(o[0], o[1], o[2], o[3]);
-            float acc = ((sq[0] + sq[1]) + (sq[2] + sq[3])) + ((sq[4] + sq[5]) + (sq[6] + sq[7]));
-            float tiny = 0.f;
-            const float smin = fminf(fmin3(sq[0], sq[1], sq[2]), fmin3(fmin3(sq[3], sq[4], sq[5]), sq[6], sq[7]));
-            if (__any_sync(0xffffffffu, smin < 0x1p-28f)) {   // some element below the fp16 normal range (or an exact zero)
-#pragma unroll
-              for (int e = 0; e < 8; ++e) tiny += sq[e] < 0x1p-28f ? sq[e] : 0.f;
-            }
-#pragma unroll
-            for (int m = 1; m <= 4; m <<= 1) {
-              acc += __shfl_xor_sync(0xffffffffu, acc, m);
-              tiny += __shfl_xor_sync(0xffffffffu, tiny, m);
-            }
-            if (chunk == 0) { xn2[r] += acc; xtiny[r] += tiny; }
-          }
-          fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-          __syncwarp();
-          if (leader) {
-            if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_conv[kb]));
-          } else {   // one forwarded arrive per sub-tile: the follower's four store warps meet, one lane posts to the leader
-            named_bar_sync(6, NUM_STORE_WARPS * 32);
-            if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_conv[kb]), 0));
-          }
-        }
-        if (chunk == 0) {   // xtiny held the squared norm so far; an element >= 65504 (or NaN / inf) shows in the row norm
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = sw * 32 + i * 4 + sub;
-            xtiny[r] = sqrtf(xtiny[r]) * 1.0001f;
-            xflag[r] = !(xn2[r] < 65504.f * 65504.f) ? 1 : 0;
-          }
-        }
-      } else {
+      {
         if (leader) {
           for (int s2 = 0; s2 < n_sub; ++s2) mbar_wait(smem_u32(&ctrl->a_full[s2]), t & 1);
-          if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready[0]), 1));
+          if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready), 1));
         } else {
-          mbar_wait_cluster(smem_u32(&ctrl->a_ready[0]), t & 1);
+          mbar_wait_cluster(smem_u32(&ctrl->a_ready), t & 1);
         }
         // two rows per lane in flight, two partial sums per row: the dependent-FMA chain, not smem, bounds this loop
         for (int i = 0; i < 8; i += 2) {
@@ -736,7 +656,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (chunk == 0) {
             ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1;
-            xflag[r0] = 0; xflag[r1] = 0; xtiny[r0] = sqrtf(alo[0]) * 1.0001f; xtiny[r1] = sqrtf(alo[1]) * 1.0001f;
+            xlo[r0] = sqrtf(alo[0]) * 1.0001f; xlo[r1] = sqrtf(alo[1]) * 1.0001f;
           }
         }
       }
@@ -899,15 +819,13 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
                        int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
-  // Pass schemes:
-  //   n_a = 1 (bf16 rows, read in place)   1: (x -> fp16, fp16 plane): ONE pass, residual 2^-12 ||c|| carried by the band
-  //                                        2: (x, c_hi) + (x, c_lo), bf16: residual-free band (round 1)
-  //   n_a = 2 (bf16 hi/lo planes of an fp32 input, vqb_input_prepare)    3: (x_hi, c_hi) + (x_hi, c_lo) + (x_lo, c_hi)
-  // The single pass sends ~18x more rows to the exact re-score (top-2 gaps shrink ~ 1/K): it pays up to K ~ 4096.
-  const int KB0 = (D + BK - 1) / BK;
-  const bool can_single = n_a == 1 && KB0 <= MAX_A_SUB;     // the conversion needs the A tile resident in smem
-  if (n_passes == 0) n_passes = n_a == 2 ? 3 : ((can_single && K <= 4096) ? 1 : 2);
-  if (n_passes < 1 || n_passes > 3 || (n_passes == 3 && n_a != 2) || (n_passes == 1 && !can_single)) return VQB_E_INVALID;
+  // Pass schemes (A operands are always bf16: the input rows themselves, or the bf16 hi / lo planes of an fp32 input):
+  //   mixed   one pass per A plane against the FP16 codebook plane (bf16 x fp16 -> fp32: the products are exact; fp16 keeps 11
+  //           mantissa bits of c instead of 8) — n_a = 1: 1 pass, n_a = 2: 2 passes.  Residual ~2^-12 ||x|| ||c|| in the band.
+  //   split   bf16 hi / lo codebook planes — n_a = 1: (x,c_hi)+(x,c_lo), n_a = 2: + (x_lo,c_hi).  Residual ~2^-17.
+  // The mixed scheme sends ~18x more rows to the exact re-score (top-2 gaps shrink ~ 1/K): it pays up to K ~ 4096.
+  if (n_passes == 0) n_passes = n_a + (K > 4096 ? 1 : 0);
+  if (n_passes < n_a || n_passes > n_a + 1) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   const int KB = (D + BK - 1) / BK;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;
@@ -920,12 +838,11 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   p.N = N; p.D = D; p.K = K;
   p.BN = code_tile(K);
   p.Kpad = vqb_padded_codes(K);
-  if (n_passes < 3) n_a = 1;  // plane 1 of A is only read by the third pass
   p.n_a = n_a; p.n_passes = n_passes; p.KB = KB;
-  p.fp16_single = n_passes == 1 ? 1 : 0;
+  p.mixed = n_passes == n_a ? 1 : 0;
   for (int i = 0; i < 3; ++i) { p.pass_a[i] = 0; p.pass_b[i] = 0; }
-  if (p.fp16_single) p.pass_b[0] = 2;                  // (x fp16, fp16 plane)
-  else { p.pass_b[1] = 1; p.pass_a[2] = 1; }           // (a0,hi) (a0,lo) (a1,hi)
+  if (p.mixed) { p.pass_b[0] = 2; p.pass_a[1] = 1; p.pass_b[1] = 2; }   // (a0,f16) [(a1,f16)]
+  else { p.pass_b[1] = 1; p.pass_a[2] = 1; }                             // (a0,hi) (a0,lo) [(a1,hi)]
   p.num_row_tiles = static_cast<int>((N + BM - 1) / BM);
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;

@@ -341,6 +341,50 @@ __global__ void rvq_accumulate_kernel(const float* __restrict__ embeds, int64_t 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// rotation-trick gradient estimator (arXiv:2410.06424; vqp:287-318), forward and backward, one warp per row.
+//   u = src / max(||src||, eps), q = tgt / max(||tgt||, eps), w = (u + q) / max(||u + q||, eps)   (all detached)
+//   out  = (e - 2 (e.w) w + 2 (e.u) q) * ||tgt|| / max(||src||, eps)          with e = src
+//   d_e  = (g - 2 (g.w) w + 2 (g.q) u) * ||tgt|| / max(||src||, eps)          (only `e` carries gradient)
+// Every scalar follows from five row reductions (||s||^2, ||t||^2, s.t, g.s, g.t): one sweep for them, one for the row.
+// ---------------------------------------------------------------------------------------------
+template <int DT, bool BWD>
+__global__ void rotate_kernel(const void* __restrict__ src, const void* __restrict__ tgt, const void* __restrict__ grad,
+                              int64_t N, int D, void* out) {
+  using E = Elem<DT>;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  constexpr float eps = 1e-6f;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
+       row += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int64_t base = row * D;
+    float ss = 0.f, tt = 0.f, st = 0.f, gs = 0.f, gt = 0.f;
+    for (int i = lane; i < D; i += 32) {
+      const float s = E::load(src, base + i), t = E::load(tgt, base + i);
+      ss = fmaf(s, s, ss); tt = fmaf(t, t, tt); st = fmaf(s, t, st);
+      if (BWD) { const float g = E::load(grad, base + i); gs = fmaf(g, s, gs); gt = fmaf(g, t, gt); }
+    }
+    ss = warp_sum(ss); tt = warp_sum(tt); st = warp_sum(st);
+    if (BWD) { gs = warp_sum(gs); gt = warp_sum(gt); }
+    const float ns = sqrtf(ss), nt = sqrtf(tt);
+    const float ins = 1.f / fmaxf(ns, eps), int_ = 1.f / fmaxf(nt, eps);        // safe_div (vqp:52-53)
+    // ||u + q||^2 = ||u||^2 + ||q||^2 + 2 u.q
+    const float nw = sqrtf(fmaxf(ss * ins * ins + tt * int_ * int_ + 2.f * st * ins * int_, 0.f));
+    const float inw = 1.f / fmaxf(nw, eps);                                      // l2norm eps (vqp:37-38)
+    const float lam = nt * ins;
+    // forward: a = e.w, b = e.u ; backward: a = g.w, b = g.q
+    const float a = BWD ? (gs * ins + gt * int_) * inw : (ss * ins + st * int_) * inw;
+    const float b = BWD ? gt * int_ : ss * ins;
+    for (int i = lane; i < D; i += 32) {
+      const float s = E::load(src, base + i), t = E::load(tgt, base + i);
+      const float u = s * ins, q = t * int_, w = (u + q) * inw;
+      const float e = BWD ? E::load(grad, base + i) : s;
+      const float r = BWD ? (e - 2.f * a * w + 2.f * b * u) : (e - 2.f * a * w + 2.f * b * q);
+      E::store(out, base + i, r * lam);
+    }
+  }
+}
+
 static inline int row_grid(int64_t rows, int wpb) {
   int64_t g = (rows + wpb - 1) / wpb;
   const int64_t cap = static_cast<int64_t>(num_sms()) * 16;
@@ -476,5 +520,21 @@ extern "C" int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int
     rvq_accumulate_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
   else
     rvq_accumulate_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_rotate(const void* src, const void* tgt, const void* grad_out, int64_t N, int D, int dtype, void* out,
+                          void* stream) {
+  if (!src || !tgt || !out || N <= 0 || D <= 0) return VQB_E_INVALID;
+  if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int g = row_grid(N, ROW_THREADS / 32);
+  if (dtype == VQB_DTYPE_F32) {
+    if (grad_out) rotate_kernel<VQB_DTYPE_F32, true><<<g, ROW_THREADS, 0, s>>>(src, tgt, grad_out, N, D, out);
+    else rotate_kernel<VQB_DTYPE_F32, false><<<g, ROW_THREADS, 0, s>>>(src, tgt, nullptr, N, D, out);
+  } else {
+    if (grad_out) rotate_kernel<VQB_DTYPE_BF16, true><<<g, ROW_THREADS, 0, s>>>(src, tgt, grad_out, N, D, out);
+    else rotate_kernel<VQB_DTYPE_BF16, false><<<g, ROW_THREADS, 0, s>>>(src, tgt, nullptr, N, D, out);
+  }
   return static_cast<int>(cudaGetLastError());
 }

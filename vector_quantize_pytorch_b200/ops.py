@@ -352,3 +352,18 @@ def ema_apply_peers(cluster_size: torch.Tensor, embed_avg: torch.Tensor, embed: 
                                       _p(code_weight), _p(ops.planes), _p(ops.bext), _p(ops.bias), _p(ops.cnorm2), _p(ops.cmax),
                                       _p(ops.scratch), _stream()), "vqb_ema_apply_peers")
     _count(2)
+
+
+def rotate(src: torch.Tensor, tgt: torch.Tensor, grad_out: torch.Tensor | None = None) -> torch.Tensor:
+    """Rotation-trick estimator (vqp:287-318): forward value (grad_out None) or the gradient w.r.t. src."""
+    _require_cuda(src, tgt, grad_out)
+    shape = src.shape
+    s2 = src.reshape(-1, shape[-1]).contiguous()
+    t2 = tgt.reshape(-1, shape[-1]).contiguous()
+    g2 = grad_out.reshape(-1, shape[-1]).contiguous() if grad_out is not None else None
+    assert s2.dtype == t2.dtype and (g2 is None or g2.dtype == s2.dtype)
+    out = torch.empty_like(s2)
+    with torch.cuda.device(s2.device):
+        check(lib.vqb_rotate(_p(s2), _p(t2), _p(g2), s2.shape[0], s2.shape[1], _dtype_code(s2), _p(out), _stream()), "vqb_rotate")
+    _count(1)
+    return out.reshape(shape)

@@ -32,20 +32,24 @@ def straight_through(src, tgt):  # vqp:282-283
     return src + (tgt - src).detach()
 
 
+class _RotateTo(torch.autograd.Function):
+    """Rotation-trick gradient estimator (arXiv:2410.06424 §4.2; reference vqp:287-318) on the sm_100a kernels: the forward
+    value (numerically the quantized vector) and d/d src — the direction / norm factors are constants of the backward pass,
+    exactly like the reference's `.detach()`s."""
+
+    @staticmethod
+    def forward(ctx, src, tgt):
+        ctx.save_for_backward(src, tgt)
+        return ops.rotate(src.detach(), tgt.detach())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        src, tgt = ctx.saved_tensors
+        return ops.rotate(src.detach(), tgt.detach(), grad_out.to(src.dtype)), None
+
+
 def rotate_to(src, tgt):
-    """Rotation-trick gradient estimator (arXiv:2410.06424 §4.2; reference vqp:287-318), PyTorch glue."""
-    shape = src.shape
-    src = src.reshape(-1, shape[-1])
-    tgt = tgt.reshape(-1, shape[-1])
-    norm_src = src.norm(dim=-1, keepdim=True)
-    norm_tgt = tgt.norm(dim=-1, keepdim=True)
-    u = _safe_div(src, norm_src)
-    q = _safe_div(tgt, norm_tgt)
-    e = src.unsqueeze(1)
-    w = F.normalize(u + q, p=2, dim=1, eps=1e-6).detach()
-    out = (e - 2 * (e @ w.unsqueeze(-1) @ w.unsqueeze(1)) + 2 * (e @ u.unsqueeze(-1).detach() @ q.unsqueeze(1).detach()))
-    rotated = out.squeeze(1) * _safe_div(norm_tgt, norm_src).detach()
-    return rotated.reshape(shape)
+    return _RotateTo.apply(src, tgt)
 
 
 def host_chunk_bounds(N: int, n_chunks: int):
