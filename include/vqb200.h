@@ -40,12 +40,14 @@ extern "C" {
 #define VQB_E_DRIVER -5      /* cuTensorMapEncodeTiled unavailable / failed */
 #define VQB_E_WORKSPACE -6   /* workspace too small */
 
-typedef struct vqb_flag_entry { /* one row whose winner the tensor-core pass could not certify */
-  int32_t row;                  /* vector index                                                   */
-  int32_t count;                /* candidates inside the band; > 2 means "rescan the whole row"    */
-  int32_t cand0;                /* best candidate of the tensor-core pass                         */
-  int32_t cand1;                /* the other candidate inside the error band (valid if count==2)  */
-                                /* (cand0, cand1) double as a 64-bit arg-max key during the rescan */
+typedef struct vqb_flag_entry { /* one row whose winner the tensor-core passes could not certify (32 bytes) */
+  int32_t row;                  /* vector index                                                            */
+  int32_t count;                /* candidates inside the band; > 3 means "rescan the whole row"              */
+  int32_t cand0;                /* best candidate of the tensor-core passes                                */
+  int32_t cand1;                /* second candidate (valid if count >= 2)                                   */
+                                /* (cand0, cand1) double as a 64-bit arg-max key during a whole-row rescan  */
+  int32_t cand2;                /* third candidate (valid if count == 3)                                    */
+  int32_t pad[3];
 } vqb_flag_entry;
 
 /* Optional fused tail of the search (gather + loss + residual update, see vqb_gather for the meaning of

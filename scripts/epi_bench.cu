@@ -148,29 +148,11 @@ epi_bench_kernel(int K, int sweeps, float W, OutRow* out, long long* cycles, uin
     const long long c1 = clock64();
     if (kReg) { if constexpr (G == 16) sr.finish(sq, st, tagmask, mul1, mulm1); }
     else if (kNew) sc.finish(sq, st, tagmask, mul1, mulm1);
-    MergeSlot* slot = &s_merge[part][row_in_tile];
-    slot->t1 = st.t1; slot->t2 = st.t2; slot->t3 = st.t3; slot->bexact = st.bexact;
-    slot->i0 = RowState::col(st.t1, st.j1); slot->i1 = RowState::col(st.t2, st.j2);
+    publish(&s_merge[part][row_in_tile], st);
     __syncthreads();
     if (part == 0) {
-      float best = -3.4e38f, tb = -3.4e38f;
-#pragma unroll
-      for (int q = 0; q < P; ++q) { best = fmaxf(best, s_merge[q][row_in_tile].bexact); tb = fmaxf(tb, s_merge[q][row_in_tile].t1); }
-      const float band = tb - W;
-      int n = 0, i0 = 0, i1 = 0;
-      float v0 = -3.4e38f, v1 = -3.4e38f;
-      auto offer = [&](float v, int i) {   // keep the two best (value desc, index asc)
-        if (v > v0 || (v == v0 && i < i0)) { v1 = v0; i1 = i0; v0 = v; i0 = i; }
-        else if (v > v1 || (v == v1 && i < i1)) { v1 = v; i1 = i; }
-      };
-#pragma unroll
-      for (int q = 0; q < P; ++q) {
-        const MergeSlot& m = s_merge[q][row_in_tile];
-        n += (m.t1 > band) + (m.t2 > band) + (m.t3 > band);
-        offer(m.t1, m.i0);
-        offer(m.t2, m.i1);
-      }
-      OutRow o; o.i0 = i0; o.i1 = i1; o.n = n; o.best = best + sink * 0.f;
+      const RowResult rr = merge_slices(st, &s_merge[1][row_in_tile], P - 1, 128);
+      OutRow o; o.i0 = rr.i0; o.i1 = rr.i1; o.n = rr.n; o.best = rr.best + sink * 0.f;
       out[row] = o;
     }
     acc += clock64() - c1;

@@ -50,18 +50,19 @@ __device__ __forceinline__ float max16(const uint32_t (&r)[16]) { return max_gro
 // inside the band" (-> whole-row exact re-scan).
 struct RowState {
   float t1, t2, t3;   // tagged top-3 scores
+  float t4;           // fourth best: only answers "is there a fourth candidate inside the band" (-> whole-row exact re-scan)
   float thr, W;       // thr = t1 - W: pieces whose exact maximum is <= thr cannot hold a candidate
   float bexact;       // exact (untagged) running maximum: the score that carries the loss
-  int j1, j2;         // first column of the groups t1 / t2 came from
+  int j1, j2, j3;     // first column of the groups t1 / t2 / t3 came from
   __device__ __forceinline__ void init(float w) {
-    W = w; t1 = t2 = t3 = -3.4e38f; bexact = -3.4e38f; thr = -3.4e38f; j1 = 0; j2 = 0;
+    W = w; t1 = t2 = t3 = t4 = -3.4e38f; bexact = -3.4e38f; thr = -3.4e38f; j1 = 0; j2 = 0; j3 = 0;
   }
   // Pipe balance: only the max of each compare-exchange is an FMNMX (alu pipe); the min is recovered on the fma pipe as
   // an integer identity on the bit patterns, min = a + b - max (exact: max returns one of its inputs), written as IMADs
   // with a multiplier ptxas cannot fold (mul1 = 1, mulm1 = -1 come in through the kernel params).
   template <int G>
   __device__ __forceinline__ void insert(const uint32_t* r, int cbase, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
-    const float o1 = t1, o2 = t2;
+    const float o1 = t1, o2 = t2, o3 = t3;
 #pragma unroll
     for (int e = 0; e < G; ++e) {
       const uint32_t ku = (r[e] & tagmask) | static_cast<uint32_t>(15 - e);
@@ -69,15 +70,26 @@ struct RowState {
       const uint32_t lo1 = __float_as_uint(n1) * mulm1 + (__float_as_uint(t1) * mul1 + ku);
       const float n2 = fmaxf(t2, __uint_as_float(lo1));
       const uint32_t lo2 = __float_as_uint(n2) * mulm1 + (__float_as_uint(t2) * mul1 + lo1);
-      t3 = fmaxf(t3, __uint_as_float(lo2));
+      const float n3 = fmaxf(t3, __uint_as_float(lo2));
+      const uint32_t lo3 = __float_as_uint(n3) * mulm1 + (__float_as_uint(t3) * mul1 + lo2);
+      t4 = fmaxf(t4, __uint_as_float(lo3));
       t1 = n1;
       t2 = n2;
+      t3 = n3;
     }
-    // where did t1 / t2 come from?  Equal tagged scores in different groups make this ambiguous, but then the
-    // equal score also sits in t2 or t3, the row has >= 3 candidates and is re-scanned exactly anyway.
-    const bool c1 = t1 != o1;
-    j2 = (t2 == o2) ? j2 : ((c1 && t2 == o1) ? j1 : cbase);
-    j1 = c1 ? cbase : j1;
+    // Where did t1 / t2 / t3 come from: an old slot (its group) or this group?  Both lists are sorted, so a greedy walk
+    // attributes them: a new slot equal to the next unconsumed old value takes that old slot's group, anything else is from
+    // this group.  (An equal tagged score in this group is then attributed to the old slot first and to this group after —
+    // every reported column stays a distinct real candidate.)
+    const int k1 = j1, k2 = j2, k3 = j3;
+    const bool m1 = t1 == o1;
+    j1 = m1 ? k1 : cbase;
+    const float q2 = m1 ? o2 : o1;
+    const bool m2 = t2 == q2;
+    j2 = m2 ? (m1 ? k2 : k1) : cbase;
+    const int used = static_cast<int>(m1) + static_cast<int>(m2);
+    const float q3 = used == 0 ? o1 : (used == 1 ? o2 : o3);
+    j3 = (t3 == q3) ? (used == 0 ? k1 : (used == 1 ? k2 : k3)) : cbase;
     thr = t1 - W;
   }
   __device__ __forceinline__ void piece(const uint32_t (&r)[16], int cbase, uint32_t tagmask, uint32_t mul1, uint32_t mulm1) {
@@ -86,7 +98,53 @@ struct RowState {
   static __device__ __forceinline__ int col(float t, int j) { return j + 15 - static_cast<int>(__float_as_uint(t) & 15u); }
 };
 
-struct MergeSlot { float t1, t2, t3, bexact; int i0, i1; };
+struct MergeSlot { float t1, t2, t3, t4, bexact; int i0, i1, i2; };
+
+// Result of merging the column slices of a row: the candidates (tagged scores inside the band W below the tagged maximum,
+// best first, ties towards the lower index), how many there are (n; indices are valid for the first min(n, 3)) and the
+// exact winning score.
+struct RowResult { int i0, i1, i2, n; float best; };
+
+struct Top3 {
+  float v0 = -3.4e38f, v1 = -3.4e38f, v2 = -3.4e38f;
+  int i0 = 0, i1 = 0, i2 = 0;
+  __device__ __forceinline__ void offer(float v, int i) {   // keep the three best (value desc, index asc)
+    if (v > v0 || (v == v0 && i < i0)) { v2 = v1; i2 = i1; v1 = v0; i1 = i0; v0 = v; i0 = i; }
+    else if (v > v1 || (v == v1 && i < i1)) { v2 = v1; i2 = i1; v1 = v; i1 = i; }
+    else if (v > v2 || (v == v2 && i < i2)) { v2 = v; i2 = i; }
+  }
+};
+
+__device__ __forceinline__ void publish(MergeSlot* slot, const RowState& st) {
+  slot->t1 = st.t1; slot->t2 = st.t2; slot->t3 = st.t3; slot->t4 = st.t4; slot->bexact = st.bexact;
+  slot->i0 = RowState::col(st.t1, st.j1); slot->i1 = RowState::col(st.t2, st.j2); slot->i2 = RowState::col(st.t3, st.j3);
+}
+
+// merge this thread's slice with `nslots` published slices of the same row (stride = distance between them)
+__device__ __forceinline__ RowResult merge_slices(const RowState& st, const MergeSlot* slots, int nslots, int stride) {
+  Top3 top;
+  float best = st.bexact, tb = st.t1;
+  top.offer(st.t1, RowState::col(st.t1, st.j1));
+  top.offer(st.t2, RowState::col(st.t2, st.j2));
+  top.offer(st.t3, RowState::col(st.t3, st.j3));
+  for (int q = 0; q < nslots; ++q) {
+    const MergeSlot& m = slots[q * stride];
+    best = fmaxf(best, m.bexact);
+    tb = fmaxf(tb, m.t1);
+    top.offer(m.t1, m.i0);
+    top.offer(m.t2, m.i1);
+    top.offer(m.t3, m.i2);
+  }
+  const float band = tb - st.W;
+  int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (st.t4 > band);
+  for (int q = 0; q < nslots; ++q) {
+    const MergeSlot& m = slots[q * stride];
+    n += (m.t1 > band) + (m.t2 > band) + (m.t3 > band) + (m.t4 > band);
+  }
+  RowResult r;
+  r.i0 = top.i0; r.i1 = top.i1; r.i2 = top.i2; r.n = n; r.best = best;
+  return r;
+}
 
 // The hot loop (see the header comment).  G = columns per group.  The queue of live groups is a separate thread-local
 // array (dynamically indexed -> local memory); keeping it out of this struct keeps the scalars below in registers.
@@ -161,7 +219,7 @@ struct ScanState {
       }
       if (max_group<G>(v) > live) st.template insert<G>(v, q.c[i], tagmask, mul1, mulm1);
     }
-    if (cnt > CAP) { st.t2 = st.t1; st.t3 = st.t1; }  // overflow: more live groups than the queue holds -> >= 3 candidates
+    if (cnt > CAP) { st.t2 = st.t1; st.t3 = st.t1; st.t4 = st.t1; }  // overflow: more live groups than the queue holds -> >= 3 candidates
   }
 };
 
@@ -249,7 +307,7 @@ struct ScanReg {
       }
       if (max_group<16>(v) > lv) st.template insert<16>(v, q.c[i], tagmask, mul1, mulm1);
     }
-    if (cnt > CAP) { st.t2 = st.t1; st.t3 = st.t1; }
+    if (cnt > CAP) { st.t2 = st.t1; st.t3 = st.t1; st.t4 = st.t1; }
   }
 };
 

@@ -61,7 +61,7 @@ constexpr int MMA_GROUP = 4;      // k-blocks issued per elected region of the M
 constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
 constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 12288;    // barriers + tmem ptr + row norms + merge area + threshold exchange
+constexpr int SMEM_CTRL_BYTES = 14336;    // barriers + tmem ptr + row norms + merge area + threshold exchange
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
@@ -498,22 +498,13 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // ---- merge the two column slices of each row (upper half publishes, lower half finishes the row)
       MergeSlot* slot = &ctrl->merge[t & 1][row_in_tile];
       if (half == 1) {
-        slot->t1 = st.t1; slot->t2 = st.t2; slot->t3 = st.t3; slot->bexact = st.bexact;
-        slot->i0 = RowState::col(st.t1, st.j1); slot->i1 = RowState::col(st.t2, st.j2);
+        publish(slot, st);
         named_bar_sync(pair_bar, 64);
       } else {
         named_bar_sync(pair_bar, 64);
-        const float b1 = slot->t1, b2 = slot->t2, b3 = slot->t3;
-        const int ib0 = slot->i0, ib1 = slot->i1;
-        const int ia0 = RowState::col(st.t1, st.j1), ia1 = RowState::col(st.t2, st.j2);
-        const float best = fmaxf(st.bexact, slot->bexact);   // exact score of the winner
-        // candidates = tagged scores inside the band below the tagged maximum, over both slices
-        const float tb = fmaxf(st.t1, b1);
-        const float band = tb - st.W;
-        const int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (b1 > band) + (b2 > band) + (b3 > band);
-        int i0, i1;
-        if (st.t1 > b1 || (st.t1 == b1 && ia0 < ib0)) { i0 = ia0; i1 = (st.t2 > b1) ? ia1 : ib0; }
-        else { i0 = ib0; i1 = (b2 > st.t1) ? ib1 : ia0; }
+        const RowResult rr = merge_slices(st, slot, 1, 0);
+        const int n = rr.n, i0 = rr.i0, i1 = rr.i1;
+        const float best = rr.best;
         const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
         if (p.copy_mode && p.fo.loss_sum && row < p.N && n < 2) {
           // ||q - x||^2 = ||x||^2 - 2(x.c - 0.5||c||^2)  — the score already holds it (cosine: bias is 0, add ||c||^2).
@@ -539,7 +530,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             e.row = static_cast<int32_t>(row);
             e.cand0 = i0;
             e.cand1 = i1;
+            e.cand2 = rr.i2;
             e.count = n;
+            e.pad[0] = e.pad[1] = e.pad[2] = 0;
             p.flagged[s] = e;
           }
         }
@@ -819,13 +812,12 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
                        int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
-  // Pass schemes (A operands are always bf16: the input rows themselves, or the bf16 hi / lo planes of an fp32 input):
-  //   mixed   one pass per A plane against the FP16 codebook plane (bf16 x fp16 -> fp32: the products are exact; fp16 keeps 11
-  //           mantissa bits of c instead of 8) — n_a = 1: 1 pass, n_a = 2: 2 passes.  Residual ~2^-12 ||x|| ||c|| in the band.
-  //   split   bf16 hi / lo codebook planes — n_a = 1: (x,c_hi)+(x,c_lo), n_a = 2: + (x_lo,c_hi).  Residual ~2^-17.
-  // The mixed scheme sends ~18x more rows to the exact re-score (top-2 gaps shrink ~ 1/K): it pays up to K ~ 4096.
-  if (n_passes == 0) n_passes = n_a + (K > 4096 ? 1 : 0);
-  if (n_passes < n_a || n_passes > n_a + 1) return VQB_E_INVALID;
+  // Pass schemes.  A operands are bf16 (the input rows themselves, or the bf16 hi / lo planes of an fp32 input):
+  //   split   bf16 hi / lo codebook planes — n_a = 1: (x,c_hi)+(x,c_lo); n_a = 2: + (x_lo,c_hi).  Residual ~2^-17 ||x|| ||c||.
+  // A single pass against the FP16 codebook plane (11 mantissa bits, residual ~2^-12) would need fp16 A operands as well:
+  // tcgen05 kind::f16 rejects bf16 x fp16 in one instruction (measured: illegal instruction), see DESIGN.md section 8.
+  if (n_passes == 0) n_passes = n_a + 1;
+  if (n_passes != n_a + 1) return VQB_E_UNSUPPORTED;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   const int KB = (D + BK - 1) / BK;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;

@@ -92,13 +92,23 @@ __global__ void fix_flagged_kernel(const void* __restrict__ x, int64_t N, int D,
       const float d2 = __fadd_rn(__fadd_rn(x2f, __ldg(cnorm2 + k)), __fmul_rn(xyf, -2.f));
       return -__fsqrt_rn(fmaxf(d2, 1e-8f));
     };
-    if (fe.count != 2) {  // >2 candidates: whole-row rescan (fix_overflow_kernel); reset its arg-max key
+    if (fe.count > 3 || fe.count < 2) {  // >3 candidates: whole-row rescan (fix_overflow_kernel); reset its arg-max key
       if (lane == 0) *reinterpret_cast<unsigned long long*>(&flagged[e].cand0) = 0ull;
       continue;
     }
-    const int ka = min(fe.cand0, fe.cand1), kb = max(fe.cand0, fe.cand1);
-    const float sa = score(ka), sb = score(kb);
-    const int best_k = (sb > sa) ? kb : ka;  // argmax keeps the FIRST maximal index (vqp:140)
+    // two or three candidates, visited in ascending index order: argmax keeps the FIRST maximal index (vqp:140)
+    int k0 = fe.cand0, k1 = fe.cand1, k2 = fe.count == 3 ? fe.cand2 : 0x7FFFFFFF;
+    if (k0 > k1) { const int t = k0; k0 = k1; k1 = t; }
+    if (k1 > k2) { const int t = k1; k1 = k2; k2 = t; }
+    if (k0 > k1) { const int t = k0; k0 = k1; k1 = t; }
+    int best_k = k0;
+    float sbest = score(k0);
+    const float s1 = score(k1);
+    if (s1 > sbest) { sbest = s1; best_k = k1; }
+    if (fe.count == 3) {
+      const float s2 = score(k2);
+      if (s2 > sbest) { sbest = s2; best_k = k2; }
+    }
     if (lane == 0) idx[fe.row] = best_k;
     if (fo.enabled) {  // finish the row the search kernel left to us: gather / loss / residual
       const double l = warp_sum(static_cast<double>(gather_row<DT>(fo, fe.row, best_k, D, lane)));
@@ -142,7 +152,7 @@ fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* _
     if (threadIdx.x < 32) s_mask[threadIdx.x] = 0u;
     __syncthreads();
     for (int64_t e = e0 + threadIdx.x; e < cnt && e < e0 + 1024; e += blockDim.x)
-      if (flagged[e].count > 2) atomicOr(&s_mask[(e - e0) >> 5], 1u << ((e - e0) & 31));
+      if (flagged[e].count > 3 || flagged[e].count < 2) atomicOr(&s_mask[(e - e0) >> 5], 1u << ((e - e0) & 31));
     __syncthreads();
     // identical list ORDER in every CTA (the grid splits the items by index): position = rank of the bit
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
@@ -240,7 +250,7 @@ __global__ void fix_finish_kernel(int64_t N, int D, const vqb_flag_entry* __rest
   for (int64_t e = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); e < cnt;
        e += static_cast<int64_t>(gridDim.x) * wpb) {
     const vqb_flag_entry fe = flagged[e];
-    if (fe.count <= 2) continue;
+    if (fe.count == 2 || fe.count == 3) continue;
     const unsigned long long key = *reinterpret_cast<const unsigned long long*>(&flagged[e].cand0);
     const int k = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
     if (lane == 0) idx[fe.row] = k;

@@ -104,7 +104,7 @@ class SearchResult:
     idx: torch.Tensor  # int32 (N,)
     x_eff: torch.Tensor  # (N, D) input as the codebook sees it (l2-normalised for cosine), in x.dtype
     flag_count: torch.Tensor  # int32 (1,) rows re-scored exactly
-    flagged: torch.Tensor  # int32 (N, 4): (row, count, cand0, cand1)
+    flagged: torch.Tensor  # int32 (N, 8): (row, count, cand0, cand1, cand2, pad x 3) — vqb_flag_entry
     best: torch.Tensor | None = None
 
 
@@ -142,7 +142,7 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
             _count(1)
             n_a = 2
         idx = torch.empty((N,), dtype=torch.int32, device=dev)
-        flagged = torch.empty((N, 4), dtype=torch.int32, device=dev)
+        flagged = torch.empty((N, 8), dtype=torch.int32, device=dev)
         count = torch.zeros((1,), dtype=torch.int32, device=dev)
         best = torch.empty((N,), dtype=torch.float32, device=dev) if debug_best else None
         fo = None
