@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vector_quantize_pytorch_b200 import ops
 dev = torch.device("cuda:0")
 D, K, N = 64, 16, 128
-for n_passes, name in ((2, "bf16 split"),):
+for n_passes, name in ((2, "bf16 split"),):  # (the single fp16 pass needs K >= 256: probed through the tests instead)
     for side in ("B (codebook)", "A (input)"):
         out = []
         for e in range(6, 30):
@@ -31,7 +31,7 @@ torch.manual_seed(0)
 xx = torch.randn(262144, 256, device=dev).bfloat16()
 cc = torch.randn(1024, 256, device=dev)
 cbb = ops.prepare_codebook(cc, False)
-for n_passes in (2,):
+for n_passes in (1, 2):
     r = ops.search(xx, cbb, cc, n_passes=n_passes, fix=False)
     torch.cuda.synchronize()
     n = int(r.flag_count.item())

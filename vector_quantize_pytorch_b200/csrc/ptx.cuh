@@ -264,10 +264,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N) {
          | ((M >> 4) << 24);// [24,29) M >> 4
 }
 
-// Same with A = bf16 (format 1) and B = fp16 (format 0): kind::f16 takes the two 16-bit formats independently.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16_f16(uint32_t M, uint32_t N) {
+// Same, A = B = fp16 (format code 0).  (kind::f16 rejects bf16 x fp16 in one instruction: measured, illegal instruction.)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t M, uint32_t N) {
   return (1u << 4)          // D = F32
-         | (1u << 7)        // A = BF16
+         | (0u << 7)        // A = F16
          | (0u << 10)       // B = F16
          | ((N >> 3) << 17)
          | ((M >> 4) << 24);
