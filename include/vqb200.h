@@ -110,7 +110,8 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
  *   margin_rel                   a row is certified when its best score leads every other code by more
  *                                than 2*margin_rel*||x||*cmax; otherwise it is appended to `flagged`
  *   idx       i32 [N]            winner of the tensor-core pass (final for unflagged rows)
- *   flagged   [N] entries, flag_count i32[1] (caller zeroes it)  -> vqb_fix_flagged
+ *   flagged   [N] entries, flag_count i32[2] (caller zeroes both): [0] rows with 2 / 3 candidates, appended from the
+ *             front; [1] rows with more (whole-row exact re-scan), appended from the back (flagged[N-1], [N-2], ...)  -> vqb_fix_flagged
  *   dbg_best  f32 [N] or NULL    best score per row (tests)
  * Supported: D % 8 == 0, 8 <= D <= 1024, 1 <= K, N >= 1, sm_100 device.  When n_a * ceil(D/64) > 8 (fp32 split input with
  * D > 256) the A tile does not stay resident in shared memory: its k-blocks are streamed with the codebook's. */

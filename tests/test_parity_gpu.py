@@ -235,22 +235,30 @@ def test_flagged_rows_are_rescored_exactly():
     K, D, N = 512, 128, 4096
     c = torch.randn(K, D)
     c[300] = c[7]                        # exact duplicate: index 7 must always beat 300
-    c[301] = c[7]                        # ... and a third copy: > 2 candidates -> whole-row rescan path
+    c[301] = c[7]                        # ... a third copy: three candidates -> exact re-score of the triple
+    c[302] = c[7]
+    c[303] = c[7]                        # ... five copies: > 3 candidates -> whole-row rescan path
+    c[500] = c[13]
+    c[501] = c[13]                       # a clean triple (13, 500, 501)
     c[400] = c[9] * (1 + 3e-7)           # inside fp32 noise of code 9
     c[401] = c[11] + 1e-4 * torch.randn(D)  # resolvable only by the exact re-score
     x = torch.randn(N, D)
     x[:64] = c[7] + 0.01 * torch.randn(64, D)
     x[64:128] = c[11] + 0.01 * torch.randn(64, D)
+    x[128:192] = c[13] + 0.01 * torch.randn(64, D)
     for dt in ("fp32", "bf16"):
         xd = x.to(TDT[dt]).to(DEV)
         cd = c.to(DEV)
         cb = ops.prepare_codebook(cd, False)
         res = ops.search(xd, cb, cd)
         idx = res.idx.cpu().numpy()
-        assert res.flag_count.item() >= 128
-        flagged = res.flagged[:res.flag_count.item()].cpu().numpy()  # (row, count, cand0, cand1)
-        assert (flagged[:, 1] > 2).sum() >= 64, "the triple tie must take the > 2 candidates path"
-        assert (idx[:64] == 7).all()
+        n_front, n_back = res.flag_count.item(), res.rescan_count.item()
+        assert n_front >= 128 and n_back >= 64
+        front = res.flagged[:n_front].cpu().numpy()  # (row, count, cand0, cand1, cand2, ...)
+        back = res.flagged[N - n_back:].cpu().numpy()
+        assert ((front[:, 1] == 2) | (front[:, 1] == 3)).all() and (front[:, 1] == 3).sum() >= 64, "triples are re-scored directly"
+        assert (back[:, 1] > 3).all(), "the five-fold tie must take the whole-row rescan path"
+        assert (idx[:64] == 7).all() and (idx[128:192] == 13).all()
         x_np = O.cast_like(x.numpy(), dt)
         ref = O.argmax_first(O.scores(x_np, c.numpy(), False))
         tie = near_tie_rows(x_np, c.numpy(), False)

@@ -139,7 +139,9 @@ __device__ __forceinline__ float tail_rows(const FusedOut& fo, const int64_t (&r
   return gather_rows<VQB_DTYPE_F32, GB>(fo, rows, ks, D, lane);
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// 448 threads x 144 registers = 64512 <= 65536: ptxas stops at 128 under __launch_bounds__(448, 1), and the epilogue's
+// live group + two TMEM buffers + scan state then spill inside the hot loop
+__global__ void __maxnreg__(144)
 vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmX, const AssignParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -551,11 +553,14 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.idx_prov) p.idx_prov[row] = (n < 2) ? i0 : -1;
           if (p.dbg_best) p.dbg_best[row] = best;
           if (n >= 2) {
-            const int s = atomicAdd(p.flag_count, 1);
+            // 2 or 3 candidates: front of the list (exact re-score of those codes); more: BACK of the list, growing
+            // downwards (whole-row exact re-scan) — the two kinds never share a slot (at most N entries in total)
+            const bool many = n > 3;
+            const int s = many ? static_cast<int>(p.N) - 1 - atomicAdd(p.flag_count + 1, 1) : atomicAdd(p.flag_count, 1);
             vqb_flag_entry e;
             e.row = static_cast<int32_t>(row);
-            e.cand0 = i0;
-            e.cand1 = i1;
+            e.cand0 = many ? 0 : i0;     // (cand0, cand1) of a re-scanned row is its 64-bit arg-max key: starts at 0
+            e.cand1 = many ? 0 : i1;
             e.cand2 = rr.i2;
             e.count = n;
             e.pad[0] = e.pad[1] = e.pad[2] = 0;

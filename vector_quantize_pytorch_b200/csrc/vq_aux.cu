@@ -92,10 +92,7 @@ __global__ void fix_flagged_kernel(const void* __restrict__ x, int64_t N, int D,
       const float d2 = __fadd_rn(__fadd_rn(x2f, __ldg(cnorm2 + k)), __fmul_rn(xyf, -2.f));
       return -__fsqrt_rn(fmaxf(d2, 1e-8f));
     };
-    if (fe.count > 3 || fe.count < 2) {  // >3 candidates: whole-row rescan (fix_overflow_kernel); reset its arg-max key
-      if (lane == 0) *reinterpret_cast<unsigned long long*>(&flagged[e].cand0) = 0ull;
-      continue;
-    }
+    if (fe.count > 3 || fe.count < 2) continue;  // (rows with more candidates live at the back of the list: fix_overflow_kernel)
     // two or three candidates, visited in ascending index order: argmax keeps the FIRST maximal index (vqp:140)
     int k0 = fe.cand0, k1 = fe.cand1, k2 = fe.count == 3 ? fe.cand2 : 0x7FFFFFFF;
     if (k0 > k1) { const int t = k0; k0 = k1; k1 = t; }
@@ -138,42 +135,15 @@ fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* _
   constexpr int MAXJ = 8;  // D <= 1024
   constexpr int CPI = 8;   // codes per warp iteration: independent L2 gathers in flight
   __shared__ unsigned long long s_key[8];
-  __shared__ int s_list[1024];
-  __shared__ uint32_t s_mask[32];  // bit i: entry e0 + i needs the whole-row rescan
-  __shared__ int s_n;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int64_t cnt = *flag_count;
-  if (cnt > N) cnt = N;
+  // the rows to re-scan are the entries at the BACK of the list: flagged[N - 1 - j], j < flag_count[1]
+  int64_t n_ovf = flag_count[1];
+  if (n_ovf > N) n_ovf = N;
   const int n_chunks = (K + OVF_CHUNK - 1) / OVF_CHUNK;
-  // Rounds of 1024 list entries: every CTA first collects the (rare) entries with > 2 candidates into smem with
-  // one parallel sweep (one global round trip), then the grid splits the (entry, code-chunk) items.  Walking the
-  // list item by item cost ~1 us of dependent L2 latency per step (measured 13-35 us for a list with no work).
-  for (int64_t e0 = 0; e0 < cnt; e0 += 1024) {
-    if (threadIdx.x < 32) s_mask[threadIdx.x] = 0u;
-    __syncthreads();
-    for (int64_t e = e0 + threadIdx.x; e < cnt && e < e0 + 1024; e += blockDim.x)
-      if (flagged[e].count > 3 || flagged[e].count < 2) atomicOr(&s_mask[(e - e0) >> 5], 1u << ((e - e0) & 31));
-    __syncthreads();
-    // identical list ORDER in every CTA (the grid splits the items by index): position = rank of the bit
-    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-      const uint32_t w = s_mask[i >> 5];
-      if (w & (1u << (i & 31))) {
-        int pos = __popc(w & ((1u << (i & 31)) - 1u));
-        for (int k = 0; k < (i >> 5); ++k) pos += __popc(s_mask[k]);
-        s_list[pos] = i;
-      }
-    }
-    if (threadIdx.x == 0) {
-      int t = 0;
-      for (int k = 0; k < 32; ++k) t += __popc(s_mask[k]);
-      s_n = t;
-    }
-    __syncthreads();
-    const int n_ovf = s_n;
-    const int items = n_ovf * n_chunks;
-  for (int it = blockIdx.x; it < items; it += gridDim.x) {
-    const int64_t e = e0 + s_list[it / n_chunks];
-    const int chunk = it % n_chunks;
+  const int64_t items = n_ovf * n_chunks;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    const int64_t e = N - 1 - it / n_chunks;
+    const int chunk = static_cast<int>(it % n_chunks);
     const vqb_flag_entry fe = flagged[e];
     const int64_t base = static_cast<int64_t>(fe.row) * D;
     float xr[MAXJ][4];
@@ -236,8 +206,6 @@ fix_overflow_kernel(const void* __restrict__ x, int64_t N, int D, const float* _
     }
     __syncthreads();
   }
-    __syncthreads();  // s_list is rewritten by the next round
-  }
 }
 
 template <int DT>
@@ -245,12 +213,12 @@ __global__ void fix_finish_kernel(int64_t N, int D, const vqb_flag_entry* __rest
                                   const int32_t* __restrict__ flag_count, int32_t* idx, const FusedOut fo) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  int64_t cnt = *flag_count;
+  int64_t cnt = flag_count[1];
   if (cnt > N) cnt = N;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); e < cnt;
-       e += static_cast<int64_t>(gridDim.x) * wpb) {
+  for (int64_t j = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); j < cnt;
+       j += static_cast<int64_t>(gridDim.x) * wpb) {
+    const int64_t e = N - 1 - j;
     const vqb_flag_entry fe = flagged[e];
-    if (fe.count == 2 || fe.count == 3) continue;
     const unsigned long long key = *reinterpret_cast<const unsigned long long*>(&flagged[e].cand0);
     const int k = static_cast<int>(0xFFFFFFFFu - static_cast<uint32_t>(key & 0xFFFFFFFFull));
     if (lane == 0) idx[fe.row] = k;
@@ -466,14 +434,16 @@ extern "C" int vqb_fix_flagged(const void* x_eff, int dtype, int64_t N, int D, c
   if (rc) return rc;
   if (fo.enabled && fo.dtype != dtype) return VQB_E_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // flag_count is only known on the device: fixed grids stride over the list.
+  // flag_count is only known on the device: fixed grids stride over the list.  The pair / triple re-score is a chain of
+  // dependent loads per row (entry -> x row in HBM -> code rows in L2): many warps in flight, about one row each.
   const int g = num_sms() * 2;
+  const int gp = num_sms() * 8;
   if (dtype == VQB_DTYPE_F32) {
-    fix_flagged_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx, fo);
+    fix_flagged_kernel<VQB_DTYPE_F32><<<gp, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx, fo);
     fix_overflow_kernel<VQB_DTYPE_F32><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count);
     fix_finish_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(N, D, flagged, flag_count, idx, fo);
   } else {
-    fix_flagged_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx, fo);
+    fix_flagged_kernel<VQB_DTYPE_BF16><<<gp, ROW_THREADS, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count, idx, fo);
     fix_overflow_kernel<VQB_DTYPE_BF16><<<g, 256, 0, s>>>(x_eff, N, D, embed, cnorm2, K, metric, flagged, flag_count);
     fix_finish_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(N, D, flagged, flag_count, idx, fo);
   }

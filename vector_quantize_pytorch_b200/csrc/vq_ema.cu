@@ -282,14 +282,21 @@ __global__ void stats_add_flagged_kernel(const void* __restrict__ x, int64_t N, 
   using E = Elem<DT>;
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
-  int64_t cnt = *flag_count;
+  // front of the list: rows with 2 / 3 candidates; back of the list (from N - 1 downwards): the re-scanned rows
+  int64_t cnt = flag_count[0], cnt_back = flag_count[1];
   if (cnt > N) cnt = N;
-  for (int64_t e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < cnt; e += warps) {
+  if (cnt_back > N - cnt) cnt_back = N - cnt;
+  for (int64_t j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; j < cnt + cnt_back; j += warps) {
+    const int64_t e = j < cnt ? j : N - 1 - (j - cnt);
     const int row = flagged[e].row;
     const int k = idx[row];
     if (lane == 0) atomicAdd(stats + k, 1.f);
     float* dst = stats + soff + static_cast<int64_t>(k) * D;
-    for (int i = lane; i < D; i += 32) atomicAdd(dst + i, E::load(x, static_cast<int64_t>(row) * D + i));
+    for (int i = lane * 4; i < D; i += 128) {   // 16-byte vector reductions (D % 8 == 0, rows 16-byte aligned)
+      const int64_t o = static_cast<int64_t>(row) * D + i;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(E::load(x, o)), "f"(E::load(x, o + 1)),
+                   "f"(E::load(x, o + 2)), "f"(E::load(x, o + 3)) : "memory");
+    }
   }
 }
 
@@ -387,7 +394,7 @@ int vqb::stats_add_flagged(const void* x_eff, int dtype, int64_t N, int D, const
                            const int32_t* flag_count, const int32_t* idx, int K, float* stats, void* stream) {
   if (!x_eff || !flagged || !flag_count || !idx || !stats) return VQB_E_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int g = num_sms();
+  const int g = num_sms() * 8;
   const int64_t soff = vqb_stats_offset(K);
   if (dtype == VQB_DTYPE_F32) stats_add_flagged_kernel<VQB_DTYPE_F32><<<g, 256, 0, s>>>(x_eff, N, D, flagged, flag_count, idx, stats, soff);
   else stats_add_flagged_kernel<VQB_DTYPE_BF16><<<g, 256, 0, s>>>(x_eff, N, D, flagged, flag_count, idx, stats, soff);

@@ -106,6 +106,7 @@ class SearchResult:
     flag_count: torch.Tensor  # int32 (1,) rows re-scored exactly
     flagged: torch.Tensor  # int32 (N, 8): (row, count, cand0, cand1, cand2, pad x 3) — vqb_flag_entry
     best: torch.Tensor | None = None
+    rescan_count: torch.Tensor | None = None  # int32 (1,) rows re-scanned whole (entries at the back of `flagged`)
 
 
 def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margin: float | None = None, n_passes: int = 0,
@@ -143,7 +144,7 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
             n_a = 2
         idx = torch.empty((N,), dtype=torch.int32, device=dev)
         flagged = torch.empty((N, 8), dtype=torch.int32, device=dev)
-        count = torch.zeros((1,), dtype=torch.int32, device=dev)
+        count = torch.zeros((2,), dtype=torch.int32, device=dev)   # [rows with 2 / 3 candidates, rows re-scanned whole]
         best = torch.empty((N,), dtype=torch.float32, device=dev) if debug_best else None
         fo = None
         if fused is not None:
@@ -166,7 +167,7 @@ def search(x: torch.Tensor, ops: CodebookOperands, embed: torch.Tensor, *, margi
         if fix:
             check(lib.vqb_fix_flagged(_p(x_eff), dt, N, D, _p(embed), _p(ops.cnorm2), ops.K, int(cosine), _p(flagged),
                                       _p(count), _p(idx), fo_ref, st), "vqb_fix_flagged")
-    return SearchResult(idx, x_eff, count, flagged, best)
+    return SearchResult(idx, x_eff, count[:1], flagged, best, count[1:])
 
 
 # 0: EMA statistics accumulated inside the search kernel (vector RED into L2); 1: separate sort + segmented sums
