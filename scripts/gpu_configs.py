@@ -38,6 +38,7 @@ def main():
         ("cfg3 RVQ Q=8 shared K=1024 x=(32,8192,256) fp32", lambda: vqb.ResidualVQ(dim=256, num_quantizers=8, codebook_size=1024, shared_codebook=True), (32, 8192, 256), torch.float32, False, 8),
         ("cfg3b RVQ Q=8 shared K=1024 x=(32,8192,256) bf16", lambda: vqb.ResidualVQ(dim=256, num_quantizers=8, codebook_size=1024, shared_codebook=True), (32, 8192, 256), torch.bfloat16, False, 8),
         ("cfg4 VQ cosine D=512 K=16384 x=(16,4096,512) bf16", lambda: vqb.VectorQuantize(dim=512, codebook_size=16384, use_cosine_sim=True), (16, 4096, 512), torch.bfloat16, True, 1),
+        ("cfg4f VQ cosine D=512 K=16384 x=(16,4096,512) fp32", lambda: vqb.VectorQuantize(dim=512, codebook_size=16384, use_cosine_sim=True), (16, 4096, 512), torch.float32, True, 1),
         ("cfg5 GRVQ G=2 Q=8 K=1024 shard x=(8,4096,256) fp32", lambda: vqb.GroupedResidualVQ(dim=256, groups=2, num_quantizers=8, codebook_size=1024), (8, 4096, 256), torch.float32, False, 16),
     ]
     for name, build, shape, dt, cosine, stages in cases:

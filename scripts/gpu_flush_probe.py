@@ -31,7 +31,7 @@ torch.manual_seed(0)
 xx = torch.randn(262144, 256, device=dev).bfloat16()
 cc = torch.randn(1024, 256, device=dev)
 cbb = ops.prepare_codebook(cc, False)
-for n_passes in (1, 2):
+for n_passes in (2,):
     r = ops.search(xx, cbb, cc, n_passes=n_passes, fix=False)
     torch.cuda.synchronize()
     n = int(r.flag_count.item())

