@@ -122,18 +122,15 @@ __device__ __forceinline__ void publish(MergeSlot* slot, const RowState& st) {
 
 // merge this thread's slice with `nslots` published slices of the same row (stride = distance between them)
 __device__ __forceinline__ RowResult merge_slices(const RowState& st, const MergeSlot* slots, int nslots, int stride) {
-  Top3 top;
+  // pass 1: exact best, tagged best and its column, number of candidates inside the band
   float best = st.bexact, tb = st.t1;
-  top.offer(st.t1, RowState::col(st.t1, st.j1));
-  top.offer(st.t2, RowState::col(st.t2, st.j2));
-  top.offer(st.t3, RowState::col(st.t3, st.j3));
+  int ib = RowState::col(st.t1, st.j1);
   for (int q = 0; q < nslots; ++q) {
     const MergeSlot& m = slots[q * stride];
     best = fmaxf(best, m.bexact);
-    tb = fmaxf(tb, m.t1);
-    top.offer(m.t1, m.i0);
-    top.offer(m.t2, m.i1);
-    top.offer(m.t3, m.i2);
+    const bool take = m.t1 > tb || (m.t1 == tb && m.i0 < ib);
+    tb = take ? m.t1 : tb;
+    ib = take ? m.i0 : ib;
   }
   const float band = tb - st.W;
   int n = (st.t1 > band) + (st.t2 > band) + (st.t3 > band) + (st.t4 > band);
@@ -142,7 +139,20 @@ __device__ __forceinline__ RowResult merge_slices(const RowState& st, const Merg
     n += (m.t1 > band) + (m.t2 > band) + (m.t3 > band) + (m.t4 > band);
   }
   RowResult r;
-  r.i0 = top.i0; r.i1 = top.i1; r.i2 = top.i2; r.n = n; r.best = best;
+  r.i0 = ib; r.i1 = 0; r.i2 = 0; r.n = n; r.best = best;
+  if (n >= 2) {  // rare (~0.1 % of the rows): the three best candidates over all slices
+    Top3 top;
+    top.offer(st.t1, RowState::col(st.t1, st.j1));
+    top.offer(st.t2, RowState::col(st.t2, st.j2));
+    top.offer(st.t3, RowState::col(st.t3, st.j3));
+    for (int q = 0; q < nslots; ++q) {
+      const MergeSlot& m = slots[q * stride];
+      top.offer(m.t1, m.i0);
+      top.offer(m.t2, m.i1);
+      top.offer(m.t3, m.i2);
+    }
+    r.i0 = top.i0; r.i1 = top.i1; r.i2 = top.i2;
+  }
   return r;
 }
 

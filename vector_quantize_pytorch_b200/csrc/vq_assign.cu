@@ -35,7 +35,7 @@
 #include "vqb_common.cuh"
 #include "gather_row.cuh"
 #include "epilogue.cuh"
-#include <cuda_fp16.h>
+#include <type_traits>
 
 // Per-role cycle accounting (scripts/gpu_roles.py): compile with -DVQB_PROFILE.  Off by default: the counters cost
 // registers in a kernel that runs at the 128-register cap.
@@ -78,12 +78,16 @@ struct AssignParams {
   const float* cmax;   // [1]
   int32_t* idx;
   int32_t* idx_prov;   // optional: idx with -1 for flagged rows
+  int32_t* hist;       // optional [slabs][K]: histogram of the certified winners per slab of (128 << hist_shift) rows — the
+  int hist_shift;      // first step of the EMA counting sort (vq_ema.cu), folded into the merge step of the epilogue
   vqb_flag_entry* flagged;
   int32_t* flag_count;
   float* dbg_best;
   long long* prof;     // optional [gridDim][16] cycle counters (diagnostics)
   FusedOut fo;         // optional fused gather tail (fo.enabled)
   int copy_mode;       // tail = pure row copy q <- codebook row (+ loss from the scores); no x re-read
+  int resid_mode;      // tail = residual only: r <- x - codebook row (+ loss from the scores): a ResidualVQ stage (rvq:524)
+  int score_loss;      // copy_mode || resid_mode: the epilogue accumulates the loss from the exact winning scores
   int metric;
   const uint16_t* b_hi;     // bf16 hi plane [Kpad][D]: bf16(c) == the quantized row for bf16 inputs
   const float* cnorm2;      // [K] (cosine loss term)
@@ -134,6 +138,9 @@ __device__ __forceinline__ float tail_rows(const FusedOut& fo, const int64_t (&r
   return gather_rows<VQB_DTYPE_F32, GB>(fo, rows, ks, D, lane);
 }
 
+// TAIL selects the work of the store warps at compile time (one instantiation each: the variants do not share a register
+// budget): 0 = none / generic (x re-read: running sum, fused statistics, cosine residual), 1 = copy mode, 2 = resid mode.
+template <int TAIL>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmX, const AssignParams p) {
@@ -502,7 +509,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n = rr.n, i0 = rr.i0, i1 = rr.i1;
         const float best = rr.best;
         const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
-        if (p.copy_mode && p.fo.loss_sum && row < p.N && n < 2) {
+        if (TAIL >= 1 && p.fo.loss_sum && row < p.N && n < 2) {
           // ||q - x||^2 = ||x||^2 - 2(x.c - 0.5||c||^2)  — the score already holds it (cosine: bias is 0, add ||c||^2).
           // Differs from the reference's bf16 evaluation by << 1e-3 relative; flagged rows get the
           // exact evaluation in vqb_fix_flagged.
@@ -519,6 +526,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (row < p.N) {
           p.idx[row] = i0;
           if (p.idx_prov) p.idx_prov[row] = (n < 2) ? i0 : -1;
+          if (p.hist && n < 2) atomicAdd(p.hist + static_cast<size_t>(tile >> p.hist_shift) * p.K + i0, 1);   // RED, fire and forget
           if (p.dbg_best) p.dbg_best[row] = best;
           if (n >= 2) {
             // 2 or 3 candidates: front of the list (exact re-score of those codes); more: BACK of the list, growing
@@ -538,7 +546,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       w_merge += PROF_CLOCK() - cm0;
     }
-    if (p.copy_mode && p.fo.loss_sum && half == 0) {
+    if (TAIL >= 1 && p.fo.loss_sum && half == 0) {
       const double w = warp_sum(static_cast<double>(epi_loss));
       if (lane == 0) atomicAdd(p.fo.loss_sum, w);
     }
@@ -604,53 +612,65 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         } else {
           mbar_wait_cluster(smem_u32(&ctrl->a_ready), t & 1);
         }
-        // two rows per lane in flight, two partial sums per row: the dependent-FMA chain, not smem, bounds this loop
-        for (int i = 0; i < 8; i += 2) {
-          const int r0 = sw * 32 + i * 4 + sub, r1 = r0 + 4;
-          const uint32_t off0 = (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4);
-          const uint32_t off1 = (r1 >> 3) * 1024 + (r1 & 7) * 128 + ((chunk ^ (r1 & 7)) << 4);
-          float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
-          float alo[2] = {0.f, 0.f};   // ||x_lo||^2 (fp32 inputs): sizes the x-side residual of the band
+        // two rows per lane in flight, two partial sums per row: the dependent-FMA chain, not smem, bounds this loop.
+        // Two instantiations: the store warps share issue slots with the epilogue warps, and the ||x_lo|| sums of the
+        // fp32 path cost the bf16 path 30 % of the epilogue's throughput when they ran unconditionally.
+        auto resident = [&](auto lo_tag) {
+          constexpr bool LO = decltype(lo_tag)::value;
+          for (int i = 0; i < 8; i += 2) {
+            const int r0 = sw * 32 + i * 4 + sub, r1 = r0 + 4;
+            const uint32_t off0 = (r0 >> 3) * 1024 + (r0 & 7) * 128 + ((chunk ^ (r0 & 7)) << 4);
+            const uint32_t off1 = (r1 >> 3) * 1024 + (r1 & 7) * 128 + ((chunk ^ (r1 & 7)) << 4);
+            float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+            float alo[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // ||x_lo||^2 (fp32 inputs): sizes the x-side residual of the band
 #pragma unroll 4
-          for (int kb = 0; kb < p.KB; ++kb) {
-            uint4 u[2], l[2];
-            u[0] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off0);
-            u[1] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off1);
-            if (p.n_a == 2) {
-              l[0] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off0);
-              l[1] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off1);
-            } else {
-              l[0] = l[1] = make_uint4(0u, 0u, 0u, 0u);
-            }
+            for (int kb = 0; kb < p.KB; ++kb) {
+              uint4 u[2], l[2];
+              u[0] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off0);
+              u[1] = *reinterpret_cast<const uint4*>(a_gen + kb * A_SUB_BYTES + off1);
+              if (LO) {
+                l[0] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off0);
+                l[1] = *reinterpret_cast<const uint4*>(a_gen + (p.KB + kb) * A_SUB_BYTES + off1);
+              }
 #pragma unroll
-            for (int b = 0; b < 2; ++b) {
-              const uint32_t w[4] = {u[b].x, u[b].y, u[b].z, u[b].w};
-              const uint32_t wl[4] = {l[b].x, l[b].y, l[b].z, l[b].w};
+              for (int b = 0; b < 2; ++b) {
+                const uint32_t w[4] = {u[b].x, u[b].y, u[b].z, u[b].w};
+                const uint32_t wl[4] = {l[b].x, l[b].y, l[b].z, l[b].w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float h0, h1, l0, l1;
-                bf16x2(w[e], h0, h1);
-                bf16x2(wl[e], l0, l1);
-                acc[b][0] = fmaf(h0 + l0, h0 + l0, acc[b][0]);
-                acc[b][1] = fmaf(h1 + l1, h1 + l1, acc[b][1]);
-                alo[b] = fmaf(l0, l0, alo[b]);
-                alo[b] = fmaf(l1, l1, alo[b]);
+                for (int e = 0; e < 4; ++e) {
+                  float h0, h1;
+                  bf16x2(w[e], h0, h1);
+                  if (LO) {
+                    float l0, l1;
+                    bf16x2(wl[e], l0, l1);
+                    alo[b][0] = fmaf(l0, l0, alo[b][0]);
+                    alo[b][1] = fmaf(l1, l1, alo[b][1]);
+                    h0 += l0;
+                    h1 += l1;
+                  }
+                  acc[b][0] = fmaf(h0, h0, acc[b][0]);
+                  acc[b][1] = fmaf(h1, h1, acc[b][1]);
+                }
               }
             }
-          }
-          float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1];
+            float a0 = acc[0][0] + acc[0][1], a1 = acc[1][0] + acc[1][1];
+            float b0 = alo[0][0] + alo[0][1], b1 = alo[1][0] + alo[1][1];
 #pragma unroll
-          for (int m = 1; m <= 4; m <<= 1) {
-            a0 += __shfl_xor_sync(0xffffffffu, a0, m);
-            a1 += __shfl_xor_sync(0xffffffffu, a1, m);
-            alo[0] += __shfl_xor_sync(0xffffffffu, alo[0], m);
-            alo[1] += __shfl_xor_sync(0xffffffffu, alo[1], m);
+            for (int m = 1; m <= 4; m <<= 1) {
+              a0 += __shfl_xor_sync(0xffffffffu, a0, m);
+              a1 += __shfl_xor_sync(0xffffffffu, a1, m);
+              if (LO) {
+                b0 += __shfl_xor_sync(0xffffffffu, b0, m);
+                b1 += __shfl_xor_sync(0xffffffffu, b1, m);
+              }
+            }
+            if (chunk == 0) {
+              ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1;
+              xlo[r0] = LO ? sqrtf(b0) * 1.0001f : 0.f; xlo[r1] = LO ? sqrtf(b1) * 1.0001f : 0.f;
+            }
           }
-          if (chunk == 0) {
-            ctrl->xn2[t & 1][r0] = a0; ctrl->xn2[t & 1][r1] = a1;
-            xlo[r0] = sqrtf(alo[0]) * 1.0001f; xlo[r1] = sqrtf(alo[1]) * 1.0001f;
-          }
-        }
+        };
+        if (p.n_a == 2) resident(std::true_type{}); else resident(std::false_type{});
       }
       __syncwarp();
       if (lane == 0) {
@@ -667,13 +687,17 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (!p.fo.enabled) continue;
       mbar_wait(smem_u32(&ctrl->g_full[t & 1]), (t >> 1) & 1);
       const int* gi = ctrl->gidx[t & 1] + sw * 32;
-      if (p.copy_mode) {
-        // q[row] <- codebook row: bf16 inputs copy the bf16 hi plane (== embed.type(bf16)), fp32 inputs the fp32 row.
+      if (TAIL >= 1) {
+        // copy mode: q[row] <- codebook row: bf16 inputs copy the bf16 hi plane (== embed.type(bf16)), fp32 inputs the fp32 row.
+        // resid mode (a ResidualVQ stage): residual[row] <- x[row] - that same row, rounded once (rvq:524, vqp:1178); the x
+        // rows were just read by the TMA (L2).  A few instructions per element: these warps share their issue slots with the
+        // epilogue (the generic tail below made a stage 75 % slower than a plain search).
         constexpr int CB = 4;  // rows per batch: independent 16-byte loads in flight per lane
-        const int row_bytes = p.D * (p.fo.dtype == VQB_DTYPE_BF16 ? 2 : 4);
-        const uint8_t* src = p.fo.dtype == VQB_DTYPE_BF16 ? reinterpret_cast<const uint8_t*>(p.b_hi)
-                                                          : reinterpret_cast<const uint8_t*>(p.fo.embed);
-        uint8_t* dst = static_cast<uint8_t*>(p.fo.q_out);
+        const bool bf = p.fo.dtype == VQB_DTYPE_BF16;
+        const int row_bytes = p.D * (bf ? 2 : 4);
+        const uint8_t* src = bf ? reinterpret_cast<const uint8_t*>(p.b_hi) : reinterpret_cast<const uint8_t*>(p.fo.embed);
+        const uint8_t* xin = TAIL == 2 ? static_cast<const uint8_t*>(p.fo.x_eff) : nullptr;
+        uint8_t* dst = static_cast<uint8_t*>(TAIL == 2 ? p.fo.resid_out : p.fo.q_out);
         for (int r0 = 0; r0 < 32; r0 += CB) {
           int ks[CB];
 #pragma unroll
@@ -691,6 +715,30 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int b = 0; b < CB; ++b)
                 if (ks[b] >= 0) v[b] = __ldg(reinterpret_cast<const uint4*>(src + static_cast<int64_t>(ks[b]) * row_bytes + off));
+              if (TAIL == 2) {
+                uint4 x[CB];
+#pragma unroll
+                for (int b = 0; b < CB; ++b)
+                  if (ks[b] >= 0) x[b] = *reinterpret_cast<const uint4*>(xin + (row_base + b) * row_bytes + off);
+#pragma unroll
+                for (int b = 0; b < CB; ++b) {
+                  if (ks[b] < 0) continue;
+                  const uint32_t xw[4] = {x[b].x, x[b].y, x[b].z, x[b].w}, cw[4] = {v[b].x, v[b].y, v[b].z, v[b].w};
+                  uint32_t rw[4];
+                  if (bf) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      const float d0 = __uint_as_float(xw[e] << 16) - __uint_as_float(cw[e] << 16);
+                      const float d1 = __uint_as_float(xw[e] & 0xFFFF0000u) - __uint_as_float(cw[e] & 0xFFFF0000u);
+                      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(rw[e]) : "f"(d1), "f"(d0));
+                    }
+                  } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) rw[e] = __float_as_uint(__uint_as_float(xw[e]) - __uint_as_float(cw[e]));
+                  }
+                  v[b] = make_uint4(rw[0], rw[1], rw[2], rw[3]);
+                }
+              }
 #pragma unroll
               for (int b = 0; b < CB; ++b)
                 if (ks[b] >= 0) *reinterpret_cast<uint4*>(dst + (row_base + b) * row_bytes + off) = v[b];
@@ -701,6 +749,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_empty[t & 1]));
         continue;
       }
+      if (TAIL != 0) continue;   // (not reached: the branch above ends with continue; lets the compiler drop the generic tail)
       constexpr int GB = 2;
       for (int r0 = 0; r0 < 32; r0 += GB) {
         int64_t rows[GB];
@@ -718,7 +767,7 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_empty[t & 1]));
     }
-    if (p.fo.enabled && p.fo.loss_sum && !p.copy_mode) {
+    if (TAIL == 0 && p.fo.enabled && p.fo.loss_sum) {
       const double w = warp_sum(static_cast<double>(lsum));
       if (lane == 0) atomicAdd(p.fo.loss_sum, w);
     }
@@ -799,16 +848,16 @@ extern "C" int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, co
                              const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx,
                              vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
                              const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream) {
-  return vqb::assign_launch(a_planes, n_a, N, D, b_planes, bext, cmax, K, margin_rel, n_passes, idx, nullptr, flagged,
-                            flag_count, dbg_best, fused, metric, cnorm2, stream);
+  return vqb::assign_launch(a_planes, n_a, N, D, b_planes, bext, cmax, K, margin_rel, n_passes, idx, nullptr, nullptr, 0,
+                            flagged, flag_count, dbg_best, fused, metric, cnorm2, stream);
 }
 
 // idx_prov (optional): like idx, but -1 for the rows handed to the exact re-score — lets the EMA sort start on the
 // certified rows while vqb_fix_flagged is still running (vq_forward.cu).
 int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                        const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, int32_t* idx_prov,
-                       vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused,
-                       int metric, const float* cnorm2, void* stream) {
+                       int32_t* hist, int hist_shift, vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
+                       const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
   // Passes (bf16 operands, fp32 accumulation): A = the input rows (n_a = 1) or the bf16 hi / lo planes of an fp32 input
@@ -835,7 +884,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   p.num_row_tiles = static_cast<int>((N + BM - 1) / BM);
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
-  p.cmax = cmax; p.idx = idx; p.idx_prov = idx_prov; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
+  p.cmax = cmax; p.idx = idx; p.idx_prov = idx_prov; p.hist = hist; p.hist_shift = hist_shift; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
   p.prof = g_prof;
   p.dbg_mode = g_dbg_mode;
   p.tagmask = 0xFFFFFFF0u; p.mul1 = 1u; p.mulm1 = 0xFFFFFFFFu;
@@ -847,6 +896,10 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   // pure-copy tail: nothing needs x again (no residual / running sum / fused statistics); the cosine loss needs ||c||^2
   p.copy_mode = p.fo.enabled && !p.fo.resid_out && !p.fo.qsum && !p.fo.stats_sum &&
                 !(metric == VQB_METRIC_COSINE && p.fo.loss_sum && !cnorm2);
+  // residual-only tail of a ResidualVQ stage on the raw rows (Euclidean, or inputs that were already unit vectors)
+  p.resid_mode = p.fo.enabled && p.fo.resid_out && !p.fo.q_out && !p.fo.qsum && !p.fo.stats_sum &&
+                 (!p.fo.x_raw || p.fo.x_raw == p.fo.x_eff) && !(metric == VQB_METRIC_COSINE && p.fo.loss_sum && !cnorm2);
+  p.score_loss = p.copy_mode || p.resid_mode;
   // A stationary in smem when it leaves room for >= 3 ring stages; else (fp32 split input with D > 256) its k-blocks are
   // streamed through the ring next to the codebook's (re-read from L2 for every code tile)
   p.stream_a = n_a * KB > MAX_A_SUB ? 1 : 0;
@@ -877,7 +930,9 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
 
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(vq_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    cudaError_t e = cudaFuncSetAttribute(vq_assign_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vq_assign_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(vq_assign_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
     if (e != cudaSuccess) return static_cast<int>(e);
     attr_set = true;
   }
@@ -896,7 +951,9 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, vq_assign_kernel, tmA, tmB, tmX, p);
+  cudaError_t le = p.copy_mode    ? cudaLaunchKernelEx(&cfg, vq_assign_kernel<1>, tmA, tmB, tmX, p)
+                   : p.resid_mode ? cudaLaunchKernelEx(&cfg, vq_assign_kernel<2>, tmA, tmB, tmX, p)
+                                  : cudaLaunchKernelEx(&cfg, vq_assign_kernel<0>, tmA, tmB, tmX, p);
   if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }

@@ -11,7 +11,7 @@
 
 namespace vqb {
 
-constexpr int SEG_CHUNK = 2048;   // rows per work item
+constexpr int SEG_CHUNK = 512;    // rows per work item (every item accumulates atomically: a finer split only balances the load)
 constexpr int SEG_THREADS = 256;
 
 struct StatsWs {  // carved out of the caller's workspace
@@ -21,6 +21,7 @@ struct StatsWs {  // carved out of the caller's workspace
   int32_t* nwork;    // [1]
   int32_t* perm;     // [N]   row ids grouped by code
   int4* work;        // [K + N/SEG_CHUNK + 1]  {code, begin, end, split}
+  int32_t* ticket;      // [1] (64 ints reserved) directly in front of cta_counts: zeroed by the same memset
   int32_t* cta_counts;  // [sort_ctas][K]  per-CTA histograms -> (in place) each CTA's insert base inside a code's segment
 };
 
@@ -40,14 +41,20 @@ static int64_t sort_ctas_bound(int64_t N, int K) {
   if (g > SORT_MAX_CELLS / K) g = SORT_MAX_CELLS / K;
   return g < 1 ? 1 : g;
 }
-static int sort_ctas(int64_t N, int K) {
+// Slabs of (128 << shift) rows — whole row tiles of the search kernel, which can therefore count its certified winners
+// per slab itself (AssignParams::hist).  At most one slab per SM (the scatter is a single wave), at least 512 rows each.
+static int sort_ctas(int64_t N, int K, int* shift) {
   // Few rows per code: a global cursor per code sees little contention, while the per-CTA histograms would move
   // sort_ctas * K counters three times (config 4: N/K = 4, measured 1.58 -> 1.71 ms per step with the CTA-local path).
-  if (K > SORT_MAX_K || N < 32 * static_cast<int64_t>(K)) return 0;   // -> global-atomic kernels
-  int64_t g = sort_ctas_bound(N, K);
-  const int64_t cap_sm = 2 * static_cast<int64_t>(num_sms());
-  if (g > cap_sm) g = cap_sm;
-  return static_cast<int>(g < 1 ? 1 : g);
+  if (K > SORT_MAX_K || N < 32 * static_cast<int64_t>(K)) { *shift = 31; return 0; }   // -> global-atomic kernels
+  const int64_t tiles = (N + 127) / 128;
+  int64_t cap = num_sms();
+  if (cap > SORT_MAX_CELLS / K) cap = SORT_MAX_CELLS / K;
+  if (cap < 1) cap = 1;
+  int sh = 2;
+  while (((tiles + (1ll << sh) - 1) >> sh) > cap) ++sh;
+  *shift = sh;
+  return static_cast<int>((tiles + (1ll << sh) - 1) >> sh);
 }
 
 static size_t carve(StatsWs* ws, void* base, int64_t N, int K) {
@@ -59,7 +66,7 @@ static size_t carve(StatsWs* ws, void* base, int64_t N, int K) {
   const size_t o_nwork = take(sizeof(int32_t));
   const size_t o_perm = take(sizeof(int32_t) * N);
   const size_t o_work = take(sizeof(int4) * max_work_items(N, K));
-  const size_t o_cta = take(sizeof(int32_t) * static_cast<size_t>(K <= SORT_MAX_K ? sort_ctas_bound(N, K) * K : 0));
+  const size_t o_cta = take(256 + sizeof(int32_t) * static_cast<size_t>(K <= SORT_MAX_K ? sort_ctas_bound(N, K) * K : 0));
   if (ws && base) {
     uint8_t* b = static_cast<uint8_t*>(base);
     ws->counts = reinterpret_cast<int32_t*>(b + o_counts);
@@ -68,7 +75,8 @@ static size_t carve(StatsWs* ws, void* base, int64_t N, int K) {
     ws->nwork = reinterpret_cast<int32_t*>(b + o_nwork);
     ws->perm = reinterpret_cast<int32_t*>(b + o_perm);
     ws->work = reinterpret_cast<int4*>(b + o_work);
-    ws->cta_counts = reinterpret_cast<int32_t*>(b + o_cta);
+    ws->ticket = reinterpret_cast<int32_t*>(b + o_cta);
+    ws->cta_counts = reinterpret_cast<int32_t*>(b + o_cta + 256);
   }
   return off;
 }
@@ -110,13 +118,71 @@ hist_cta_kernel(const int32_t* __restrict__ idx, int64_t N, int K, int64_t rows_
   for (int i = threadIdx.x; i < K; i += SORT_THREADS) out[i] = sh[i];
 }
 
-// Exclusive scan down the CTA axis (in place) + each code's total.  A block owns 32 adjacent codes (coalesced
-// 128-byte rows of the [G][K] matrix); its 8 warps split the CTA axis, scan their stretch, and are stitched together
-// through smem — two short passes instead of one G-long dependent chain per code.
+// offsets = exclusive_scan(counts) over the codes; the work list of the segmented sums; the cluster_size part of the
+// statistics (added atomically: the buffer was zeroed, and the re-scored rows may be added concurrently).  Runs on ONE
+// block of any size (a multiple of 32 threads).
+__device__ void scan_codes_block(const int32_t* counts, int K, int32_t* offsets, int32_t* cursor, int4* work, int32_t* nwork,
+                                 float* stats) {
+  __shared__ int32_t s_c[32], s_w[32];
+  __shared__ int32_t carry_cnt, carry_wk, tot_cnt, tot_wk;
+  const int nt = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nt >> 5;
+  if (threadIdx.x == 0) { carry_cnt = 0; carry_wk = 0; }
+  __syncthreads();
+  for (int base = 0; base < K; base += nt) {
+    const int k = base + threadIdx.x;
+    const int c = k < K ? __ldcg(counts + k) : 0;
+    const int w = (c + SEG_CHUNK - 1) / SEG_CHUNK;   // 0 for an empty code: its sums stay at the zero they were set to
+    int ic = c, iw = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, ic, o), b = __shfl_up_sync(0xffffffffu, iw, o);
+      if (lane >= o) { ic += a; iw += b; }
+    }
+    if (lane == 31) { s_c[warp] = ic; s_w[warp] = iw; }
+    __syncthreads();
+    if (warp == 0) {
+      int a = lane < nwarps ? s_c[lane] : 0, b = lane < nwarps ? s_w[lane] : 0;
+      const int a0 = a, b0 = b;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, a, o), y = __shfl_up_sync(0xffffffffu, b, o);
+        if (lane >= o) { a += x; b += y; }
+      }
+      s_c[lane] = a - a0;   // exclusive prefix of the warps
+      s_w[lane] = b - b0;
+      if (lane == 31) { tot_cnt = a; tot_wk = b; }
+    }
+    __syncthreads();
+    const int wc = s_c[warp], ww = s_w[warp];
+    const int ex_cnt = carry_cnt + wc + ic - c;
+    const int ex_wk = carry_wk + ww + iw - w;
+    if (k < K) {
+      offsets[k] = ex_cnt;
+      if (cursor) cursor[k] = ex_cnt;
+      if (c) atomicAdd(stats + k, static_cast<float>(c));  // cluster_size = onehot.sum(1)   vqp:602 (exact: integers < 2^24)
+      for (int j = 0; j < w; ++j) {
+        const int b = ex_cnt + j * SEG_CHUNK;
+        const int e = min(ex_cnt + c, b + SEG_CHUNK);
+        work[ex_wk + j] = make_int4(k, b, e, 0);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { carry_cnt += tot_cnt; carry_wk += tot_wk; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *nwork = carry_wk;
+}
+
+// Exclusive scan down the slab axis (in place) + each code's total, then — in the LAST block to finish (ticket) — the
+// scan over the codes: one launch instead of two on the critical path of the step.  A block owns 32 adjacent codes
+// (coalesced 128-byte rows of the [G][K] matrix); its 8 warps split the slab axis, scan their stretch, and are stitched
+// together through smem — two short passes instead of one G-long dependent chain per code.
 constexpr int CS_CODES = 32, CS_PARTS = 8;
 __global__ void __launch_bounds__(CS_CODES * CS_PARTS)
-colscan_kernel(int32_t* __restrict__ cta_counts, int G, int K, int32_t* __restrict__ counts) {
+colscan_kernel(int32_t* __restrict__ cta_counts, int G, int K, int32_t* __restrict__ counts, int32_t* ticket,
+               int32_t* offsets, int4* work, int32_t* nwork, float* stats) {
   __shared__ int32_t part[CS_PARTS][CS_CODES];
+  __shared__ int s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int k = blockIdx.x * CS_CODES + lane;
   const int per = (G + CS_PARTS - 1) / CS_PARTS;
@@ -127,24 +193,33 @@ colscan_kernel(int32_t* __restrict__ cta_counts, int G, int K, int32_t* __restri
     for (; g + 4 <= g1; g += 4) {
       int v[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = cta_counts[static_cast<size_t>(g + q) * K + k];
+      for (int q = 0; q < 4; ++q) v[q] = __ldcg(cta_counts + static_cast<size_t>(g + q) * K + k);   // written by REDs: L2
       sum += (v[0] + v[1]) + (v[2] + v[3]);
     }
-    for (; g < g1; ++g) sum += cta_counts[static_cast<size_t>(g) * K + k];
+    for (; g < g1; ++g) sum += __ldcg(cta_counts + static_cast<size_t>(g) * K + k);
   }
   part[w][lane] = sum;
   __syncthreads();
   int run = 0, total = 0;
 #pragma unroll
   for (int q = 0; q < CS_PARTS; ++q) { const int v = part[q][lane]; run += (q < w) ? v : 0; total += v; }
-  if (k >= K) return;
-  for (int g = g0; g < g1; ++g) {  // the values are in L1/L2 from the first pass
-    int32_t* cell = cta_counts + static_cast<size_t>(g) * K + k;
-    const int v = *cell;
-    *cell = run;
-    run += v;
+  if (k < K) {
+    for (int g = g0; g < g1; ++g) {  // the values are in L2 from the first pass
+      int32_t* cell = cta_counts + static_cast<size_t>(g) * K + k;
+      const int v = __ldcg(cell);
+      *cell = run;
+      run += v;
+    }
+    if (w == 0) counts[k] = total;
   }
-  if (w == 0) counts[k] = total;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1) == static_cast<int>(gridDim.x) - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *ticket = 0;   // ready for the next launch
+  scan_codes_block(counts, K, offsets, nullptr, work, nwork, stats);
 }
 
 // CTA c scatters the row ids of its slab: position = offsets[k] + (its base inside the code's segment) + smem cursor
@@ -165,45 +240,10 @@ scatter_cta_kernel(const int32_t* __restrict__ idx, int64_t N, int K, int64_t ro
   }
 }
 
-// single CTA: offsets = exclusive_scan(counts); work list; cluster_size part of stats
+// single CTA (global-cursor path): offsets = exclusive_scan(counts); work list; cluster_size part of stats
 __global__ void scan_kernel(const int32_t* __restrict__ counts, int K, int32_t* offsets, int32_t* cursor, int4* work,
                             int32_t* nwork, float* stats) {
-  __shared__ int32_t s_cnt[1024], s_wk[1024];
-  __shared__ int32_t carry_cnt, carry_wk;
-  if (threadIdx.x == 0) { carry_cnt = 0; carry_wk = 0; }
-  __syncthreads();
-  for (int base = 0; base < K; base += 1024) {
-    const int k = base + threadIdx.x;
-    const int c = k < K ? counts[k] : 0;
-    const int w = k < K ? max(1, (c + SEG_CHUNK - 1) / SEG_CHUNK) : 0;
-    s_cnt[threadIdx.x] = c;
-    s_wk[threadIdx.x] = w;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-      int a = 0, b = 0;
-      if (threadIdx.x >= o) { a = s_cnt[threadIdx.x - o]; b = s_wk[threadIdx.x - o]; }
-      __syncthreads();
-      s_cnt[threadIdx.x] += a;
-      s_wk[threadIdx.x] += b;
-      __syncthreads();
-    }
-    const int ex_cnt = carry_cnt + s_cnt[threadIdx.x] - c;
-    const int ex_wk = carry_wk + s_wk[threadIdx.x] - w;
-    if (k < K) {
-      offsets[k] = ex_cnt;
-      cursor[k] = ex_cnt;
-      stats[k] = static_cast<float>(c);  // cluster_size = onehot.sum(1)   vqp:602
-      for (int j = 0; j < w; ++j) {
-        const int b = ex_cnt + j * SEG_CHUNK;
-        const int e = min(ex_cnt + c, b + SEG_CHUNK);
-        work[ex_wk + j] = make_int4(k, b, e, w > 1 ? 1 : 0);
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 1023) { carry_cnt += s_cnt[1023]; carry_wk += s_wk[1023]; }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) *nwork = carry_wk;
+  scan_codes_block(counts, K, offsets, cursor, work, nwork, stats);
 }
 
 __global__ void scatter_kernel(const int32_t* __restrict__ idx, int64_t N, int32_t* cursor, int32_t* perm) {
@@ -270,7 +310,7 @@ segsum_kernel(const void* __restrict__ x, int D, const int32_t* __restrict__ per
     float s = 0.f;
     for (int y = 0; y < NY; ++y) s += red[y * D + i];
     float* out = embed_sum + static_cast<int64_t>(wk.x) * D + i;
-    if (wk.w) atomicAdd(out, s); else *out = s;
+    atomicAdd(out, s);   // onto zeros (or onto the re-scored rows of this code, added concurrently)
   }
 }
 
@@ -406,21 +446,53 @@ extern "C" size_t vqb_ema_stats_workspace(int64_t N, int K) {
   return carve(nullptr, nullptr, N, K);
 }
 
-extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats,
-                             void* workspace, size_t workspace_bytes, void* stream) {
-  if (!x_eff || !idx || !stats || !workspace || N <= 0 || D <= 0 || K <= 0) return VQB_E_INVALID;
+// ---- the statistics chain in three steps, so that vq_forward.cu can interleave it with the search and the re-score:
+//   stats_begin  (before the search)  zero the packed statistics and the histogram the search kernel counts into
+//   stats_scan   (after the search)   [histogram, unless the search made it] + slab scan + code scan + cluster sizes
+//   stats_sum    (after stats_scan)   scatter of the row ids + segmented row sums
+static int stats_check(const void* x_eff, int dtype, int64_t N, int D, int K, const float* stats, const void* workspace,
+                       size_t workspace_bytes, StatsWs* ws) {
+  if (!stats || !workspace || N <= 0 || D <= 0 || K <= 0) return VQB_E_INVALID;
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
   if (D % 8 != 0 || D > 4 * SEG_THREADS) return VQB_E_UNSUPPORTED;  // TX = D/VEC <= SEG_THREADS
   if (N >= (static_cast<int64_t>(1) << 31)) return VQB_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x_eff) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(stats)) & 15)
     return VQB_E_ALIGN;
+  if (carve(ws, const_cast<void*>(workspace), N, K) > workspace_bytes) return VQB_E_WORKSPACE;
+  return VQB_OK;
+}
+
+int vqb::stats_begin(float* stats, int dtype, int64_t N, int D, int K, void* workspace, size_t workspace_bytes, int prehist,
+                     int32_t** hist, int* hist_shift, void* stream) {
   StatsWs ws;
-  if (carve(&ws, workspace, N, K) > workspace_bytes) return VQB_E_WORKSPACE;
+  int rc = stats_check(stats, dtype, N, D, K, stats, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int64_t soff = vqb_stats_offset(K);
-  cudaError_t e = cudaMemsetAsync(stats + soff, 0, sizeof(float) * static_cast<size_t>(K) * D, s);  // split items accumulate
+  // everything below accumulates onto zeros: the cluster sizes (scan), the row sums (segmented sums, split or not) and the
+  // re-scored rows (stats_add_flagged), in any order
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * static_cast<size_t>(vqb_stats_floats(K, D)), s);
   if (e != cudaSuccess) return static_cast<int>(e);
-  const int G = sort_ctas(N, K);
+  int shift = 31;
+  const int G = sort_ctas(N, K, &shift);
+  if (G > 0)   // ticket + (when the search kernel counts) the slab histograms
+    e = cudaMemsetAsync(ws.ticket, 0, prehist ? 256 + sizeof(int32_t) * static_cast<size_t>(G) * K : 256, s);
+  else
+    e = cudaMemsetAsync(ws.counts, 0, sizeof(int32_t) * K, s);
+  if (e != cudaSuccess) return static_cast<int>(e);
+  if (hist) *hist = G > 0 ? ws.cta_counts : ws.counts;
+  if (hist_shift) *hist_shift = shift;
+  return VQB_OK;
+}
+
+int vqb::stats_scan(const int32_t* idx, int dtype, int64_t N, int D, int K, float* stats, void* workspace,
+                    size_t workspace_bytes, int prehist, void* stream) {
+  StatsWs ws;
+  int rc = stats_check(stats, dtype, N, D, K, stats, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (!idx) return VQB_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int shift = 31;
+  const int G = sort_ctas(N, K, &shift);
   if (G > 0) {
     static bool attr_set = false;
     if (!attr_set) {  // K ints of dynamic smem: up to 64 KiB
@@ -428,22 +500,41 @@ extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, con
       cudaFuncSetAttribute(scatter_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_MAX_K * 4);
       attr_set = true;
     }
-    const int64_t rows_per_cta = (N + G - 1) / G;
-    const size_t sh = static_cast<size_t>(K) * sizeof(int32_t);
-    hist_cta_kernel<<<G, SORT_THREADS, sh, s>>>(idx, N, K, rows_per_cta, ws.cta_counts);
-    colscan_kernel<<<(K + CS_CODES - 1) / CS_CODES, CS_CODES * CS_PARTS, 0, s>>>(ws.cta_counts, G, K, ws.counts);
-    scan_kernel<<<1, 1024, 0, s>>>(ws.counts, K, ws.offsets, ws.cursor, ws.work, ws.nwork, stats);
-    scatter_cta_kernel<<<G, SORT_THREADS, sh, s>>>(idx, N, K, rows_per_cta, ws.cta_counts, ws.offsets, ws.perm);
+    const int64_t rows_per_cta = static_cast<int64_t>(128) << shift;
+    if (!prehist) hist_cta_kernel<<<G, SORT_THREADS, static_cast<size_t>(K) * sizeof(int32_t), s>>>(idx, N, K, rows_per_cta, ws.cta_counts);
+    colscan_kernel<<<(K + CS_CODES - 1) / CS_CODES, CS_CODES * CS_PARTS, 0, s>>>(ws.cta_counts, G, K, ws.counts, ws.ticket,
+                                                                              ws.offsets, ws.work, ws.nwork, stats);
   } else {
-    e = cudaMemsetAsync(ws.counts, 0, sizeof(int32_t) * K, s);
-    if (e != cudaSuccess) return static_cast<int>(e);
+    if (!prehist) {
+      int g = static_cast<int>((N + 1023) / 1024);
+      const int cap = num_sms() * 4;
+      if (g > cap) g = cap;
+      hist_kernel<<<g, 256, K <= 8192 ? K * sizeof(int32_t) : 0, s>>>(idx, N, K, ws.counts);
+    }
+    scan_kernel<<<1, 1024, 0, s>>>(ws.counts, K, ws.offsets, ws.cursor, ws.work, ws.nwork, stats);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+int vqb::stats_sum(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  StatsWs ws;
+  int rc = stats_check(x_eff, dtype, N, D, K, stats, workspace, workspace_bytes, &ws);
+  if (rc) return rc;
+  if (!x_eff || !idx) return VQB_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int shift = 31;
+  const int G = sort_ctas(N, K, &shift);
+  if (G > 0) {
+    scatter_cta_kernel<<<G, SORT_THREADS, static_cast<size_t>(K) * sizeof(int32_t), s>>>(idx, N, K, static_cast<int64_t>(128) << shift,
+                                                                                        ws.cta_counts, ws.offsets, ws.perm);
+  } else {
     int g = static_cast<int>((N + 1023) / 1024);
     const int cap = num_sms() * 4;
     if (g > cap) g = cap;
-    hist_kernel<<<g, 256, K <= 8192 ? K * sizeof(int32_t) : 0, s>>>(idx, N, K, ws.counts);
-    scan_kernel<<<1, 1024, 0, s>>>(ws.counts, K, ws.offsets, ws.cursor, ws.work, ws.nwork, stats);
     scatter_kernel<<<g, 256, 0, s>>>(idx, N, ws.cursor, ws.perm);
   }
+  const int64_t soff = vqb_stats_offset(K);
   const int items = static_cast<int>(max_work_items(N, K));
   const int TX = D / (dtype == VQB_DTYPE_BF16 ? 8 : 4);
   const size_t red_bytes = SEG_CHUNK * sizeof(int32_t) + static_cast<size_t>(SEG_THREADS / TX) * D * sizeof(float);
@@ -452,6 +543,16 @@ extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, con
   else
     segsum_kernel<VQB_DTYPE_BF16><<<items, SEG_THREADS, red_bytes, s>>>(x_eff, D, ws.perm, ws.work, ws.nwork, stats + soff);
   return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (!x_eff || !idx) return VQB_E_INVALID;
+  int rc = stats_begin(stats, dtype, N, D, K, workspace, workspace_bytes, 0, nullptr, nullptr, stream);
+  if (rc) return rc;
+  rc = stats_scan(idx, dtype, N, D, K, stats, workspace, workspace_bytes, 0, stream);
+  if (rc) return rc;
+  return stats_sum(x_eff, dtype, N, D, idx, K, stats, workspace, workspace_bytes, stream);
 }
 
 extern "C" int vqb_ema_apply(float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
@@ -465,6 +566,14 @@ extern "C" int vqb_ema_apply_weighted(float* cluster_size, float* embed_avg, flo
                                       double decay, double eps, int metric, int do_lerp, int do_normalise,
                                       const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2,
                                       float* cmax, float* scratch, void* stream) {
+  return ema_apply_part(3, cluster_size, embed_avg, embed, stats, K, D, decay, eps, metric, do_lerp, do_normalise, code_weight,
+                        planes, bext, bias, cnorm2, cmax, scratch, stream);
+}
+
+// part: 1 = the cluster sizes (needs only the counts of the statistics), 2 = the rows (needs part 1 and the row sums), 3 = both
+int vqb::ema_apply_part(int part, float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+                        double decay, double eps, int metric, int do_lerp, int do_normalise, const float* code_weight,
+                        void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream) {
   if (!cluster_size || !embed_avg || !embed || !scratch || K <= 0 || D <= 0) return VQB_E_INVALID;
   if (do_lerp && !stats) return VQB_E_INVALID;
   if (do_normalise && (!planes || !bext || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
@@ -477,11 +586,14 @@ extern "C" int vqb_ema_apply_weighted(float* cluster_size, float* embed_avg, flo
   const float w = static_cast<float>(1.0 - decay);  // (1. - decay) evaluated in python float, then fp32 (vqp:97)
   const float epsf = static_cast<float>(eps);
   const float keps = static_cast<float>(static_cast<double>(K) * eps);  // n_categories * eps in python float (vqp:154)
-  ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, w, code_weight, do_lerp, scratch, do_normalise ? cmax : nullptr);
-  const int Kpad = vqb_padded_codes(K);
-  const int wpb = 8;
-  ema_rows_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(cluster_size, embed_avg, embed, stats, soff, K, Kpad, D, w, code_weight, epsf, keps,
-                                                            metric, do_lerp, do_normalise, scratch,
-                                                            static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
+  if (part & 1)
+    ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, w, code_weight, do_lerp, scratch, do_normalise ? cmax : nullptr);
+  if (part & 2) {
+    const int Kpad = vqb_padded_codes(K);
+    const int wpb = 8;
+    ema_rows_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(cluster_size, embed_avg, embed, stats, soff, K, Kpad, D, w, code_weight, epsf, keps,
+                                                              metric, do_lerp, do_normalise, scratch,
+                                                              static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
+  }
   return static_cast<int>(cudaGetLastError());
 }

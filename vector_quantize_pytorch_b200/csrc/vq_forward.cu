@@ -121,7 +121,7 @@ void make_keys(const vqb_vq_forward_args* a, void* stream, uint64_t* sk, uint64_
 // Side stream of the forward chain: the EMA sort runs on it, next to the exact re-score on the caller's stream.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr, counts = nullptr;
   bool ok = false;
 };
 SideStream* side_stream() {
@@ -135,7 +135,8 @@ SideStream* side_stream() {
     dev = cur;
     ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
             cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.counts, cudaEventDisableTiming) == cudaSuccess;
     if (!ss.ok) cudaGetLastError();
   }
   // one process drives one GPU; a call on another device simply runs the chain in one stream
@@ -367,26 +368,37 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   const bool split_tail = a->qsum && !fused_stats;
   const bool want_tail = !split_tail && (a->q_out || a->idx64_out || a->loss_out || fused_stats);
   vqb_flag_entry* flagged = reinterpret_cast<vqb_flag_entry*>(ws + w.flagged);
-  // The EMA sort (histogram -> scans -> scatter -> segmented sums) only needs the indices, and all but ~0.3 % of them
+  // The EMA sort (histogram -> scans -> scatter -> segmented sums) only needs the indices, and all but ~0.1 % of them
   // are final when the search kernel ends.  So the search also writes a provisional index array (-1 for the rows
-  // it hands to the exact re-score), the sort of those runs on a side stream NEXT TO the re-score, and the few
-  // re-scored rows are added to the packed statistics afterwards.  Both chains are latency-bound strings of small
-  // kernels; overlapped they take max() instead of sum() (measured: DESIGN.md section 8).
+  // it hands to the exact re-score) and counts the certified winners per slab of rows (the histogram of the counting
+  // sort); the rest of the sort runs on a side stream NEXT TO the re-score; the few re-scored rows are added to the
+  // (zero-initialised, accumulate-only) statistics by the main stream as soon as the code scan has written the cluster
+  // sizes, and the cluster-size half of the EMA follows them there.  Only the row half of the EMA waits for the segmented
+  // sums.  Critical path after the search: scan -> scatter -> sums -> EMA rows (was: hist -> colscan -> scan -> scatter ->
+  // sums -> re-scored rows -> EMA sizes -> EMA rows).
   SideStream* side = (a->update && !fused_stats) ? side_stream() : nullptr;
   int32_t* idx_prov = side ? reinterpret_cast<int32_t*>(ws + w.idx_prov) : nullptr;
+  const size_t stats_ws_bytes = a->update ? vqb_ema_stats_workspace(a->N, a->K) : 0;
+  int32_t* hist = nullptr;
+  int hist_shift = 0;
+  if (side) {
+    rc = stats_begin(a->stats, a->dtype, a->N, a->D, a->K, ws + w.stats_ws, stats_ws_bytes, 1, &hist, &hist_shift, stream);
+    if (rc) return rc;
+  }
   if (a->ev_search_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_begin), s);
   rc = assign_launch(a_planes, n_a, a->N, a->D, a->planes, a->bext, a->cmax, a->K, a->margin_rel, 0, a->idx32, idx_prov,
-                     flagged, flag_count, nullptr, want_tail ? &f : nullptr, a->metric, a->cnorm2, stream);
+                     hist, hist_shift, flagged, flag_count, nullptr, want_tail ? &f : nullptr, a->metric, a->cnorm2, stream);
   if (rc) return rc;
   if (a->ev_search_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_end), s);
   if (side) {  // fork: certified rows -> statistics
     if (cudaEventRecord(side->fork, s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork, 0) != cudaSuccess)
       return static_cast<int>(cudaGetLastError());
-    rc = vqb_ema_stats(x_eff, a->dtype, a->N, a->D, idx_prov, a->K, a->stats, ws + w.stats_ws,
-                       vqb_ema_stats_workspace(a->N, a->K), side->stream);
+    rc = stats_scan(idx_prov, a->dtype, a->N, a->D, a->K, a->stats, ws + w.stats_ws, stats_ws_bytes, 1, side->stream);
+    const cudaError_t ce = cudaEventRecord(side->counts, side->stream);
+    if (!rc) rc = stats_sum(x_eff, a->dtype, a->N, a->D, idx_prov, a->K, a->stats, ws + w.stats_ws, stats_ws_bytes, side->stream);
     const cudaError_t je = cudaEventRecord(side->join, side->stream);
     if (rc) return rc;
-    if (je != cudaSuccess) return static_cast<int>(cudaGetLastError());
+    if (ce != cudaSuccess || je != cudaSuccess) return static_cast<int>(cudaGetLastError());
   }
   rc = vqb_fix_flagged(x_eff, a->dtype, a->N, a->D, a->embed, a->cnorm2, a->K, a->metric, flagged, flag_count, a->idx32,
                        want_tail ? &f : nullptr, stream);
@@ -402,19 +414,26 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   }
   // ---- EMA (vqp:586-617, :576-584)
   if (a->update && !fused_stats) {
-    if (side) {  // join, then the re-scored rows are added to the statistics of the certified ones
-      if (cudaStreamWaitEvent(s, side->join, 0) != cudaSuccess) return static_cast<int>(cudaGetLastError());
+    if (side) {  // the re-scored rows join the statistics of the certified ones (cluster sizes are in place after the scan)
+      if (cudaStreamWaitEvent(s, side->counts, 0) != cudaSuccess) return static_cast<int>(cudaGetLastError());
       rc = stats_add_flagged(x_eff, a->dtype, a->N, a->D, flagged, flag_count, a->idx32, a->K, a->stats, stream);
+      if (rc) return rc;
+      if (a->update == 2) {  // cluster-size half of the EMA: does not need the row sums
+        rc = ema_apply_part(1, a->cluster_size, a->embed_avg, a->embed, a->stats, a->K, a->D, a->decay, a->eps, a->metric, 1,
+                            a->do_normalise, nullptr, a->planes, a->bext, a->bias, a->cnorm2, a->cmax, a->scratch, stream);
+        if (rc) return rc;
+      }
+      if (cudaStreamWaitEvent(s, side->join, 0) != cudaSuccess) return static_cast<int>(cudaGetLastError());
     } else {
-      rc = vqb_ema_stats(x_eff, a->dtype, a->N, a->D, a->idx32, a->K, a->stats, ws + w.stats_ws,
-                         vqb_ema_stats_workspace(a->N, a->K), stream);
+      rc = vqb_ema_stats(x_eff, a->dtype, a->N, a->D, a->idx32, a->K, a->stats, ws + w.stats_ws, stats_ws_bytes, stream);
+      if (rc) return rc;
     }
-    if (rc) return rc;
   }
   if (a->update) {
     if (a->update == 2) {
-      rc = vqb_ema_apply(a->cluster_size, a->embed_avg, a->embed, a->stats, a->K, a->D, a->decay, a->eps, a->metric, 1,
-                         a->do_normalise, a->planes, a->bext, a->bias, a->cnorm2, a->cmax, a->scratch, stream);
+      rc = ema_apply_part((side && !fused_stats) ? 2 : 3, a->cluster_size, a->embed_avg, a->embed, a->stats, a->K, a->D, a->decay,
+                          a->eps, a->metric, 1, a->do_normalise, nullptr, a->planes, a->bext, a->bias, a->cnorm2, a->cmax,
+                          a->scratch, stream);
       if (rc) return rc;
     } else if (a->update == 3) {  // multi-GPU: barrier, then every rank sums all ranks' statistics inside its EMA kernels
       rc = vqb_peer_barrier(a->peer_flags, a->peer_rank, a->peer_world, a->peer_epoch, stream);

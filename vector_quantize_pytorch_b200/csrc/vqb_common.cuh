@@ -75,11 +75,24 @@ __device__ __forceinline__ float warp_sum(float v) {
 // vq_assign.cu: vqb_assign_ex plus an optional provisional index array (-1 for rows handed to the exact re-score)
 int assign_launch(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                   const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, int32_t* idx_prov,
-                  vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best, const vqb_fused_outputs* fused,
-                  int metric, const float* cnorm2, void* stream);
+                  int32_t* hist, int hist_shift, vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
+                  const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream);
 // vq_ema.cu: add the rows listed in `flagged` (final code = idx[row]) to packed statistics that were built from an
 // index array in which those rows were marked -1
 int stats_add_flagged(const void* x_eff, int dtype, int64_t N, int D, const vqb_flag_entry* flagged,
                       const int32_t* flag_count, const int32_t* idx, int K, float* stats, void* stream);
+// vq_ema.cu: the statistics chain in three steps (vqb_ema_stats = all three, histogram by its own kernel).  With
+// prehist the search kernel counts the certified winners into *hist (slabs of 128 << *hist_shift rows) itself.
+int stats_begin(float* stats, int dtype, int64_t N, int D, int K, void* workspace, size_t workspace_bytes, int prehist,
+                int32_t** hist, int* hist_shift, void* stream);
+int stats_scan(const int32_t* idx, int dtype, int64_t N, int D, int K, float* stats, void* workspace, size_t workspace_bytes,
+               int prehist, void* stream);
+int stats_sum(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats, void* workspace,
+              size_t workspace_bytes, void* stream);
+// vq_ema.cu: vqb_ema_apply_weighted in two launches (part 1: cluster sizes, 2: rows, 3: both)
+int ema_apply_part(int part, float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
+                   double decay, double eps, int metric, int do_lerp, int do_normalise, const float* code_weight,
+                   void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream);
+
 
 }  // namespace vqb
