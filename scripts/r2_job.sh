@@ -8,6 +8,7 @@ timeout 300 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_$TAG.json 2
 python scripts/gpu_flush_probe.py > gpurun_out/flush_$TAG.txt 2>&1; cat gpurun_out/flush_$TAG.txt
 VQB_BENCH_SKIP_E2E=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 --no-sustained > /dev/null 2>&1; python scripts/launch_summary.py gpurun_out/launches_$TAG.csv | head -24
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_cfg3_$TAG.csv python scripts/gpu_cfg.py 3 > /dev/null 2>&1; python scripts/launch_summary.py gpurun_out/launches_cfg3_$TAG.csv | head -24
+python scripts/gpu_cfg.py 5 | tail -1; timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_cfg5_$TAG.csv python scripts/gpu_cfg.py 5 > /dev/null 2>&1; python scripts/launch_summary.py gpurun_out/launches_cfg5_$TAG.csv | head -30
 bash scripts/roles_job.sh 2,0 > gpurun_out/roles_$TAG.txt 2>&1; cat gpurun_out/roles_$TAG.txt
 
 python -c "from vector_quantize_pytorch_b200 import build; build.build(force=True)" > /dev/null 2>&1; timeout 600 python scripts/gpu_configs.py > gpurun_out/configs_$TAG.jsonl 2>&1; cat gpurun_out/configs_$TAG.jsonl

@@ -394,7 +394,8 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // Exact norms of what the pass scheme leaves out of the codebook operand (code_operands.cuh): ||c - fp16 plane|| for the
     // mixed passes, ||c - hi - lo|| for the bf16 split.  fp32 inputs (x = hi + lo + res, |res| <= 2^-8 |lo| per element) add
     // x_res . c and, in the split scheme, the omitted x_lo . c_lo:  ||x_lo|| * caux.
-    const float cres = __ldg(p.cmax + 2);
+    // (a hi-only single pass, n_passes == 1, also leaves out the lo plane: diagnostics / pass-scheme experiments)
+    const float cres = __ldg(p.cmax + 2) + (p.n_passes == 1 ? __ldg(p.cmax + 3) : 0.f);
     const float caux = p.n_a == 2 ? 0x1.02p-8f * cmax + __ldg(p.cmax + 3) : 0.f;
     const uint32_t te_remote0 = mapa_cluster(smem_u32(&ctrl->t_empty[0]), 0);
     const uint32_t te_remote1 = mapa_cluster(smem_u32(&ctrl->t_empty[1]), 0);
@@ -867,7 +868,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   // had to be converted to fp16 in a double-buffered A tile by the store warps; the kernel then turned epilogue-bound
   // (261 vs 282 kcycles) while 22x more rows went to the exact re-score — slower per step.  DESIGN.md section 8.
   if (n_passes == 0) n_passes = n_a + 1;
-  if (n_passes != n_a + 1) return VQB_E_UNSUPPORTED;
+  if (n_passes != n_a + 1 && !(n_passes == 1 && n_a == 1)) return VQB_E_UNSUPPORTED;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   const int KB = (D + BK - 1) / BK;
   if (N > (static_cast<int64_t>(1) << 31) - BM) return VQB_E_UNSUPPORTED;

@@ -267,55 +267,148 @@ __global__ void loss_finalize_kernel(const double* loss_sum, int64_t numel, int 
 // ---------------------------------------------------------------------------------------------
 // decode: out[row] = sum_q embed_q[idx[row, q]]   (index -1 -> zeros)      rvq:324-382
 // ---------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void decode_kernel(const float* __restrict__ embeds, int64_t embed_stride, int Q, int K, int D,
-                              const int64_t* __restrict__ idx, int64_t N, void* out) {
-  using E = Elem<DT>;
-  const int lane = threadIdx.x & 31;
-  const int wpb = blockDim.x >> 5;
-  for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
-       row += static_cast<int64_t>(gridDim.x) * wpb) {
-    for (int i = lane * 4; i < D; i += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = 0; q < Q; ++q) {
-        const int64_t k = idx[row * Q + q];
-        if (k < 0) continue;
-        const float4 c = __ldg(reinterpret_cast<const float4*>(embeds + q * embed_stride + k * D + i));
-        acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
-      }
-      E::store(out, row * D + i, acc.x);
-      E::store(out, row * D + i + 1, acc.y);
-      E::store(out, row * D + i + 2, acc.z);
-      E::store(out, row * D + i + 3, acc.w);
-    }
-  }
-}
-
 // quantized_out of ResidualVQ.forward rebuilt from the stage indices:  out = (((q_0) + q_1) + ...), q_j = embed_j[idx_j].type(dtype),
 // every partial sum rounded to dtype exactly where the reference's `quantized_out = quantized_out + quantized` rounds
 // (rvq:525, vqp:1178).  One pass over the indices, code rows from L2, ONE write of (N x D) instead of a read-modify-write
 // of the running sum in every stage.
-template <int DT>
-__global__ void rvq_accumulate_kernel(const float* __restrict__ embeds, int64_t embed_stride, int Q, int D,
+// A warp per row, 8 elements per lane; the Q indices of the row are read once (one lane each) and broadcast; the code rows
+// of up to 8 stages are in flight together (the first version chained index load -> row load -> rounding per stage and was
+// latency- and instruction-bound: 279 us at config 3 for a 134 MB write).  bf16: round(acc + round(c)) is one packed
+// cvt.rn.bf16x2.f32 plus one add.rn.bf16x2 per element pair.
+// ROUNDED = false is the decode of get_output_from_indices (rvq:324-382): plain fp32 sum of the gathered rows, index -1 (a
+// dropped-out stage) contributes zeros, one rounding at the store.
+template <int DT, bool ROUNDED>
+__global__ void __launch_bounds__(256, 2) rvq_accumulate_kernel(const float* __restrict__ embeds, int64_t embed_stride, int Q, int D,
                                       const int64_t* __restrict__ idx, int64_t N, void* out) {
-  using E = Elem<DT>;
+  constexpr int QB = 8;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
        row += static_cast<int64_t>(gridDim.x) * wpb) {
-    for (int i = lane * 4; i < D; i += 128) {
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int q = 0; q < Q; ++q) {
-        const int64_t k = idx[row * Q + q];
-        const float4 c = __ldg(reinterpret_cast<const float4*>(embeds + q * embed_stride + k * D + i));
-        acc.x = E::round(acc.x + E::round(c.x)); acc.y = E::round(acc.y + E::round(c.y));
-        acc.z = E::round(acc.z + E::round(c.z)); acc.w = E::round(acc.w + E::round(c.w));
+    for (int i0 = 0; i0 < D; i0 += 256) {   // warp-uniform trip count (shuffles inside)
+      const int i = i0 + lane * 8;
+      const bool active = i < D;
+      float accf[8];
+      uint32_t acch[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) accf[e] = 0.f;
+      for (int qc = 0; qc < Q; qc += 32) {   // indices of (up to) 32 stages: one lane each
+        const int64_t kq = (qc + lane < Q) ? idx[row * Q + qc + lane] : 0;
+        const int nq = min(32, Q - qc);
+        for (int q0 = 0; q0 < nq; q0 += QB) {
+          float4 c[QB][2];
+          uint32_t skip = 0u;   // stages whose index is -1
+#pragma unroll
+          for (int b = 0; b < QB; ++b) {
+            const int64_t k = __shfl_sync(0xffffffffu, kq, (q0 + b) & 31);
+            if (k < 0) skip |= 1u << b;
+            if (q0 + b < nq && active && k >= 0) {
+              const float4* src = reinterpret_cast<const float4*>(embeds + (qc + q0 + b) * embed_stride + k * D + i);
+              c[b][0] = __ldg(src);
+              c[b][1] = __ldg(src + 1);
+            }
+          }
+#pragma unroll
+          for (int b = 0; b < QB; ++b) {
+            if (q0 + b >= nq || !active) continue;
+            if ((skip >> b) & 1u) continue;
+            const float v[8] = {c[b][0].x, c[b][0].y, c[b][0].z, c[b][0].w, c[b][1].x, c[b][1].y, c[b][1].z, c[b][1].w};
+            if (ROUNDED && DT == VQB_DTYPE_BF16) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                uint32_t h;
+                asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v[2 * e + 1]), "f"(v[2 * e]));   // round(c)
+                asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[e]) : "r"(acch[e]), "r"(h));              // round(acc + round(c))
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) accf[e] += v[e];
+            }
+          }
+        }
       }
-      E::store(out, row * D + i, acc.x);
-      E::store(out, row * D + i + 1, acc.y);
-      E::store(out, row * D + i + 2, acc.z);
-      E::store(out, row * D + i + 3, acc.w);
+      if (!active) continue;
+      if (DT == VQB_DTYPE_BF16) {
+        if (!ROUNDED) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(acch[e]) : "f"(accf[2 * e + 1]), "f"(accf[2 * e]));
+        }
+        *reinterpret_cast<uint4*>(static_cast<uint16_t*>(out) + row * D + i) = make_uint4(acch[0], acch[1], acch[2], acch[3]);
+      } else {
+        float4* dst = reinterpret_cast<float4*>(static_cast<float*>(out) + row * D + i);
+        dst[0] = make_float4(accf[0], accf[1], accf[2], accf[3]);
+        dst[1] = make_float4(accf[4], accf[5], accf[6], accf[7]);
+      }
     }
+  }
+}
+
+// Same result with the codebook slice in shared memory.  The kernel above reads Q code rows per output row from L2
+// (config 3: 262144 x 8 x 1 KiB = 2.1 GB -> 250 us, L2-bandwidth bound for a 134 MB write).  When one W-column slice of
+// every codebook the stages searched fits in smem (a shared codebook: K x W x esz <= 192 KiB), a CTA converts its slice
+// once and then serves all its rows from smem: L2 traffic drops to the indices (re-read once per slice) and HBM to the
+// output write.  A row is handled by LPR = W*esz/16 adjacent lanes (16 bytes each), 32/LPR rows per warp.
+template <int DT>
+__global__ void __launch_bounds__(256, 1)
+rvq_accumulate_smem_kernel(const float* __restrict__ embeds, int64_t embed_stride, int nbooks, int Q, int K, int D, int W,
+                           const int64_t* __restrict__ idx, int64_t N, void* out, int ctas_per_slice) {
+  extern __shared__ uint4 code_smem[];   // [nbooks][K][W] elements of the output dtype
+  constexpr int ESZ = DT == VQB_DTYPE_BF16 ? 2 : 4;
+  const int slice = blockIdx.x / ctas_per_slice, part = blockIdx.x % ctas_per_slice;
+  const int c0 = slice * W;
+  {  // stage the slice: 4 consecutive columns per thread
+    const int64_t quads = static_cast<int64_t>(nbooks) * K * (W / 4);
+    for (int64_t e = threadIdx.x; e < quads; e += blockDim.x) {
+      const int c = static_cast<int>(e % (W / 4)) * 4;
+      const int64_t r = e / (W / 4);   // book * K + code
+      const int book = static_cast<int>(r / K), code = static_cast<int>(r % K);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(embeds + book * embed_stride + static_cast<int64_t>(code) * D + c0 + c));
+      uint8_t* dst = reinterpret_cast<uint8_t*>(code_smem) + (r * W + c) * ESZ;
+      if (DT == VQB_DTYPE_BF16) {
+        uint32_t h0, h1;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+      } else {
+        *reinterpret_cast<float4*>(dst) = v;
+      }
+    }
+  }
+  __syncthreads();
+  const int LPR = W * ESZ / 16;             // lanes per row (power of two, 4..32)
+  const int rpw = 32 / LPR;                 // rows per warp and iteration
+  const int lane = threadIdx.x & 31;
+  const int lir = lane & (LPR - 1), riw = lane / LPR;
+  const int row_u4 = W * ESZ / 16;          // uint4 per staged code row (== LPR)
+  const int64_t gw = static_cast<int64_t>(part) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t step = static_cast<int64_t>(ctas_per_slice) * (blockDim.x >> 5) * rpw;
+  for (int64_t base = gw * rpw; base < N; base += step) {   // warp-uniform trip count (shuffles inside)
+    const int64_t row = base + riw;
+    const bool active = row < N;
+    uint32_t acch[4] = {0u, 0u, 0u, 0u};
+    float accf[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int qc = 0; qc < Q; qc += LPR) {
+      const int64_t kq = (active && qc + lir < Q) ? idx[row * Q + qc + lir] : 0;
+      const int nq = min(LPR, Q - qc);
+      for (int b = 0; b < nq; ++b) {
+        const int k = static_cast<int>(__shfl_sync(0xffffffffu, kq, riw * LPR + b));
+        const int book = nbooks > 1 ? qc + b : 0;
+        const uint4 v = code_smem[(static_cast<int64_t>(book) * K + k) * row_u4 + lir];
+        if (DT == VQB_DTYPE_BF16) {
+          asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[0]) : "r"(acch[0]), "r"(v.x));
+          asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[1]) : "r"(acch[1]), "r"(v.y));
+          asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[2]) : "r"(acch[2]), "r"(v.z));
+          asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[3]) : "r"(acch[3]), "r"(v.w));
+        } else {
+          accf[0] += __uint_as_float(v.x); accf[1] += __uint_as_float(v.y);
+          accf[2] += __uint_as_float(v.z); accf[3] += __uint_as_float(v.w);
+        }
+      }
+    }
+    if (!active) continue;
+    uint8_t* dst = static_cast<uint8_t*>(out) + (row * D + c0) * ESZ + lir * 16;
+    if (DT == VQB_DTYPE_BF16) *reinterpret_cast<uint4*>(dst) = make_uint4(acch[0], acch[1], acch[2], acch[3]);
+    else *reinterpret_cast<float4*>(dst) = make_float4(accf[0], accf[1], accf[2], accf[3]);
   }
 }
 
@@ -479,13 +572,13 @@ extern "C" int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int 
                           void* out, int dtype, void* stream) {
   if (!embeds || !idx || !out || Q <= 0 || K <= 0 || D <= 0 || N <= 0) return VQB_E_INVALID;
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
-  if (D % 4 != 0) return VQB_E_UNSUPPORTED;
+  if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int g = row_grid(N, ROW_THREADS / 32);
   if (dtype == VQB_DTYPE_F32)
-    decode_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, K, D, idx, N, out);
+    rvq_accumulate_kernel<VQB_DTYPE_F32, false><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
   else
-    decode_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, K, D, idx, N, out);
+    rvq_accumulate_kernel<VQB_DTYPE_BF16, false><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -493,13 +586,36 @@ extern "C" int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int
                                   void* out, int dtype, void* stream) {
   if (!embeds || !idx || !out || Q <= 0 || K <= 0 || D <= 0 || N <= 0) return VQB_E_INVALID;
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
-  if (D % 4 != 0) return VQB_E_UNSUPPORTED;
+  if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // smem variant: the widest power-of-two column slice W of all searched codebooks that fits (>= 64 bytes per row piece)
+  const int esz = dtype == VQB_DTYPE_BF16 ? 2 : 4;
+  const int nbooks = embed_stride ? Q : 1;
+  int W = 0;
+  for (int w = 512 / esz; w * esz >= 64; w >>= 1)   // at most 32 lanes x 16 bytes per row piece
+    if (D % w == 0 && static_cast<size_t>(nbooks) * K * w * esz <= 196608) { W = w; break; }
+  if (W && N >= 4096) {
+    const size_t smem = static_cast<size_t>(nbooks) * K * W * esz;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(rvq_accumulate_smem_kernel<VQB_DTYPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
+      cudaFuncSetAttribute(rvq_accumulate_smem_kernel<VQB_DTYPE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
+      attr_set = true;
+    }
+    const int slices = D / W;
+    int cps = num_sms() / slices;
+    if (cps < 1) cps = 1;
+    if (dtype == VQB_DTYPE_F32)
+      rvq_accumulate_smem_kernel<VQB_DTYPE_F32><<<slices * cps, 256, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
+    else
+      rvq_accumulate_smem_kernel<VQB_DTYPE_BF16><<<slices * cps, 256, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
+    return static_cast<int>(cudaGetLastError());
+  }
   const int g = row_grid(N, ROW_THREADS / 32);
   if (dtype == VQB_DTYPE_F32)
-    rvq_accumulate_kernel<VQB_DTYPE_F32><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
+    rvq_accumulate_kernel<VQB_DTYPE_F32, true><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
   else
-    rvq_accumulate_kernel<VQB_DTYPE_BF16><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
+    rvq_accumulate_kernel<VQB_DTYPE_BF16, true><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -60,13 +60,15 @@ static int sort_ctas(int64_t N, int K, int* shift) {
 static size_t carve(StatsWs* ws, void* base, int64_t N, int K) {
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  // ticket block + slab histograms FIRST: vq_forward.cu zeroes its own counters (the 256 bytes in front of this workspace)
+  // with the same memset
+  const size_t o_cta = take(256 + sizeof(int32_t) * static_cast<size_t>(K <= SORT_MAX_K ? sort_ctas_bound(N, K) * K : 0));
   const size_t o_counts = take(sizeof(int32_t) * K);
   const size_t o_offsets = take(sizeof(int32_t) * K);
   const size_t o_cursor = take(sizeof(int32_t) * K);
   const size_t o_nwork = take(sizeof(int32_t));
   const size_t o_perm = take(sizeof(int32_t) * N);
   const size_t o_work = take(sizeof(int4) * max_work_items(N, K));
-  const size_t o_cta = take(256 + sizeof(int32_t) * static_cast<size_t>(K <= SORT_MAX_K ? sort_ctas_bound(N, K) * K : 0));
   if (ws && base) {
     uint8_t* b = static_cast<uint8_t*>(base);
     ws->counts = reinterpret_cast<int32_t*>(b + o_counts);
@@ -463,22 +465,27 @@ static int stats_check(const void* x_eff, int dtype, int64_t N, int D, int K, co
 }
 
 int vqb::stats_begin(float* stats, int dtype, int64_t N, int D, int K, void* workspace, size_t workspace_bytes, int prehist,
-                     int32_t** hist, int* hist_shift, void* stream) {
+                     size_t zero_before, int32_t** hist, int* hist_shift, void* stats_stream, void* stream) {
   StatsWs ws;
   int rc = stats_check(stats, dtype, N, D, K, stats, workspace, workspace_bytes, &ws);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // everything below accumulates onto zeros: the cluster sizes (scan), the row sums (segmented sums, split or not) and the
-  // re-scored rows (stats_add_flagged), in any order
-  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * static_cast<size_t>(vqb_stats_floats(K, D)), s);
+  // re-scored rows (stats_add_flagged), in any order.  Nothing touches the statistics before the search has finished, so
+  // this memset may run on another stream next to it (stats_stream).
+  cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(float) * static_cast<size_t>(vqb_stats_floats(K, D)),
+                                  static_cast<cudaStream_t>(stats_stream ? stats_stream : stream));
   if (e != cudaSuccess) return static_cast<int>(e);
   int shift = 31;
   const int G = sort_ctas(N, K, &shift);
-  if (G > 0)   // ticket + (when the search kernel counts) the slab histograms
-    e = cudaMemsetAsync(ws.ticket, 0, prehist ? 256 + sizeof(int32_t) * static_cast<size_t>(G) * K : 256, s);
-  else
-    e = cudaMemsetAsync(ws.counts, 0, sizeof(int32_t) * K, s);
+  // [caller's counters (zero_before bytes) | ticket block | slab histograms, when the search kernel counts into them]
+  e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(ws.ticket) - zero_before, 0,
+                      zero_before + 256 + ((G > 0 && prehist) ? sizeof(int32_t) * static_cast<size_t>(G) * K : 0), s);
   if (e != cudaSuccess) return static_cast<int>(e);
+  if (G == 0) {
+    e = cudaMemsetAsync(ws.counts, 0, sizeof(int32_t) * K, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
   if (hist) *hist = G > 0 ? ws.cta_counts : ws.counts;
   if (hist_shift) *hist_shift = shift;
   return VQB_OK;
@@ -548,7 +555,7 @@ int vqb::stats_sum(const void* x_eff, int dtype, int64_t N, int D, const int32_t
 extern "C" int vqb_ema_stats(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats,
                              void* workspace, size_t workspace_bytes, void* stream) {
   if (!x_eff || !idx) return VQB_E_INVALID;
-  int rc = stats_begin(stats, dtype, N, D, K, workspace, workspace_bytes, 0, nullptr, nullptr, stream);
+  int rc = stats_begin(stats, dtype, N, D, K, workspace, workspace_bytes, 0, 0, nullptr, nullptr, nullptr, stream);
   if (rc) return rc;
   rc = stats_scan(idx, dtype, N, D, K, stats, workspace, workspace_bytes, 0, stream);
   if (rc) return rc;

@@ -121,7 +121,7 @@ void make_keys(const vqb_vq_forward_args* a, void* stream, uint64_t* sk, uint64_
 // Side stream of the forward chain: the EMA sort runs on it, next to the exact re-score on the caller's stream.
 struct SideStream {
   cudaStream_t stream = nullptr;
-  cudaEvent_t fork = nullptr, join = nullptr, counts = nullptr;
+  cudaEvent_t fork0 = nullptr, fork = nullptr, join = nullptr, counts = nullptr;
   bool ok = false;
 };
 SideStream* side_stream() {
@@ -134,6 +134,7 @@ SideStream* side_stream() {
     tried = true;
     dev = cur;
     ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&ss.fork0, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&ss.counts, cudaEventDisableTiming) == cudaSuccess;
@@ -341,8 +342,8 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   }
   int32_t* flag_count = reinterpret_cast<int32_t*>(ws + w.counters);
   double* loss_sum = reinterpret_cast<double*>(ws + w.counters + 8);
-  cudaError_t e = cudaMemsetAsync(ws + w.counters, 0, 16, s);
-  if (e != cudaSuccess) return static_cast<int>(e);
+  cudaError_t e = cudaSuccess;
+  bool counters_zeroed = false;
 
   // ---- search with the fused gather / loss / residual tail (vqp:743-747, :766, :1178, :1327; rvq:524-525)
   vqb_fused_outputs f;
@@ -382,8 +383,19 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   int32_t* hist = nullptr;
   int hist_shift = 0;
   if (side) {
-    rc = stats_begin(a->stats, a->dtype, a->N, a->D, a->K, ws + w.stats_ws, stats_ws_bytes, 1, &hist, &hist_shift, stream);
+    // ONE memset in front of the search: [flag / loss counters | sort ticket | slab histograms]; the statistics are zeroed
+    // on the side stream, next to the search kernel (its CTAs leave room for a memset kernel on every SM)
+    if (cudaEventRecord(side->fork0, s) != cudaSuccess || cudaStreamWaitEvent(side->stream, side->fork0, 0) != cudaSuccess)
+      return static_cast<int>(cudaGetLastError());
+    static_assert(sizeof(vqb_flag_entry) == 32, "flag entry layout");
+    rc = stats_begin(a->stats, a->dtype, a->N, a->D, a->K, ws + w.stats_ws, stats_ws_bytes, 1, w.stats_ws - w.counters, &hist,
+                     &hist_shift, side->stream, stream);
     if (rc) return rc;
+    counters_zeroed = true;
+  }
+  if (!counters_zeroed) {
+    e = cudaMemsetAsync(ws + w.counters, 0, 16, s);
+    if (e != cudaSuccess) return static_cast<int>(e);
   }
   if (a->ev_search_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_begin), s);
   rc = assign_launch(a_planes, n_a, a->N, a->D, a->planes, a->bext, a->cmax, a->K, a->margin_rel, 0, a->idx32, idx_prov,

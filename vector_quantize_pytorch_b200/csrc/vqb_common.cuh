@@ -83,8 +83,10 @@ int stats_add_flagged(const void* x_eff, int dtype, int64_t N, int D, const vqb_
                       const int32_t* flag_count, const int32_t* idx, int K, float* stats, void* stream);
 // vq_ema.cu: the statistics chain in three steps (vqb_ema_stats = all three, histogram by its own kernel).  With
 // prehist the search kernel counts the certified winners into *hist (slabs of 128 << *hist_shift rows) itself.
+// zero_before: bytes directly in front of the workspace zeroed by the same memset; stats_stream: optional stream for the
+// memset of the statistics (they are not touched before the search ends).
 int stats_begin(float* stats, int dtype, int64_t N, int D, int K, void* workspace, size_t workspace_bytes, int prehist,
-                int32_t** hist, int* hist_shift, void* stream);
+                size_t zero_before, int32_t** hist, int* hist_shift, void* stats_stream, void* stream);
 int stats_scan(const int32_t* idx, int dtype, int64_t N, int D, int K, float* stats, void* workspace, size_t workspace_bytes,
                int prehist, void* stream);
 int stats_sum(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats, void* workspace,
