@@ -142,11 +142,12 @@ def run_reference_arm(args):
 # clocks sampler (B200_PROFILING.md "clocks line")
 # ------------------------------------------------------------------------------------------------
 
+NCU_SUMMARY = "r2_assign_benched_summary.txt"   # ncu --set full of the search launch as benched (scripts/r2_profile.sh)
+
+
 def ncu_dram_bytes():
     """dram read + write bytes of one vq_assign_kernel launch, from the committed ncu summary (None if it is missing)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_assign_benched_summary.txt")
-    if not os.path.exists(path):
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_assign_final_summary.txt")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", NCU_SUMMARY)
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     total, seen = 0.0, 0
     try:

@@ -251,6 +251,28 @@ int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int K, int D, c
 int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
                        void* out, int dtype, void* stream);
 
+/* A whole ResidualVQ / GroupedResidualVQ forward in ONE call (residual_vq.py:469-568 the stage loop, :593-601 the
+ * deferred codebook updates, :676-724 the groups): the ops are enqueued in order and replayed together from one cached
+ * CUDA graph, so the host pays one FFI call per forward instead of one per stage, and the chains of different lanes —
+ * the independent groups of GroupedResidualVQ — run on parallel streams that fork from / join into `stream`.
+ *   VQB_RVQ_STAGE       vqb_vq_forward(stage)             one quantizer (update = 1: its EMA is deferred to a later EMA op)
+ *   VQB_RVQ_EMA         vqb_ema_apply_weighted(ema ...)   residual_vq.py:593-597 / vector_quantize_pytorch.py:616-617, :576-584
+ *   VQB_RVQ_ACCUMULATE  vqb_rvq_accumulate(acc ...)       quantized_out from the indices (residual_vq.py:525)
+ * At most 62 ops, lanes 0..3; ops of one lane execute in list order. */
+enum { VQB_RVQ_STAGE = 0, VQB_RVQ_EMA = 1, VQB_RVQ_ACCUMULATE = 2 };
+typedef struct vqb_rvq_op {
+  int kind, lane;
+  vqb_vq_forward_args stage;
+  struct {
+    float* cluster_size; float* embed_avg; float* embed; const float* stats; int K, D; double decay, eps;
+    int metric, do_lerp, do_normalise; void* planes; void* bext; float* bias; float* cnorm2; float* cmax; float* scratch;
+  } ema;
+  struct {
+    const float* embeds; int64_t embed_stride; int Q, K, D; const int64_t* idx; int64_t N; void* out; int dtype;
+  } acc;
+} vqb_rvq_op;
+int vqb_rvq_forward(const vqb_rvq_op* ops, int n_ops, void* stream);
+
 /* Rotation-trick gradient estimator (vector_quantize_pytorch.py:287-318, default when x.requires_grad, :856, :1225-1228).
  *   grad_out == NULL: forward   out = rotate_to(src, tgt)        (numerically ~ tgt, carries d out / d src)
  *   grad_out != NULL: backward  out = d loss / d src given d loss / d rotate_to(src, tgt)

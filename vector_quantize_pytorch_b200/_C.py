@@ -34,6 +34,24 @@ class VQForwardArgs(ctypes.Structure):
                 ("peer_slice_offset", _i64)]
 
 
+class RvqEmaArgs(ctypes.Structure):
+    _fields_ = [("cluster_size", _vp), ("embed_avg", _vp), ("embed", _vp), ("stats", _vp), ("K", _i32), ("D", _i32),
+                ("decay", _f64), ("eps", _f64), ("metric", _i32), ("do_lerp", _i32), ("do_normalise", _i32),
+                ("planes", _vp), ("bext", _vp), ("bias", _vp), ("cnorm2", _vp), ("cmax", _vp), ("scratch", _vp)]
+
+
+class RvqAccArgs(ctypes.Structure):
+    _fields_ = [("embeds", _vp), ("embed_stride", _i64), ("Q", _i32), ("K", _i32), ("D", _i32), ("idx", _vp), ("N", _i64),
+                ("out", _vp), ("dtype", _i32)]
+
+
+class RvqOp(ctypes.Structure):
+    """Mirror of `vqb_rvq_op` (include/vqb200.h)."""
+    _fields_ = [("kind", _i32), ("lane", _i32), ("stage", VQForwardArgs), ("ema", RvqEmaArgs), ("acc", RvqAccArgs)]
+
+
+RVQ_STAGE, RVQ_EMA, RVQ_ACCUMULATE = 0, 1, 2
+
 SIGNATURES = {
     "vqb_version": (_i32, []),
     "vqb_strerror": (_c.c_char_p, [_i32]),
@@ -62,6 +80,7 @@ SIGNATURES = {
     "vqb_debug_graph_stats": (_i32, [_vp]),
     "vqb_decode": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
     "vqb_rvq_accumulate": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp, _i32, _vp]),
+    "vqb_rvq_forward": (_i32, [_vp, _i32, _vp]),
 }
 
 

@@ -48,7 +48,7 @@ extern "C" size_t vqb_vq_forward_workspace(int64_t N, int D, int K, int dtype, i
   return carve_fwd(N, D, K, dtype, metric, update).total;
 }
 
-static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream);
+static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int lane = 0);
 
 // ---------------------------------------------------------------------------------------------
 // CUDA-graph cache.  The chain is ~15 small launches around one big kernel; replaying it as a graph removes the
@@ -124,24 +124,27 @@ struct SideStream {
   cudaEvent_t fork0 = nullptr, fork = nullptr, join = nullptr, counts = nullptr;
   bool ok = false;
 };
-SideStream* side_stream() {
-  static SideStream ss;
-  static bool tried = false;
+constexpr int kLanes = 4;   // independent chains in flight inside one vqb_rvq_forward (the groups of GroupedResidualVQ)
+SideStream* side_stream(int lane = 0) {
+  static SideStream ss[kLanes];
+  static bool tried[kLanes] = {false, false, false, false};
   static int dev = -1;
+  if (lane < 0 || lane >= kLanes) return nullptr;
   int cur = -1;
   if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); return nullptr; }
-  if (!tried) {
-    tried = true;
-    dev = cur;
-    ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ss.fork0, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess &&
-            cudaEventCreateWithFlags(&ss.counts, cudaEventDisableTiming) == cudaSuccess;
-    if (!ss.ok) cudaGetLastError();
+  if (dev < 0) dev = cur;
+  SideStream& s = ss[lane];
+  if (!tried[lane]) {
+    tried[lane] = true;
+    s.ok = cur == dev && cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.fork0, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&s.counts, cudaEventDisableTiming) == cudaSuccess;
+    if (!s.ok) cudaGetLastError();
   }
   // one process drives one GPU; a call on another device simply runs the chain in one stream
-  return (ss.ok && cur == dev) ? &ss : nullptr;
+  return (s.ok && cur == dev) ? &s : nullptr;
 }
 
 // one line on stderr the first time the graph path is unavailable (the chain then runs launch by launch: same
@@ -167,8 +170,11 @@ cudaStream_t capture_stream() {
   return cs;
 }
 
-// capture the chain for `a` into a fresh graph (nothing executes)
-int capture_chain(const vqb_vq_forward_args* a, cudaStream_t s, cudaGraph_t* out) {
+// A chain = a function that enqueues work on a stream (vq_forward_enqueue for one call, rvq_enqueue for a list of ops)
+typedef int (*EnqueueFn)(const void* ctx, void* stream);
+
+// capture the chain into a fresh graph (nothing executes)
+int capture_chain(EnqueueFn fn, const void* ctx, cudaStream_t s, cudaGraph_t* out) {
   *out = nullptr;
   const cudaError_t be = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
   if (be != cudaSuccess) {  // e.g. the legacy default stream: CUDA does not capture it
@@ -176,7 +182,7 @@ int capture_chain(const vqb_vq_forward_args* a, cudaStream_t s, cudaGraph_t* out
     note_graph_error("cudaStreamBeginCapture", be);
     return kCaptureFailed;
   }
-  const int rc = vq_forward_enqueue(a, s);
+  const int rc = fn(ctx, s);
   cudaGraph_t graph = nullptr;
   const cudaError_t ee = cudaStreamEndCapture(s, &graph);
   if (rc != VQB_OK || ee != cudaSuccess || !graph) {
@@ -188,28 +194,21 @@ int capture_chain(const vqb_vq_forward_args* a, cudaStream_t s, cudaGraph_t* out
   *out = graph;
   return VQB_OK;
 }
-}  // namespace
 
-extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
-  if (!a) return VQB_E_INVALID;
-  std::lock_guard<std::mutex> lock(g_cache_mutex);
+// Serve one call of a chain from the cache (g_cache_mutex held).  sk / pk: structural and pointer key, kKeyWords each.
+int run_cached(const uint64_t* sk, const uint64_t* pk, EnqueueFn fn, const void* ctx, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  if (!graph_mode() || g_graph_disabled || a->ev_search_begin || a->ev_search_end || vqb_debug_active() ||
-      cudaStreamIsCapturing(s, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone)
-    return vq_forward_enqueue(a, stream);
+  constexpr size_t kKeyBytes = sizeof(uint64_t) * kKeyWords;
   if (!g_struct) {
     g_struct = static_cast<StructEntry*>(calloc(kMaxStruct, sizeof(StructEntry)));
-    if (!g_struct) return vq_forward_enqueue(a, stream);
+    if (!g_struct) return fn(ctx, stream);
   }
   cudaStream_t cap_s = capture_stream();   // created here, outside any capture
-  if (!cap_s) return vq_forward_enqueue(a, stream);
-  uint64_t sk[kKeyWords], pk[kKeyWords];
-  make_keys(a, stream, sk, pk);
+  if (!cap_s) return fn(ctx, stream);
   ++g_tick;
   StructEntry* se = nullptr;
   for (int i = 0; i < kMaxStruct; ++i)
-    if (g_struct[i].used && memcmp(g_struct[i].skey, sk, sizeof(sk)) == 0) { se = &g_struct[i]; break; }
+    if (g_struct[i].used && memcmp(g_struct[i].skey, sk, kKeyBytes) == 0) { se = &g_struct[i]; break; }
   if (!se) {  // first call of this structure: remember it, run directly
     int slot = 0;
     for (int i = 0; i < kMaxStruct; ++i) {
@@ -220,14 +219,14 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
     for (int v = 0; v < se->n_var; ++v)
       if (se->var[v].exec) cudaGraphExecDestroy(se->var[v].exec);
     memset(se, 0, sizeof(*se));
-    memcpy(se->skey, sk, sizeof(sk));
+    memcpy(se->skey, sk, kKeyBytes);
     se->used = true;
     se->last_use = g_tick;
-    return vq_forward_enqueue(a, stream);
+    return fn(ctx, stream);
   }
   se->last_use = g_tick;
   for (int v = 0; v < se->n_var; ++v)
-    if (se->var[v].exec && memcmp(se->var[v].pkey, pk, sizeof(pk)) == 0) {  // replay
+    if (se->var[v].exec && memcmp(se->var[v].pkey, pk, kKeyBytes) == 0) {  // replay
       se->var[v].last_use = g_tick;
       ++g_n_replay;
       return static_cast<int>(cudaGraphLaunch(se->var[v].exec, s));
@@ -236,12 +235,12 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   // stall the whole launch queue), so a set earns its own executable only on its SECOND sighting ("pending" record);
   // until then the call is served by patching the least recently used executable in place.
   cudaGraph_t graph = nullptr;
-  const int rc = capture_chain(a, cap_s, &graph);
+  const int rc = capture_chain(fn, ctx, cap_s, &graph);
   if (rc != VQB_OK) {
     if (rc != kCaptureFailed) return rc;              // error reported by the chain itself (nothing ran)
     if (++g_graph_failures > 4) g_graph_disabled = true;
     ++g_n_direct;
-    return vq_forward_enqueue(a, stream);             // capture failed: nothing ran, enqueue directly
+    return fn(ctx, stream);                           // capture failed: nothing ran, enqueue directly
   }
   Variant* pend = nullptr;     // pending record of this pointer set
   Variant* donor = nullptr;    // least recently used executable
@@ -249,7 +248,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   for (int v = 0; v < se->n_var; ++v) {
     Variant* q = &se->var[v];
     if (q->exec) { if (!donor || q->last_use < donor->last_use) donor = q; }
-    else if (memcmp(q->pkey, pk, sizeof(pk)) == 0) pend = q;
+    else if (memcmp(q->pkey, pk, kKeyBytes) == 0) pend = q;
     else if (!spare || q->last_use < spare->last_use) spare = q;
   }
   if (se->n_var < kVariants) spare = &se->var[se->n_var];
@@ -258,7 +257,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
     cudaGetLastError();
     cudaGraphDestroy(graph);
     if (++g_graph_failures > 4) g_graph_disabled = true;
-    return vq_forward_enqueue(a, stream);
+    return fn(ctx, stream);
   };
   Variant* use = nullptr;
   if (pend || !donor) {  // second sighting (or nothing to patch yet): instantiate
@@ -272,7 +271,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
   } else {
     if (spare) {  // remember the sighting
       if (spare == &se->var[se->n_var]) ++se->n_var;
-      memcpy(spare->pkey, pk, sizeof(pk));
+      memcpy(spare->pkey, pk, kKeyBytes);
       spare->exec = nullptr;
       spare->last_use = g_tick;
     }
@@ -283,7 +282,7 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
       donor->exec = nullptr;
       if (cudaGraphInstantiate(&donor->exec, graph, 0) != cudaSuccess || !donor->exec) {
         donor->exec = nullptr;
-        memset(donor->pkey, 0xFF, sizeof(donor->pkey));  // a pending record that matches nothing
+        memset(donor->pkey, 0xFF, kKeyBytes);  // a pending record that matches nothing
         return fail();
       }
     }
@@ -291,9 +290,143 @@ extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
     ++g_n_update;
   }
   cudaGraphDestroy(graph);
-  memcpy(use->pkey, pk, sizeof(pk));
+  memcpy(use->pkey, pk, kKeyBytes);
   use->last_use = g_tick;
   return static_cast<int>(cudaGraphLaunch(use->exec, s));
+}
+
+bool graphs_usable(cudaStream_t s) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  return graph_mode() && !g_graph_disabled && !vqb_debug_active() && cudaStreamIsCapturing(s, &cap) == cudaSuccess &&
+         cap == cudaStreamCaptureStatusNone;
+}
+
+int enqueue_one(const void* ctx, void* stream) { return vq_forward_enqueue(static_cast<const vqb_vq_forward_args*>(ctx), stream); }
+
+// ---- a list of ops (vqb_rvq_forward) ----
+struct RvqCtx { const vqb_rvq_op* ops; int n; };
+
+struct LaneStreams {
+  cudaStream_t stream[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t begin = nullptr, done[kLanes] = {nullptr, nullptr, nullptr, nullptr};
+  bool ok = false;
+};
+LaneStreams* lane_streams() {
+  static LaneStreams ls;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    ls.ok = cudaEventCreateWithFlags(&ls.begin, cudaEventDisableTiming) == cudaSuccess;
+    for (int l = 1; l < kLanes && ls.ok; ++l)
+      ls.ok = cudaStreamCreateWithFlags(&ls.stream[l], cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ls.done[l], cudaEventDisableTiming) == cudaSuccess;
+    if (!ls.ok) cudaGetLastError();
+  }
+  return ls.ok ? &ls : nullptr;
+}
+
+int rvq_enqueue(const void* ctx, void* stream) {
+  const RvqCtx* c = static_cast<const RvqCtx*>(ctx);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bool used[kLanes] = {false, false, false, false};
+  for (int i = 0; i < c->n; ++i) {
+    if (c->ops[i].lane < 0 || c->ops[i].lane >= kLanes) return VQB_E_INVALID;
+    used[c->ops[i].lane] = true;
+  }
+  LaneStreams* ls = (used[1] || used[2] || used[3]) ? lane_streams() : nullptr;
+  cudaStream_t lane_s[kLanes] = {s, s, s, s};   // without lane streams everything runs in order on the caller's stream
+  if (ls) {
+    if (cudaEventRecord(ls->begin, s) != cudaSuccess) return static_cast<int>(cudaGetLastError());
+    for (int l = 1; l < kLanes; ++l)
+      if (used[l]) {
+        if (cudaStreamWaitEvent(ls->stream[l], ls->begin, 0) != cudaSuccess) return static_cast<int>(cudaGetLastError());
+        lane_s[l] = ls->stream[l];
+      }
+  }
+  int rc = VQB_OK;
+  for (int i = 0; i < c->n && rc == VQB_OK; ++i) {
+    const vqb_rvq_op& op = c->ops[i];
+    cudaStream_t os = lane_s[op.lane];
+    if (op.kind == VQB_RVQ_STAGE) {
+      rc = vq_forward_enqueue(&op.stage, os, ls ? op.lane : 0);
+    } else if (op.kind == VQB_RVQ_EMA) {
+      rc = vqb_ema_apply_weighted(op.ema.cluster_size, op.ema.embed_avg, op.ema.embed, op.ema.stats, op.ema.K, op.ema.D,
+                                  op.ema.decay, op.ema.eps, op.ema.metric, op.ema.do_lerp, op.ema.do_normalise, nullptr,
+                                  op.ema.planes, op.ema.bext, op.ema.bias, op.ema.cnorm2, op.ema.cmax, op.ema.scratch, os);
+    } else if (op.kind == VQB_RVQ_ACCUMULATE) {
+      rc = vqb_rvq_accumulate(op.acc.embeds, op.acc.embed_stride, op.acc.Q, op.acc.K, op.acc.D, op.acc.idx, op.acc.N,
+                              op.acc.out, op.acc.dtype, os);
+    } else {
+      rc = VQB_E_INVALID;
+    }
+  }
+  if (ls) {  // join the lanes even after an error: a capture must not end with unjoined streams
+    for (int l = 1; l < kLanes; ++l)
+      if (used[l]) {
+        if (cudaEventRecord(ls->done[l], ls->stream[l]) != cudaSuccess || cudaStreamWaitEvent(s, ls->done[l], 0) != cudaSuccess)
+          if (rc == VQB_OK) rc = static_cast<int>(cudaGetLastError());
+      }
+  }
+  return rc;
+}
+
+uint64_t hash_words(const uint64_t* w, int n, uint64_t seed) {
+  uint64_t h = seed ^ 0x9E3779B97F4A7C15ull;
+  for (int i = 0; i < n; ++i) {
+    h ^= w[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xFF51AFD7ED558CCDull;
+    h ^= h >> 33;
+  }
+  return h;
+}
+}  // namespace
+
+extern "C" int vqb_vq_forward(const vqb_vq_forward_args* a, void* stream) {
+  if (!a) return VQB_E_INVALID;
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  if (a->ev_search_begin || a->ev_search_end || !graphs_usable(static_cast<cudaStream_t>(stream)))
+    return vq_forward_enqueue(a, stream);
+  uint64_t sk[kKeyWords], pk[kKeyWords];
+  make_keys(a, stream, sk, pk);
+  return run_cached(sk, pk, enqueue_one, a, stream);
+}
+
+extern "C" int vqb_rvq_forward(const vqb_rvq_op* ops, int n_ops, void* stream) {
+  if (!ops || n_ops <= 0 || n_ops > kKeyWords - 2) return VQB_E_INVALID;
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  RvqCtx ctx{ops, n_ops};
+  bool events = false;
+  for (int i = 0; i < n_ops; ++i)
+    events |= ops[i].kind == VQB_RVQ_STAGE && (ops[i].stage.ev_search_begin || ops[i].stage.ev_search_end);
+  if (events || !graphs_usable(static_cast<cudaStream_t>(stream))) return rvq_enqueue(&ctx, stream);
+  // one key word per op: hashes of its structural words and of its pointers
+  uint64_t sk[kKeyWords], pk[kKeyWords];
+  memset(sk, 0, sizeof(sk));
+  memset(pk, 0, sizeof(pk));
+  for (int i = 0; i < n_ops; ++i) {
+    const vqb_rvq_op& op = ops[i];
+    uint64_t s1[kKeyWords], p1[kKeyWords];
+    memset(s1, 0, sizeof(s1));
+    memset(p1, 0, sizeof(p1));
+    if (op.kind == VQB_RVQ_STAGE) {
+      make_keys(&op.stage, nullptr, s1, p1);
+    } else if (op.kind == VQB_RVQ_EMA) {
+      const void* ptrs[] = {op.ema.cluster_size, op.ema.embed_avg, op.ema.embed, op.ema.stats, op.ema.planes, op.ema.bext,
+                            op.ema.bias, op.ema.cnorm2, op.ema.cmax, op.ema.scratch};
+      for (int j = 0; j < 10; ++j) p1[j] = reinterpret_cast<uint64_t>(ptrs[j]);
+      s1[0] = op.ema.K; s1[1] = op.ema.D; s1[2] = op.ema.metric; s1[3] = op.ema.do_lerp; s1[4] = op.ema.do_normalise;
+      memcpy(&s1[5], &op.ema.decay, 8); memcpy(&s1[6], &op.ema.eps, 8);
+    } else {
+      p1[0] = reinterpret_cast<uint64_t>(op.acc.embeds); p1[1] = reinterpret_cast<uint64_t>(op.acc.idx);
+      p1[2] = reinterpret_cast<uint64_t>(op.acc.out);
+      s1[0] = op.acc.embed_stride; s1[1] = op.acc.Q; s1[2] = op.acc.K; s1[3] = op.acc.D; s1[4] = op.acc.N; s1[5] = op.acc.dtype;
+    }
+    sk[i] = hash_words(s1, kKeyWords, (static_cast<uint64_t>(op.kind) << 8) | static_cast<uint64_t>(op.lane));
+    pk[i] = hash_words(p1, kKeyWords, 1);
+  }
+  sk[kKeyWords - 2] = static_cast<uint64_t>(n_ops) | (1ull << 40);   // never equal to a single-call key (word 62 is 0 there)
+  sk[kKeyWords - 1] = reinterpret_cast<uint64_t>(stream);
+  return run_cached(sk, pk, rvq_enqueue, &ctx, stream);
 }
 
 // diagnostics: how the graph cache served the calls so far {replayed, patched, instantiated, fell back after a failure}
@@ -303,7 +436,7 @@ extern "C" int vqb_debug_graph_stats(long long* out4) {
   return VQB_OK;
 }
 
-static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
+static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int lane) {
   if (!a || !a->x || !a->embed || !a->planes || !a->bext || !a->cnorm2 || !a->cmax || !a->idx32 || !a->workspace)
     return VQB_E_INVALID;
   if (a->N <= 0 || a->D <= 0 || a->K <= 0) return VQB_E_INVALID;
@@ -377,7 +510,7 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream) {
   // sizes, and the cluster-size half of the EMA follows them there.  Only the row half of the EMA waits for the segmented
   // sums.  Critical path after the search: scan -> scatter -> sums -> EMA rows (was: hist -> colscan -> scan -> scatter ->
   // sums -> re-scored rows -> EMA sizes -> EMA rows).
-  SideStream* side = (a->update && !fused_stats) ? side_stream() : nullptr;
+  SideStream* side = (a->update && !fused_stats) ? side_stream(lane) : nullptr;
   int32_t* idx_prov = side ? reinterpret_cast<int32_t*>(ws + w.idx_prov) : nullptr;
   const size_t stats_ws_bytes = a->update ? vqb_ema_stats_workspace(a->N, a->K) : 0;
   int32_t* hist = nullptr;

@@ -185,15 +185,12 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
     return buf
 
 
-def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: int, do_normalise: bool, decay: float,
-               eps: float, q_out=None, idx64_out=None, idx_stride: int = 1, loss_out=None, loss_weight: float = 1.0,
-               resid_out=None, qsum=None, stats=None, margin: float | None = None, already_normalised: bool = False,
-               ws_key=None, stats_accumulate: bool = False, peer=None, peer_ptrs=None,
-               peer_slice_offset: int = 0) -> tuple[torch.Tensor, torch.Tensor | None]:
-    """ONE C call for the arithmetic of VectorQuantize.forward / one ResidualVQ stage (vqb_vq_forward).
-
-    state = (cluster_size (K,), embed_avg (K, D), embed (K, D)).  update: 0 none, 1 statistics only (returned
-    packed; the caller all-reduces and calls `ema_apply`), 2 statistics + EMA apply.  Returns (idx32, stats)."""
+def vq_forward_args(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: int, do_normalise: bool, decay: float,
+                    eps: float, q_out=None, idx64_out=None, idx_stride: int = 1, loss_out=None, loss_weight: float = 1.0,
+                    resid_out=None, qsum=None, stats=None, margin: float | None = None, already_normalised: bool = False,
+                    ws_key=None, stats_accumulate: bool = False, peer=None, peer_ptrs=None, peer_slice_offset: int = 0):
+    """The argument block of one vqb_vq_forward call (also one VQB_RVQ_STAGE op of vqb_rvq_forward).
+    Returns (args, idx32, stats, n_launches)."""
     _require_cuda(x, state[2])
     assert x.dim() == 2 and x.is_contiguous()
     N, D = x.shape
@@ -220,7 +217,18 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
         a.peer_flags = ctypes.cast(peer.flag_ptrs, ctypes.c_void_p)
         a.peer_epoch = peer.epoch.data_ptr()
         a.peer_rank, a.peer_world, a.peer_slice_offset = peer.rank, peer.world, int(peer_slice_offset)
-    with torch.cuda.device(dev):
+    n_launch = (4 + (1 if dt == _C.DTYPE_F32 or ops.cosine else 0) + (1 if loss_out is not None else 0) + (5 if update else 0)
+                + (2 if update == 2 else 0) + (3 if update == 3 else 0))
+    return a, idx32, stats, n_launch
+
+
+def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, **kw) -> tuple[torch.Tensor, torch.Tensor | None]:
+    """ONE C call for the arithmetic of VectorQuantize.forward / one ResidualVQ stage (vqb_vq_forward).
+
+    state = (cluster_size (K,), embed_avg (K, D), embed (K, D)).  update: 0 none, 1 statistics only (returned
+    packed; the caller all-reduces and calls `ema_apply`), 2 statistics + EMA apply.  Returns (idx32, stats)."""
+    a, idx32, stats, n_launch = vq_forward_args(x, ops, state, **kw)
+    with torch.cuda.device(x.device):
         prof = PROFILE_EVENTS
         if prof is not None:  # bench instrumentation: CUDA events around the search kernel, recorded from C
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -228,9 +236,64 @@ def vq_forward(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: 
             a.ev_search_begin, a.ev_search_end = ev0.cuda_event, ev1.cuda_event
             prof.append((ev0, ev1))
         check(lib.vqb_vq_forward(ctypes.byref(a), _stream()), "vqb_vq_forward")
-    _count(4 + (1 if dt == _C.DTYPE_F32 or ops.cosine else 0) + (1 if loss_out is not None else 0) + (5 if update else 0)
-           + (2 if update == 2 else 0) + (3 if update == 3 else 0))
+    _count(n_launch)
     return idx32, stats
+
+
+class RvqProgram:
+    """The op list of one vqb_rvq_forward call: a whole ResidualVQ / GroupedResidualVQ forward — stages, running sum, deferred
+    EMA updates — enqueued by ONE FFI call and replayed from one CUDA graph.  Ops of one lane run in order; lanes (the groups
+    of GroupedResidualVQ) run on parallel streams."""
+    MAX_OPS = 62
+
+    def __init__(self, device):
+        self.device = device
+        self.ops = []
+        self.keep = []       # tensors the ops point into
+        self.launches = 0
+
+    def stage(self, lane, x, cb_ops, state, **kw):
+        a, idx32, stats, n = vq_forward_args(x, cb_ops, state, **kw)
+        op = _C.RvqOp(kind=_C.RVQ_STAGE, lane=lane)
+        op.stage = a
+        self.ops.append(op)
+        self.keep.append((x, cb_ops, state, kw, idx32, stats))
+        self.launches += n
+        return idx32, stats
+
+    def ema(self, lane, cluster_size, embed_avg, embed, stats, cb_ops, *, decay, eps, do_lerp, do_normalise):
+        K, D = embed.shape
+        op = _C.RvqOp(kind=_C.RVQ_EMA, lane=lane)
+        op.ema = _C.RvqEmaArgs(cluster_size=_p(cluster_size), embed_avg=_p(embed_avg), embed=_p(embed), stats=_p(stats), K=K, D=D,
+                               decay=float(decay), eps=float(eps), metric=int(cb_ops.cosine), do_lerp=int(do_lerp),
+                               do_normalise=int(do_normalise), planes=_p(cb_ops.planes), bext=_p(cb_ops.bext), bias=_p(cb_ops.bias),
+                               cnorm2=_p(cb_ops.cnorm2), cmax=_p(cb_ops.cmax), scratch=_p(cb_ops.scratch))
+        self.ops.append(op)
+        self.keep.append((cluster_size, embed_avg, embed, stats, cb_ops))
+        self.launches += 2
+
+    def accumulate(self, lane, embeds, indices, out):
+        N, Q = indices.shape
+        if embeds.dim() == 2:
+            K, D = embeds.shape
+            stride = 0
+        else:
+            _, K, D = embeds.shape
+            stride = K * D
+        op = _C.RvqOp(kind=_C.RVQ_ACCUMULATE, lane=lane)
+        op.acc = _C.RvqAccArgs(embeds=_p(embeds), embed_stride=stride, Q=Q, K=K, D=D, idx=_p(indices), N=N, out=_p(out),
+                               dtype=_DT[out.dtype])
+        self.ops.append(op)
+        self.keep.append((embeds, indices, out))
+        self.launches += 1
+
+    def run(self):
+        n = len(self.ops)
+        assert 0 < n <= self.MAX_OPS
+        arr = (_C.RvqOp * n)(*self.ops)
+        with torch.cuda.device(self.device):
+            check(lib.vqb_rvq_forward(ctypes.cast(arr, ctypes.c_void_p), n, _stream()), "vqb_rvq_forward")
+        _count(self.launches)
 
 
 def gather(x_eff: torch.Tensor, embed: torch.Tensor, idx: torch.Tensor, *, q_out: torch.Tensor | None = None,

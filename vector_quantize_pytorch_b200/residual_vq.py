@@ -9,6 +9,8 @@ per forward instead of the reference's 2 per codebook per stage.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as distributed
 from torch import nn
@@ -130,7 +132,7 @@ class ResidualVQ(nn.Module):
 
     def forward(self, x, mask=None, indices=None, return_all_codes=False, sample_codebook_temp=None,
                 freeze_codebook=False, beam_size=None, rand_quantize_dropout_fixed_seed=None,
-                _stats_sink=None):
+                _stats_sink=None, _program=None):
         if mask is not None or indices is not None:
             _unsupported("ResidualVQ.forward(mask=/indices=)")
         if beam_size is not None and beam_size > 1:
@@ -167,6 +169,15 @@ class ResidualVQ(nn.Module):
         stage_inputs = []
 
         do_update = [training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
+        if _program is not None or self._program_ok(books, do_update):
+            # the whole forward — stages, running sum, deferred EMA updates — as ONE vqb_rvq_forward call / one CUDA graph
+            own = _program is None
+            prog, lane = (ops.RvqProgram(dev), 0) if own else _program
+            finish = self._plan_program(prog, lane, flat, shape, dtype, books, do_update, losses, all_idx, return_all_codes)
+            if not own:
+                return finish        # GroupedResidualVQ runs the shared program, then calls finish()
+            prog.run()
+            return finish()
         # A shared codebook that replaces dead codes is modified BETWEEN stages by the reference (every layer's
         # update_codebook ends with expire_codes_, vqp:641, on the one aliased Codebook): such stages cannot be deferred.
         inline = [u and self.shared_codebook and b.has_dead_code_replacement for b, u in zip(books, do_update)]
@@ -214,6 +225,72 @@ class ResidualVQ(nn.Module):
         if return_all_codes:
             ret = (*ret, self.get_codes_from_indices(ret[1]))
         return ret
+
+    def _program_ok(self, books, do_update):
+        """One-call path (ops.RvqProgram): every stage deferred, no collective, no dead-code expiry, nothing parked on `.grad`
+        (accum_ema_update), codebooks initialised and stackable."""
+        if os.environ.get("VQB_RVQ_PROGRAM", "1") == "0":
+            return False
+        if ops.PROFILE_EVENTS is not None or not self.uniform_codebook_size:
+            return False
+        n_ops = len(books) + 1 + sum(do_update) + 1
+        if n_ops > ops.RvqProgram.MAX_OPS:
+            return False
+        for b, u in zip(books, do_update):
+            if not b._initted_host:
+                return False
+            if u and (b.use_ddp or b.has_dead_code_replacement or b.cluster_size.grad is not None or b.embed_avg.grad is not None):
+                return False
+        return True
+
+    def _plan_program(self, prog, lane, flat, shape, dtype, books, do_update, losses, all_idx, return_all_codes):
+        """Append this forward to `prog` (stage ops rvq:469-568, running sum rvq:525, EMA ops rvq:593-597 / vqp:616-617, :576-584);
+        returns the function that assembles the outputs once the program has run."""
+        N, D = flat.shape
+        Q = self.num_quantizers
+        dev = flat.device
+        training = self.training
+        bufs = [torch.empty_like(flat) for _ in range(min(2, Q - 1))]
+        stat_sizes = [ops.stats_floats(b.codebook_size, D) if u else 0 for b, u in zip(books, do_update)]
+        offs = [sum(stat_sizes[:i]) for i in range(Q)]
+        packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
+        residual = flat
+        for q, book in enumerate(books):
+            nxt = bufs[q & 1] if q + 1 < Q else None
+            want_loss = training and self.layers[q].has_commitment_loss
+            prog.stage(lane, residual, book.operands(), book._state2d(), update=1 if do_update[q] else 0, do_normalise=False,
+                       decay=book.decay, eps=book.eps, idx64_out=all_idx[:, q], idx_stride=Q,
+                       loss_out=losses[q:q + 1] if want_loss else None, loss_weight=self.layers[q].commitment_weight,
+                       resid_out=nxt, stats=packed[offs[q]:offs[q] + stat_sizes[q]] if stat_sizes[q] else None, ws_key=id(book))
+            residual = nxt
+        embeds = books[0].embed[0] if self.shared_codebook else torch.stack([b.embed[0] for b in books])
+        quantized_out = torch.empty((N, D), dtype=dtype, device=dev)
+        prog.accumulate(lane, embeds, all_idx, quantized_out)     # reads the codebooks the stages searched: before the EMA ops
+        refreshed = []
+        for q, book in enumerate(books):
+            if not stat_sizes[q]:
+                continue
+            normalise = book.ema_update and not book.manual_ema_update
+            cs, ea, emb = book._state2d()
+            prog.ema(lane, cs, ea, emb, packed[offs[q]:offs[q] + stat_sizes[q]], book.operands(), decay=book.decay, eps=book.eps,
+                     do_lerp=True, do_normalise=normalise)
+            if normalise:
+                refreshed.append(book)
+        if training and self.shared_codebook and self.vq_is_ema_updating and any(do_update):   # rvq:593-597
+            shared = books[0]
+            cs, ea, emb = shared._state2d()
+            prog.ema(lane, cs, ea, emb, None, shared.operands(), decay=shared.decay, eps=shared.eps, do_lerp=False, do_normalise=True)
+            refreshed.append(shared)
+
+        def finish():
+            for b in refreshed:
+                b._mark_operands_fresh()
+            out = self.project_out(quantized_out.reshape(shape))  # rvq:610
+            ret = (out, all_idx.reshape(*shape[:-1], Q), losses.clone())
+            if return_all_codes:
+                ret = (*ret, self.get_codes_from_indices(ret[1]))
+            return ret
+        return finish
 
     def _finish_update(self, packed, offs, stat_sizes, do_update, stage_inputs, synced):
         """ONE all-reduce for all stages (reference: 2 per stage, vqp:603/:607), then the per-stage lerps in
@@ -294,6 +371,23 @@ class GroupedResidualVQ(nn.Module):
     def get_output_from_indices(self, indices):
         return torch.cat(tuple(rvq.get_output_from_indices(i) for rvq, i in zip(self.rvqs, indices)), dim=-1)
 
+    def _program_ok(self, chunks, freeze_codebook):
+        """All groups in one ops.RvqProgram: every group qualifies (ResidualVQ._program_ok), no gradient path, and the op list fits."""
+        if torch.is_grad_enabled() and any(c.requires_grad for c in chunks):
+            return False
+        total = 0
+        for rvq, c in zip(self.rvqs, chunks):
+            if not c.is_cuda or c.dtype not in (torch.float32, torch.bfloat16):
+                return False
+            if torch.is_grad_enabled() and any(p.requires_grad for p in rvq.project_in.parameters()):
+                return False
+            books = rvq._stage_plan()
+            upd = [rvq.training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
+            if not rvq._program_ok(books, upd):
+                return False
+            total += len(books) + 1 + sum(upd) + 1
+        return total <= ops.RvqProgram.MAX_OPS
+
     def forward(self, x, indices=None, return_all_codes=False, sample_codebook_temp=None, freeze_codebook=False, mask=None):
         if indices is not None or mask is not None:
             _unsupported("GroupedResidualVQ.forward(indices=/mask=)")
@@ -305,9 +399,18 @@ class GroupedResidualVQ(nn.Module):
             seed = torch.randint(0, 10_000, (), device=x.device)
             if distributed.is_available() and distributed.is_initialized() and distributed.get_world_size() > 1:
                 distributed.all_reduce(seed)
-        sink = []
-        outs = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _stats_sink=sink)
-                for rvq, c in zip(self.rvqs, chunks)]  # rvq:706
+        if self._program_ok(chunks, freeze_codebook):
+            # every group's stages in ONE vqb_rvq_forward call: the groups are independent chains on parallel lanes
+            prog = ops.RvqProgram(x.device)
+            fins = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _program=(prog, g % 4))
+                    for g, (rvq, c) in enumerate(zip(self.rvqs, chunks))]
+            prog.run()
+            outs = [f() for f in fins]
+            sink = []
+        else:
+            sink = []
+            outs = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _stats_sink=sink)
+                    for rvq, c in zip(self.rvqs, chunks)]  # rvq:706
         if sink:
             need_sync = any(b.use_ddp for rvq, *_ in sink for b in rvq._stage_plan()) and all(e[5][2] is None for e in sink)
             if need_sync:  # no peer memory: ONE NCCL collective for every codebook of every group
