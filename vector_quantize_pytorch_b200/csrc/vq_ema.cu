@@ -49,6 +49,7 @@ static int sort_ctas(int64_t N, int K, int* shift) {
   if (K > SORT_MAX_K || N < 32 * static_cast<int64_t>(K)) { *shift = 31; return 0; }   // -> global-atomic kernels
   const int64_t tiles = (N + 127) / 128;
   int64_t cap = num_sms();
+  if (cap > 256) cap = 256;   // colscan_kernel: 32 warps x 8 slabs in registers
   if (cap > SORT_MAX_CELLS / K) cap = SORT_MAX_CELLS / K;
   if (cap < 1) cap = 1;
   int sh = 2;
@@ -179,38 +180,34 @@ __device__ void scan_codes_block(const int32_t* counts, int K, int32_t* offsets,
 // scan over the codes: one launch instead of two on the critical path of the step.  A block owns 32 adjacent codes
 // (coalesced 128-byte rows of the [G][K] matrix); its 8 warps split the slab axis, scan their stretch, and are stitched
 // together through smem — two short passes instead of one G-long dependent chain per code.
-constexpr int CS_CODES = 32, CS_PARTS = 8;
+constexpr int CS_CODES = 32, CS_PARTS = 32, CS_PER = 8;   // 32 warps per block; a warp scans at most CS_PER slabs from registers
 __global__ void __launch_bounds__(CS_CODES * CS_PARTS)
 colscan_kernel(int32_t* __restrict__ cta_counts, int G, int K, int32_t* __restrict__ counts, int32_t* ticket,
                int32_t* offsets, int4* work, int32_t* nwork, float* stats) {
-  __shared__ int32_t part[CS_PARTS][CS_CODES];
+  __shared__ int32_t part[CS_PARTS][CS_CODES + 1];
   __shared__ int s_last;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int k = blockIdx.x * CS_CODES + lane;
-  const int per = (G + CS_PARTS - 1) / CS_PARTS;
+  const int per = (G + CS_PARTS - 1) / CS_PARTS;   // <= CS_PER (host: G <= CS_PARTS * CS_PER)
   const int g0 = min(G, w * per), g1 = min(G, g0 + per);
+  // one round trip: every slab count of this warp's stretch is loaded before the first use and stays in registers
+  int v[CS_PER];
   int sum = 0;
-  if (k < K) {
-    int g = g0;
-    for (; g + 4 <= g1; g += 4) {
-      int v[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) v[q] = __ldcg(cta_counts + static_cast<size_t>(g + q) * K + k);   // written by REDs: L2
-      sum += (v[0] + v[1]) + (v[2] + v[3]);
-    }
-    for (; g < g1; ++g) sum += __ldcg(cta_counts + static_cast<size_t>(g) * K + k);
+  for (int j = 0; j < CS_PER; ++j) {
+    v[j] = (k < K && g0 + j < g1) ? __ldcg(cta_counts + static_cast<size_t>(g0 + j) * K + k) : 0;   // written by REDs: L2
+    sum += v[j];
   }
   part[w][lane] = sum;
   __syncthreads();
   int run = 0, total = 0;
-#pragma unroll
-  for (int q = 0; q < CS_PARTS; ++q) { const int v = part[q][lane]; run += (q < w) ? v : 0; total += v; }
+#pragma unroll 8
+  for (int q = 0; q < CS_PARTS; ++q) { const int x = part[q][lane]; run += (q < w) ? x : 0; total += x; }
   if (k < K) {
-    for (int g = g0; g < g1; ++g) {  // the values are in L2 from the first pass
-      int32_t* cell = cta_counts + static_cast<size_t>(g) * K + k;
-      const int v = __ldcg(cell);
-      *cell = run;
-      run += v;
+#pragma unroll
+    for (int j = 0; j < CS_PER; ++j) {
+      if (g0 + j < g1) cta_counts[static_cast<size_t>(g0 + j) * K + k] = run;
+      run += v[j];
     }
     if (w == 0) counts[k] = total;
   }
