@@ -347,9 +347,11 @@ __global__ void __launch_bounds__(256, 2) rvq_accumulate_kernel(const float* __r
 // (config 3: 262144 x 8 x 1 KiB = 2.1 GB -> 250 us, L2-bandwidth bound for a 134 MB write).  When one W-column slice of
 // every codebook the stages searched fits in smem (a shared codebook: K x W x esz <= 192 KiB), a CTA converts its slice
 // once and then serves all its rows from smem: L2 traffic drops to the indices (re-read once per slice) and HBM to the
-// output write.  A row is handled by LPR = W*esz/16 adjacent lanes (16 bytes each), 32/LPR rows per warp.
+// output write.  A row is handled by LPR = W*esz/16 adjacent lanes (16 bytes each), 32/LPR rows per warp; 32 warps per
+// CTA (one CTA per SM: the slice fills its smem) keep enough index loads in flight — with 8 warps the kernel was as slow as
+// the L2 version (244 us: one dependent index load -> smem read chain per warp at a time).
 template <int DT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(1024, 1)
 rvq_accumulate_smem_kernel(const float* __restrict__ embeds, int64_t embed_stride, int nbooks, int Q, int K, int D, int W,
                            const int64_t* __restrict__ idx, int64_t N, void* out, int ctas_per_slice) {
   extern __shared__ uint4 code_smem[];   // [nbooks][K][W] elements of the output dtype
@@ -382,13 +384,17 @@ rvq_accumulate_smem_kernel(const float* __restrict__ embeds, int64_t embed_strid
   const int row_u4 = W * ESZ / 16;          // uint4 per staged code row (== LPR)
   const int64_t gw = static_cast<int64_t>(part) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t step = static_cast<int64_t>(ctas_per_slice) * (blockDim.x >> 5) * rpw;
+  // the first chunk of indices of the NEXT iteration is requested before this one is consumed
+  int64_t kq_next = (gw * rpw + riw < N && lir < Q) ? idx[(gw * rpw + riw) * Q + lir] : 0;
   for (int64_t base = gw * rpw; base < N; base += step) {   // warp-uniform trip count (shuffles inside)
     const int64_t row = base + riw;
     const bool active = row < N;
     uint32_t acch[4] = {0u, 0u, 0u, 0u};
     float accf[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t kq_first = kq_next;
+    kq_next = (row + step < N && lir < Q) ? idx[(row + step) * Q + lir] : 0;
     for (int qc = 0; qc < Q; qc += LPR) {
-      const int64_t kq = (active && qc + lir < Q) ? idx[row * Q + qc + lir] : 0;
+      const int64_t kq = qc == 0 ? kq_first : ((active && qc + lir < Q) ? idx[row * Q + qc + lir] : 0);
       const int nq = min(LPR, Q - qc);
       for (int b = 0; b < nq; ++b) {
         const int k = static_cast<int>(__shfl_sync(0xffffffffu, kq, riw * LPR + b));
@@ -606,9 +612,9 @@ extern "C" int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int
     int cps = num_sms() / slices;
     if (cps < 1) cps = 1;
     if (dtype == VQB_DTYPE_F32)
-      rvq_accumulate_smem_kernel<VQB_DTYPE_F32><<<slices * cps, 256, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
+      rvq_accumulate_smem_kernel<VQB_DTYPE_F32><<<slices * cps, 1024, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
     else
-      rvq_accumulate_smem_kernel<VQB_DTYPE_BF16><<<slices * cps, 256, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
+      rvq_accumulate_smem_kernel<VQB_DTYPE_BF16><<<slices * cps, 1024, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
     return static_cast<int>(cudaGetLastError());
   }
   const int g = row_grid(N, ROW_THREADS / 32);

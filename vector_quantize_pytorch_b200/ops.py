@@ -287,12 +287,21 @@ class RvqProgram:
         self.keep.append((embeds, indices, out))
         self.launches += 1
 
-    def run(self):
+    def freeze(self):
+        """Materialise the op array once; afterwards only `arr` is patched (cached programs: residual_vq.py)."""
         n = len(self.ops)
         assert 0 < n <= self.MAX_OPS
-        arr = (_C.RvqOp * n)(*self.ops)
+        self.arr = (_C.RvqOp * n)(*self.ops)
+        self.n = n
+        self.ops = None
+        self.keep = None     # the owner of a cached program keeps its persistent tensors alive itself (and re-binds the rest)
+        return self
+
+    def run(self):
+        if getattr(self, "arr", None) is None:
+            self.freeze()
         with torch.cuda.device(self.device):
-            check(lib.vqb_rvq_forward(ctypes.cast(arr, ctypes.c_void_p), n, _stream()), "vqb_rvq_forward")
+            check(lib.vqb_rvq_forward(ctypes.cast(self.arr, ctypes.c_void_p), self.n, _stream()), "vqb_rvq_forward")
         _count(self.launches)
 
 

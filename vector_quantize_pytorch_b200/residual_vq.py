@@ -21,6 +21,94 @@ from .dist import allreduce_packed, PeerReducer
 from .vector_quantize import VectorQuantize
 
 
+class _PlanCache(dict):
+    """Cached op lists of a module (raw device pointers inside): never copied or pickled along with the module."""
+
+    def __deepcopy__(self, memo):
+        return _PlanCache()
+
+    def __reduce__(self):
+        return (_PlanCache, ())
+
+
+class _PlanPart:
+    """One ResidualVQ forward inside an ops.RvqProgram: stage ops (rvq:469-568), the running sum (rvq:525), the deferred EMA
+    ops (rvq:593-597 / vqp:616-617, :576-584).  Built once per configuration; `bind` patches the per-call pointers."""
+
+    def __init__(self, rvq, prog, lane, flat, books, do_update):
+        N, D = flat.shape
+        Q = rvq.num_quantizers
+        dev, dtype = flat.device, flat.dtype
+        training = rvq.training
+        self.rvq, self.N, self.D, self.Q, self.dtype, self.dev = rvq, N, D, Q, dtype, dev
+        self.bufs = [torch.empty_like(flat) for _ in range(min(2, Q - 1))]          # persistent: the residual ping-pong
+        stat_sizes = [ops.stats_floats(b.codebook_size, D) if u else 0 for b, u in zip(books, do_update)]
+        offs = [sum(stat_sizes[:i]) for i in range(Q)]
+        self.packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
+        self.losses = rvq._loss_buf
+        self.books = books
+        all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)               # placeholders: `bind` patches the pointers
+        self.first = len(prog.ops)
+        residual = flat
+        for q, book in enumerate(books):
+            nxt = self.bufs[q & 1] if q + 1 < Q else None
+            want_loss = training and rvq.layers[q].has_commitment_loss
+            prog.stage(lane, residual, book.operands(), book._state2d(), update=1 if do_update[q] else 0, do_normalise=False,
+                       decay=book.decay, eps=book.eps, idx64_out=all_idx[:, q], idx_stride=Q,
+                       loss_out=self.losses[q:q + 1] if want_loss else None, loss_weight=rvq.layers[q].commitment_weight,
+                       resid_out=nxt, stats=self.packed[offs[q]:offs[q] + stat_sizes[q]] if stat_sizes[q] else None,
+                       ws_key=id(book))
+            residual = nxt
+        # the running sum reads the codebooks the stages searched: before the EMA ops
+        self.stack = None if rvq.shared_codebook else torch.stack([b.embed[0] for b in books])
+        embeds = books[0].embed[0] if rvq.shared_codebook else self.stack
+        self.acc = len(prog.ops)
+        prog.accumulate(lane, embeds, all_idx, torch.empty((N, D), dtype=dtype, device=dev))
+        self.refreshed = []
+        for q, book in enumerate(books):
+            if not stat_sizes[q]:
+                continue
+            normalise = book.ema_update and not book.manual_ema_update
+            cs, ea, emb = book._state2d()
+            prog.ema(lane, cs, ea, emb, self.packed[offs[q]:offs[q] + stat_sizes[q]], book.operands(), decay=book.decay,
+                     eps=book.eps, do_lerp=True, do_normalise=normalise)
+            if normalise:
+                self.refreshed.append(book)
+        if training and rvq.shared_codebook and rvq.vq_is_ema_updating and any(do_update):   # rvq:593-597
+            shared = books[0]
+            cs, ea, emb = shared._state2d()
+            prog.ema(lane, cs, ea, emb, None, shared.operands(), decay=shared.decay, eps=shared.eps, do_lerp=False,
+                     do_normalise=True)
+            self.refreshed.append(shared)
+
+    def bind(self, arr, flat):
+        """Fresh outputs for this call + the pointers of the cached ops that change from call to call."""
+        all_idx = torch.empty((self.N, self.Q), dtype=torch.int64, device=self.dev)
+        out = torch.empty((self.N, self.D), dtype=self.dtype, device=self.dev)
+        if self.stack is not None:
+            torch.stack([b.embed[0] for b in self.books], out=self.stack)
+        if not self.rvq.training:
+            self.losses.zero_()
+        ip = all_idx.data_ptr()
+        arr[self.first].stage.x = flat.data_ptr()
+        for q in range(self.Q):
+            arr[self.first + q].stage.idx64_out = ip + 8 * q
+        arr[self.acc].acc.idx = ip
+        arr[self.acc].acc.out = out.data_ptr()
+        return all_idx, out, flat
+
+    def finish(self, bound, shape, return_all_codes):
+        all_idx, out, _ = bound
+        rvq = self.rvq
+        for b in self.refreshed:
+            b._mark_operands_fresh()
+        out = rvq.project_out(out.reshape(shape))  # rvq:610
+        ret = (out, all_idx.reshape(*shape[:-1], self.Q), self.losses.clone())
+        if return_all_codes:
+            ret = (*ret, rvq.get_codes_from_indices(ret[1]))
+        return ret
+
+
 class ResidualVQ(nn.Module):
     def __init__(
         self,
@@ -132,7 +220,7 @@ class ResidualVQ(nn.Module):
 
     def forward(self, x, mask=None, indices=None, return_all_codes=False, sample_codebook_temp=None,
                 freeze_codebook=False, beam_size=None, rand_quantize_dropout_fixed_seed=None,
-                _stats_sink=None, _program=None):
+                _stats_sink=None):
         if mask is not None or indices is not None:
             _unsupported("ResidualVQ.forward(mask=/indices=)")
         if beam_size is not None and beam_size > 1:
@@ -154,30 +242,33 @@ class ResidualVQ(nn.Module):
         training = self.training
         books = self._stage_plan()
 
+        losses = self._ensure_loss_buf(dev)
+        do_update = [training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
+        if self._program_ok(books, do_update):
+            # the whole forward — stages, running sum, deferred EMA updates — as ONE vqb_rvq_forward call / one CUDA graph,
+            # from a cached op list in which only the per-call pointers (input, indices, output) are patched
+            key = self._part_key(flat, books, do_update)
+            plans = self.__dict__.setdefault("_plans", _PlanCache())
+            plan = plans.get(key)
+            if plan is None:
+                if len(plans) >= 8:
+                    plans.clear()
+                prog = ops.RvqProgram(dev)
+                part = self._plan_part(prog, 0, flat, books, do_update)
+                plan = plans[key] = (prog.freeze(), part)
+            prog, part = plan
+            bound = part.bind(prog.arr, flat)
+            prog.run()
+            return part.finish(bound, shape, return_all_codes)
+
         all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)
-        loss_buf = getattr(self, "_loss_buf", None)  # persistent (stable pointers for the graph cache), cloned out below
-        if loss_buf is None or loss_buf.device != dev or loss_buf.numel() != Q:
-            loss_buf = torch.zeros((Q,), dtype=torch.float32, device=dev)
-            self._loss_buf = loss_buf
         if not training:
-            loss_buf.zero_()
-        losses = loss_buf
+            losses.zero_()
         # dead-code expiry samples from the stage inputs after the (deferred) EMA update: keep them all then
         keep_inputs = training and not freeze_codebook and any(b.has_dead_code_replacement for b in books)
         bufs = [torch.empty_like(flat) for _ in range(Q - 1 if keep_inputs else min(2, Q - 1))]
         residual = flat  # rvq:411 (never written: stage 0 reads the caller's tensor)
         stage_inputs = []
-
-        do_update = [training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
-        if _program is not None or self._program_ok(books, do_update):
-            # the whole forward — stages, running sum, deferred EMA updates — as ONE vqb_rvq_forward call / one CUDA graph
-            own = _program is None
-            prog, lane = (ops.RvqProgram(dev), 0) if own else _program
-            finish = self._plan_program(prog, lane, flat, shape, dtype, books, do_update, losses, all_idx, return_all_codes)
-            if not own:
-                return finish        # GroupedResidualVQ runs the shared program, then calls finish()
-            prog.run()
-            return finish()
         # A shared codebook that replaces dead codes is modified BETWEEN stages by the reference (every layer's
         # update_codebook ends with expire_codes_, vqp:641, on the one aliased Codebook): such stages cannot be deferred.
         inline = [u and self.shared_codebook and b.has_dead_code_replacement for b, u in zip(books, do_update)]
@@ -243,54 +334,22 @@ class ResidualVQ(nn.Module):
                 return False
         return True
 
-    def _plan_program(self, prog, lane, flat, shape, dtype, books, do_update, losses, all_idx, return_all_codes):
-        """Append this forward to `prog` (stage ops rvq:469-568, running sum rvq:525, EMA ops rvq:593-597 / vqp:616-617, :576-584);
-        returns the function that assembles the outputs once the program has run."""
-        N, D = flat.shape
-        Q = self.num_quantizers
-        dev = flat.device
-        training = self.training
-        bufs = [torch.empty_like(flat) for _ in range(min(2, Q - 1))]
-        stat_sizes = [ops.stats_floats(b.codebook_size, D) if u else 0 for b, u in zip(books, do_update)]
-        offs = [sum(stat_sizes[:i]) for i in range(Q)]
-        packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
-        residual = flat
-        for q, book in enumerate(books):
-            nxt = bufs[q & 1] if q + 1 < Q else None
-            want_loss = training and self.layers[q].has_commitment_loss
-            prog.stage(lane, residual, book.operands(), book._state2d(), update=1 if do_update[q] else 0, do_normalise=False,
-                       decay=book.decay, eps=book.eps, idx64_out=all_idx[:, q], idx_stride=Q,
-                       loss_out=losses[q:q + 1] if want_loss else None, loss_weight=self.layers[q].commitment_weight,
-                       resid_out=nxt, stats=packed[offs[q]:offs[q] + stat_sizes[q]] if stat_sizes[q] else None, ws_key=id(book))
-            residual = nxt
-        embeds = books[0].embed[0] if self.shared_codebook else torch.stack([b.embed[0] for b in books])
-        quantized_out = torch.empty((N, D), dtype=dtype, device=dev)
-        prog.accumulate(lane, embeds, all_idx, quantized_out)     # reads the codebooks the stages searched: before the EMA ops
-        refreshed = []
-        for q, book in enumerate(books):
-            if not stat_sizes[q]:
-                continue
-            normalise = book.ema_update and not book.manual_ema_update
-            cs, ea, emb = book._state2d()
-            prog.ema(lane, cs, ea, emb, packed[offs[q]:offs[q] + stat_sizes[q]], book.operands(), decay=book.decay, eps=book.eps,
-                     do_lerp=True, do_normalise=normalise)
-            if normalise:
-                refreshed.append(book)
-        if training and self.shared_codebook and self.vq_is_ema_updating and any(do_update):   # rvq:593-597
-            shared = books[0]
-            cs, ea, emb = shared._state2d()
-            prog.ema(lane, cs, ea, emb, None, shared.operands(), decay=shared.decay, eps=shared.eps, do_lerp=False, do_normalise=True)
-            refreshed.append(shared)
+    def _ensure_loss_buf(self, dev):
+        """Per-stage losses land in a persistent buffer (stable pointers for the graph cache); callers get a clone."""
+        loss_buf = getattr(self, "_loss_buf", None)
+        if loss_buf is None or loss_buf.device != dev or loss_buf.numel() != self.num_quantizers:
+            loss_buf = torch.zeros((self.num_quantizers,), dtype=torch.float32, device=dev)
+            self._loss_buf = loss_buf
+        return loss_buf
 
-        def finish():
-            for b in refreshed:
-                b._mark_operands_fresh()
-            out = self.project_out(quantized_out.reshape(shape))  # rvq:610
-            ret = (out, all_idx.reshape(*shape[:-1], Q), losses.clone())
-            if return_all_codes:
-                ret = (*ret, self.get_codes_from_indices(ret[1]))
-            return ret
-        return finish
+    def _part_key(self, flat, books, do_update):
+        """Everything a cached op list depends on, except the per-call pointers `_PlanPart.bind` patches.  `book.operands()`
+        refreshes the tensor-core operands if `embed` was changed from outside since the last forward."""
+        return (tuple(flat.shape), flat.dtype, flat.device, self.training, tuple(do_update),
+                tuple((id(b), id(b.operands()), b.embed.data_ptr(), b.cluster_size.data_ptr(), b.embed_avg.data_ptr()) for b in books))
+
+    def _plan_part(self, prog, lane, flat, books, do_update):
+        return _PlanPart(self, prog, lane, flat, books, do_update)
 
     def _finish_update(self, packed, offs, stat_sizes, do_update, stage_inputs, synced):
         """ONE all-reduce for all stages (reference: 2 per stage, vqp:603/:607), then the per-stage lerps in
@@ -400,12 +459,30 @@ class GroupedResidualVQ(nn.Module):
             if distributed.is_available() and distributed.is_initialized() and distributed.get_world_size() > 1:
                 distributed.all_reduce(seed)
         if self._program_ok(chunks, freeze_codebook):
-            # every group's stages in ONE vqb_rvq_forward call: the groups are independent chains on parallel lanes
-            prog = ops.RvqProgram(x.device)
-            fins = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _program=(prog, g % 4))
-                    for g, (rvq, c) in enumerate(zip(self.rvqs, chunks))]
+            # every group's stages in ONE vqb_rvq_forward call: the groups are independent chains on parallel lanes; the op
+            # list is cached, only the per-call pointers are patched
+            flats, keys = [], []
+            for rvq, c in zip(self.rvqs, chunks):
+                xin = rvq.project_in(c)
+                flat = xin.detach().reshape(-1, xin.shape[-1]).contiguous()
+                books = rvq._stage_plan()
+                upd = [rvq.training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
+                rvq._ensure_loss_buf(flat.device)
+                flats.append((flat, xin.shape, books, upd))
+                keys.append(rvq._part_key(flat, books, upd))
+            key = tuple(keys)
+            plans = self.__dict__.setdefault("_plans", _PlanCache())
+            plan = plans.get(key)
+            if plan is None:
+                if len(plans) >= 8:
+                    plans.clear()
+                prog = ops.RvqProgram(x.device)
+                parts = [rvq._plan_part(prog, g % 4, f[0], f[2], f[3]) for g, (rvq, f) in enumerate(zip(self.rvqs, flats))]
+                plan = plans[key] = (prog.freeze(), parts)
+            prog, parts = plan
+            bound = [part.bind(prog.arr, f[0]) for part, f in zip(parts, flats)]
             prog.run()
-            outs = [f() for f in fins]
+            outs = [part.finish(b, f[1], return_all_codes) for part, b, f in zip(parts, bound, flats)]
             sink = []
         else:
             sink = []
