@@ -35,7 +35,12 @@ class _PlanPart:
     """One ResidualVQ forward inside an ops.RvqProgram: stage ops (rvq:469-568), the running sum (rvq:525), the deferred EMA
     ops (rvq:593-597 / vqp:616-617, :576-584).  Built once per configuration; `bind` patches the per-call pointers."""
 
-    def __init__(self, rvq, prog, lane, flat, books, do_update):
+    def __init__(self, rvq, prog, lane, flat, books, do_update, persistent_io=False):
+        # persistent_io (GroupedResidualVQ: its cat / stack copy the results anyway): input, indices and output live in
+        # buffers owned by the plan, so every pointer of the graph is stable and a forward is a pure replay
+        self.io = None
+        if persistent_io:
+            flat = flat.clone(memory_format=torch.contiguous_format)
         N, D = flat.shape
         Q = rvq.num_quantizers
         dev, dtype = flat.device, flat.dtype
@@ -48,6 +53,9 @@ class _PlanPart:
         self.losses = rvq._loss_buf
         self.books = books
         all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)               # placeholders: `bind` patches the pointers
+        out0 = torch.empty((N, D), dtype=dtype, device=dev)
+        if persistent_io:
+            self.io = (flat, all_idx, out0)
         self.first = len(prog.ops)
         residual = flat
         for q, book in enumerate(books):
@@ -63,7 +71,7 @@ class _PlanPart:
         self.stack = None if rvq.shared_codebook else torch.stack([b.embed[0] for b in books])
         embeds = books[0].embed[0] if rvq.shared_codebook else self.stack
         self.acc = len(prog.ops)
-        prog.accumulate(lane, embeds, all_idx, torch.empty((N, D), dtype=dtype, device=dev))
+        prog.accumulate(lane, embeds, all_idx, out0)
         self.refreshed = []
         for q, book in enumerate(books):
             if not stat_sizes[q]:
@@ -83,12 +91,16 @@ class _PlanPart:
 
     def bind(self, arr, flat):
         """Fresh outputs for this call + the pointers of the cached ops that change from call to call."""
-        all_idx = torch.empty((self.N, self.Q), dtype=torch.int64, device=self.dev)
-        out = torch.empty((self.N, self.D), dtype=self.dtype, device=self.dev)
         if self.stack is not None:
             torch.stack([b.embed[0] for b in self.books], out=self.stack)
         if not self.rvq.training:
             self.losses.zero_()
+        if self.io is not None:
+            if flat is not self.io[0]:
+                self.io[0].copy_(flat.reshape(self.N, self.D))
+            return self.io[1], self.io[2], None
+        all_idx = torch.empty((self.N, self.Q), dtype=torch.int64, device=self.dev)
+        out = torch.empty((self.N, self.D), dtype=self.dtype, device=self.dev)
         ip = all_idx.data_ptr()
         arr[self.first].stage.x = flat.data_ptr()
         for q in range(self.Q):
@@ -348,8 +360,8 @@ class ResidualVQ(nn.Module):
         return (tuple(flat.shape), flat.dtype, flat.device, self.training, tuple(do_update),
                 tuple((id(b), id(b.operands()), b.embed.data_ptr(), b.cluster_size.data_ptr(), b.embed_avg.data_ptr()) for b in books))
 
-    def _plan_part(self, prog, lane, flat, books, do_update):
-        return _PlanPart(self, prog, lane, flat, books, do_update)
+    def _plan_part(self, prog, lane, flat, books, do_update, persistent_io=False):
+        return _PlanPart(self, prog, lane, flat, books, do_update, persistent_io)
 
     def _finish_update(self, packed, offs, stat_sizes, do_update, stage_inputs, synced):
         """ONE all-reduce for all stages (reference: 2 per stage, vqp:603/:607), then the per-stage lerps in
@@ -463,8 +475,8 @@ class GroupedResidualVQ(nn.Module):
             # list is cached, only the per-call pointers are patched
             flats, keys = [], []
             for rvq, c in zip(self.rvqs, chunks):
-                xin = rvq.project_in(c)
-                flat = xin.detach().reshape(-1, xin.shape[-1]).contiguous()
+                xin = rvq.project_in(c).detach()
+                flat = xin.reshape(-1, xin.shape[-1])     # a strided view of the group's columns: copied into the plan's buffer
                 books = rvq._stage_plan()
                 upd = [rvq.training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
                 rvq._ensure_loss_buf(flat.device)
@@ -477,7 +489,8 @@ class GroupedResidualVQ(nn.Module):
                 if len(plans) >= 8:
                     plans.clear()
                 prog = ops.RvqProgram(x.device)
-                parts = [rvq._plan_part(prog, g % 4, f[0], f[2], f[3]) for g, (rvq, f) in enumerate(zip(self.rvqs, flats))]
+                parts = [rvq._plan_part(prog, g % 4, f[0], f[2], f[3], persistent_io=True)
+                         for g, (rvq, f) in enumerate(zip(self.rvqs, flats))]
                 plan = plans[key] = (prog.freeze(), parts)
             prog, parts = plan
             bound = [part.bind(prog.arr, f[0]) for part, f in zip(parts, flats)]
