@@ -315,3 +315,40 @@ def test_gradient_estimators_match_reference(name):
     got = x.grad.float().cpu().numpy()
     scale = np.abs(ref).max()
     np.testing.assert_allclose(got, ref, rtol=tol, atol=tol * scale)
+
+
+# ------------------------------------------------------------------------------------------------ vqb_rvq_forward
+@pytest.mark.parametrize("kind", ["rvq_shared_bf16", "rvq_separate_fp32", "rvq_cosine_fp32", "grvq_fp32", "rvq_eval_bf16"])
+def test_rvq_program_equals_stagewise_path(kind, monkeypatch):
+    """One vqb_rvq_forward call (cached op list, one CUDA graph, groups on parallel lanes) must give the results of the
+    stage-by-stage path bit for bit: same kernels, same order (residual_vq.py:469-568, :593-601, :690-724)."""
+    import copy
+    m = vqb()
+    torch.manual_seed(11)
+    cosine = "cosine" in kind
+    dt = torch.bfloat16 if "bf16" in kind else torch.float32
+    if kind.startswith("grvq"):
+        mod = m.GroupedResidualVQ(dim=128, groups=2, num_quantizers=3, codebook_size=96).to(DEV)
+        width = 128
+    else:
+        mod = m.ResidualVQ(dim=64, num_quantizers=4, codebook_size=200, shared_codebook="shared" in kind or "eval" in kind,
+                           use_cosine_sim=cosine).to(DEV)
+        width = 64
+    ref = copy.deepcopy(mod)
+    if "eval" in kind:
+        mod.eval(); ref.eval()
+    for step in range(4):   # step 0 initialises (stage-wise in both), later steps replay the cached program
+        x = torch.randn(3, 1500, width, device=DEV).to(dt)
+        monkeypatch.setenv("VQB_RVQ_PROGRAM", "1")
+        q1, i1, l1 = mod(x)[:3]
+        monkeypatch.setenv("VQB_RVQ_PROGRAM", "0")
+        q0, i0, l0 = ref(x)[:3]
+        torch.cuda.synchronize()
+        assert torch.equal(i1, i0), f"step {step}: indices differ"
+        assert torch.equal(q1, q0), f"step {step}: quantized differs"
+        assert torch.equal(l1, l0), f"step {step}: losses differ"
+        # the statistics add a code's re-scored rows with atomics: two such rows on one code may land in either order
+        for a, b in zip(mod.buffers(), ref.buffers()):
+            torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6, msg=f"step {step}: codebook state differs")
+        ref.load_state_dict(mod.state_dict())   # identical pre-state for the next step: outputs must then be bit-equal
+    assert len(mod.__dict__.get("_plans", {})) >= 1, "the program path was not taken"

@@ -38,3 +38,36 @@ def test_shard_rows_partitions_the_batch():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             lens = [hi - lo for lo, hi in spans]
             assert max(lens) - min(lens) <= 1
+
+
+def test_plan_cache_is_never_copied_with_the_module():
+    """The cached op lists of ResidualVQ / GroupedResidualVQ hold raw device pointers: deepcopy / pickle of a module must
+    start with an empty cache instead of copying them."""
+    import copy, pickle
+    from vector_quantize_pytorch_b200.residual_vq import _PlanCache
+    c = _PlanCache()
+    c[("key",)] = (object(), object())
+    assert len(copy.deepcopy(c)) == 0
+    assert len(pickle.loads(pickle.dumps(c))) == 0
+    holder = {"_plans": c, "other": [1, 2]}
+    dup = copy.deepcopy(holder)
+    assert dup["other"] == [1, 2] and len(dup["_plans"]) == 0 and isinstance(dup["_plans"], _PlanCache)
+
+
+def test_rvq_op_layout_matches_the_header():
+    """ctypes mirror of vqb_rvq_op (include/vqb200.h): the nested structs must sit where the C compiler puts them."""
+    import ctypes, subprocess, tempfile, os, shutil
+    from vector_quantize_pytorch_b200 import _C
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "vqb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu", sizeof(vqb_rvq_op), ' \
+          'offsetof(vqb_rvq_op, stage), offsetof(vqb_rvq_op, ema), offsetof(vqb_rvq_op, acc), sizeof(vqb_vq_forward_args));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run([cc, "-I", os.path.join(root, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        got = [int(v) for v in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [ctypes.sizeof(_C.RvqOp), _C.RvqOp.stage.offset, _C.RvqOp.ema.offset, _C.RvqOp.acc.offset,
+                   ctypes.sizeof(_C.VQForwardArgs)]
