@@ -240,6 +240,15 @@ def test_decode_matches_oracle_with_dropout_entries():
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-6, atol=1e-6)
     codes = rvq.get_codes_from_indices(idx)
     assert codes.shape == (5, 3, 77, 64)
+    # large batches take the shared-memory slice kernel (N >= 4096): same sums, -1 entries included; shared codebook too
+    big = torch.randint(-1, 96, (4, 1500, 5), device=DEV)
+    out = rvq.get_output_from_indices(big)
+    ref = O.rvq_output_from_indices(embeds, big.cpu().numpy())
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-6, atol=1e-5)
+    shared = m.ResidualVQ(dim=64, num_quantizers=4, codebook_size=200, shared_codebook=True).to(DEV)
+    big = torch.randint(0, 200, (2, 3000, 4), device=DEV)
+    ref = O.rvq_output_from_indices([shared.layers[0]._codebook.embed[0].cpu().numpy()] * 4, big.cpu().numpy())
+    np.testing.assert_allclose(shared.get_output_from_indices(big).cpu().numpy(), ref, rtol=1e-6, atol=1e-5)
     vq = m.VectorQuantize(dim=64, codebook_size=96).to(DEV)
     i1 = torch.randint(0, 96, (2, 33), device=DEV)
     np.testing.assert_array_equal(vq.get_codes_from_indices(i1).cpu().numpy(),

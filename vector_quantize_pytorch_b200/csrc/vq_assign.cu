@@ -501,11 +501,9 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
       // ---- merge the two column slices of each row (upper half publishes, lower half finishes the row)
       MergeSlot* slot = &ctrl->merge[t & 1][row_in_tile];
-      if (half == 1) {
-        publish(slot, st);
-        named_bar_sync(pair_bar, 64);
-      } else {
-        named_bar_sync(pair_bar, 64);
+      if (half == 1) publish(slot, st);
+      named_bar_sync(pair_bar, 64);   // ONE call site for both warps of the pair (compute-sanitizer synccheck pairs barriers by PC)
+      if (half == 0) {
         const RowResult rr = merge_slices(st, slot, 1, 0);
         const int n = rr.n, i0 = rr.i0, i1 = rr.i1;
         const float best = rr.best;

@@ -350,23 +350,26 @@ __global__ void __launch_bounds__(256, 2) rvq_accumulate_kernel(const float* __r
 // output write.  A row is handled by LPR = W*esz/16 adjacent lanes (16 bytes each), 32/LPR rows per warp; 32 warps per
 // CTA (one CTA per SM: the slice fills its smem) keep enough index loads in flight — with 8 warps the kernel was as slow as
 // the L2 version (244 us: one dependent index load -> smem read chain per warp at a time).
-template <int DT>
+// ROUNDED = false: the decode (fp32 slice, fp32 sum, index -1 contributes zeros, one rounding at the store).
+template <int DT, bool ROUNDED>
 __global__ void __launch_bounds__(1024, 1)
 rvq_accumulate_smem_kernel(const float* __restrict__ embeds, int64_t embed_stride, int nbooks, int Q, int K, int D, int W,
                            const int64_t* __restrict__ idx, int64_t N, void* out, int ctas_per_slice) {
-  extern __shared__ uint4 code_smem[];   // [nbooks][K][W] elements of the output dtype
-  constexpr int ESZ = DT == VQB_DTYPE_BF16 ? 2 : 4;
+  extern __shared__ uint4 code_smem[];   // [nbooks][K][W] staged elements: bf16 for the rounded bf16 sum, fp32 otherwise
+  constexpr bool HALF = ROUNDED && DT == VQB_DTYPE_BF16;
+  constexpr int ESZ = HALF ? 2 : 4;                          // staged element
+  constexpr int OSZ = DT == VQB_DTYPE_BF16 ? 2 : 4;          // output element
   const int slice = blockIdx.x / ctas_per_slice, part = blockIdx.x % ctas_per_slice;
   const int c0 = slice * W;
   {  // stage the slice: 4 consecutive columns per thread
-    const int64_t quads = static_cast<int64_t>(nbooks) * K * (W / 4);
-    for (int64_t e = threadIdx.x; e < quads; e += blockDim.x) {
-      const int c = static_cast<int>(e % (W / 4)) * 4;
-      const int64_t r = e / (W / 4);   // book * K + code
-      const int book = static_cast<int>(r / K), code = static_cast<int>(r % K);
+    const int quads = nbooks * K * (W / 4);
+    for (int e = threadIdx.x; e < quads; e += blockDim.x) {
+      const int c = (e % (W / 4)) * 4;
+      const int r = e / (W / 4);   // book * K + code
+      const int book = r / K, code = r % K;
       const float4 v = __ldg(reinterpret_cast<const float4*>(embeds + book * embed_stride + static_cast<int64_t>(code) * D + c0 + c));
-      uint8_t* dst = reinterpret_cast<uint8_t*>(code_smem) + (r * W + c) * ESZ;
-      if (DT == VQB_DTYPE_BF16) {
+      uint8_t* dst = reinterpret_cast<uint8_t*>(code_smem) + (static_cast<size_t>(r) * W + c) * ESZ;
+      if (HALF) {
         uint32_t h0, h1;
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(v.y), "f"(v.x));
         asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(v.w), "f"(v.z));
@@ -377,30 +380,38 @@ rvq_accumulate_smem_kernel(const float* __restrict__ embeds, int64_t embed_strid
     }
   }
   __syncthreads();
-  const int LPR = W * ESZ / 16;             // lanes per row (power of two, 4..32)
+  const int LPR = W * ESZ / 16;             // lanes per row (power of two, 4..32) == uint4 per staged code row
   const int rpw = 32 / LPR;                 // rows per warp and iteration
   const int lane = threadIdx.x & 31;
   const int lir = lane & (LPR - 1), riw = lane / LPR;
-  const int row_u4 = W * ESZ / 16;          // uint4 per staged code row (== LPR)
+  const int src_lane0 = riw * LPR;
+  const int book_stride = nbooks > 1 ? K * LPR : 0;
   const int64_t gw = static_cast<int64_t>(part) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t step = static_cast<int64_t>(ctas_per_slice) * (blockDim.x >> 5) * rpw;
+  const int opl = 16 / ESZ;                 // output elements per lane (8 or 4)
+  // running pointers: no 64-bit multiplications in the loop
+  const int64_t row0 = gw * rpw + riw;
+  const int64_t* ip = idx + row0 * Q + lir;
+  uint8_t* op = static_cast<uint8_t*>(out) + (row0 * D + c0 + lir * opl) * OSZ;
+  const int64_t ip_step = step * Q;
+  const int64_t op_step = step * D * OSZ;
   // the first chunk of indices of the NEXT iteration is requested before this one is consumed
-  int64_t kq_next = (gw * rpw + riw < N && lir < Q) ? idx[(gw * rpw + riw) * Q + lir] : 0;
-  for (int64_t base = gw * rpw; base < N; base += step) {   // warp-uniform trip count (shuffles inside)
-    const int64_t row = base + riw;
+  int kq_next = (row0 < N && lir < Q) ? static_cast<int>(*ip) : 0;
+  for (int64_t row = row0, base = gw * rpw; base < N; base += step, row += step, ip += ip_step, op += op_step) {   // warp-uniform
     const bool active = row < N;
     uint32_t acch[4] = {0u, 0u, 0u, 0u};
     float accf[4] = {0.f, 0.f, 0.f, 0.f};
-    const int64_t kq_first = kq_next;
-    kq_next = (row + step < N && lir < Q) ? idx[(row + step) * Q + lir] : 0;
+    const int kq_first = kq_next;
+    kq_next = (row + step < N && lir < Q) ? static_cast<int>(ip[ip_step]) : 0;
     for (int qc = 0; qc < Q; qc += LPR) {
-      const int64_t kq = qc == 0 ? kq_first : ((active && qc + lir < Q) ? idx[row * Q + qc + lir] : 0);
+      const int kq = qc == 0 ? kq_first : ((active && qc + lir < Q) ? static_cast<int>(ip[qc]) : 0);
       const int nq = min(LPR, Q - qc);
-      for (int b = 0; b < nq; ++b) {
-        const int k = static_cast<int>(__shfl_sync(0xffffffffu, kq, riw * LPR + b));
-        const int book = nbooks > 1 ? qc + b : 0;
-        const uint4 v = code_smem[(static_cast<int64_t>(book) * K + k) * row_u4 + lir];
-        if (DT == VQB_DTYPE_BF16) {
+      int sbase = qc * book_stride + lir;
+      for (int b = 0; b < nq; ++b, sbase += book_stride) {
+        const int k = __shfl_sync(0xffffffffu, kq, src_lane0 + b);
+        if (!ROUNDED && k < 0) continue;    // (uniform per row group only; the load below is skipped per lane)
+        const uint4 v = code_smem[sbase + k * LPR];
+        if (HALF) {
           asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[0]) : "r"(acch[0]), "r"(v.x));
           asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[1]) : "r"(acch[1]), "r"(v.y));
           asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(acch[2]) : "r"(acch[2]), "r"(v.z));
@@ -412,9 +423,16 @@ rvq_accumulate_smem_kernel(const float* __restrict__ embeds, int64_t embed_strid
       }
     }
     if (!active) continue;
-    uint8_t* dst = static_cast<uint8_t*>(out) + (row * D + c0) * ESZ + lir * 16;
-    if (DT == VQB_DTYPE_BF16) *reinterpret_cast<uint4*>(dst) = make_uint4(acch[0], acch[1], acch[2], acch[3]);
-    else *reinterpret_cast<float4*>(dst) = make_float4(accf[0], accf[1], accf[2], accf[3]);
+    if (HALF) {
+      *reinterpret_cast<uint4*>(op) = make_uint4(acch[0], acch[1], acch[2], acch[3]);
+    } else if (DT == VQB_DTYPE_BF16) {
+      uint32_t h0, h1;
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h0) : "f"(accf[1]), "f"(accf[0]));
+      asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h1) : "f"(accf[3]), "f"(accf[2]));
+      *reinterpret_cast<uint2*>(op) = make_uint2(h0, h1);
+    } else {
+      *reinterpret_cast<float4*>(op) = make_float4(accf[0], accf[1], accf[2], accf[3]);
+    }
   }
 }
 
@@ -574,12 +592,41 @@ extern "C" int vqb_loss_finalize(const double* loss_sum, int64_t numel, int dtyp
   return static_cast<int>(cudaGetLastError());
 }
 
+// smem variant of the gather-sum (rounded running sum / decode): the widest power-of-two column slice W of all the codebooks
+// that fits (a row piece of at least 64 staged bytes); false when nothing fits and the caller uses the L2 kernel
+template <bool ROUNDED>
+static bool gather_sum_smem(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N, void* out,
+                            int dtype, cudaStream_t s) {
+  const int esz = (ROUNDED && dtype == VQB_DTYPE_BF16) ? 2 : 4;
+  const int nbooks = embed_stride ? Q : 1;
+  int W = 0;
+  for (int w = 512 / esz; w * esz >= 64; w >>= 1)   // at most 32 lanes x 16 bytes per row piece
+    if (D % w == 0 && static_cast<size_t>(nbooks) * K * w * esz <= 196608) { W = w; break; }
+  if (!W || N < 4096) return false;
+  const size_t smem = static_cast<size_t>(nbooks) * K * W * esz;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(rvq_accumulate_smem_kernel<VQB_DTYPE_F32, ROUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
+    cudaFuncSetAttribute(rvq_accumulate_smem_kernel<VQB_DTYPE_BF16, ROUNDED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
+    attr_set = true;
+  }
+  const int slices = D / W;
+  int cps = num_sms() / slices;
+  if (cps < 1) cps = 1;
+  if (dtype == VQB_DTYPE_F32)
+    rvq_accumulate_smem_kernel<VQB_DTYPE_F32, ROUNDED><<<slices * cps, 1024, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
+  else
+    rvq_accumulate_smem_kernel<VQB_DTYPE_BF16, ROUNDED><<<slices * cps, 1024, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
+  return true;
+}
+
 extern "C" int vqb_decode(const float* embeds, int64_t embed_stride, int Q, int K, int D, const int64_t* idx, int64_t N,
                           void* out, int dtype, void* stream) {
   if (!embeds || !idx || !out || Q <= 0 || K <= 0 || D <= 0 || N <= 0) return VQB_E_INVALID;
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (gather_sum_smem<false>(embeds, embed_stride, Q, K, D, idx, N, out, dtype, s)) return static_cast<int>(cudaGetLastError());
   const int g = row_grid(N, ROW_THREADS / 32);
   if (dtype == VQB_DTYPE_F32)
     rvq_accumulate_kernel<VQB_DTYPE_F32, false><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
@@ -594,29 +641,7 @@ extern "C" int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // smem variant: the widest power-of-two column slice W of all searched codebooks that fits (>= 64 bytes per row piece)
-  const int esz = dtype == VQB_DTYPE_BF16 ? 2 : 4;
-  const int nbooks = embed_stride ? Q : 1;
-  int W = 0;
-  for (int w = 512 / esz; w * esz >= 64; w >>= 1)   // at most 32 lanes x 16 bytes per row piece
-    if (D % w == 0 && static_cast<size_t>(nbooks) * K * w * esz <= 196608) { W = w; break; }
-  if (W && N >= 4096) {
-    const size_t smem = static_cast<size_t>(nbooks) * K * W * esz;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(rvq_accumulate_smem_kernel<VQB_DTYPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
-      cudaFuncSetAttribute(rvq_accumulate_smem_kernel<VQB_DTYPE_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608);
-      attr_set = true;
-    }
-    const int slices = D / W;
-    int cps = num_sms() / slices;
-    if (cps < 1) cps = 1;
-    if (dtype == VQB_DTYPE_F32)
-      rvq_accumulate_smem_kernel<VQB_DTYPE_F32><<<slices * cps, 1024, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
-    else
-      rvq_accumulate_smem_kernel<VQB_DTYPE_BF16><<<slices * cps, 1024, smem, s>>>(embeds, embed_stride, nbooks, Q, K, D, W, idx, N, out, cps);
-    return static_cast<int>(cudaGetLastError());
-  }
+  if (gather_sum_smem<true>(embeds, embed_stride, Q, K, D, idx, N, out, dtype, s)) return static_cast<int>(cudaGetLastError());
   const int g = row_grid(N, ROW_THREADS / 32);
   if (dtype == VQB_DTYPE_F32)
     rvq_accumulate_kernel<VQB_DTYPE_F32, true><<<g, ROW_THREADS, 0, s>>>(embeds, embed_stride, Q, D, idx, N, out);
