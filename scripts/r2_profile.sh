@@ -17,25 +17,7 @@ VQB_BENCH_SKIP_E2E=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-co
 python scripts/launch_summary.py $O/r2_launches_bench.csv > $O/r2_launches_bench_summary.txt 2>&1
 cat $O/r2_launches_bench_summary.txt | head -30
 # sanitizers on small shapes (every kernel of the step, both dtypes, streamed A, RVQ)
-cat > /tmp/san_small.py <<'PY'
-import os, sys, torch
-sys.path.insert(0, os.getcwd())
-import vector_quantize_pytorch_b200 as vqb
-dev = torch.device("cuda:0")
-torch.manual_seed(0)
-for (B, T, D, K, dt, cos) in ((1, 300, 32, 64, torch.float32, False), (2, 1024, 256, 1024, torch.bfloat16, False),
-                              (1, 512, 512, 600, torch.float32, True), (1, 700, 128, 1000, torch.bfloat16, True)):
-    vq = vqb.VectorQuantize(dim=D, codebook_size=K, use_cosine_sim=cos).to(dev)
-    x = torch.randn(B, T, D, device=dev).to(dt)
-    for _ in range(2):
-        q, i, l = vq(x)
-    torch.cuda.synchronize()
-    print("ok vq", B, T, D, K, dt, cos)
-rvq = vqb.ResidualVQ(dim=64, num_quantizers=3, codebook_size=96, shared_codebook=True).to(dev)
-y = torch.randn(2, 400, 64, device=dev).bfloat16()
-q, i, l = rvq(y); o = rvq.get_output_from_indices(i); torch.cuda.synchronize(); print("ok rvq")
-PY
 for tool in memcheck racecheck synccheck; do
-  VQB_GRAPH=0 timeout 900 compute-sanitizer --tool $tool --print-limit 10 python /tmp/san_small.py > $O/r2_sanitizer_$tool.txt 2>&1
+  VQB_GRAPH=0 timeout 900 compute-sanitizer --tool $tool --print-limit 10 python scripts/san_small.py > $O/r2_sanitizer_$tool.txt 2>&1
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|^ok|Error|error" $O/r2_sanitizer_$tool.txt | tail -12
 done
