@@ -258,8 +258,10 @@ int vqb_rvq_accumulate(const float* embeds, int64_t embed_stride, int Q, int K, 
  *   VQB_RVQ_STAGE       vqb_vq_forward(stage)             one quantizer (update = 1: its EMA is deferred to a later EMA op)
  *   VQB_RVQ_EMA         vqb_ema_apply_weighted(ema ...)   residual_vq.py:593-597 / vector_quantize_pytorch.py:616-617, :576-584
  *   VQB_RVQ_ACCUMULATE  vqb_rvq_accumulate(acc ...)       quantized_out from the indices (residual_vq.py:525)
+ *   VQB_RVQ_BARRIER     vqb_peer_barrier(bar ...)         multi-GPU: every rank's statistics of this forward are in place
+ *   VQB_RVQ_EMA_PEERS   vqb_ema_apply_peers(emap ...)     the EMA op with the sum over ranks taken inside (vqp:603, :607)
  * At most 62 ops, lanes 0..3; ops of one lane execute in list order. */
-enum { VQB_RVQ_STAGE = 0, VQB_RVQ_EMA = 1, VQB_RVQ_ACCUMULATE = 2 };
+enum { VQB_RVQ_STAGE = 0, VQB_RVQ_EMA = 1, VQB_RVQ_ACCUMULATE = 2, VQB_RVQ_BARRIER = 3, VQB_RVQ_EMA_PEERS = 4 };
 typedef struct vqb_rvq_op {
   int kind, lane;
   vqb_vq_forward_args stage;
@@ -270,6 +272,11 @@ typedef struct vqb_rvq_op {
   struct {
     const float* embeds; int64_t embed_stride; int Q, K, D; const int64_t* idx; int64_t N; void* out; int dtype;
   } acc;
+  struct { void* const* flags; uint32_t* epoch; int rank, world; } bar;
+  struct {
+    float* cluster_size; float* embed_avg; float* embed; const void* const* peer_stats; int64_t slice_offset; int world, K, D;
+    double decay, eps; int metric, do_normalise; void* planes; void* bext; float* bias; float* cnorm2; float* cmax; float* scratch;
+  } emap;
 } vqb_rvq_op;
 int vqb_rvq_forward(const vqb_rvq_op* ops, int n_ops, void* stream);
 

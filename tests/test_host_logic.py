@@ -63,11 +63,13 @@ def test_rvq_op_layout_matches_the_header():
         import pytest
         pytest.skip("no C compiler")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    src = '#include <stdio.h>\n#include <stddef.h>\n#include "vqb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu", sizeof(vqb_rvq_op), ' \
-          'offsetof(vqb_rvq_op, stage), offsetof(vqb_rvq_op, ema), offsetof(vqb_rvq_op, acc), sizeof(vqb_vq_forward_args));return 0;}\n'
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "vqb200.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu", sizeof(vqb_rvq_op), ' \
+          'offsetof(vqb_rvq_op, stage), offsetof(vqb_rvq_op, ema), offsetof(vqb_rvq_op, acc), sizeof(vqb_vq_forward_args), ' \
+          'offsetof(vqb_rvq_op, bar), offsetof(vqb_rvq_op, emap), offsetof(vqb_rvq_op, emap.scratch));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.run([cc, "-I", os.path.join(root, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         got = [int(v) for v in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [ctypes.sizeof(_C.RvqOp), _C.RvqOp.stage.offset, _C.RvqOp.ema.offset, _C.RvqOp.acc.offset,
-                   ctypes.sizeof(_C.VQForwardArgs)]
+                   ctypes.sizeof(_C.VQForwardArgs), _C.RvqOp.bar.offset, _C.RvqOp.emap.offset,
+                   _C.RvqOp.emap.offset + _C.RvqEmaPeersArgs.scratch.offset]

@@ -45,12 +45,24 @@ class RvqAccArgs(ctypes.Structure):
                 ("out", _vp), ("dtype", _i32)]
 
 
+class RvqBarArgs(ctypes.Structure):
+    _fields_ = [("flags", _vp), ("epoch", _vp), ("rank", _i32), ("world", _i32)]
+
+
+class RvqEmaPeersArgs(ctypes.Structure):
+    _fields_ = [("cluster_size", _vp), ("embed_avg", _vp), ("embed", _vp), ("peer_stats", _vp), ("slice_offset", _i64),
+                ("world", _i32), ("K", _i32), ("D", _i32), ("decay", _f64), ("eps", _f64), ("metric", _i32),
+                ("do_normalise", _i32), ("planes", _vp), ("bext", _vp), ("bias", _vp), ("cnorm2", _vp), ("cmax", _vp),
+                ("scratch", _vp)]
+
+
 class RvqOp(ctypes.Structure):
     """Mirror of `vqb_rvq_op` (include/vqb200.h)."""
-    _fields_ = [("kind", _i32), ("lane", _i32), ("stage", VQForwardArgs), ("ema", RvqEmaArgs), ("acc", RvqAccArgs)]
+    _fields_ = [("kind", _i32), ("lane", _i32), ("stage", VQForwardArgs), ("ema", RvqEmaArgs), ("acc", RvqAccArgs),
+                ("bar", RvqBarArgs), ("emap", RvqEmaPeersArgs)]
 
 
-RVQ_STAGE, RVQ_EMA, RVQ_ACCUMULATE = 0, 1, 2
+RVQ_STAGE, RVQ_EMA, RVQ_ACCUMULATE, RVQ_BARRIER, RVQ_EMA_PEERS = 0, 1, 2, 3, 4
 
 SIGNATURES = {
     "vqb_version": (_i32, []),

@@ -272,6 +272,26 @@ class RvqProgram:
         self.keep.append((cluster_size, embed_avg, embed, stats, cb_ops))
         self.launches += 2
 
+    def barrier(self, lane, peer):
+        op = _C.RvqOp(kind=_C.RVQ_BARRIER, lane=lane)
+        op.bar = _C.RvqBarArgs(flags=ctypes.cast(peer.flag_ptrs, ctypes.c_void_p), epoch=peer.epoch.data_ptr(), rank=peer.rank,
+                               world=peer.world)
+        self.ops.append(op)
+        self.keep.append(peer)
+        self.launches += 1
+
+    def ema_peers(self, lane, cluster_size, embed_avg, embed, peer, peer_ptrs, slice_offset, cb_ops, *, decay, eps, do_normalise):
+        K, D = embed.shape
+        op = _C.RvqOp(kind=_C.RVQ_EMA_PEERS, lane=lane)
+        op.emap = _C.RvqEmaPeersArgs(cluster_size=_p(cluster_size), embed_avg=_p(embed_avg), embed=_p(embed),
+                                     peer_stats=ctypes.cast(peer_ptrs, ctypes.c_void_p), slice_offset=int(slice_offset),
+                                     world=peer.world, K=K, D=D, decay=float(decay), eps=float(eps), metric=int(cb_ops.cosine),
+                                     do_normalise=int(do_normalise), planes=_p(cb_ops.planes), bext=_p(cb_ops.bext),
+                                     bias=_p(cb_ops.bias), cnorm2=_p(cb_ops.cnorm2), cmax=_p(cb_ops.cmax), scratch=_p(cb_ops.scratch))
+        self.ops.append(op)
+        self.keep.append((cluster_size, embed_avg, embed, peer, peer_ptrs, cb_ops))
+        self.launches += 2
+
     def accumulate(self, lane, embeds, indices, out):
         N, Q = indices.shape
         if embeds.dim() == 2:

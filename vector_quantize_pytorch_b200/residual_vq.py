@@ -49,7 +49,12 @@ class _PlanPart:
         self.bufs = [torch.empty_like(flat) for _ in range(min(2, Q - 1))]          # persistent: the residual ping-pong
         stat_sizes = [ops.stats_floats(b.codebook_size, D) if u else 0 for b, u in zip(books, do_update)]
         offs = [sum(stat_sizes[:i]) for i in range(Q)]
-        self.packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
+        self.peer = rvq._peer if (sum(stat_sizes) and any(b.use_ddp and u for b, u in zip(books, do_update))) else None
+        if self.peer is not None:   # this plan is bound to ONE of the two alternating symmetric buffers (the key holds the parity)
+            par = self.peer.step & 1
+            self.packed, peer_ptrs = self.peer.bufs[par][:sum(stat_sizes)], self.peer.stats_ptrs[par]
+        else:
+            self.packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev) if sum(stat_sizes) else None
         self.losses = rvq._loss_buf
         self.books = books
         all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)               # placeholders: `bind` patches the pointers
@@ -73,13 +78,19 @@ class _PlanPart:
         self.acc = len(prog.ops)
         prog.accumulate(lane, embeds, all_idx, out0)
         self.refreshed = []
+        if self.peer is not None:
+            prog.barrier(lane, self.peer)      # every rank's statistics of this forward are in place (vqp:603, :607)
         for q, book in enumerate(books):
             if not stat_sizes[q]:
                 continue
             normalise = book.ema_update and not book.manual_ema_update
             cs, ea, emb = book._state2d()
-            prog.ema(lane, cs, ea, emb, self.packed[offs[q]:offs[q] + stat_sizes[q]], book.operands(), decay=book.decay,
-                     eps=book.eps, do_lerp=True, do_normalise=normalise)
+            if self.peer is not None:
+                prog.ema_peers(lane, cs, ea, emb, self.peer, peer_ptrs, offs[q], book.operands(), decay=book.decay, eps=book.eps,
+                               do_normalise=normalise)
+            else:
+                prog.ema(lane, cs, ea, emb, self.packed[offs[q]:offs[q] + stat_sizes[q]], book.operands(), decay=book.decay,
+                         eps=book.eps, do_lerp=True, do_normalise=normalise)
             if normalise:
                 self.refreshed.append(book)
         if training and rvq.shared_codebook and rvq.vq_is_ema_updating and any(do_update):   # rvq:593-597
@@ -95,6 +106,8 @@ class _PlanPart:
             torch.stack([b.embed[0] for b in self.books], out=self.stack)
         if not self.rvq.training:
             self.losses.zero_()
+        if self.peer is not None:
+            self.peer.step += 1          # the next forward uses the other symmetric buffer (and the plan cached for it)
         if self.io is not None:
             if flat is not self.io[0]:
                 self.io[0].copy_(flat.reshape(self.N, self.D))
@@ -336,13 +349,23 @@ class ResidualVQ(nn.Module):
             return False
         if ops.PROFILE_EVENTS is not None or not self.uniform_codebook_size:
             return False
-        n_ops = len(books) + 1 + sum(do_update) + 1
+        n_ops = len(books) + 1 + sum(do_update) + 2
         if n_ops > ops.RvqProgram.MAX_OPS:
             return False
         for b, u in zip(books, do_update):
             if not b._initted_host:
                 return False
-            if u and (b.use_ddp or b.has_dead_code_replacement or b.cluster_size.grad is not None or b.embed_avg.grad is not None):
+            if u and (b.has_dead_code_replacement or b.cluster_size.grad is not None or b.embed_avg.grad is not None):
+                return False
+        ddp = [b.use_ddp for b, u in zip(books, do_update) if u]
+        if any(ddp):
+            # multi-GPU: the statistics go to symmetric memory and the EMA ops sum over the ranks (barrier + peer loads inside
+            # the program); without peer memory the stage-wise path does ONE NCCL all-reduce instead
+            if not all(ddp):
+                return False
+            dev, D = books[0].embed.device, books[0].embed.shape[-1]
+            numel = sum(ops.stats_floats(b.codebook_size, D) for b, u in zip(books, do_update) if u)
+            if self._peer_reducer(numel, dev) is None:
                 return False
         return True
 
@@ -357,7 +380,8 @@ class ResidualVQ(nn.Module):
     def _part_key(self, flat, books, do_update):
         """Everything a cached op list depends on, except the per-call pointers `_PlanPart.bind` patches.  `book.operands()`
         refreshes the tensor-core operands if `embed` was changed from outside since the last forward."""
-        return (tuple(flat.shape), flat.dtype, flat.device, self.training, tuple(do_update),
+        peer = getattr(self, "_peer", None) if any(b.use_ddp and u for b, u in zip(books, do_update)) else None
+        return (tuple(flat.shape), flat.dtype, flat.device, self.training, tuple(do_update), None if peer is None else peer.step & 1,
                 tuple((id(b), id(b.operands()), b.embed.data_ptr(), b.cluster_size.data_ptr(), b.embed_avg.data_ptr()) for b in books))
 
     def _plan_part(self, prog, lane, flat, books, do_update, persistent_io=False):
@@ -456,7 +480,7 @@ class GroupedResidualVQ(nn.Module):
             upd = [rvq.training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
             if not rvq._program_ok(books, upd):
                 return False
-            total += len(books) + 1 + sum(upd) + 1
+            total += len(books) + 1 + sum(upd) + 2
         return total <= ops.RvqProgram.MAX_OPS
 
     def forward(self, x, indices=None, return_all_codes=False, sample_codebook_temp=None, freeze_codebook=False, mask=None):
