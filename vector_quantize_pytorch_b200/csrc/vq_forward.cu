@@ -590,6 +590,15 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
         rc = ema_apply_part(1, a->cluster_size, a->embed_avg, a->embed, a->stats, a->K, a->D, a->decay, a->eps, a->metric, 1,
                             a->do_normalise, nullptr, a->planes, a->bext, a->bias, a->cnorm2, a->cmax, a->scratch, stream);
         if (rc) return rc;
+      } else if (a->update == 3) {
+        // multi-GPU: a first barrier as soon as this rank's COUNTS are complete — it absorbs the skew between the ranks while
+        // the segmented sums still run — and the cluster-size half of the EMA over every rank's counts
+        rc = vqb_peer_barrier(a->peer_flags, a->peer_rank, a->peer_world, a->peer_epoch, stream);
+        if (rc) return rc;
+        rc = ema_apply_peers_part(1, a->cluster_size, a->embed_avg, a->embed, a->peer_stats, a->peer_world, a->peer_slice_offset,
+                                  a->K, a->D, a->decay, a->eps, a->metric, a->do_normalise, nullptr, a->planes, a->bext, a->bias,
+                                  a->cnorm2, a->cmax, a->scratch, stream);
+        if (rc) return rc;
       }
       if (cudaStreamWaitEvent(s, side->join, 0) != cudaSuccess) return static_cast<int>(cudaGetLastError());
     } else {
@@ -606,9 +615,9 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
     } else if (a->update == 3) {  // multi-GPU: barrier, then every rank sums all ranks' statistics inside its EMA kernels
       rc = vqb_peer_barrier(a->peer_flags, a->peer_rank, a->peer_world, a->peer_epoch, stream);
       if (rc) return rc;
-      rc = vqb_ema_apply_peers(a->cluster_size, a->embed_avg, a->embed, a->peer_stats, a->peer_world, a->peer_slice_offset,
-                               a->K, a->D, a->decay, a->eps, a->metric, a->do_normalise, nullptr, a->planes, a->bext, a->bias,
-                               a->cnorm2, a->cmax, a->scratch, stream);
+      rc = ema_apply_peers_part((side && !fused_stats) ? 2 : 3, a->cluster_size, a->embed_avg, a->embed, a->peer_stats,
+                                a->peer_world, a->peer_slice_offset, a->K, a->D, a->decay, a->eps, a->metric, a->do_normalise,
+                                nullptr, a->planes, a->bext, a->bias, a->cnorm2, a->cmax, a->scratch, stream);
       if (rc) return rc;
     }
   }

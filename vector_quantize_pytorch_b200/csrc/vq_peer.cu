@@ -160,6 +160,15 @@ extern "C" int vqb_ema_apply_peers(float* cluster_size, float* embed_avg, float*
                                    int world, int64_t slice_offset, int K, int D, double decay, double eps, int metric,
                                    int do_normalise, const float* code_weight, void* planes, void* bext, float* bias,
                                    float* cnorm2, float* cmax, float* scratch, void* stream) {
+  return ema_apply_peers_part(3, cluster_size, embed_avg, embed, peer_stats_host, world, slice_offset, K, D, decay, eps, metric,
+                              do_normalise, code_weight, planes, bext, bias, cnorm2, cmax, scratch, stream);
+}
+
+// part 1: cluster sizes (needs every rank's COUNTS), part 2: rows (needs part 1 and every rank's row sums), 3: both
+int vqb::ema_apply_peers_part(int part, float* cluster_size, float* embed_avg, float* embed, const void* const* peer_stats_host,
+                              int world, int64_t slice_offset, int K, int D, double decay, double eps, int metric,
+                              int do_normalise, const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2,
+                              float* cmax, float* scratch, void* stream) {
   if (!cluster_size || !embed_avg || !embed || !scratch || !peer_stats_host || K <= 0 || D <= 0) return VQB_E_INVALID;
   if (world < 1 || world > MAX_PEERS || slice_offset < 0 || (slice_offset & 3)) return VQB_E_INVALID;
   if (do_normalise && (!planes || !bext || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
@@ -176,11 +185,14 @@ extern "C" int vqb_ema_apply_peers(float* cluster_size, float* embed_avg, float*
   const float w = static_cast<float>(1.0 - decay);
   const float epsf = static_cast<float>(eps);
   const float keps = static_cast<float>(static_cast<double>(K) * eps);
-  ema_sizes_peers_kernel<<<1, 1024, 0, s>>>(cluster_size, pr, K, w, code_weight, scratch, do_normalise ? cmax : nullptr);
-  const int Kpad = vqb_padded_codes(K);
-  const int wpb = 8;
-  ema_rows_peers_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(
-      cluster_size, embed_avg, embed, pr, soff, K, Kpad, D, w, code_weight, epsf, keps, metric, do_normalise, scratch,
-      static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
+  if (part & 1)
+    ema_sizes_peers_kernel<<<1, 1024, 0, s>>>(cluster_size, pr, K, w, code_weight, scratch, do_normalise ? cmax : nullptr);
+  if (part & 2) {
+    const int Kpad = vqb_padded_codes(K);
+    const int wpb = 8;
+    ema_rows_peers_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(
+        cluster_size, embed_avg, embed, pr, soff, K, Kpad, D, w, code_weight, epsf, keps, metric, do_normalise, scratch,
+        static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
+  }
   return static_cast<int>(cudaGetLastError());
 }

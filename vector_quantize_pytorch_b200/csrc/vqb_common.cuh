@@ -91,6 +91,11 @@ int stats_scan(const int32_t* idx, int dtype, int64_t N, int D, int K, float* st
                int prehist, void* stream);
 int stats_sum(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx, int K, float* stats, void* workspace,
               size_t workspace_bytes, void* stream);
+// vq_peer.cu: vqb_ema_apply_peers in two launches (part 1: cluster sizes — needs the ranks' counts —, 2: rows, 3: both)
+int ema_apply_peers_part(int part, float* cluster_size, float* embed_avg, float* embed, const void* const* peer_stats_host,
+                         int world, int64_t slice_offset, int K, int D, double decay, double eps, int metric, int do_normalise,
+                         const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2, float* cmax,
+                         float* scratch, void* stream);
 // vq_ema.cu: vqb_ema_apply_weighted in two launches (part 1: cluster sizes, 2: rows, 3: both)
 int ema_apply_part(int part, float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
                    double decay, double eps, int metric, int do_lerp, int do_normalise, const float* code_weight,
