@@ -268,6 +268,8 @@ typedef struct vqb_rvq_op {
   struct {
     float* cluster_size; float* embed_avg; float* embed; const float* stats; int K, D; double decay, eps;
     int metric, do_lerp, do_normalise; void* planes; void* bext; float* bias; float* cnorm2; float* cmax; float* scratch;
+    int n_lerp; int64_t slice_stride;  /* n_lerp > 1: that many statistics slices, slice_stride floats apart, are lerped in order
+                                          in one launch — the stages of a shared codebook (residual_vq.py:302-306) */
   } ema;
   struct {
     const float* embeds; int64_t embed_stride; int Q, K, D; const int64_t* idx; int64_t N; void* out; int dtype;
@@ -276,6 +278,7 @@ typedef struct vqb_rvq_op {
   struct {
     float* cluster_size; float* embed_avg; float* embed; const void* const* peer_stats; int64_t slice_offset; int world, K, D;
     double decay, eps; int metric, do_normalise; void* planes; void* bext; float* bias; float* cnorm2; float* cmax; float* scratch;
+    int n_lerp; int64_t slice_stride;  /* as in `ema` */
   } emap;
 } vqb_rvq_op;
 int vqb_rvq_forward(const vqb_rvq_op* ops, int n_ops, void* stream);

@@ -37,7 +37,8 @@ class VQForwardArgs(ctypes.Structure):
 class RvqEmaArgs(ctypes.Structure):
     _fields_ = [("cluster_size", _vp), ("embed_avg", _vp), ("embed", _vp), ("stats", _vp), ("K", _i32), ("D", _i32),
                 ("decay", _f64), ("eps", _f64), ("metric", _i32), ("do_lerp", _i32), ("do_normalise", _i32),
-                ("planes", _vp), ("bext", _vp), ("bias", _vp), ("cnorm2", _vp), ("cmax", _vp), ("scratch", _vp)]
+                ("planes", _vp), ("bext", _vp), ("bias", _vp), ("cnorm2", _vp), ("cmax", _vp), ("scratch", _vp),
+                ("n_lerp", _i32), ("slice_stride", _i64)]
 
 
 class RvqAccArgs(ctypes.Structure):
@@ -53,7 +54,7 @@ class RvqEmaPeersArgs(ctypes.Structure):
     _fields_ = [("cluster_size", _vp), ("embed_avg", _vp), ("embed", _vp), ("peer_stats", _vp), ("slice_offset", _i64),
                 ("world", _i32), ("K", _i32), ("D", _i32), ("decay", _f64), ("eps", _f64), ("metric", _i32),
                 ("do_normalise", _i32), ("planes", _vp), ("bext", _vp), ("bias", _vp), ("cnorm2", _vp), ("cmax", _vp),
-                ("scratch", _vp)]
+                ("scratch", _vp), ("n_lerp", _i32), ("slice_stride", _i64)]
 
 
 class RvqOp(ctypes.Structure):

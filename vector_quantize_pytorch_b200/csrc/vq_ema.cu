@@ -347,15 +347,17 @@ __device__ __forceinline__ float lerp_f32(float a, float b, float w) {  // torch
 }
 
 // single CTA: cluster_size.lerp_ (vqp:616) and its sum (vqp:577); zero cmax for the atomicMax that follows
+// n_lerp statistics slices (slice_stride floats apart) are applied one after the other — the Q stages of a ResidualVQ that
+// share one codebook (rvq:302-306: every layer lerps the same buffers in turn) in ONE launch.
 __global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K, float w, const float* __restrict__ code_weight,
-                                 int do_lerp, float* scratch, float* cmax) {
+                                 int n_lerp, int64_t slice_stride, float* scratch, float* cmax) {
   __shared__ double part[32];
   double s = 0.0;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     float c = cluster_size[k];
-    if (do_lerp) {  // (1 - decay) * weight, an fp32 product (vqp:86-97)
+    if (n_lerp) {  // (1 - decay) * weight, an fp32 product (vqp:86-97)
       const float wk = code_weight ? __fmul_rn(w, code_weight[k]) : w;
-      c = lerp_f32(c, stats[k], wk);
+      for (int j = 0; j < n_lerp; ++j) c = lerp_f32(c, stats[j * slice_stride + k], wk);
       cluster_size[k] = c;
     }
     s += c;
@@ -376,8 +378,8 @@ __global__ void ema_sizes_kernel(float* cluster_size, const float* stats, int K,
 __global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* embed_avg, float* embed,
                                 const float* __restrict__ stats, int64_t soff, int K, int Kpad, int D, float w,
                                 const float* __restrict__ code_weight, float eps, float keps, int metric,
-                                int do_lerp, int do_normalise, const float* __restrict__ scratch, uint16_t* planes,
-                                uint16_t* bext, float* bias, float* cnorm2, float* cmax) {
+                                int n_lerp, int64_t slice_stride, int do_normalise, const float* __restrict__ scratch,
+                                uint16_t* planes, uint16_t* bext, float* bias, float* cnorm2, float* cmax) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= Kpad) return;
@@ -387,13 +389,15 @@ __global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* e
   }
   float* avg = embed_avg + static_cast<int64_t>(k) * D;
   float* emb = embed + static_cast<int64_t>(k) * D;
-  if (do_lerp) {
+  if (n_lerp) {
     if (code_weight) w = __fmul_rn(w, code_weight[k]);
     const float* es = stats + soff + static_cast<int64_t>(k) * D;
     for (int i = lane * 4; i < D; i += 128) {
       float4 a = *reinterpret_cast<float4*>(avg + i);
-      const float4 b = *reinterpret_cast<const float4*>(es + i);
-      a.x = lerp_f32(a.x, b.x, w); a.y = lerp_f32(a.y, b.y, w); a.z = lerp_f32(a.z, b.z, w); a.w = lerp_f32(a.w, b.w, w);
+      for (int j = 0; j < n_lerp; ++j) {
+        const float4 b = *reinterpret_cast<const float4*>(es + j * slice_stride + i);
+        a.x = lerp_f32(a.x, b.x, w); a.y = lerp_f32(a.y, b.y, w); a.z = lerp_f32(a.z, b.z, w); a.w = lerp_f32(a.w, b.w, w);
+      }
       *reinterpret_cast<float4*>(avg + i) = a;
     }
   }
@@ -570,16 +574,18 @@ extern "C" int vqb_ema_apply_weighted(float* cluster_size, float* embed_avg, flo
                                       double decay, double eps, int metric, int do_lerp, int do_normalise,
                                       const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2,
                                       float* cmax, float* scratch, void* stream) {
-  return ema_apply_part(3, cluster_size, embed_avg, embed, stats, K, D, decay, eps, metric, do_lerp, do_normalise, code_weight,
+  return ema_apply_part(3, cluster_size, embed_avg, embed, stats, K, D, decay, eps, metric, do_lerp ? 1 : 0, do_normalise, code_weight,
                         planes, bext, bias, cnorm2, cmax, scratch, stream);
 }
 
 // part: 1 = the cluster sizes (needs only the counts of the statistics), 2 = the rows (needs part 1 and the row sums), 3 = both
 int vqb::ema_apply_part(int part, float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
-                        double decay, double eps, int metric, int do_lerp, int do_normalise, const float* code_weight,
-                        void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream) {
-  if (!cluster_size || !embed_avg || !embed || !scratch || K <= 0 || D <= 0) return VQB_E_INVALID;
-  if (do_lerp && !stats) return VQB_E_INVALID;
+                        double decay, double eps, int metric, int n_lerp, int do_normalise, const float* code_weight,
+                        void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream,
+                        int64_t slice_stride) {
+  if (!cluster_size || !embed_avg || !embed || !scratch || K <= 0 || D <= 0 || n_lerp < 0) return VQB_E_INVALID;
+  const int do_lerp = n_lerp > 0;
+  if (do_lerp && (!stats || (slice_stride & 3))) return VQB_E_INVALID;
   if (do_normalise && (!planes || !bext || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(embed_avg) | reinterpret_cast<uintptr_t>(embed) | reinterpret_cast<uintptr_t>(planes)) & 15)
@@ -591,12 +597,12 @@ int vqb::ema_apply_part(int part, float* cluster_size, float* embed_avg, float* 
   const float epsf = static_cast<float>(eps);
   const float keps = static_cast<float>(static_cast<double>(K) * eps);  // n_categories * eps in python float (vqp:154)
   if (part & 1)
-    ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, w, code_weight, do_lerp, scratch, do_normalise ? cmax : nullptr);
+    ema_sizes_kernel<<<1, 1024, 0, s>>>(cluster_size, stats, K, w, code_weight, n_lerp, slice_stride, scratch, do_normalise ? cmax : nullptr);
   if (part & 2) {
     const int Kpad = vqb_padded_codes(K);
     const int wpb = 8;
     ema_rows_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(cluster_size, embed_avg, embed, stats, soff, K, Kpad, D, w, code_weight, epsf, keps,
-                                                              metric, do_lerp, do_normalise, scratch,
+                                                              metric, n_lerp, slice_stride, do_normalise, scratch,
                                                               static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
   }
   return static_cast<int>(cudaGetLastError());

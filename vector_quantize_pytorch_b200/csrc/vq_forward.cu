@@ -350,19 +350,20 @@ int rvq_enqueue(const void* ctx, void* stream) {
     if (op.kind == VQB_RVQ_STAGE) {
       rc = vq_forward_enqueue(&op.stage, os, ls ? op.lane : 0);
     } else if (op.kind == VQB_RVQ_EMA) {
-      rc = vqb_ema_apply_weighted(op.ema.cluster_size, op.ema.embed_avg, op.ema.embed, op.ema.stats, op.ema.K, op.ema.D,
-                                  op.ema.decay, op.ema.eps, op.ema.metric, op.ema.do_lerp, op.ema.do_normalise, nullptr,
-                                  op.ema.planes, op.ema.bext, op.ema.bias, op.ema.cnorm2, op.ema.cmax, op.ema.scratch, os);
+      rc = ema_apply_part(3, op.ema.cluster_size, op.ema.embed_avg, op.ema.embed, op.ema.stats, op.ema.K, op.ema.D, op.ema.decay,
+                          op.ema.eps, op.ema.metric, op.ema.do_lerp ? (op.ema.n_lerp > 1 ? op.ema.n_lerp : 1) : 0,
+                          op.ema.do_normalise, nullptr, op.ema.planes, op.ema.bext, op.ema.bias, op.ema.cnorm2, op.ema.cmax,
+                          op.ema.scratch, os, op.ema.slice_stride);
     } else if (op.kind == VQB_RVQ_ACCUMULATE) {
       rc = vqb_rvq_accumulate(op.acc.embeds, op.acc.embed_stride, op.acc.Q, op.acc.K, op.acc.D, op.acc.idx, op.acc.N,
                               op.acc.out, op.acc.dtype, os);
     } else if (op.kind == VQB_RVQ_BARRIER) {
       rc = vqb_peer_barrier(op.bar.flags, op.bar.rank, op.bar.world, op.bar.epoch, os);
     } else if (op.kind == VQB_RVQ_EMA_PEERS) {
-      rc = vqb_ema_apply_peers(op.emap.cluster_size, op.emap.embed_avg, op.emap.embed, op.emap.peer_stats, op.emap.world,
-                               op.emap.slice_offset, op.emap.K, op.emap.D, op.emap.decay, op.emap.eps, op.emap.metric,
-                               op.emap.do_normalise, nullptr, op.emap.planes, op.emap.bext, op.emap.bias, op.emap.cnorm2,
-                               op.emap.cmax, op.emap.scratch, os);
+      rc = ema_apply_peers_part(3, op.emap.cluster_size, op.emap.embed_avg, op.emap.embed, op.emap.peer_stats, op.emap.world,
+                                op.emap.slice_offset, op.emap.K, op.emap.D, op.emap.decay, op.emap.eps, op.emap.metric,
+                                op.emap.do_normalise, nullptr, op.emap.planes, op.emap.bext, op.emap.bias, op.emap.cnorm2,
+                                op.emap.cmax, op.emap.scratch, os, op.emap.n_lerp > 1 ? op.emap.n_lerp : 1, op.emap.slice_stride);
     } else {
       rc = VQB_E_INVALID;
     }
@@ -423,6 +424,7 @@ extern "C" int vqb_rvq_forward(const vqb_rvq_op* ops, int n_ops, void* stream) {
       for (int j = 0; j < 10; ++j) p1[j] = reinterpret_cast<uint64_t>(ptrs[j]);
       s1[0] = op.ema.K; s1[1] = op.ema.D; s1[2] = op.ema.metric; s1[3] = op.ema.do_lerp; s1[4] = op.ema.do_normalise;
       memcpy(&s1[5], &op.ema.decay, 8); memcpy(&s1[6], &op.ema.eps, 8);
+      s1[7] = static_cast<uint64_t>(op.ema.n_lerp); s1[8] = static_cast<uint64_t>(op.ema.slice_stride);
     } else if (op.kind == VQB_RVQ_BARRIER) {
       if (!op.bar.flags || op.bar.world < 1 || op.bar.world > 16) return VQB_E_INVALID;
       for (int r = 0; r < op.bar.world; ++r) p1[r] = reinterpret_cast<uint64_t>(op.bar.flags[r]);
@@ -437,6 +439,7 @@ extern "C" int vqb_rvq_forward(const vqb_rvq_op* ops, int n_ops, void* stream) {
       s1[0] = op.emap.K; s1[1] = op.emap.D; s1[2] = op.emap.metric; s1[3] = op.emap.do_normalise; s1[4] = op.emap.world;
       s1[5] = static_cast<uint64_t>(op.emap.slice_offset);
       memcpy(&s1[6], &op.emap.decay, 8); memcpy(&s1[7], &op.emap.eps, 8);
+      s1[8] = static_cast<uint64_t>(op.emap.n_lerp); s1[9] = static_cast<uint64_t>(op.emap.slice_stride);
     } else if (op.kind == VQB_RVQ_ACCUMULATE) {
       p1[0] = reinterpret_cast<uint64_t>(op.acc.embeds); p1[1] = reinterpret_cast<uint64_t>(op.acc.idx);
       p1[2] = reinterpret_cast<uint64_t>(op.acc.out);

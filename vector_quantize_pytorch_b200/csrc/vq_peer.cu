@@ -66,14 +66,17 @@ struct Peers {
 
 // single CTA: cluster_size.lerp_(sum over ranks) (vqp:603, :616) and its total (vqp:577); zero cmax
 __global__ void ema_sizes_peers_kernel(float* cluster_size, const Peers pr, int K, float w, const float* __restrict__ code_weight,
-                                       float* scratch, float* cmax) {
+                                       float* scratch, float* cmax, int n_lerp, int64_t slice_stride) {
   __shared__ double part[32];
   double s = 0.0;
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    float n = 0.f;
-    for (int r = 0; r < pr.world; ++r) n += pr.stats[r][k];   // rank order: identical on every rank
     const float wk = code_weight ? __fmul_rn(w, code_weight[k]) : w;
-    const float c = lerp_f32p(cluster_size[k], n, wk);
+    float c = cluster_size[k];
+    for (int j = 0; j < n_lerp; ++j) {   // the stages of a shared codebook, in order
+      float n = 0.f;
+      for (int r = 0; r < pr.world; ++r) n += pr.stats[r][j * slice_stride + k];   // rank order: identical on every rank
+      c = lerp_f32p(c, n, wk);
+    }
     cluster_size[k] = c;
     s += c;
   }
@@ -93,7 +96,8 @@ __global__ void ema_sizes_peers_kernel(float* cluster_size, const Peers pr, int 
 __global__ void ema_rows_peers_kernel(const float* __restrict__ cluster_size, float* embed_avg, float* embed, const Peers pr,
                                       int64_t soff, int K, int Kpad, int D, float w, const float* __restrict__ code_weight,
                                       float eps, float keps, int metric, int do_normalise, const float* __restrict__ scratch,
-                                      uint16_t* planes, uint16_t* bext, float* bias, float* cnorm2, float* cmax) {
+                                      uint16_t* planes, uint16_t* bext, float* bias, float* cnorm2, float* cmax, int n_lerp,
+                                      int64_t slice_stride) {
   const int lane = threadIdx.x & 31;
   const int k = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (k >= Kpad) return;
@@ -106,16 +110,18 @@ __global__ void ema_rows_peers_kernel(const float* __restrict__ cluster_size, fl
   if (code_weight) w = __fmul_rn(w, code_weight[k]);
   const int64_t roff = soff + static_cast<int64_t>(k) * D;
   for (int i = lane * 4; i < D; i += 128) {
-    float4 v[MAX_PEERS];
-#pragma unroll
-    for (int r = 0; r < MAX_PEERS; ++r)   // all peer loads in flight before the first add (NVLink latency ~2 us)
-      if (r < pr.world) v[r] = *reinterpret_cast<const float4*>(pr.stats[r] + roff + i);
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int r = 0; r < MAX_PEERS; ++r)
-      if (r < pr.world) { b.x += v[r].x; b.y += v[r].y; b.z += v[r].z; b.w += v[r].w; }
     float4 a = *reinterpret_cast<float4*>(avg + i);
-    a.x = lerp_f32p(a.x, b.x, w); a.y = lerp_f32p(a.y, b.y, w); a.z = lerp_f32p(a.z, b.z, w); a.w = lerp_f32p(a.w, b.w, w);
+    for (int j = 0; j < n_lerp; ++j) {
+      float4 v[MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < MAX_PEERS; ++r)   // all peer loads in flight before the first add (NVLink latency ~2 us)
+        if (r < pr.world) v[r] = *reinterpret_cast<const float4*>(pr.stats[r] + j * slice_stride + roff + i);
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int r = 0; r < MAX_PEERS; ++r)
+        if (r < pr.world) { b.x += v[r].x; b.y += v[r].y; b.z += v[r].z; b.w += v[r].w; }
+      a.x = lerp_f32p(a.x, b.x, w); a.y = lerp_f32p(a.y, b.y, w); a.z = lerp_f32p(a.z, b.z, w); a.w = lerp_f32p(a.w, b.w, w);
+    }
     *reinterpret_cast<float4*>(avg + i) = a;
   }
   if (!do_normalise) return;
@@ -168,8 +174,9 @@ extern "C" int vqb_ema_apply_peers(float* cluster_size, float* embed_avg, float*
 int vqb::ema_apply_peers_part(int part, float* cluster_size, float* embed_avg, float* embed, const void* const* peer_stats_host,
                               int world, int64_t slice_offset, int K, int D, double decay, double eps, int metric,
                               int do_normalise, const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2,
-                              float* cmax, float* scratch, void* stream) {
+                              float* cmax, float* scratch, void* stream, int n_lerp, int64_t slice_stride) {
   if (!cluster_size || !embed_avg || !embed || !scratch || !peer_stats_host || K <= 0 || D <= 0) return VQB_E_INVALID;
+  if (n_lerp < 1 || (slice_stride & 3)) return VQB_E_INVALID;
   if (world < 1 || world > MAX_PEERS || slice_offset < 0 || (slice_offset & 3)) return VQB_E_INVALID;
   if (do_normalise && (!planes || !bext || !bias || !cnorm2 || !cmax)) return VQB_E_INVALID;
   if (D % 8 != 0) return VQB_E_UNSUPPORTED;
@@ -186,13 +193,13 @@ int vqb::ema_apply_peers_part(int part, float* cluster_size, float* embed_avg, f
   const float epsf = static_cast<float>(eps);
   const float keps = static_cast<float>(static_cast<double>(K) * eps);
   if (part & 1)
-    ema_sizes_peers_kernel<<<1, 1024, 0, s>>>(cluster_size, pr, K, w, code_weight, scratch, do_normalise ? cmax : nullptr);
+    ema_sizes_peers_kernel<<<1, 1024, 0, s>>>(cluster_size, pr, K, w, code_weight, scratch, do_normalise ? cmax : nullptr, n_lerp, slice_stride);
   if (part & 2) {
     const int Kpad = vqb_padded_codes(K);
     const int wpb = 8;
     ema_rows_peers_kernel<<<(Kpad + wpb - 1) / wpb, wpb * 32, 0, s>>>(
         cluster_size, embed_avg, embed, pr, soff, K, Kpad, D, w, code_weight, epsf, keps, metric, do_normalise, scratch,
-        static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax);
+        static_cast<uint16_t*>(planes), static_cast<uint16_t*>(bext), bias, cnorm2, cmax, n_lerp, slice_stride);
   }
   return static_cast<int>(cudaGetLastError());
 }

@@ -95,11 +95,13 @@ int stats_sum(const void* x_eff, int dtype, int64_t N, int D, const int32_t* idx
 int ema_apply_peers_part(int part, float* cluster_size, float* embed_avg, float* embed, const void* const* peer_stats_host,
                          int world, int64_t slice_offset, int K, int D, double decay, double eps, int metric, int do_normalise,
                          const float* code_weight, void* planes, void* bext, float* bias, float* cnorm2, float* cmax,
-                         float* scratch, void* stream);
+                         float* scratch, void* stream, int n_lerp = 1, int64_t slice_stride = 0);
 // vq_ema.cu: vqb_ema_apply_weighted in two launches (part 1: cluster sizes, 2: rows, 3: both)
+// n_lerp statistics slices, slice_stride floats apart, are applied in order (0: no lerp, only the normalisation)
 int ema_apply_part(int part, float* cluster_size, float* embed_avg, float* embed, const float* stats, int K, int D,
-                   double decay, double eps, int metric, int do_lerp, int do_normalise, const float* code_weight,
-                   void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream);
+                   double decay, double eps, int metric, int n_lerp, int do_normalise, const float* code_weight,
+                   void* planes, void* bext, float* bias, float* cnorm2, float* cmax, float* scratch, void* stream,
+                   int64_t slice_stride = 0);
 
 
 }  // namespace vqb

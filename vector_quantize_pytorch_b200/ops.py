@@ -261,13 +261,14 @@ class RvqProgram:
         self.launches += n
         return idx32, stats
 
-    def ema(self, lane, cluster_size, embed_avg, embed, stats, cb_ops, *, decay, eps, do_lerp, do_normalise):
+    def ema(self, lane, cluster_size, embed_avg, embed, stats, cb_ops, *, decay, eps, do_lerp, do_normalise, n_lerp=1, slice_stride=0):
         K, D = embed.shape
         op = _C.RvqOp(kind=_C.RVQ_EMA, lane=lane)
         op.ema = _C.RvqEmaArgs(cluster_size=_p(cluster_size), embed_avg=_p(embed_avg), embed=_p(embed), stats=_p(stats), K=K, D=D,
                                decay=float(decay), eps=float(eps), metric=int(cb_ops.cosine), do_lerp=int(do_lerp),
                                do_normalise=int(do_normalise), planes=_p(cb_ops.planes), bext=_p(cb_ops.bext), bias=_p(cb_ops.bias),
-                               cnorm2=_p(cb_ops.cnorm2), cmax=_p(cb_ops.cmax), scratch=_p(cb_ops.scratch))
+                               cnorm2=_p(cb_ops.cnorm2), cmax=_p(cb_ops.cmax), scratch=_p(cb_ops.scratch),
+                               n_lerp=int(n_lerp), slice_stride=int(slice_stride))
         self.ops.append(op)
         self.keep.append((cluster_size, embed_avg, embed, stats, cb_ops))
         self.launches += 2
@@ -280,14 +281,16 @@ class RvqProgram:
         self.keep.append(peer)
         self.launches += 1
 
-    def ema_peers(self, lane, cluster_size, embed_avg, embed, peer, peer_ptrs, slice_offset, cb_ops, *, decay, eps, do_normalise):
+    def ema_peers(self, lane, cluster_size, embed_avg, embed, peer, peer_ptrs, slice_offset, cb_ops, *, decay, eps, do_normalise,
+                  n_lerp=1, slice_stride=0):
         K, D = embed.shape
         op = _C.RvqOp(kind=_C.RVQ_EMA_PEERS, lane=lane)
         op.emap = _C.RvqEmaPeersArgs(cluster_size=_p(cluster_size), embed_avg=_p(embed_avg), embed=_p(embed),
                                      peer_stats=ctypes.cast(peer_ptrs, ctypes.c_void_p), slice_offset=int(slice_offset),
                                      world=peer.world, K=K, D=D, decay=float(decay), eps=float(eps), metric=int(cb_ops.cosine),
                                      do_normalise=int(do_normalise), planes=_p(cb_ops.planes), bext=_p(cb_ops.bext),
-                                     bias=_p(cb_ops.bias), cnorm2=_p(cb_ops.cnorm2), cmax=_p(cb_ops.cmax), scratch=_p(cb_ops.scratch))
+                                     bias=_p(cb_ops.bias), cnorm2=_p(cb_ops.cnorm2), cmax=_p(cb_ops.cmax), scratch=_p(cb_ops.scratch),
+                                     n_lerp=int(n_lerp), slice_stride=int(slice_stride))
         self.ops.append(op)
         self.keep.append((cluster_size, embed_avg, embed, peer, peer_ptrs, cb_ops))
         self.launches += 2

@@ -80,6 +80,21 @@ class _PlanPart:
         self.refreshed = []
         if self.peer is not None:
             prog.barrier(lane, self.peer)      # every rank's statistics of this forward are in place (vqp:603, :607)
+        final_ema = training and rvq.shared_codebook and rvq.vq_is_ema_updating and any(do_update)   # rvq:593-597
+        if rvq.shared_codebook and all(stat_sizes) and Q > 1 and books[0].manual_ema_update:
+            # one codebook, Q stages: every stage lerps the same buffers in turn (rvq:302-306) and update_ema follows once
+            # (rvq:593-597) — ONE launch pair applies the Q statistics slices in order and normalises
+            shared = books[0]
+            cs, ea, emb = shared._state2d()
+            if self.peer is not None:
+                prog.ema_peers(lane, cs, ea, emb, self.peer, peer_ptrs, 0, shared.operands(), decay=shared.decay, eps=shared.eps,
+                               do_normalise=final_ema, n_lerp=Q, slice_stride=stat_sizes[0])
+            else:
+                prog.ema(lane, cs, ea, emb, self.packed, shared.operands(), decay=shared.decay, eps=shared.eps, do_lerp=True,
+                         do_normalise=final_ema, n_lerp=Q, slice_stride=stat_sizes[0])
+            if final_ema:
+                self.refreshed.append(shared)
+            return
         for q, book in enumerate(books):
             if not stat_sizes[q]:
                 continue
@@ -93,7 +108,7 @@ class _PlanPart:
                          eps=book.eps, do_lerp=True, do_normalise=normalise)
             if normalise:
                 self.refreshed.append(book)
-        if training and rvq.shared_codebook and rvq.vq_is_ema_updating and any(do_update):   # rvq:593-597
+        if final_ema:
             shared = books[0]
             cs, ea, emb = shared._state2d()
             prog.ema(lane, cs, ea, emb, None, shared.operands(), decay=shared.decay, eps=shared.eps, do_lerp=False,
