@@ -73,8 +73,14 @@ __global__ void ema_sizes_peers_kernel(float* cluster_size, const Peers pr, int 
     const float wk = code_weight ? __fmul_rn(w, code_weight[k]) : w;
     float c = cluster_size[k];
     for (int j = 0; j < n_lerp; ++j) {   // the stages of a shared codebook, in order
+      float v[MAX_PEERS];
+#pragma unroll
+      for (int r = 0; r < MAX_PEERS; ++r)   // all peer loads in flight before the first add
+        if (r < pr.world) v[r] = pr.stats[r][j * slice_stride + k];
       float n = 0.f;
-      for (int r = 0; r < pr.world; ++r) n += pr.stats[r][j * slice_stride + k];   // rank order: identical on every rank
+#pragma unroll
+      for (int r = 0; r < MAX_PEERS; ++r)   // rank order: identical on every rank
+        if (r < pr.world) n += v[r];
       c = lerp_f32p(c, n, wk);
     }
     cluster_size[k] = c;
