@@ -67,6 +67,8 @@ typedef struct vqb_fused_outputs {
   float* stats_cnt;    /* [K] cluster_size += 1 per row, or NULL (caller zeroes)                 */
   float* stats_sum;    /* [K][D] embed_sum += x_eff row (vector RED), or NULL (caller zeroes)    */
   int dtype;           /* VQB_DTYPE_*                                                          */
+  void* planes_out;    /* optional, fp32 rows with resid_out: the bf16 hi / lo split of the residual, [2][N][D] — the MMA
+                          operand of the NEXT ResidualVQ stage, which then skips vqb_input_prepare (NULL to skip)          */
 } vqb_fused_outputs;
 
 int vqb_version(void);
@@ -234,6 +236,9 @@ typedef struct vqb_vq_forward_args {
    * the whole multi-GPU step is one chain / one CUDA graph.  Unused (NULL / 0) otherwise. */
   const void* const* peer_stats; void* const* peer_flags; uint32_t* peer_epoch; int peer_rank, peer_world;
   int64_t peer_slice_offset;
+  /* ResidualVQ stages on fp32 rows (Euclidean): a stage can take the bf16 hi / lo split of its input ([2][N][D], written by the
+   * previous stage's tail through `planes_out`) instead of running vqb_input_prepare.  NULL = not used. */
+  const void* a_planes_in; void* planes_out;
 } vqb_vq_forward_args;
 size_t vqb_vq_forward_workspace(int64_t N, int D, int K, int dtype, int metric, int update);
 int vqb_vq_forward(const vqb_vq_forward_args* args, void* stream);

@@ -18,7 +18,7 @@ class FusedOutputs(ctypes.Structure):
     """Mirror of `vqb_fused_outputs` (include/vqb200.h)."""
     _fields_ = [("x_eff", _vp), ("embed", _vp), ("q_out", _vp), ("idx64_out", _vp), ("idx_stride", _i64),
                 ("loss_sum", _vp), ("x_raw", _vp), ("resid_out", _vp), ("qsum", _vp), ("stats_cnt", _vp), ("stats_sum", _vp),
-                ("dtype", _i32)]
+                ("dtype", _i32), ("planes_out", _vp)]
 
 
 class VQForwardArgs(ctypes.Structure):
@@ -31,7 +31,7 @@ class VQForwardArgs(ctypes.Structure):
                 ("decay", _f64), ("eps", _f64), ("stats", _vp), ("margin_rel", _f32), ("workspace", _vp),
                 ("workspace_bytes", _sz), ("ev_search_begin", _vp), ("ev_search_end", _vp),
                 ("peer_stats", _vp), ("peer_flags", _vp), ("peer_epoch", _vp), ("peer_rank", _i32), ("peer_world", _i32),
-                ("peer_slice_offset", _i64)]
+                ("peer_slice_offset", _i64), ("a_planes_in", _vp), ("planes_out", _vp)]
 
 
 class RvqEmaArgs(ctypes.Structure):

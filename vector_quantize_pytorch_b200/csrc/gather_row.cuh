@@ -23,9 +23,11 @@ struct FusedOut {  // device-side copy of vqb_fused_outputs
   float* stats_sum;   // optional: embed_sum[k][:] += x_eff[row] (vqp:605), vector RED into the L2-resident buffer
   int dtype;
   int enabled;
+  uint16_t* planes_out;   // optional (fp32 rows): bf16 hi / lo split of the residual, [2][N][D]
+  int64_t planes_stride;  // N * D
 };
 
-inline int make_fused(FusedOut* o, const vqb_fused_outputs* f, int D) {
+inline int make_fused(FusedOut* o, const vqb_fused_outputs* f, int D, int64_t N = 0) {
   *o = FusedOut{};  // every pointer null, enabled = 0: a disabled tail must be inert wherever the kernels test a field
   if (!f) return VQB_OK;
   if (!f->x_eff || !f->embed) return VQB_E_INVALID;
@@ -39,6 +41,11 @@ inline int make_fused(FusedOut* o, const vqb_fused_outputs* f, int D) {
   o->idx_stride = f->idx_stride; o->loss_sum = f->loss_sum; o->x_raw = f->x_raw ? f->x_raw : f->x_eff;
   o->resid_out = f->resid_out; o->qsum = f->qsum; o->dtype = f->dtype; o->enabled = 1;
   o->stats_cnt = f->stats_cnt; o->stats_sum = f->stats_sum;
+  if (f->planes_out) {  // the split rides on the fp32 residual
+    if (f->dtype != VQB_DTYPE_F32 || !f->resid_out || N <= 0 || (reinterpret_cast<uintptr_t>(f->planes_out) & 15)) return VQB_E_INVALID;
+    o->planes_out = static_cast<uint16_t*>(f->planes_out);
+    o->planes_stride = N * D;
+  }
   if ((reinterpret_cast<uintptr_t>(f->stats_sum) & 15) != 0) return VQB_E_ALIGN;
   return VQB_OK;
 }
@@ -52,6 +59,18 @@ __device__ __forceinline__ void stats_add(const FusedOut& o, int k, int D, int i
   float* dst = o.stats_sum + static_cast<int64_t>(k) * D + i;
   red_add_v4(dst, xv[0], xv[1], xv[2], xv[3]);
   if (VEC == 8) red_add_v4(dst + 4, xv[4], xv[5], xv[6], xv[7]);
+}
+
+// bf16 hi / lo split of four fp32 values (the same arithmetic as input_prepare_kernel) -> the two operand planes
+__device__ __forceinline__ void store_planes4(uint16_t* planes, int64_t stride, int64_t at, const float* v) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    h[e] = float_to_bf16_bits(v[e]);
+    l[e] = float_to_bf16_bits(v[e] - bf16_bits_to_float(static_cast<uint16_t>(h[e])));
+  }
+  *reinterpret_cast<uint2*>(planes + at) = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+  *reinterpret_cast<uint2*>(planes + stride + at) = make_uint2(l[0] | (l[1] << 16), l[2] | (l[3] << 16));
 }
 
 template <int DT>
@@ -115,6 +134,7 @@ __device__ __forceinline__ float gather_row(const FusedOut& o, int64_t row, int 
 #pragma unroll
       for (int e = 0; e < VEC; ++e) rv[e] -= qv[e];
       *reinterpret_cast<uint4*>(reinterpret_cast<T*>(o.resid_out) + base + i) = pack16<DT>(rv);
+      if (DT == VQB_DTYPE_F32 && o.planes_out) store_planes4(o.planes_out, o.planes_stride, base + i, rv);
     }
     if (o.qsum) {
       float sv[8];
@@ -188,6 +208,7 @@ __device__ __forceinline__ float gather_rows(const FusedOut& o, const int64_t (&
 #pragma unroll
         for (int e = 0; e < VEC; ++e) rv[e] -= qv[e];
         *reinterpret_cast<uint4*>(reinterpret_cast<T*>(o.resid_out) + off) = pack16<DT>(rv);
+        if (DT == VQB_DTYPE_F32 && o.planes_out) store_planes4(o.planes_out, o.planes_stride, off, rv);
       }
       if (o.qsum) {
         float sv[8];

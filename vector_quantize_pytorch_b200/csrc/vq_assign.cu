@@ -734,6 +734,10 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   } else {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) rw[e] = __float_as_uint(__uint_as_float(xw[e]) - __uint_as_float(cw[e]));
+                    if (p.fo.planes_out) {  // the next stage's MMA operand: bf16 hi / lo split of the residual
+                      const float rf[4] = {__uint_as_float(rw[0]), __uint_as_float(rw[1]), __uint_as_float(rw[2]), __uint_as_float(rw[3])};
+                      store_planes4(p.fo.planes_out, p.fo.planes_stride, ((row_base + b) * row_bytes + off) >> 2, rf);
+                    }
                   }
                   v[b] = make_uint4(rw[0], rw[1], rw[2], rw[3]);
                 }
@@ -887,7 +891,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   p.prof = g_prof;
   p.dbg_mode = g_dbg_mode;
   p.tagmask = 0xFFFFFFF0u; p.mul1 = 1u; p.mulm1 = 0xFFFFFFFFu;
-  rc = make_fused(&p.fo, fused, D);
+  rc = make_fused(&p.fo, fused, D, N);
   if (rc) return rc;
   p.metric = metric;
   p.cnorm2 = cnorm2;

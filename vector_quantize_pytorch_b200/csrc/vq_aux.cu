@@ -22,37 +22,66 @@ __global__ void codebook_prepare_kernel(const float* __restrict__ embed, int K, 
 // ---------------------------------------------------------------------------------------------
 // input staging: l2norm in the input dtype (cosine) and bf16 hi/lo split
 // ---------------------------------------------------------------------------------------------
+// Vector width: 4 elements per lane and step (16-byte fp32 loads / 8-byte bf16 stores); D % 4 == 0 (host-checked).
 template <int DT>
 __global__ void input_prepare_kernel(const void* __restrict__ x, int64_t N, int D, int metric, void* x_eff,
                                      uint16_t* planes, int n_planes) {
   using E = Elem<DT>;
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
+  const bool cosine = metric == VQB_METRIC_COSINE;
+  auto load4 = [&](int64_t at, float* v) {
+    if (DT == VQB_DTYPE_F32) {
+      const float4 f = *reinterpret_cast<const float4*>(static_cast<const float*>(x) + at);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    } else {
+      const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const uint16_t*>(x) + at);
+      v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xFFFF0000u);
+      v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xFFFF0000u);
+    }
+  };
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * wpb + (threadIdx.x >> 5); row < N;
        row += static_cast<int64_t>(gridDim.x) * wpb) {
     const int64_t base = row * D;
-    float inv = 1.f;
-    bool cosine = metric == VQB_METRIC_COSINE;
     float nrm = 1.f;
     if (cosine) {
       double s = 0.0;
-      for (int i = lane; i < D; i += 32) {
-        const float v = E::load(x, base + i);
-        s += static_cast<double>(v) * v;
+      for (int i = lane * 4; i < D; i += 128) {
+        float v[4];
+        load4(base + i, v);
+        s += static_cast<double>(v[0]) * v[0] + static_cast<double>(v[1]) * v[1] + static_cast<double>(v[2]) * v[2] +
+             static_cast<double>(v[3]) * v[3];
       }
       s = warp_sum(s);
       nrm = E::round(static_cast<float>(sqrt(s)));  // F.normalize: norm in the tensor dtype ...
       nrm = fmaxf(nrm, 1e-6f);                      // ... clamp_min(eps)
-      (void)inv;
     }
-    for (int i = lane; i < D; i += 32) {
-      float v = E::load(x, base + i);
-      if (cosine) v = E::round(__fdiv_rn(v, nrm));  // ... x / norm, rounded to the dtype
-      if (x_eff) E::store(x_eff, base + i, v);
+    for (int i = lane * 4; i < D; i += 128) {
+      float v[4];
+      load4(base + i, v);
+      if (cosine) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = E::round(__fdiv_rn(v[e], nrm));  // ... x / norm, rounded to the dtype
+      }
+      if (x_eff) {
+        if (DT == VQB_DTYPE_F32) {
+          *reinterpret_cast<float4*>(static_cast<float*>(x_eff) + base + i) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+          const uint32_t w0 = float_to_bf16_bits(v[0]) | (static_cast<uint32_t>(float_to_bf16_bits(v[1])) << 16);
+          const uint32_t w1 = float_to_bf16_bits(v[2]) | (static_cast<uint32_t>(float_to_bf16_bits(v[3])) << 16);
+          *reinterpret_cast<uint2*>(static_cast<uint16_t*>(x_eff) + base + i) = make_uint2(w0, w1);
+        }
+      }
       if (planes) {
-        const uint16_t h = float_to_bf16_bits(v);
-        planes[base + i] = h;
-        if (n_planes == 2) planes[N * D + base + i] = float_to_bf16_bits(v - bf16_bits_to_float(h));
+        uint16_t h[4], l[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          h[e] = float_to_bf16_bits(v[e]);
+          l[e] = float_to_bf16_bits(v[e] - bf16_bits_to_float(h[e]));
+        }
+        *reinterpret_cast<uint2*>(planes + base + i) = make_uint2(h[0] | (uint32_t(h[1]) << 16), h[2] | (uint32_t(h[3]) << 16));
+        if (n_planes == 2)
+          *reinterpret_cast<uint2*>(planes + N * D + base + i) = make_uint2(l[0] | (uint32_t(l[1]) << 16), l[2] | (uint32_t(l[3]) << 16));
       }
     }
   }
@@ -531,6 +560,8 @@ extern "C" int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
   if (a_planes && n_planes != 1 && n_planes != 2) return VQB_E_INVALID;
   if (!x_eff && !a_planes) return VQB_E_INVALID;
+  if (D % 4 != 0) return VQB_E_UNSUPPORTED;   // 4 elements per lane and step
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_eff) | reinterpret_cast<uintptr_t>(a_planes)) & 15) return VQB_E_ALIGN;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int g = row_grid(N, ROW_THREADS / 32);
   if (dtype == VQB_DTYPE_F32)
@@ -547,7 +578,7 @@ extern "C" int vqb_fix_flagged(const void* x_eff, int dtype, int64_t N, int D, c
   if (dtype != VQB_DTYPE_F32 && dtype != VQB_DTYPE_BF16) return VQB_E_INVALID;
   if (D > 1024) return VQB_E_UNSUPPORTED;
   FusedOut fo;
-  int rc = make_fused(&fo, fused, D);
+  int rc = make_fused(&fo, fused, D, N);
   if (rc) return rc;
   if (fo.enabled && fo.dtype != dtype) return VQB_E_INVALID;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -571,7 +602,7 @@ extern "C" int vqb_gather(const void* x_eff, int dtype, int64_t N, int D, const 
                           void* q_out, int64_t* idx64_out, int64_t idx_stride, double* loss_sum, const void* x_raw,
                           void* resid_out, void* qsum, void* stream) {
   if (!x_eff || !embed || !idx || N <= 0 || D <= 0) return VQB_E_INVALID;
-  vqb_fused_outputs f;
+  vqb_fused_outputs f = {};
   f.x_eff = x_eff; f.embed = embed; f.q_out = q_out; f.idx64_out = idx64_out; f.idx_stride = idx_stride;
   f.loss_sum = loss_sum; f.x_raw = x_raw; f.resid_out = resid_out; f.qsum = qsum; f.dtype = dtype;
   f.stats_cnt = nullptr; f.stats_sum = nullptr;

@@ -107,7 +107,7 @@ void make_keys(const vqb_vq_forward_args* a, void* stream, uint64_t* sk, uint64_
   auto F = [&](double v) { uint64_t u; memcpy(&u, &v, 8); sk[si++] = u; };
   P(a->x); P(a->cluster_size); P(a->embed_avg); P(a->embed); P(a->planes); P(a->bext); P(a->bias); P(a->cnorm2); P(a->cmax);
   P(a->scratch); P(a->q_out); P(a->idx64_out); P(a->loss_out); P(a->resid_out); P(a->qsum); P(a->idx32); P(a->stats);
-  P(a->workspace);
+  P(a->workspace); P(a->a_planes_in); P(a->planes_out);
   P(a->peer_epoch);
   for (int r = 0; r < a->peer_world && r < 16; ++r) { P(a->peer_stats ? a->peer_stats[r] : nullptr); P(a->peer_flags ? a->peer_flags[r] : nullptr); }
   I(a->dtype); I(a->metric); I(a->N); I(a->D); I(a->K); I(a->already_normalised); I(a->idx_stride); F(a->loss_weight);
@@ -492,6 +492,11 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
       x_eff = ws + w.x_eff;
       a_planes = x_eff;
     }
+  } else if (a->a_planes_in && !l2) {
+    // the previous ResidualVQ stage's tail already wrote the bf16 hi / lo split of these rows (planes_out)
+    if (reinterpret_cast<uintptr_t>(a->a_planes_in) & 15) return VQB_E_ALIGN;
+    a_planes = a->a_planes_in;
+    n_a = 2;
   } else {
     rc = vqb_input_prepare(a->x, a->dtype, a->N, a->D, l2 ? 1 : 0, l2 ? ws + w.x_eff : nullptr, ws + w.a_planes, 2, stream);
     if (rc) return rc;
@@ -505,11 +510,12 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
   bool counters_zeroed = false;
 
   // ---- search with the fused gather / loss / residual tail (vqp:743-747, :766, :1178, :1327; rvq:524-525)
-  vqb_fused_outputs f;
+  vqb_fused_outputs f = {};
   f.x_eff = x_eff; f.embed = a->embed; f.q_out = a->q_out; f.idx64_out = a->idx64_out; f.idx_stride = a->idx_stride;
   f.loss_sum = a->loss_out ? loss_sum : nullptr;
   f.x_raw = (x_eff != a->x) ? a->x : nullptr;
   f.resid_out = a->resid_out; f.qsum = a->qsum; f.dtype = a->dtype;
+  f.planes_out = (a->dtype == VQB_DTYPE_F32 && a->resid_out && !l2) ? a->planes_out : nullptr;
   const bool fused_stats = a->update && a->stats_mode == 0;
   f.stats_cnt = nullptr; f.stats_sum = nullptr;
   if (fused_stats) {  // statistics ride on the store warps: zero the packed buffer, accumulate with vector REDs
@@ -526,6 +532,7 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
   // read it —, code row from L2, one (N x D) write) stays fused: ResidualVQ rebuilds the running sum from the indices
   // at the end (vqb_rvq_accumulate).  The VectorQuantize tail (row copy + loss from the scores) is always fused.
   const bool split_tail = a->qsum && !fused_stats;
+  if (a->planes_out && (split_tail || a->dtype != VQB_DTYPE_F32 || !a->resid_out || l2)) return VQB_E_UNSUPPORTED;
   const bool want_tail = !split_tail && (a->q_out || a->idx64_out || a->loss_out || fused_stats);
   vqb_flag_entry* flagged = reinterpret_cast<vqb_flag_entry*>(ws + w.flagged);
   // The EMA sort (histogram -> scans -> scatter -> segmented sums) only needs the indices, and all but ~0.1 % of them

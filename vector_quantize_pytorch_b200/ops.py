@@ -188,7 +188,8 @@ def _workspace(key, nbytes: int, device) -> torch.Tensor:
 def vq_forward_args(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, update: int, do_normalise: bool, decay: float,
                     eps: float, q_out=None, idx64_out=None, idx_stride: int = 1, loss_out=None, loss_weight: float = 1.0,
                     resid_out=None, qsum=None, stats=None, margin: float | None = None, already_normalised: bool = False,
-                    ws_key=None, stats_accumulate: bool = False, peer=None, peer_ptrs=None, peer_slice_offset: int = 0):
+                    ws_key=None, stats_accumulate: bool = False, peer=None, peer_ptrs=None, peer_slice_offset: int = 0,
+                    a_planes_in=None, planes_out=None):
     """The argument block of one vqb_vq_forward call (also one VQB_RVQ_STAGE op of vqb_rvq_forward).
     Returns (args, idx32, stats, n_launches)."""
     _require_cuda(x, state[2])
@@ -211,7 +212,8 @@ def vq_forward_args(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, upd
         idx_stride=int(idx_stride), loss_out=_p(loss_out), loss_weight=float(loss_weight), resid_out=_p(resid_out),
         qsum=_p(qsum), idx32=_p(idx32), update=int(update), stats_mode=STATS_MODE, stats_accumulate=int(stats_accumulate), do_normalise=int(do_normalise), decay=float(decay),
         eps=float(eps), stats=_p(stats), margin_rel=float(DEFAULT_MARGIN if margin is None else margin),
-        workspace=_p(ws), workspace_bytes=nbytes, ev_search_begin=None, ev_search_end=None)
+        workspace=_p(ws), workspace_bytes=nbytes, ev_search_begin=None, ev_search_end=None,
+        a_planes_in=_p(a_planes_in), planes_out=_p(planes_out))
     if update == 3:  # multi-GPU: statistics -> peer barrier -> EMA kernels summing every rank's statistics (vq_peer.cu)
         a.peer_stats = ctypes.cast(peer_ptrs, ctypes.c_void_p)
         a.peer_flags = ctypes.cast(peer.flag_ptrs, ctypes.c_void_p)

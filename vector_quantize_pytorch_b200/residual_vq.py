@@ -61,6 +61,10 @@ class _PlanPart:
         out0 = torch.empty((N, D), dtype=dtype, device=dev)
         if persistent_io:
             self.io = (flat, all_idx, out0)
+        # fp32 rows (Euclidean): a stage's tail also writes the bf16 hi / lo split of its residual — the next stage's MMA operand —
+        # so that only stage 0 runs the split kernel over its input (536 MB of HBM traffic per stage at config 3)
+        split = dtype == torch.float32 and not books[0].use_cosine_sim and Q > 1
+        self.planes = [torch.empty((2, N, D), dtype=torch.bfloat16, device=dev) for _ in range(min(2, Q - 1))] if split else None
         self.first = len(prog.ops)
         residual = flat
         for q, book in enumerate(books):
@@ -70,7 +74,9 @@ class _PlanPart:
                        decay=book.decay, eps=book.eps, idx64_out=all_idx[:, q], idx_stride=Q,
                        loss_out=self.losses[q:q + 1] if want_loss else None, loss_weight=rvq.layers[q].commitment_weight,
                        resid_out=nxt, stats=self.packed[offs[q]:offs[q] + stat_sizes[q]] if stat_sizes[q] else None,
-                       ws_key=id(book))
+                       ws_key=id(book),
+                       a_planes_in=self.planes[(q - 1) & 1] if (split and q > 0) else None,
+                       planes_out=self.planes[q & 1] if (split and nxt is not None) else None)
             residual = nxt
         # the running sum reads the codebooks the stages searched: before the EMA ops
         self.stack = None if rvq.shared_codebook else torch.stack([b.embed[0] for b in books])
