@@ -1,7 +1,7 @@
 """Driver for ncu captures of the kernels AS THEY RUN in a step (run under gpurun + ncu, VQB_GRAPH=0).
 
     python scripts/ncu_step.py vq      # BASELINE config 2 training step: vq_assign_kernel with the fused tail, the EMA chain
-    python scripts/ncu_step.py rvq     # a 2-stage ResidualVQ step + decode (rvq_accumulate_kernel, decode_kernel)
+    python scripts/ncu_step.py rvq     # an 8-stage ResidualVQ step + decode (rvq_accumulate_kernel, decode_kernel)
     python scripts/ncu_step.py gemm    # cuBLAS bf16 8192^3 (the tensor-pipe reference the search kernel is compared with)
 """
 import os, sys
@@ -26,7 +26,7 @@ elif what == "vq":
         q, i, l = vq(x)
     torch.cuda.synchronize()
 else:
-    rvq = vqb.ResidualVQ(dim=256, num_quantizers=2, codebook_size=1024, shared_codebook=True).to(dev)
+    rvq = vqb.ResidualVQ(dim=256, num_quantizers=8, codebook_size=1024, shared_codebook=True).to(dev)
     with torch.no_grad():
         e = torch.randn(1, 1024, 256, device=dev); rvq.layers[0]._codebook.embed.copy_(e); rvq.layers[0]._codebook.embed_avg.copy_(e)
     x = torch.randn(64, 4096, 256, device=dev).bfloat16()
