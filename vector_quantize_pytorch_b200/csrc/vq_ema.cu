@@ -389,6 +389,61 @@ __global__ void ema_rows_kernel(const float* __restrict__ cluster_size, float* e
   }
   float* avg = embed_avg + static_cast<int64_t>(k) * D;
   float* emb = embed + static_cast<int64_t>(k) * D;
+  if (D <= 512 && do_normalise) {
+    // Register-resident row (the common case): one round trip for the loads, every later phase — lerp, divide, l2norm, operand
+    // split — works on registers; the memory version below re-reads the row between the phases (4 dependent round trips of a
+    // kernel that sits on the critical path of every step).  Same arithmetic in the same order.
+    constexpr int NV = 4;
+    float4 a[NV];
+    if (code_weight) w = __fmul_rn(w, code_weight[k]);
+    const float* es = stats + soff + static_cast<int64_t>(k) * D;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = j * 128 + lane * 4;
+      a[j] = i < D ? *reinterpret_cast<const float4*>(avg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int q = 0; q < n_lerp; ++q) {
+      float4 b[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int i = j * 128 + lane * 4;
+        if (i < D) b[j] = *reinterpret_cast<const float4*>(es + q * slice_stride + i);
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int i = j * 128 + lane * 4;
+        if (i >= D) continue;
+        a[j].x = lerp_f32(a[j].x, b[j].x, w); a[j].y = lerp_f32(a[j].y, b[j].y, w);
+        a[j].z = lerp_f32(a[j].z, b[j].z, w); a[j].w = lerp_f32(a[j].w, b[j].w, w);
+      }
+    }
+    const float total = scratch[0];
+    const float denom = __fmul_rn(__fdiv_rn(__fadd_rn(cluster_size[k], eps), __fadd_rn(total, keps)), total);
+    double n2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = j * 128 + lane * 4;
+      if (i >= D) continue;
+      if (n_lerp) *reinterpret_cast<float4*>(avg + i) = a[j];
+      a[j] = make_float4(__fdiv_rn(a[j].x, denom), __fdiv_rn(a[j].y, denom), __fdiv_rn(a[j].z, denom), __fdiv_rn(a[j].w, denom));
+      if (metric == VQB_METRIC_COSINE)
+        n2 += static_cast<double>(a[j].x) * a[j].x + static_cast<double>(a[j].y) * a[j].y + static_cast<double>(a[j].z) * a[j].z +
+              static_cast<double>(a[j].w) * a[j].w;
+    }
+    if (metric == VQB_METRIC_COSINE) {  // l2norm(embed_normalized)     vqp:581-582, eps 1e-6 (:37-38)
+      const float nrm = fmaxf(static_cast<float>(sqrt(warp_sum(n2))), 1e-6f);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        a[j] = make_float4(__fdiv_rn(a[j].x, nrm), __fdiv_rn(a[j].y, nrm), __fdiv_rn(a[j].z, nrm), __fdiv_rn(a[j].w, nrm));
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = j * 128 + lane * 4;
+      if (i < D) *reinterpret_cast<float4*>(emb + i) = a[j];
+    }
+    write_code_operands_regs<NV>(a, k, K, Kpad, D, metric, planes, bext, bias, cnorm2, cmax, lane);
+    return;
+  }
   if (n_lerp) {
     if (code_weight) w = __fmul_rn(w, code_weight[k]);
     const float* es = stats + soff + static_cast<int64_t>(k) * D;
