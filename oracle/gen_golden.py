@@ -162,7 +162,32 @@ def grad_cases():
               dict(kind="rvq", dim=32, codebook_size=48, num_quantizers=3, shared_codebook=False))
 
 
+def simvq_cases():
+    """SimVQ (sim_vq.py:99-139): seeded x and upstream G; the reference's outputs and the gradients of sum(quantize * G) + loss
+    with respect to x and to the weight of the codebook transform."""
+    ref = load_reference()
+    for name, rotation in (("simvq_rotation_fp32", True), ("simvq_ste_fp32", False)):
+        torch.manual_seed(4321)
+        gen = torch.Generator().manual_seed(8642)
+        m = ref.SimVQ(dim=32, codebook_size=80, rotation_trick=rotation)
+        x = torch.randn(2, 96, 32, generator=gen).requires_grad_(True)
+        G = torch.randn(2, 96, 32, generator=gen)
+        q, ind, loss = m(x)
+        ((q * G).sum() + loss).backward()
+        store = dict(s0_x=f32(x), s0_G=f32(G), s0_quantize=f32(q), s0_indices=ind.cpu().numpy().astype(np.int64), s0_loss=f32(loss),
+                     s0_xgrad=f32(x.grad), s0_wgrad=f32(m.code_transform.weight.grad), frozen=f32(m.frozen_codebook),
+                     weight=f32(m.code_transform.weight))
+        meta = dict(kind="simvq", name=name, dim=32, codebook_size=80, rotation_trick=rotation, dtype="fp32", steps=["train"],
+                    x_shape=[2, 96, 32], torch=torch.__version__)
+        store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **store)
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
+    if "--simvq" in sys.argv:
+        return simvq_cases()
     if "--grad" in sys.argv:
         return grad_cases()
     if "--expire" in sys.argv:

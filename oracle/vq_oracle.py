@@ -460,3 +460,25 @@ def top2_gap_f64(x: np.ndarray, embed: np.ndarray, cosine: bool):
     part = np.partition(s, -2, axis=-1)
     gap = (part[:, -1] - part[:, -2]) / scale
     return np.argmax(s, axis=-1), gap
+
+
+# --------------------------------------------------------------------------------------------
+# SimVQ (sim_vq.py:99-139): frozen codebook through a linear map; cdist + argmin; two commitment terms
+# --------------------------------------------------------------------------------------------
+def simvq_forward(x: np.ndarray, frozen: np.ndarray, weight: np.ndarray, input_to_quantize_commit_loss_weight=0.25,
+                  commitment_weight=1.0):
+    """x (b, n, d) fp32, frozen (K, f) fp32, weight (d, f) of nn.Linear(f, d, bias=False) (sim_vq.py:64).
+    Returns (quantized before the gradient estimator — the rotation trick reproduces it numerically, sim_vq.py:126-128 —,
+    indices, loss)."""
+    x = x.astype(F32)
+    codes = (frozen.astype(F32) @ weight.astype(F32).T).astype(F32)           # sim_vq.py:81-83
+    flat = x.reshape(-1, x.shape[-1])
+    # torch.cdist (sim_vq.py:112) in its euclidean-via-matmul form, like vqp:58-62
+    x2 = (flat * flat).sum(-1, dtype=F32)[:, None]
+    y2 = (codes * codes).sum(-1, dtype=F32)[None, :]
+    d2 = np.maximum((x2 + y2).astype(F32) - (F32(2) * (flat @ codes.T)).astype(F32), F32(0))
+    ind = np.argmin(np.sqrt(d2), axis=-1).reshape(x.shape[:-1])               # first minimum, like torch.argmin
+    q = codes[ind]
+    mse = np.mean((x - q).astype(F32) ** 2, dtype=F32)
+    loss = F32(mse + mse * F32(input_to_quantize_commit_loss_weight)) * F32(commitment_weight)   # sim_vq.py:121-124, :139
+    return q.astype(F32), ind.astype(np.int64), loss

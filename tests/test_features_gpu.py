@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from golden_util import Golden, grad_golden_names
+from golden_util import GOLDEN_DIR, Golden, grad_golden_names, simvq_golden_names
 from oracle import vq_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -361,3 +361,42 @@ def test_rvq_program_equals_stagewise_path(kind, monkeypatch):
             torch.testing.assert_close(a, b, rtol=1e-6, atol=1e-6, msg=f"step {step}: codebook state differs")
         ref.load_state_dict(mod.state_dict())   # identical pre-state for the next step: outputs must then be bit-equal
     assert len(mod.__dict__.get("_plans", {})) >= 1, "the program path was not taken"
+
+
+# ------------------------------------------------------------------------------------------------ SimVQ (sim_vq.py)
+@pytest.mark.parametrize("name", simvq_golden_names())
+def test_simvq_matches_reference(name):
+    """SimVQ on the search kernel: indices, quantized, loss and the gradients to x and to the codebook transform against the
+    reference's (sim_vq.py:99-139); plus a config-2-sized search against brute-force fp64 arg-min."""
+    import json, os
+    m = vqb()
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = json.loads(bytes(g["meta"]).decode())
+    mod = m.SimVQ(dim=meta["dim"], codebook_size=meta["codebook_size"], rotation_trick=meta["rotation_trick"]).to(DEV)
+    with torch.no_grad():
+        mod.frozen_codebook.copy_(torch.from_numpy(g["frozen"]))
+        mod.code_transform.weight.copy_(torch.from_numpy(g["weight"]))
+    x = torch.from_numpy(g["s0_x"]).to(DEV).requires_grad_(True)
+    G = torch.from_numpy(g["s0_G"]).to(DEV)
+    q, ind, loss = mod(x)
+    ((q * G).sum() + loss).backward()
+    assert np.array_equal(ind.cpu().numpy(), g["s0_indices"])
+    np.testing.assert_allclose(q.detach().cpu().numpy(), g["s0_quantize"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(loss.item(), float(g["s0_loss"]), rtol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g["s0_xgrad"], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(mod.code_transform.weight.grad.cpu().numpy(), g["s0_wgrad"], rtol=1e-4, atol=2e-5)
+    codes = mod.indices_to_codes(ind)
+    np.testing.assert_allclose(codes.detach().cpu().numpy(), (torch.from_numpy(g["frozen"]) @ torch.from_numpy(g["weight"]).T)[g["s0_indices"]].numpy(),
+                               rtol=1e-5, atol=1e-5)
+    if name.endswith("rotation_fp32"):   # one larger search: exact arg-min up to fp64 near-ties
+        torch.manual_seed(3)
+        big = m.SimVQ(dim=256, codebook_size=1024).to(DEV)
+        xb = torch.randn(4, 4096, 256, device=DEV)
+        _, ib, _ = big(xb)
+        cb = big.codebook.detach().double()
+        d = torch.cdist(xb.reshape(-1, 256).double(), cb)
+        best = d.argmin(-1)
+        bad = ib.reshape(-1) != best
+        if bad.any():
+            two = d[bad].topk(2, largest=False).values
+            assert ((two[:, 1] - two[:, 0]) / two[:, 1] < 1e-5).all(), "SimVQ index differs from the fp64 arg-min outside near ties"

@@ -6,7 +6,7 @@ Bar: indices identical except on rows the reference itself resolves inside fp32 
 import numpy as np
 import pytest
 
-from golden_util import Golden, golden_names, near_tie_rows, cpu_pick_fn
+from golden_util import GOLDEN_DIR, Golden, golden_names, near_tie_rows, cpu_pick_fn, simvq_golden_names
 from oracle import vq_oracle as O
 
 
@@ -98,3 +98,14 @@ def test_torch_port_is_bit_identical_to_reference(name):
         np.testing.assert_allclose(q.float().numpy(), g[f"s{step}_quantize"], rtol=1e-6, atol=1e-6)
         np.testing.assert_allclose(float(l), float(g[f"s{step}_loss"]), rtol=1e-6)
         np.testing.assert_allclose(st.embed[0].numpy(), g[f"s{step}_post_cb0_embed"], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", simvq_golden_names())
+def test_simvq_oracle_matches_reference(name):
+    """sim_vq.py:99-139 restated in numpy against the reference's own outputs (oracle/gen_golden.py --simvq)."""
+    import os
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    q, ind, loss = O.simvq_forward(g["s0_x"], g["frozen"], g["weight"])
+    assert np.array_equal(ind, g["s0_indices"])
+    np.testing.assert_allclose(q, g["s0_quantize"], rtol=1e-5, atol=1e-5)   # the estimators reproduce the quantized value
+    np.testing.assert_allclose(loss, g["s0_loss"], rtol=1e-5)
