@@ -185,7 +185,19 @@ def simvq_cases():
         print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def heads_cases():
+    """heads > 1 with ONE codebook shared by the heads (vqp:1044-1049, :1266-1270, :1354-1358); codebook_dim = dim / heads, so
+    there is no projection."""
+    T, E = "train", "eval"
+    run_case("vq_heads4_fp32", lambda r: r.VectorQuantize(dim=64, heads=4, codebook_dim=16, codebook_size=64), (2, 80, 64), "fp32",
+             [T, T, E], dict(kind="vq", dim=64, heads=4, codebook_dim=16, codebook_size=64))
+    run_case("vq_heads2_cosine_bf16", lambda r: r.VectorQuantize(dim=64, heads=2, codebook_dim=32, codebook_size=64, use_cosine_sim=True),
+             (2, 80, 64), "bf16", [T, T, E], dict(kind="vq", dim=64, heads=2, codebook_dim=32, codebook_size=64, use_cosine_sim=True))
+
+
 def main():
+    if "--heads" in sys.argv:
+        return heads_cases()
     if "--simvq" in sys.argv:
         return simvq_cases()
     if "--grad" in sys.argv:

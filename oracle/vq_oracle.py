@@ -324,6 +324,7 @@ class VQConfig:
     ema_update: bool = True
     threshold_ema_dead_code: float = 0  # vqp:818
     kmeans_iters: int = 10  # vqp:816
+    heads: int = 1  # vqp:807 (codebook shared across the heads; `dim` is then the per-head codebook dim)
 
 
 def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *, training: bool = True,
@@ -334,6 +335,17 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
     Returns (quantize (..., D) in dtype, indices (...,) int64, loss fp32 scalar, loss_fp32_unrounded).
     """
     shape = x.shape
+    if cfg.heads > 1:  # vqp:1044-1049: 'b n (h d) -> 1 (b h) n d' — every head's sub-vector is a row of the ONE codebook
+        b, n, hd = shape
+        h, d = cfg.heads, hd // cfg.heads
+        xs = x.reshape(b, n, h, d).transpose(0, 2, 1, 3).reshape(b * h, n, d)
+        q, ind, loss, loss32 = vq_forward(xs, dtype, state, VQConfig(**{**cfg.__dict__, "heads": 1}), training=training,
+                                          freeze_codebook=freeze_codebook, all_reduce=all_reduce, faithful=faithful,
+                                          ema_update_weight=ema_update_weight, pick_fn=pick_fn, accum=accum,
+                                          accum_ema_update=accum_ema_update)
+        q = q.reshape(b, h, n, d).transpose(0, 2, 1, 3).reshape(b, n, hd)          # vqp:1354-1358
+        ind = ind.reshape(b, h, n).transpose(0, 2, 1)                              # vqp:1266-1270: 'b n h'
+        return q, ind, loss, loss32
     x = cast_like(x, dtype).reshape(-1, shape[-1])
     if cfg.use_cosine_sim:  # vqp:1159 -> :376 : l2norm in the INPUT dtype
         x = l2norm(x, dtype)

@@ -49,8 +49,8 @@ class Golden:
     @property
     def cfg(self):
         m = self.meta
-        dim = m["dim"] // m.get("groups", 1)
-        return O.VQConfig(dim=dim, codebook_size=m["codebook_size"], use_cosine_sim=m.get("use_cosine_sim", False),
+        dim = m.get("codebook_dim", m["dim"] // m.get("groups", 1))
+        return O.VQConfig(dim=dim, codebook_size=m["codebook_size"], use_cosine_sim=m.get("use_cosine_sim", False), heads=m.get("heads", 1),
                           decay=m.get("decay", 0.8), eps=m.get("eps", 1e-5),
                           commitment_weight=m.get("commitment_weight", 1.0),
                           threshold_ema_dead_code=m.get("threshold_ema_dead_code", 0), kmeans_iters=m.get("kmeans_iters", 10))

@@ -112,7 +112,7 @@ def test_reference_state_dict_loads(tmp_path):
 
 def test_unsupported_options_raise():
     import vector_quantize_pytorch_b200 as m
-    for kw in (dict(heads=2), dict(learnable_codebook=True), dict(stochastic_sample_codes=True),
+    for kw in (dict(heads=2, separate_codebook_per_head=True), dict(learnable_codebook=True), dict(stochastic_sample_codes=True),
                dict(orthogonal_reg_weight=1.0), dict(affine_param=True)):
         with pytest.raises(NotImplementedError):
             m.VectorQuantize(dim=64, codebook_size=32, **kw)

@@ -79,7 +79,7 @@ def test_decode_invariant():
     np.testing.assert_allclose(out, q, atol=1e-5)
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("vq_")])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("vq_") and "heads" not in n])
 def test_torch_port_is_bit_identical_to_reference(name):
     """oracle/vq_oracle_torch.py (the CPU-baseline arm of bench.py) replays the reference's ATen ops."""
     import torch

@@ -40,7 +40,7 @@ def ours_codebooks(module):
 def build_module(meta):
     m = vqb()
     kw = {}
-    for k in ("use_cosine_sim", "decay", "eps", "commitment_weight"):
+    for k in ("use_cosine_sim", "decay", "eps", "commitment_weight", "heads", "codebook_dim"):
         if k in meta:
             kw[k] = meta[k]
     if meta["kind"] == "vq":

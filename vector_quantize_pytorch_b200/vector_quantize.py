@@ -121,8 +121,8 @@ class VectorQuantize(nn.Module):
     ):
         super().__init__()
         # ---- options outside the accelerated path fail loudly
-        if heads != 1 or separate_codebook_per_head:
-            _unsupported("heads > 1")
+        if separate_codebook_per_head:
+            _unsupported("separate_codebook_per_head")   # heads > 1 share ONE codebook (vqp:1044-1049)
         if directional_reparam or vq_bridge is not None or learnable_codebook:
             _unsupported("directional_reparam / vq_bridge / learnable_codebook")
         if in_place_codebook_optimizer is not None:
@@ -221,6 +221,8 @@ class VectorQuantize(nn.Module):
     def update_indices(self, x, indices, mask=None):  # vqp:1056-1091
         if mask is not None:
             _unsupported("update_indices with a mask")
+        if self.heads > 1:
+            _unsupported("update_indices with heads > 1")
         x, _ = self._to_rows_layout(x)
         x = self.project_in(x)
         x = self._codebook.transform_input(x)
@@ -263,8 +265,8 @@ class VectorQuantize(nn.Module):
         `out` = optional (quantize, indices, loss) host tensors to fill (pinned for full overlap).
         The device->host copies are ASYNCHRONOUS on an internal stream that the current stream waits for: synchronise
         the current stream (or the device) before reading the returned host tensors."""
-        if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last:
-            _unsupported("forward_host with projections / feature-map layouts")
+        if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last or self.heads > 1:
+            _unsupported("forward_host with projections / feature-map layouts / heads > 1")
         cbk = self._codebook
         emb = cbk.embed
         if not emb.is_cuda:
@@ -349,8 +351,8 @@ class VectorQuantize(nn.Module):
         """mask (B, N) bool.  The kernels run on the compacted unmasked rows: masked positions take no part in the
         statistics or the loss (the reference zeroes their one-hot rows, vqp:599-600, and averages the loss over the
         unmasked elements against the ORIGINAL input, vqp:1317-1325) and come back as zeros / index -1."""
-        if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last:
-            _unsupported("mask / lens together with projections or feature-map layouts")
+        if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last or self.heads > 1:
+            _unsupported("mask / lens together with projections, feature-map layouts or heads > 1")
         if x.requires_grad and torch.is_grad_enabled():
             _unsupported("mask / lens on inputs that require grad")
         if not x.is_cuda:
@@ -415,6 +417,9 @@ class VectorQuantize(nn.Module):
             x = x.unsqueeze(1)
         x, restore = self._to_rows_layout(x)
         x = self.project_in(x)  # vqp:1151
+        heads, batch = self.heads, x.shape[0]
+        if heads > 1:  # vqp:1044-1049: 'b n (h d) -> 1 (b h) n d' — every head's sub-vector is a row for the ONE codebook
+            x = x.reshape(batch, x.shape[1], heads, -1).transpose(1, 2).reshape(batch * heads, x.shape[1], -1)
         # decided AFTER project_in: with a projection the commitment loss must stay differentiable w.r.t. its weights
         # even when the raw input carries no grad (vqp:1151, :1327)
         input_requires_grad = x.requires_grad and torch.is_grad_enabled()
@@ -464,6 +469,10 @@ class VectorQuantize(nn.Module):
                 x_t = cbk.transform_input(x)
                 quantize = rotate_to(x_t, quantize) if self.rotation_trick else straight_through(x_t, quantize)
 
+        if heads > 1:  # vqp:1354-1358 '1 (b h) n d -> b n (h d)', :1266-1270 '1 (b h) n -> b n h'
+            n = quantize.shape[1]
+            quantize = quantize.reshape(batch, heads, n, -1).transpose(1, 2).reshape(batch, n, -1)
+            embed_ind = embed_ind.reshape(batch, heads, n).transpose(1, 2)
         quantize = self.project_out(quantize)  # vqp:1360
         if restore is not None:  # vqp:1364-1373, :1265-1275
             kind, dims = restore
@@ -472,7 +481,7 @@ class VectorQuantize(nn.Module):
             else:
                 b = quantize.shape[0]
                 quantize = quantize.reshape(b, *dims, quantize.shape[-1]).movedim(-1, 1)
-                embed_ind = embed_ind.reshape(b, *dims)
+                embed_ind = embed_ind.reshape(b, *dims, *embed_ind.shape[2:])
         if only_one:
             quantize = quantize.squeeze(1)
             embed_ind = embed_ind.squeeze(1)
