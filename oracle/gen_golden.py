@@ -38,10 +38,13 @@ def codebooks_of(module):
 
 
 def snap(module, tag, store):
-    for i, cb in enumerate(codebooks_of(module)):
-        store[f"{tag}_cb{i}_embed"] = f32(cb.embed[0])
-        store[f"{tag}_cb{i}_embed_avg"] = f32(cb.embed_avg[0])
-        store[f"{tag}_cb{i}_cluster_size"] = f32(cb.cluster_size[0])
+    i = 0
+    for cb in codebooks_of(module):
+        for j in range(cb.embed.shape[0]):   # num_codebooks > 1: separate_codebook_per_head
+            store[f"{tag}_cb{i}_embed"] = f32(cb.embed[j])
+            store[f"{tag}_cb{i}_embed_avg"] = f32(cb.embed_avg[j])
+            store[f"{tag}_cb{i}_cluster_size"] = f32(cb.cluster_size[j])
+            i += 1
 
 
 def randomize_codebooks(module, gen, scale=1.0, cosine=False):
@@ -85,7 +88,7 @@ def run_case(name, build, x_shape, dtype, steps, meta, randomize=True, scale=1.0
         store[f"s{step}_loss"] = f32(out[2])
         snap(module, f"s{step}_post", store)
     meta = dict(meta, name=name, dtype=dtype, steps=list(steps), x_shape=list(x_shape),
-                torch=torch.__version__, n_codebooks=len(codebooks_of(module)))
+                torch=torch.__version__, n_codebooks=sum(cb.embed.shape[0] for cb in codebooks_of(module)))
     store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
     os.makedirs(OUT, exist_ok=True)
     path = os.path.join(OUT, name + ".npz")
@@ -191,6 +194,12 @@ def heads_cases():
     T, E = "train", "eval"
     run_case("vq_heads4_fp32", lambda r: r.VectorQuantize(dim=64, heads=4, codebook_dim=16, codebook_size=64), (2, 80, 64), "fp32",
              [T, T, E], dict(kind="vq", dim=64, heads=4, codebook_dim=16, codebook_size=64))
+    run_case("vq_sepheads4_fp32", lambda r: r.VectorQuantize(dim=64, heads=4, codebook_dim=16, codebook_size=48, separate_codebook_per_head=True),
+             (2, 80, 64), "fp32", [T, T, E], dict(kind="vq", dim=64, heads=4, codebook_dim=16, codebook_size=48, separate_codebook_per_head=True))
+    run_case("vq_sepheads2_cosine_bf16", lambda r: r.VectorQuantize(dim=64, heads=2, codebook_dim=32, codebook_size=48, use_cosine_sim=True,
+                                                                    separate_codebook_per_head=True),
+             (2, 80, 64), "bf16", [T, T, E], dict(kind="vq", dim=64, heads=2, codebook_dim=32, codebook_size=48, use_cosine_sim=True,
+                                                  separate_codebook_per_head=True))
     run_case("vq_heads2_cosine_bf16", lambda r: r.VectorQuantize(dim=64, heads=2, codebook_dim=32, codebook_size=64, use_cosine_sim=True),
              (2, 80, 64), "bf16", [T, T, E], dict(kind="vq", dim=64, heads=2, codebook_dim=32, codebook_size=64, use_cosine_sim=True))
 

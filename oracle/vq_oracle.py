@@ -325,6 +325,7 @@ class VQConfig:
     threshold_ema_dead_code: float = 0  # vqp:818
     kmeans_iters: int = 10  # vqp:816
     heads: int = 1  # vqp:807 (codebook shared across the heads; `dim` is then the per-head codebook dim)
+    separate_codebook_per_head: bool = False  # vqp:808: `state` is then a list of `heads` CodebookState
 
 
 def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *, training: bool = True,
@@ -335,6 +336,25 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
     Returns (quantize (..., D) in dtype, indices (...,) int64, loss fp32 scalar, loss_fp32_unrounded).
     """
     shape = x.shape
+    if cfg.heads > 1 and cfg.separate_codebook_per_head:
+        # vqp:1044-1049 'b n (h d) -> h b n d', Codebook(num_codebooks = h): h independent codebooks, processed in head order
+        # (the per-head RNG draws of k-means / expiry follow that order, vqp:166-167); ONE mse over all heads (vqp:1327)
+        b, n, hd = shape
+        h, d = cfg.heads, hd // cfg.heads
+        sub = VQConfig(**{**cfg.__dict__, "heads": 1, "separate_codebook_per_head": False})
+        xc = cast_like(x, dtype)
+        qs, inds, l32 = [], [], []
+        for i in range(h):
+            q, ind, _, loss32 = vq_forward(xc[..., i * d:(i + 1) * d], dtype, state[i], sub, training=training,
+                                           freeze_codebook=freeze_codebook, all_reduce=all_reduce, faithful=faithful, pick_fn=pick_fn)
+            qs.append(q); inds.append(ind); l32.append(loss32)
+        q = np.concatenate(qs, axis=-1)
+        ind = np.stack(inds, axis=-1)
+        loss32 = F32(np.mean(np.array(l32, dtype=F32), dtype=F32))
+        loss = loss32
+        if dtype == "bf16" and training and cfg.commitment_weight > 0:
+            loss = bf16_round(np.array([loss32], dtype=F32))[0]
+        return q, ind, F32(loss), loss32
     if cfg.heads > 1:  # vqp:1044-1049: 'b n (h d) -> 1 (b h) n d' — every head's sub-vector is a row of the ONE codebook
         b, n, hd = shape
         h, d = cfg.heads, hd // cfg.heads

@@ -51,6 +51,7 @@ class Golden:
         m = self.meta
         dim = m.get("codebook_dim", m["dim"] // m.get("groups", 1))
         return O.VQConfig(dim=dim, codebook_size=m["codebook_size"], use_cosine_sim=m.get("use_cosine_sim", False), heads=m.get("heads", 1),
+                          separate_codebook_per_head=m.get("separate_codebook_per_head", False),
                           decay=m.get("decay", 0.8), eps=m.get("eps", 1e-5),
                           commitment_weight=m.get("commitment_weight", 1.0),
                           threshold_ema_dead_code=m.get("threshold_ema_dead_code", 0), kmeans_iters=m.get("kmeans_iters", 10))
@@ -66,7 +67,7 @@ class Golden:
         n = m["n_codebooks"]
         flat = [self.state(tag, i) for i in range(n)]
         if m["kind"] == "vq":
-            return flat[0]
+            return flat if m.get("separate_codebook_per_head") else flat[0]
         Q = m["num_quantizers"]
         if m["kind"] == "rvq":
             return [flat[0]] * Q if m["shared_codebook"] else flat
@@ -78,7 +79,7 @@ class Golden:
     def flat_states(self, states):
         m = self.meta
         if m["kind"] == "vq":
-            return [states]
+            return list(states) if m.get("separate_codebook_per_head") else [states]
         if m["kind"] == "rvq":
             return [states[0]] if m["shared_codebook"] else list(states)
         out = []

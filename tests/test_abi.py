@@ -98,6 +98,9 @@ def test_reference_state_dict_loads(tmp_path):
     import vector_quantize_pytorch_b200 as m
     for build in (lambda mod: mod.VectorQuantize(dim=64, codebook_size=32, use_cosine_sim=True),
                   lambda mod: mod.ResidualVQ(dim=32, num_quantizers=3, codebook_size=16),
+                  lambda mod: mod.VectorQuantize(dim=64, codebook_size=32, heads=4, codebook_dim=16),
+                  lambda mod: mod.VectorQuantize(dim=48, codebook_size=32, heads=2, separate_codebook_per_head=True),
+                  lambda mod: mod.SimVQ(dim=32, codebook_size=40),
                   lambda mod: mod.GroupedResidualVQ(dim=64, groups=2, num_quantizers=2, codebook_size=16, shared_codebook=True)):
         torch.manual_seed(0)
         a = build(ref)
@@ -112,7 +115,7 @@ def test_reference_state_dict_loads(tmp_path):
 
 def test_unsupported_options_raise():
     import vector_quantize_pytorch_b200 as m
-    for kw in (dict(heads=2, separate_codebook_per_head=True), dict(learnable_codebook=True), dict(stochastic_sample_codes=True),
+    for kw in (dict(learnable_codebook=True), dict(stochastic_sample_codes=True),
                dict(orthogonal_reg_weight=1.0), dict(affine_param=True)):
         with pytest.raises(NotImplementedError):
             m.VectorQuantize(dim=64, codebook_size=32, **kw)

@@ -40,7 +40,7 @@ def ours_codebooks(module):
 def build_module(meta):
     m = vqb()
     kw = {}
-    for k in ("use_cosine_sim", "decay", "eps", "commitment_weight", "heads", "codebook_dim"):
+    for k in ("use_cosine_sim", "decay", "eps", "commitment_weight", "heads", "codebook_dim", "separate_codebook_per_head"):
         if k in meta:
             kw[k] = meta[k]
     if meta["kind"] == "vq":
@@ -52,13 +52,18 @@ def build_module(meta):
                                codebook_size=meta["codebook_size"], shared_codebook=meta["shared_codebook"], **kw)
 
 
+def codebook_slots(module):
+    """(Codebook module, slot) for every (K, D) codebook: a Codebook with num_codebooks > 1 (separate_codebook_per_head) has several."""
+    return [(cb, j) for cb in ours_codebooks(module) for j in range(cb.embed.shape[0])]
+
+
 def load_state(module, g, tag):
-    for i, cb in enumerate(ours_codebooks(module)):
+    for i, (cb, j) in enumerate(codebook_slots(module)):
         st = g.state(tag, i)
         with torch.no_grad():
-            cb.embed.copy_(torch.from_numpy(st.embed)[None])
-            cb.embed_avg.copy_(torch.from_numpy(st.embed_avg)[None])
-            cb.cluster_size.copy_(torch.from_numpy(st.cluster_size)[None])
+            cb.embed[j].copy_(torch.from_numpy(st.embed))
+            cb.embed_avg[j].copy_(torch.from_numpy(st.embed_avg))
+            cb.cluster_size[j].copy_(torch.from_numpy(st.cluster_size))
 
 
 @pytest.mark.parametrize("name", replayable_on_gpu(golden_names()))
@@ -88,11 +93,11 @@ def test_modules_match_reference_goldens(name):
         assert mism.sum() == 0, f"{name} step {step}: {mism.sum()} index mismatches"
         np.testing.assert_allclose(q.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
         np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"s{step}_loss"], rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
-        for i, cb in enumerate(ours_codebooks(module)):
+        for i, (cb, j) in enumerate(codebook_slots(module)):
             ref = g.state(f"s{step}_post", i)
-            np.testing.assert_allclose(cb.cluster_size[0].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-6)
-            np.testing.assert_allclose(cb.embed_avg[0].cpu().numpy(), ref.embed_avg, rtol=1e-5, atol=1e-5)
-            np.testing.assert_allclose(cb.embed[0].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(cb.cluster_size[j].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(cb.embed_avg[j].cpu().numpy(), ref.embed_avg, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(cb.embed[j].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
 
 
 SEARCH_CASES = [

@@ -54,8 +54,8 @@ class Codebook(nn.Module):
         vq_bridge=None,
     ):
         super().__init__()
-        if num_codebooks != 1:
-            _unsupported("num_codebooks > 1 (multi-head codebooks)")
+        if num_codebooks < 1:
+            raise ValueError("num_codebooks must be >= 1")
         if kmeans_init and use_ddp and sync_kmeans:
             _unsupported("kmeans_init with distributed sampling (use_ddp + sync_kmeans, vqp:211-229)")
         if learnable_codebook:
@@ -99,6 +99,10 @@ class Codebook(nn.Module):
         self.register_buffer("embed_avg", embed.clone())  # vqp:417
         self.register_buffer("embed", embed)  # vqp:423
 
+        # num_codebooks > 1 (VectorQuantize(separate_codebook_per_head=True), vqp:1044-1049): every head is served by a light
+        # view of this module (`head(i)`): same buffers, own slot, own operand cache
+        self._slot = 0
+        self._head_views = None
         self._operands: ops.CodebookOperands | None = None
         self._operands_key = None
         self._peer = None          # dist.PeerReducer of this codebook's packed statistics (use_ddp, created on first use)
@@ -107,7 +111,25 @@ class Codebook(nn.Module):
     # ------------------------------------------------------------------ operand cache
     def _state2d(self):
         """(cluster_size (K,), embed_avg (K, D), embed (K, D)) views sharing storage with the buffers."""
-        return self.cluster_size[0], self.embed_avg[0], self.embed[0]
+        i = self._slot
+        return self.cluster_size[i], self.embed_avg[i], self.embed[i]
+
+    def head(self, i: int) -> "Codebook":
+        """The view of this module that works on codebook `i` of the (num_codebooks, K, D) buffers.  A shallow copy: it shares
+        the buffer dict with its parent (so `.to()`, `load_state_dict` reach it) and keeps its own slot and operand cache."""
+        if self.num_codebooks == 1:
+            return self
+        if self._head_views is None:
+            import copy
+            views = []
+            for j in range(self.num_codebooks):
+                v = copy.copy(self)
+                v._slot, v._head_views, v._operands, v._operands_key, v._peer, v._peer_tried = j, None, None, None, None, False
+                views.append(v)
+            self._head_views = views
+        v = self._head_views[i]
+        v.training = self.training
+        return v
 
     def operands(self) -> ops.CodebookOperands:
         """bf16 hi/lo planes + bias of the current `embed`, rebuilt whenever `embed` was changed by
@@ -120,7 +142,7 @@ class Codebook(nn.Module):
         key = (embed.data_ptr(), embed._version, embed.device)
         if self._operands is None or self._operands_key != key:
             reuse = self._operands if (self._operands is not None and self._operands.planes.device == embed.device) else None
-            self._operands = ops.prepare_codebook(embed[0], self.use_cosine_sim, out=reuse)
+            self._operands = ops.prepare_codebook(embed[self._slot], self.use_cosine_sim, out=reuse)
             self._operands_key = key
         return self._operands
 
@@ -214,6 +236,13 @@ class Codebook(nn.Module):
         if bool(self.initted):  # e.g. a loaded checkpoint: one host sync, then never again
             self._initted_host = True
             return
+        self._kmeans_init(data)
+        self.initted.data.copy_(torch.tensor(True))
+        self._initted_host = True
+
+    @torch.no_grad()
+    def _kmeans_init(self, data):
+        """The Lloyd iterations of `init_embed_` for THIS slot (no `initted` bookkeeping)."""
         samples = data.reshape(-1, data.shape[-1]).float().contiguous()
         n, K = samples.shape[0], self.codebook_size
         # sample_vectors (vqp:156-163)
@@ -232,12 +261,10 @@ class Codebook(nn.Module):
             if self.use_cosine_sim:
                 new = F.normalize(new, p=2, dim=-1, eps=1e-6)               # vqp:269-270
             means = torch.where((bins == 0)[:, None], means, new).contiguous()  # vqp:272-276
-        self.embed_avg.data.copy_((means * bins[:, None])[None])            # vqp:467-469
-        self.cluster_size.data.copy_(bins[None])                            # vqp:470
+        self.embed_avg.data[self._slot].copy_(means * bins[:, None])        # vqp:467-469
+        self.cluster_size.data[self._slot].copy_(bins)                      # vqp:470
         self._operands_key = None
         self.update_ema()                                                   # vqp:471
-        self.initted.data.copy_(torch.tensor(True))
-        self._initted_host = True
 
     @torch.no_grad()
     def expire_codes_(self, batch_samples):  # vqp:544-574 (PyTorch glue: RNG-bound, cold, off by default)
@@ -245,7 +272,7 @@ class Codebook(nn.Module):
         tensors in the input dtype from ResidualVQ's final expiry (rvq:601) — `replace` re-normalises in THAT dtype."""
         if not self.has_dead_code_replacement or not self.training:
             return
-        expired = self.cluster_size[0] < self.threshold_ema_dead_code
+        expired = self.cluster_size[self._slot] < self.threshold_ema_dead_code
         if not torch.any(expired):  # host sync, exactly like the reference (vqp:570)
             return
         samples = batch_samples.reshape(-1, batch_samples.shape[-1])
@@ -258,9 +285,9 @@ class Codebook(nn.Module):
         else:
             pick = torch.randint(0, n, (num,), device=samples.device)
         sampled = samples[pick].to(self.embed.dtype)
-        self.embed.data[0][expired] = sampled
-        self.cluster_size.data[0][expired] = self.reset_cluster_size
-        self.embed_avg.data[0][expired] = sampled * self.reset_cluster_size
+        self.embed.data[self._slot][expired] = sampled
+        self.cluster_size.data[self._slot][expired] = self.reset_cluster_size
+        self.embed_avg.data[self._slot][expired] = sampled * self.reset_cluster_size
         # `.data[...] =` does not bump embed._version: without this the next search would still use the bf16 planes /
         # bias of the replaced rows
         self._operands_key = None
@@ -361,6 +388,8 @@ class Codebook(nn.Module):
             _unsupported("codebook_transform_fn (implicit neural codebooks)")
         if topk is not None:
             _unsupported("topk")
+        if self.num_codebooks > 1 and self._head_views is None and self._slot == 0 and x.ndim == 4:
+            _unsupported("Codebook.forward on (h, b, n, d) inputs: go through VectorQuantize(separate_codebook_per_head=True)")
         ema_update = self.ema_update if ema_update is None else ema_update
         shape = x.shape
         flat = x.reshape(-1, shape[-1])

@@ -121,8 +121,7 @@ class VectorQuantize(nn.Module):
     ):
         super().__init__()
         # ---- options outside the accelerated path fail loudly
-        if separate_codebook_per_head:
-            _unsupported("separate_codebook_per_head")   # heads > 1 share ONE codebook (vqp:1044-1049)
+
         if directional_reparam or vq_bridge is not None or learnable_codebook:
             _unsupported("directional_reparam / vq_bridge / learnable_codebook")
         if in_place_codebook_optimizer is not None:
@@ -171,7 +170,7 @@ class VectorQuantize(nn.Module):
         self.use_cosine_sim = use_cosine_sim
         self._codebook = Codebook(
             dim=codebook_dim,
-            num_codebooks=1,
+            num_codebooks=heads if separate_codebook_per_head else 1,  # vqp:931
             codebook_size=codebook_size,
             decay=decay,
             eps=eps,
@@ -200,14 +199,19 @@ class VectorQuantize(nn.Module):
 
     @property
     def codebook(self):  # vqp:982-989
+        if self.separate_codebook_per_head:
+            return self._codebook.embed
         return self._codebook.embed[0]
 
     @codebook.setter
     def codebook(self, codes):  # vqp:991-996
-        self._codebook.embed.copy_(codes.unsqueeze(0))
+        self._codebook.embed.copy_(codes if self.separate_codebook_per_head else codes.unsqueeze(0))
 
     def get_codes_from_indices(self, indices):  # vqp:998-1018
-        codes = ops.decode(self.codebook, indices.unsqueeze(-1))
+        if self.separate_codebook_per_head:   # 'b * h' indices -> every head gathers from its own codebook -> 'b * (h d)'
+            codes = torch.cat([ops.decode(self._codebook.embed[h], indices[..., h:h + 1].contiguous()) for h in range(self.heads)], dim=-1)
+        else:
+            codes = ops.decode(self.codebook, indices.unsqueeze(-1))
         if not self.channel_last or self.accept_image_fmap or self.accept_3d_fmap:
             codes = codes.movedim(-1, 1)
         return codes
@@ -393,6 +397,78 @@ class VectorQuantize(nn.Module):
             return quantize, embed_ind, loss
         return quantize, embed_ind, loss, LossBreakdown(commit_loss, self.zero, self.zero, self.zero)
 
+    def _forward_separate_heads(self, x, restore, only_one, freeze_codebook, ema_update, return_loss_breakdown,
+                                ema_update_weight, accum_ema_update):
+        """separate_codebook_per_head (vqp:1044-1049 'b n (h d) -> h b n d', Codebook(num_codebooks=h), :1266-1268, :1354-1356):
+        head i searches / updates codebook i of the (h, K, d) buffers — h independent chains on the same kernels, in head
+        order (k-means init and dead-code expiry draw from the RNG head by head, like the reference's batched_sample_vectors)."""
+        heads = self.heads
+        b, n, hd = x.shape
+        d = hd // heads
+        dtype = x.dtype
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError(f"vqb200 supports float32 and bfloat16 inputs, got {dtype}")
+        if accum_ema_update or ema_update_weight is not None:
+            _unsupported("ema_update_weight / accum_ema_update with separate_codebook_per_head")
+        input_requires_grad = x.requires_grad and torch.is_grad_enabled()
+        cbk = self._codebook
+        training = self.training
+        do_update = training and not freeze_codebook and (ema_update or cbk.has_dead_code_replacement)
+        fused_loss = training and self.has_commitment_loss and not input_requires_grad
+        views = [cbk.head(i) for i in range(heads)]
+        xs = [x[..., i * d:(i + 1) * d].detach().reshape(-1, d).contiguous() for i in range(heads)]
+        if not cbk._initted_host:   # vqp:703: every head's k-means on the first batch, then ONE `initted` flag
+            if not bool(cbk.initted):
+                for v, xi in zip(views, xs):
+                    v._kmeans_init(v.transform_input(xi).float())
+                cbk.initted.data.copy_(torch.tensor(True))
+            cbk._initted_host = True
+        for v in views:
+            v._initted_host = True
+        loss_buf = getattr(self, "_head_loss_buf", None)
+        if loss_buf is None or loss_buf.device != x.device or loss_buf.numel() != heads:
+            loss_buf = self._head_loss_buf = torch.zeros((heads,), dtype=torch.float32, device=x.device)
+        qs, inds = [], []
+        for i, (v, xi) in enumerate(zip(views, xs)):
+            q = torch.empty_like(xi)
+            idx64 = torch.empty((xi.shape[0],), dtype=torch.int64, device=xi.device)
+            v.quantize_rows(xi, update=do_update, q_out=q, idx64_out=idx64, loss_out=loss_buf[i:i + 1] if fused_loss else None,
+                            loss_weight=self.commitment_weight, ema_update=ema_update)
+            qs.append(q.reshape(b, n, d))
+            inds.append(idx64.reshape(b, n))
+        quantize = torch.stack(qs, dim=2)            # (b, n, h, d)
+        embed_ind = torch.stack(inds, dim=-1)        # 'h b n -> b n h'  (vqp:1266-1268)
+        commit_loss = self.zero
+        if training and fused_loss:
+            # one mse over all heads (vqp:1327) == the mean of the heads' (equal-sized) means
+            commit_loss = loss_buf.mean()
+            loss = commit_loss.clone().requires_grad_(torch.is_grad_enabled())
+        else:
+            loss = torch.tensor(0., device=x.device, requires_grad=training and torch.is_grad_enabled())  # vqp:1282
+        if training:
+            x_h = x.reshape(b, n, heads, d)
+            if self.has_commitment_loss and not fused_loss:
+                commit_loss = F.mse_loss(quantize.detach(), cbk.transform_input(x_h))
+                loss = loss + commit_loss * self.commitment_weight
+            if input_requires_grad and self.route_gradients_to_input:  # vqp:1225-1233
+                x_t = cbk.transform_input(x_h)
+                quantize = rotate_to(x_t, quantize) if self.rotation_trick else straight_through(x_t, quantize)
+        quantize = self.project_out(quantize.reshape(b, n, hd))   # vqp:1354-1360
+        if restore is not None:
+            kind, dims = restore
+            if kind == "transpose":
+                quantize = quantize.transpose(1, 2)
+            else:
+                quantize = quantize.reshape(b, *dims, quantize.shape[-1]).movedim(-1, 1)
+                embed_ind = embed_ind.reshape(b, *dims, heads)
+        if only_one:
+            quantize = quantize.squeeze(1)
+            embed_ind = embed_ind.squeeze(1)
+        if not return_loss_breakdown:
+            return quantize, embed_ind, loss
+        return quantize, embed_ind, loss, LossBreakdown(commit_loss if self.commitment_weight == 1. or not fused_loss else commit_loss / self.commitment_weight,
+                                                       self.zero, self.zero, self.zero)
+
     def forward(self, x, indices=None, mask=None, lens=None, topk=None, sample_codebook_temp=None, freeze_codebook=None,
                 return_loss_breakdown=False, codebook_transform_fn=None, ema_update_weight=None, accum_ema_update=False,
                 ema_update=None):
@@ -418,6 +494,9 @@ class VectorQuantize(nn.Module):
         x, restore = self._to_rows_layout(x)
         x = self.project_in(x)  # vqp:1151
         heads, batch = self.heads, x.shape[0]
+        if heads > 1 and self.separate_codebook_per_head:
+            return self._forward_separate_heads(x, restore, only_one, freeze_codebook, ema_update, return_loss_breakdown,
+                                                ema_update_weight, accum_ema_update)
         if heads > 1:  # vqp:1044-1049: 'b n (h d) -> 1 (b h) n d' — every head's sub-vector is a row for the ONE codebook
             x = x.reshape(batch, x.shape[1], heads, -1).transpose(1, 2).reshape(batch * heads, x.shape[1], -1)
         # decided AFTER project_in: with a projection the commitment loss must stay differentiable w.r.t. its weights
