@@ -399,7 +399,7 @@ class Codebook(nn.Module):
         if not self._initted_host:
             self.init_embed_(flat.float())   # vqp:703
         cb = self.operands()
-        embed2d = self.embed[0]
+        embed2d = self.embed[self._slot]
         with torch.no_grad():
             res = ops.search(flat, cb, embed2d, normalise=False)  # the caller already applied transform_input
             q = torch.empty((flat.shape[0], shape[-1]), dtype=torch.float32, device=flat.device)
