@@ -104,13 +104,17 @@ int vqb_input_prepare(const void* x, int dtype, int64_t N, int D, int metric, vo
  * TMEM, fused running arg-max.  Scores are x.c - 0.5||c||^2 (euclid) or x.c (cosine).
  *   a_planes  n_a = 1: bf16 rows [N][D] (the input itself, read in place); n_a = 2: bf16 hi/lo planes [2][N][D] of an fp32
  *             input (vqb_input_prepare).
- *   n_passes  n_a     : "mixed" scheme, one pass per A plane against the FP16 codebook plane (bf16 x fp16 -> fp32 MMA);
- *             n_a + 1 : "split" scheme, bf16 hi / lo codebook planes: (x,c_hi)+(x,c_lo) [+ (x_lo,c_hi)];
- *             0       : automatic — mixed for K <= 4096, split above (the mixed scheme's wider band sends ~18x more rows
- *                       to the exact re-score, and top-2 gaps shrink ~ 1/K).
+ *   n_passes  n_a + 1 : the "split" scheme, bf16 hi / lo codebook planes into ONE fp32 accumulator:
+ *                       (x,c_hi)+(x,c_lo) for bf16 rows, +(x_lo,c_hi) for fp32 rows;
+ *             0       : automatic (= n_a + 1);
+ *             1       : diagnostics only (n_a == 1): hi plane alone, band widened by max||c_lo||.
+ *             Anything else returns VQB_E_UNSUPPORTED.  (A single pass on the fp16 plane was built, measured slower per
+ *             step and removed: tcgen05 kind::f16 rejects bf16 x fp16 operands in one instruction.)
  *   b_planes/bext/cmax           from vqb_codebook_prepare / vqb_ema_apply
- *   margin_rel                   a row is certified when its best score leads every other code by more
- *                                than 2*margin_rel*||x||*cmax; otherwise it is appended to `flagged`
+ *   margin_rel                   m, the tensor-core accumulation share of the certification band
+ *                                W = 2(||x|| cres + ||x_lo|| caux + m ||x|| cmax + 2^-21 cmax^2) + tag slack + sqrt-collapse
+ *                                width: a row is certified when its best score leads every other code
+ *                                by more than W; otherwise it is appended to `flagged`
  *   idx       i32 [N]            winner of the tensor-core pass (final for unflagged rows)
  *   flagged   [N] entries, flag_count i32[2] (caller zeroes both): [0] rows with 2 / 3 candidates, appended from the
  *             front; [1] rows with more (whole-row exact re-scan), appended from the back (flagged[N-1], [N-2], ...)  -> vqb_fix_flagged
