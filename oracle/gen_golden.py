@@ -204,7 +204,57 @@ def heads_cases():
              (2, 80, 64), "bf16", [T, T, E], dict(kind="vq", dim=64, heads=2, codebook_dim=32, codebook_size=64, use_cosine_sim=True))
 
 
+def mask_cases():
+    """Variable-length input (vqp:1116-1119 `mask` / `lens`, :599-600 masked statistics, :1317-1325 loss over the unmasked
+    elements against the ORIGINAL input, :1378-1396 padding comes back as zeros / the input and index -1)."""
+    ref = load_reference()
+    T, E = "train", "eval"
+    cases = [
+        ("mask_vq_fp32", dict(dim=64, codebook_size=96), (3, 70, 64), "fp32", [T, T, E], "mask"),
+        ("mask_vq_lens_bf16", dict(dim=64, codebook_size=96), (3, 70, 64), "bf16", [T, T, E], "lens"),
+        ("mask_vq_cosine_keep_fp32", dict(dim=32, codebook_size=48, use_cosine_sim=True, return_zeros_for_masked_padding=False,
+                                          commitment_weight=0.5), (2, 90, 32), "fp32", [T, E], "mask"),
+    ]
+    for name, kw, x_shape, dtype, steps, how in cases:
+        torch.manual_seed(1234)
+        gen = torch.Generator().manual_seed(97531)
+        module = ref.VectorQuantize(**kw)
+        randomize_codebooks(module, gen, 1.0, bool(kw.get("use_cosine_sim", False)))
+        tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        store = {}
+        for step, mode in enumerate(steps):
+            x = torch.randn(*x_shape, generator=gen).to(tdtype)
+            if how == "lens":
+                lens = torch.randint(1, x_shape[1] + 1, (x_shape[0],), generator=gen)
+                lens[0] = x_shape[1]
+                mask = torch.arange(x_shape[1])[None, :] < lens[:, None]
+                call = dict(lens=lens)
+                store[f"s{step}_lens"] = lens.numpy().astype(np.int64)
+            else:
+                mask = torch.rand(x_shape[:2], generator=gen) < 0.7
+                call = dict(mask=mask)
+            module.train(mode == "train")
+            if step == 0:
+                snap(module, "s0_pre", store)
+            with torch.no_grad():
+                out = module(x, **call)
+            store[f"s{step}_x"] = f32(x)
+            store[f"s{step}_mask"] = mask.numpy()
+            store[f"s{step}_quantize"] = f32(out[0])
+            store[f"s{step}_indices"] = out[1].cpu().numpy().astype(np.int64)
+            store[f"s{step}_loss"] = f32(out[2])
+            snap(module, f"s{step}_post", store)
+        meta = dict(kw, kind="vq", name=name, dtype=dtype, steps=list(steps), x_shape=list(x_shape), how=how,
+                    torch=torch.__version__, n_codebooks=1)
+        store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **store)
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
+    if "--mask" in sys.argv:
+        return mask_cases()
     if "--heads" in sys.argv:
         return heads_cases()
     if "--simvq" in sys.argv:

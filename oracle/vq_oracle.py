@@ -245,15 +245,19 @@ def codebook_forward(x: np.ndarray, state: CodebookState, *, cosine: bool = Fals
                      decay: float = 0.8, eps: float = 1e-5, ema_update: bool = True,
                      manual_ema_update: bool = False, freeze_codebook: bool = False, all_reduce=None,
                      ema_update_weight=None, faithful: bool = False, threshold_ema_dead_code: float = 0,
-                     pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False, kmeans_iters: int = 10):
+                     pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False, kmeans_iters: int = 10,
+                     row_mask: np.ndarray | None = None):
     """x: (N, D) fp32 (already upcast, vqp:692; already l2-normalised if cosine, vqp:1159).
+    row_mask (N,) bool (vqp:700-701): EVERY row is searched, but only the rows with mask True enter the k-means init
+    (vqp:456-458), the batch statistics (vqp:599-600: their one-hot rows are zeroed) and the expiry samples (vqp:549-550).
 
     Returns (quantize (N, D) fp32, embed_ind (N,) int64).  Mutates `state` like the reference:
     the search and the returned quantize use the PRE-update codebook (vqp:766 precedes :783-784).
     """
     x = np.asarray(x, dtype=F32)
+    xs = x if row_mask is None else x[row_mask]   # the rows that count for init / statistics / expiry
     if not state.initted:  # vqp:703
-        init_embed(state, x, kmeans_iters=kmeans_iters, cosine=cosine, eps=eps, pick_fn=pick_fn)
+        init_embed(state, xs, kmeans_iters=kmeans_iters, cosine=cosine, eps=eps, pick_fn=pick_fn)
     embed = state.embed  # vqp:710-712
     dist = scores(x, embed, cosine)  # vqp:741 / :743
     ind = argmax_first(dist)  # vqp:747 -> :140
@@ -265,6 +269,9 @@ def codebook_forward(x: np.ndarray, state: CodebookState, *, cosine: bool = Fals
         quantize = embed[ind].copy()
     has_expiry = threshold_ema_dead_code > 0
     if training and not freeze_codebook and (ema_update or has_expiry):  # vqp:783-784, :619-641
+        ind_all = ind
+        if row_mask is not None:
+            x, ind = xs, ind[row_mask]
         if accum is not None:  # vqp:70-74, :80-82, :612-614: statistics parked on `.grad` across calls
             K = state.cluster_size.shape[0]
             cs, es = batch_stats(x, ind, K, faithful)
@@ -273,7 +280,7 @@ def codebook_forward(x: np.ndarray, state: CodebookState, *, cosine: bool = Fals
             if accum_ema_update:
                 accum["cs"] = accum.get("cs", 0) + cs
                 accum["es"] = accum.get("es", 0) + es
-                return quantize, ind
+                return quantize, ind_all
             cs = cs + accum.pop("cs", 0)
             es = es + accum.pop("es", 0)
             ema_inplace(state.cluster_size, cs, decay, ema_update_weight)
@@ -288,6 +295,7 @@ def codebook_forward(x: np.ndarray, state: CodebookState, *, cosine: bool = Fals
             update_ema(state, eps, cosine)
         if has_expiry:  # vqp:641
             expire_codes(state, x, threshold_ema_dead_code, threshold_ema_dead_code, pick_fn, cosine)
+        ind = ind_all
     return quantize, ind
 
 
@@ -330,12 +338,16 @@ class VQConfig:
 
 def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *, training: bool = True,
                freeze_codebook: bool = False, all_reduce=None, faithful: bool = False, ema_update_weight=None,
-               pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False):
+               pick_fn=None, accum: dict | None = None, accum_ema_update: bool = False, mask: np.ndarray | None = None,
+               return_zeros_for_masked_padding: bool = True):
     """x: (..., D) values of dtype `dtype` held in float32.  x.requires_grad is False (bench setting).
+    mask (B, N) bool — variable-length input (vqp:1116-1119; heads == 1 here): see the masked branches below.
 
     Returns (quantize (..., D) in dtype, indices (...,) int64, loss fp32 scalar, loss_fp32_unrounded).
     """
     shape = x.shape
+    if mask is not None:
+        assert cfg.heads == 1 and mask.shape == tuple(shape[:-1])
     if cfg.heads > 1 and cfg.separate_codebook_per_head:
         # vqp:1044-1049 'b n (h d) -> h b n d', Codebook(num_codebooks = h): h independent codebooks, processed in head order
         # (the per-head RNG draws of k-means / expiry follow that order, vqp:166-167); ONE mse over all heads (vqp:1327)
@@ -367,6 +379,8 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
         ind = ind.reshape(b, h, n).transpose(0, 2, 1)                              # vqp:1266-1270: 'b n h'
         return q, ind, loss, loss32
     x = cast_like(x, dtype).reshape(-1, shape[-1])
+    orig_input = x  # vqp:1108
+    row_mask = None if mask is None else np.asarray(mask, dtype=bool).reshape(-1)
     if cfg.use_cosine_sim:  # vqp:1159 -> :376 : l2norm in the INPUT dtype
         x = l2norm(x, dtype)
     quantize, ind = codebook_forward(  # vqp:1176
@@ -374,17 +388,24 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
         ema_update=cfg.ema_update, manual_ema_update=cfg.manual_ema_update, freeze_codebook=freeze_codebook,
         all_reduce=all_reduce, faithful=faithful, ema_update_weight=ema_update_weight,
         threshold_ema_dead_code=cfg.threshold_ema_dead_code, pick_fn=pick_fn, accum=accum, accum_ema_update=accum_ema_update,
-        kmeans_iters=cfg.kmeans_iters)
+        kmeans_iters=cfg.kmeans_iters, row_mask=row_mask)
     quantize = cast_like(quantize, dtype)  # vqp:1178
     loss = F32(0.0)
     loss_f32 = F32(0.0)
     if training and cfg.commitment_weight > 0:  # vqp:1282-1329
-        cl, cl32 = mse_loss(quantize, x, dtype)  # vqp:1327 (x = post-l2norm input)
+        if row_mask is not None:  # vqp:1317-1325: mse(reduction none) against the ORIGINAL input, mean over the unmasked elements
+            cl, cl32 = mse_loss(quantize[row_mask], orig_input[row_mask], dtype)
+        else:
+            cl, cl32 = mse_loss(quantize, x, dtype)  # vqp:1327 (x = post-l2norm input)
         prod = cl * F32(cfg.commitment_weight)  # vqp:1329: a bf16 tensor times a python float stays bf16
         if dtype == "bf16":
             prod = bf16_round(np.array([prod], dtype=F32))[0]
         loss = F32(F32(0.0) + prod)  # vqp:1282: promoted by the fp32 accumulator
         loss_f32 = F32(cl32 * F32(cfg.commitment_weight))
+    if row_mask is not None:  # vqp:1378-1396: padding comes back as zeros (or the input) and index -1
+        fill = np.zeros_like(orig_input) if return_zeros_for_masked_padding else orig_input
+        quantize = np.where(row_mask[:, None], quantize, fill)
+        ind = np.where(row_mask, ind, -1)
     return quantize.reshape(shape), ind.reshape(shape[:-1]), loss, loss_f32
 
 

@@ -13,12 +13,17 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names():
     """Small fixtures that store their inputs (the `big*` ones are replayed by tests/test_big_golden.py)."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith(("big", "grad", "simvq")))
+                  if not n.startswith(("big", "grad", "simvq", "mask")))
 
 
 def simvq_golden_names():
     """SimVQ fixtures (oracle/gen_golden.py --simvq): inputs, codebook, transform weight, the reference's outputs and gradients."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "simvq_*.npz"))))
+
+
+def mask_golden_names():
+    """Variable-length fixtures (oracle/gen_golden.py --mask): `mask` / `lens` calls of the reference, s{step}_mask stored."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "mask_*.npz"))))
 
 
 def grad_golden_names():

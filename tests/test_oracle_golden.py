@@ -6,7 +6,7 @@ Bar: indices identical except on rows the reference itself resolves inside fp32 
 import numpy as np
 import pytest
 
-from golden_util import GOLDEN_DIR, Golden, golden_names, near_tie_rows, cpu_pick_fn, simvq_golden_names
+from golden_util import GOLDEN_DIR, Golden, golden_names, near_tie_rows, cpu_pick_fn, simvq_golden_names, mask_golden_names
 from oracle import vq_oracle as O
 
 
@@ -109,3 +109,25 @@ def test_simvq_oracle_matches_reference(name):
     assert np.array_equal(ind, g["s0_indices"])
     np.testing.assert_allclose(q, g["s0_quantize"], rtol=1e-5, atol=1e-5)   # the estimators reproduce the quantized value
     np.testing.assert_allclose(loss, g["s0_loss"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", mask_golden_names())
+def test_masked_oracle_matches_reference(name):
+    """`mask` / `lens` calls (vqp:1116-1119): every row is searched, the statistics see the unmasked rows only (vqp:599-600), the
+    loss is the mean over the unmasked elements against the original input (vqp:1317-1325), padding comes back as zeros / the
+    input with index -1 (vqp:1378-1396)."""
+    g = Golden(name)
+    m = g.meta
+    state = g.states("s0_pre")
+    vtol = 1e-5 if m["dtype"] == "fp32" else 8e-3
+    for step, mode in enumerate(m["steps"]):
+        q, ind, loss, _ = O.vq_forward(g[f"s{step}_x"], m["dtype"], state, g.cfg, training=mode == "train", mask=g[f"s{step}_mask"],
+                                       return_zeros_for_masked_padding=m.get("return_zeros_for_masked_padding", True))
+        assert np.array_equal(ind, g[f"s{step}_indices"]), f"{name} step {step}"
+        assert (ind[~g[f"s{step}_mask"]] == -1).all()
+        np.testing.assert_allclose(q, g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss, g[f"s{step}_loss"], rtol=1e-5 if m["dtype"] == "fp32" else 8e-3, atol=1e-7)
+        ref = g.state(f"s{step}_post", 0)
+        np.testing.assert_allclose(state.cluster_size, ref.cluster_size, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(state.embed_avg, ref.embed_avg, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(state.embed, ref.embed, rtol=1e-5, atol=1e-5)
