@@ -1,17 +1,19 @@
 """bench.py — vectors quantized / second at dim=256, codebook=1024 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg5]
 
 Workload (N=1 and per GPU for N>1): BASELINE.json configs[1] — VectorQuantize(dim=256, codebook_size=1024),
 x = (64, 4096, 256) bf16, training-mode forward with the EMA codebook update.  A "step" is one such
 forward over one synthetic batch.  `value` times the device-resident path with CUDA events; `e2e` times
 the public module call with HOST (pinned) buffers, host<->device copies inside the timed region.
-Under torchrun every rank runs the same per-GPU batch (weak scaling) with sync_codebook=True, i.e. one
-NCCL all-reduce of the packed EMA statistics per step; the time is the max over ranks.
+Under torchrun every rank runs the same per-GPU batch (weak scaling) with sync_codebook=True: the packed EMA
+statistics are summed over the ranks inside the EMA kernels (NVLink peer loads from symmetric memory after one
+barrier kernel; ONE NCCL all-reduce if symmetric memory is unavailable); the time is the max over ranks.
 
-`--impl reference` times the reference's own algorithm on the host cores (the torch-CPU oracle port
-oracle/vq_oracle_torch.py: (N x K) distance matrix, one-hot, three GEMMs — vector_quantize_pytorch.py:674-791)
-on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference package (baseline/_ref) on the host cores — its own
+VectorQuantize(dim=256, codebook_size=1024) training-mode forward on the full 262144-vector batch — and falls back
+to the torch-CPU oracle port (oracle/vq_oracle_torch.py, the same ATen op sequence) only if the package cannot be
+imported, saying so in `cpu_baseline.kind`.
 """
 import argparse
 import json
@@ -447,7 +449,7 @@ def run_gpu_arm(args):
         sustained["frac_of_sustained_peak"] = sustained["kernel_tflops"] / pk
         sustained["peak"] = pk
         sustained["peak_source"] = peak_src + " bf16_tflops_sustained"
-    cpu_v, _ = time_cpu(steps=2, warmup=1)
+    cpu_v = time_cpu(steps=2, warmup=1)[0] if world == 1 else None   # reported baseline: rank 0 at N=1 only
     line = {
         "metric": METRIC, "value": world * n_vec / (ms_dev * 1e-3), "unit": "vectors/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
@@ -463,7 +465,7 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "roofline": roof,
         "sustained": sustained,
-        "cpu_baseline": cpu_baseline_block(cpu_v),
+        "cpu_baseline": cpu_baseline_block(cpu_v) if cpu_v is not None else None,
     }
     if cfg5:
         line["stage_vectors_per_s"] = world * n_vec * 16 / (ms_dev * 1e-3)
