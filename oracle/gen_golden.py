@@ -252,7 +252,26 @@ def mask_cases():
         print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def layout_cases():
+    """Input layouts (vqp:1121-1125 one token, :1136-1147 image / 3-D feature maps and channel-first, restored at :1265-1277 and
+    :1364-1376); codebook_dim * heads == dim everywhere, so there is no projection and the fixtures replay exactly."""
+    T, E = "train", "eval"
+    run_case("layout_vq_image_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=48, accept_image_fmap=True), (2, 32, 6, 9), "fp32",
+             [T, T, E], dict(kind="vq", layout="image", dim=32, codebook_size=48))
+    run_case("layout_vq_3d_bf16", lambda r: r.VectorQuantize(dim=32, codebook_size=48, accept_3d_fmap=True), (2, 32, 3, 4, 5), "bf16",
+             [T, T, E], dict(kind="vq", layout="3d", dim=32, codebook_size=48))
+    run_case("layout_vq_chfirst_cosine_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=48, channel_last=False, use_cosine_sim=True),
+             (2, 32, 50), "fp32", [T, T, E], dict(kind="vq", layout="channel_first", dim=32, codebook_size=48, use_cosine_sim=True))
+    run_case("layout_vq_single_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=48), (37, 32), "fp32",
+             [T, T, E], dict(kind="vq", layout="single", dim=32, codebook_size=48))
+    run_case("layout_vq_image_heads2_fp32", lambda r: r.VectorQuantize(dim=32, codebook_size=48, accept_image_fmap=True, heads=2,
+                                                                       codebook_dim=16), (2, 32, 5, 7), "fp32",
+             [T, T, E], dict(kind="vq", layout="image", dim=32, codebook_size=48, heads=2, codebook_dim=16))
+
+
 def main():
+    if "--layout" in sys.argv:
+        return layout_cases()
     if "--mask" in sys.argv:
         return mask_cases()
     if "--heads" in sys.argv:

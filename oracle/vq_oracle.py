@@ -409,6 +409,29 @@ def vq_forward(x: np.ndarray, dtype: str, state: CodebookState, cfg: VQConfig, *
     return quantize.reshape(shape), ind.reshape(shape[:-1]), loss, loss_f32
 
 
+def vq_forward_layout(x: np.ndarray, dtype: str, state, cfg: VQConfig, *, layout: str | None, **kw):
+    """VectorQuantize.forward on the reference's other input layouts (everything else as `vq_forward`):
+      "single"        x (b, d): one token per batch element, 'b d -> b 1 d' and back (vqp:1121-1125, :1277, :1375-1376)
+      "image"         x (b, c, h, w)    'b c h w -> b (h w) c'      (vqp:1136-1139); indices come back (b, h, w[, heads])
+      "3d"            x (b, c, d, h, w) 'b c d h w -> b (d h w) c'  (vqp:1141-1144); indices (b, d, h, w[, heads])
+      "channel_first" x (b, d, n)       'b d n -> b n d'            (vqp:1146-1147); indices stay (b, n)
+    quantize is restored to the input layout (vqp:1364-1376)."""
+    if layout is None:
+        return vq_forward(x, dtype, state, cfg, **kw)
+    if layout == "single":
+        q, ind, loss, l32 = vq_forward(x[:, None, :], dtype, state, cfg, **kw)
+        return q[:, 0], ind[:, 0], loss, l32
+    if layout == "channel_first":
+        q, ind, loss, l32 = vq_forward(np.ascontiguousarray(x.transpose(0, 2, 1)), dtype, state, cfg, **kw)
+        return np.ascontiguousarray(q.transpose(0, 2, 1)), ind, loss, l32
+    assert layout in ("image", "3d")
+    b, c, *sp = x.shape
+    rows = np.ascontiguousarray(np.moveaxis(x, 1, -1)).reshape(b, -1, c)
+    q, ind, loss, l32 = vq_forward(rows, dtype, state, cfg, **kw)
+    q = np.ascontiguousarray(np.moveaxis(q.reshape(b, *sp, c), -1, 1))
+    return q, ind.reshape(b, *sp, *ind.shape[2:]), loss, l32
+
+
 # --------------------------------------------------------------------------------------------
 # ResidualVQ.forward  (rvq:384-630) — plain loop: no beam, no dropout, no projection
 # --------------------------------------------------------------------------------------------

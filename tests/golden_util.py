@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names():
     """Small fixtures that store their inputs (the `big*` ones are replayed by tests/test_big_golden.py)."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith(("big", "grad", "simvq", "mask")))
+                  if not n.startswith(("big", "grad", "simvq", "mask", "layout")))
 
 
 def simvq_golden_names():
@@ -24,6 +24,11 @@ def simvq_golden_names():
 def mask_golden_names():
     """Variable-length fixtures (oracle/gen_golden.py --mask): `mask` / `lens` calls of the reference, s{step}_mask stored."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "mask_*.npz"))))
+
+
+def layout_golden_names():
+    """Input-layout fixtures (oracle/gen_golden.py --layout): feature maps, channel-first, one token per batch element."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "layout_*.npz"))))
 
 
 def grad_golden_names():

@@ -12,7 +12,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from golden_util import GOLDEN_DIR, Golden, grad_golden_names, mask_golden_names, simvq_golden_names
+from golden_util import GOLDEN_DIR, Golden, grad_golden_names, simvq_golden_names
 from oracle import vq_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -401,37 +401,3 @@ def test_simvq_matches_reference(name):
             two = d[bad].topk(2, largest=False).values
             assert ((two[:, 1] - two[:, 0]) / two[:, 1] < 1e-5).all(), "SimVQ index differs from the fp64 arg-min outside near ties"
 
-
-# ------------------------------------------------------------------------------------------------ mask / lens (vqp:1116-1119)
-@pytest.mark.parametrize("name", mask_golden_names())
-def test_masked_calls_match_reference(name):
-    """`mask` / `lens` calls against the reference's own outputs (oracle/gen_golden.py --mask): indices (-1 on the padding),
-    quantized (zeros / the input on the padding), the loss over the unmasked elements (vqp:1317-1325) and the codebook after
-    the masked EMA update (vqp:599-600)."""
-    m = vqb()
-    g = Golden(name)
-    meta = g.meta
-    kw = {k: meta[k] for k in ("use_cosine_sim", "commitment_weight", "return_zeros_for_masked_padding") if k in meta}
-    mod = m.VectorQuantize(dim=meta["dim"], codebook_size=meta["codebook_size"], **kw).to(DEV)
-    cb = mod._codebook
-    st = g.state("s0_pre", 0)
-    with torch.no_grad():
-        cb.embed[0].copy_(torch.from_numpy(st.embed))
-        cb.embed_avg[0].copy_(torch.from_numpy(st.embed_avg))
-        cb.cluster_size[0].copy_(torch.from_numpy(st.cluster_size))
-    dt = meta["dtype"]
-    vtol = 1e-5 if dt == "fp32" else 8e-3
-    for step, mode in enumerate(meta["steps"]):
-        mod.train(mode == "train")
-        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(torch.bfloat16 if dt == "bf16" else torch.float32)
-        mask = g[f"s{step}_mask"]
-        if meta["how"] == "lens":
-            q, ind, loss = mod(x, lens=torch.from_numpy(g[f"s{step}_lens"]).to(DEV))
-        else:
-            q, ind, loss = mod(x, mask=torch.from_numpy(mask).to(DEV))
-        torch.cuda.synchronize()
-        assert q.dtype == x.dtype and q.shape == x.shape and ind.dtype == torch.int64 and loss.dtype == torch.float32
-        assert np.array_equal(ind.cpu().numpy(), g[f"s{step}_indices"]), f"{name} step {step}"
-        np.testing.assert_allclose(q.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
-        np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"s{step}_loss"], rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
-        assert_state(cb, g.state(f"s{step}_post", 0))

@@ -6,7 +6,7 @@ Bar: indices identical except on rows the reference itself resolves inside fp32 
 import numpy as np
 import pytest
 
-from golden_util import GOLDEN_DIR, Golden, golden_names, near_tie_rows, cpu_pick_fn, simvq_golden_names, mask_golden_names
+from golden_util import GOLDEN_DIR, Golden, golden_names, near_tie_rows, cpu_pick_fn, simvq_golden_names, mask_golden_names, layout_golden_names
 from oracle import vq_oracle as O
 
 
@@ -130,4 +130,21 @@ def test_masked_oracle_matches_reference(name):
         ref = g.state(f"s{step}_post", 0)
         np.testing.assert_allclose(state.cluster_size, ref.cluster_size, rtol=1e-5, atol=1e-6)
         np.testing.assert_allclose(state.embed_avg, ref.embed_avg, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(state.embed, ref.embed, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", layout_golden_names())
+def test_layout_oracle_matches_reference(name):
+    """Feature-map / channel-first / single-token layouts (vqp:1121-1147, restored at :1265-1277, :1364-1376)."""
+    g = Golden(name)
+    m = g.meta
+    state = g.states("s0_pre")
+    vtol = 1e-5 if m["dtype"] == "fp32" else 8e-3
+    for step, mode in enumerate(m["steps"]):
+        q, ind, loss, _ = O.vq_forward_layout(g[f"s{step}_x"], m["dtype"], state, g.cfg, layout=m["layout"], training=mode == "train")
+        assert ind.shape == g[f"s{step}_indices"].shape and q.shape == g[f"s{step}_quantize"].shape
+        assert np.array_equal(ind, g[f"s{step}_indices"]), f"{name} step {step}"
+        np.testing.assert_allclose(q, g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss, g[f"s{step}_loss"], rtol=1e-5 if m["dtype"] == "fp32" else 8e-3, atol=1e-7)
+        ref = g.state(f"s{step}_post", 0)
         np.testing.assert_allclose(state.embed, ref.embed, rtol=1e-5, atol=1e-5)

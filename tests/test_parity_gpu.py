@@ -13,7 +13,7 @@ import os
 import pytest
 import torch
 
-from golden_util import Golden, golden_names, near_tie_rows, replayable_on_gpu
+from golden_util import Golden, golden_names, layout_golden_names, mask_golden_names, near_tie_rows, replayable_on_gpu
 from oracle import vq_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -552,3 +552,77 @@ def test_config5_grouped_single_gpu_shard():
     q, ind, losses = g(x, freeze_codebook=True)
     assert q.shape == x.shape and ind.shape == (2, 8, 4096, 8) and losses.shape == (2, 8)
     assert torch.allclose(q, g.get_output_from_indices(ind), atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ mask / lens (vqp:1116-1119)
+@pytest.mark.parametrize("name", mask_golden_names())
+def test_masked_calls_match_reference(name):
+    """`mask` / `lens` calls against the reference's own outputs (oracle/gen_golden.py --mask): indices (-1 on the padding),
+    quantized (zeros / the input on the padding), the loss over the unmasked elements (vqp:1317-1325) and the codebook after
+    the masked EMA update (vqp:599-600)."""
+    m = vqb()
+    g = Golden(name)
+    meta = g.meta
+    kw = {k: meta[k] for k in ("use_cosine_sim", "commitment_weight", "return_zeros_for_masked_padding") if k in meta}
+    mod = m.VectorQuantize(dim=meta["dim"], codebook_size=meta["codebook_size"], **kw).to(DEV)
+    cb = mod._codebook
+    st = g.state("s0_pre", 0)
+    with torch.no_grad():
+        cb.embed[0].copy_(torch.from_numpy(st.embed))
+        cb.embed_avg[0].copy_(torch.from_numpy(st.embed_avg))
+        cb.cluster_size[0].copy_(torch.from_numpy(st.cluster_size))
+    dt = meta["dtype"]
+    vtol = 1e-5 if dt == "fp32" else 8e-3
+    for step, mode in enumerate(meta["steps"]):
+        mod.train(mode == "train")
+        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(torch.bfloat16 if dt == "bf16" else torch.float32)
+        mask = g[f"s{step}_mask"]
+        if meta["how"] == "lens":
+            q, ind, loss = mod(x, lens=torch.from_numpy(g[f"s{step}_lens"]).to(DEV))
+        else:
+            q, ind, loss = mod(x, mask=torch.from_numpy(mask).to(DEV))
+        torch.cuda.synchronize()
+        assert q.dtype == x.dtype and q.shape == x.shape and ind.dtype == torch.int64 and loss.dtype == torch.float32
+        assert np.array_equal(ind.cpu().numpy(), g[f"s{step}_indices"]), f"{name} step {step}"
+        np.testing.assert_allclose(q.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"s{step}_loss"], rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
+        ref = g.state(f"s{step}_post", 0)
+        np.testing.assert_allclose(cb.cluster_size[0].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(cb.embed_avg[0].cpu().numpy(), ref.embed_avg, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(cb.embed[0].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ input layouts (vqp:1121-1147)
+@pytest.mark.parametrize("name", layout_golden_names())
+def test_input_layouts_match_reference(name):
+    """accept_image_fmap / accept_3d_fmap / channel_last=False / one token per batch element against the reference's own
+    outputs (oracle/gen_golden.py --layout): shapes and values of quantize and indices, the loss, the codebook afterwards."""
+    m = vqb()
+    g = Golden(name)
+    meta = g.meta
+    kw = {k: meta[k] for k in ("use_cosine_sim", "heads", "codebook_dim") if k in meta}
+    kw.update({"image": dict(accept_image_fmap=True), "3d": dict(accept_3d_fmap=True), "channel_first": dict(channel_last=False),
+               "single": {}}[meta["layout"]])
+    mod = m.VectorQuantize(dim=meta["dim"], codebook_size=meta["codebook_size"], **kw).to(DEV)
+    load_state(mod, g, "s0_pre")
+    cb = mod._codebook
+    dt = meta["dtype"]
+    vtol = 1e-5 if dt == "fp32" else 8e-3
+    for step, mode in enumerate(meta["steps"]):
+        mod.train(mode == "train")
+        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(TDT[dt])
+        q, ind, loss = mod(x)
+        torch.cuda.synchronize()
+        assert q.dtype == x.dtype and q.shape == x.shape and ind.dtype == torch.int64
+        assert tuple(ind.shape) == g[f"s{step}_indices"].shape
+        assert np.array_equal(ind.cpu().numpy(), g[f"s{step}_indices"]), f"{name} step {step}"
+        np.testing.assert_allclose(q.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"s{step}_loss"], rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
+        ref = g.state(f"s{step}_post", 0)
+        np.testing.assert_allclose(cb.cluster_size[0].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(cb.embed[0].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
+        if mode == "eval" and meta.get("heads", 1) == 1:  # decode restores the layout too (vqp:1015-1016)
+            codes = mod.get_codes_from_indices(ind)
+            assert codes.shape == q.shape
+            np.testing.assert_allclose(codes.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+
