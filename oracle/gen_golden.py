@@ -269,7 +269,49 @@ def layout_cases():
              [T, T, E], dict(kind="vq", layout="image", dim=32, codebook_size=48, heads=2, codebook_dim=16))
 
 
+def mask_rvq_cases():
+    """ResidualVQ / GroupedResidualVQ with a mask (rvq:493-500: every layer receives it; rvq:698 the groups pass it on):
+    padding comes back as zeros / index -1 in every stage, the losses and the EMA statistics see the unmasked rows only."""
+    ref = load_reference()
+    T, E = "train", "eval"
+    cases = [
+        ("mask_rvq_shared_bf16", "rvq", dict(dim=32, num_quantizers=3, codebook_size=64, shared_codebook=True), (3, 40, 32), "bf16", [T, T, E]),
+        ("mask_rvq_separate_fp32", "rvq", dict(dim=32, num_quantizers=3, codebook_size=64), (3, 40, 32), "fp32", [T, T, E]),
+        ("mask_grvq_fp32", "grvq", dict(dim=64, groups=2, num_quantizers=2, codebook_size=48), (2, 44, 64), "fp32", [T, E]),
+    ]
+    for name, kind, kw, x_shape, dtype, steps in cases:
+        torch.manual_seed(1234)
+        gen = torch.Generator().manual_seed(86420)
+        module = ref.ResidualVQ(**kw) if kind == "rvq" else ref.GroupedResidualVQ(**kw)
+        randomize_codebooks(module, gen, 1.0, False)
+        tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        store = {}
+        for step, mode in enumerate(steps):
+            x = torch.randn(*x_shape, generator=gen).to(tdtype)
+            mask = torch.rand(x_shape[:2], generator=gen) < 0.7
+            module.train(mode == "train")
+            if step == 0:
+                snap(module, "s0_pre", store)
+            with torch.no_grad():
+                out = module(x, mask=mask)
+            store[f"s{step}_x"] = f32(x)
+            store[f"s{step}_mask"] = mask.numpy()
+            store[f"s{step}_quantize"] = f32(out[0])
+            store[f"s{step}_indices"] = out[1].cpu().numpy().astype(np.int64)
+            store[f"s{step}_loss"] = f32(out[2])
+            snap(module, f"s{step}_post", store)
+        meta = dict(kw, kind=kind, name=name, dtype=dtype, steps=list(steps), x_shape=list(x_shape), how="mask",
+                    shared_codebook=bool(kw.get("shared_codebook", False)), torch=torch.__version__,
+                    n_codebooks=len(codebooks_of(module)))
+        store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **store)
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
+
+
 def main():
+    if "--mask-rvq" in sys.argv:
+        return mask_rvq_cases()
     if "--layout" in sys.argv:
         return layout_cases()
     if "--mask" in sys.argv:

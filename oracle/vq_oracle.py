@@ -442,7 +442,8 @@ def _bin(a: np.ndarray, dtype: str) -> np.ndarray:
 
 
 def rvq_forward(x: np.ndarray, dtype: str, states: list, cfg: VQConfig, *, shared_codebook: bool = False,
-                training: bool = True, freeze_codebook: bool = False, all_reduce=None, faithful: bool = False, pick_fn=None):
+                training: bool = True, freeze_codebook: bool = False, all_reduce=None, faithful: bool = False, pick_fn=None,
+                mask: np.ndarray | None = None):
     """states: list of Q CodebookState (for shared_codebook all entries are THE SAME object, rvq:302-306).
 
     Returns (quantized_out (..., D) in dtype, indices (..., Q) int64, losses (Q,) fp32, losses_fp32 (Q,)).
@@ -459,7 +460,7 @@ def rvq_forward(x: np.ndarray, dtype: str, states: list, cfg: VQConfig, *, share
         all_residuals.append(residual)  # rvq:489
         quantized, ind, loss, loss32 = vq_forward(residual, dtype, states[q], layer_cfg, training=training,
                                                   freeze_codebook=freeze_codebook, all_reduce=all_reduce,
-                                                  faithful=faithful, pick_fn=pick_fn)  # rvq:493
+                                                  faithful=faithful, pick_fn=pick_fn, mask=mask)  # rvq:493 (every layer gets the mask, :495)
         residual = _bin(residual - quantized, dtype)  # rvq:524 (quant_grad_frac=0 -> detach)
         quantized_out = _bin(quantized_out + quantized, dtype)  # rvq:525
         all_ind.append(ind)

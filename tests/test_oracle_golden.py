@@ -115,22 +115,32 @@ def test_simvq_oracle_matches_reference(name):
 def test_masked_oracle_matches_reference(name):
     """`mask` / `lens` calls (vqp:1116-1119): every row is searched, the statistics see the unmasked rows only (vqp:599-600), the
     loss is the mean over the unmasked elements against the original input (vqp:1317-1325), padding comes back as zeros / the
-    input with index -1 (vqp:1378-1396)."""
+    input with index -1 (vqp:1378-1396).  ResidualVQ hands the mask to every layer (rvq:495), the grouped module to every group."""
     g = Golden(name)
     m = g.meta
-    state = g.states("s0_pre")
+    states = g.states("s0_pre")
     vtol = 1e-5 if m["dtype"] == "fp32" else 8e-3
     for step, mode in enumerate(m["steps"]):
-        q, ind, loss, _ = O.vq_forward(g[f"s{step}_x"], m["dtype"], state, g.cfg, training=mode == "train", mask=g[f"s{step}_mask"],
-                                       return_zeros_for_masked_padding=m.get("return_zeros_for_masked_padding", True))
+        mask = g[f"s{step}_mask"]
+        kw = dict(training=mode == "train", mask=mask)
+        if m["kind"] == "vq":
+            q, ind, loss, _ = O.vq_forward(g[f"s{step}_x"], m["dtype"], states, g.cfg,
+                                           return_zeros_for_masked_padding=m.get("return_zeros_for_masked_padding", True), **kw)
+            assert (ind[~mask] == -1).all()
+        elif m["kind"] == "rvq":
+            q, ind, loss, _ = O.rvq_forward(g[f"s{step}_x"], m["dtype"], states, g.cfg, shared_codebook=m["shared_codebook"], **kw)
+            assert (ind[~mask] == -1).all()
+        else:
+            q, ind, loss, _ = O.grouped_rvq_forward(g[f"s{step}_x"], m["dtype"], states, g.cfg, shared_codebook=m["shared_codebook"], **kw)
+            assert (ind[:, ~mask] == -1).all()
         assert np.array_equal(ind, g[f"s{step}_indices"]), f"{name} step {step}"
-        assert (ind[~g[f"s{step}_mask"]] == -1).all()
         np.testing.assert_allclose(q, g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
         np.testing.assert_allclose(loss, g[f"s{step}_loss"], rtol=1e-5 if m["dtype"] == "fp32" else 8e-3, atol=1e-7)
-        ref = g.state(f"s{step}_post", 0)
-        np.testing.assert_allclose(state.cluster_size, ref.cluster_size, rtol=1e-5, atol=1e-6)
-        np.testing.assert_allclose(state.embed_avg, ref.embed_avg, rtol=1e-5, atol=1e-5)
-        np.testing.assert_allclose(state.embed, ref.embed, rtol=1e-5, atol=1e-5)
+        for i, st in enumerate(g.flat_states(states)):
+            ref = g.state(f"s{step}_post", i)
+            np.testing.assert_allclose(st.cluster_size, ref.cluster_size, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(st.embed_avg, ref.embed_avg, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(st.embed, ref.embed, rtol=1e-5, atol=1e-5)
 
 
 @pytest.mark.parametrize("name", layout_golden_names())

@@ -557,25 +557,23 @@ def test_config5_grouped_single_gpu_shard():
 # ------------------------------------------------------------------------------------------------ mask / lens (vqp:1116-1119)
 @pytest.mark.parametrize("name", mask_golden_names())
 def test_masked_calls_match_reference(name):
-    """`mask` / `lens` calls against the reference's own outputs (oracle/gen_golden.py --mask): indices (-1 on the padding),
-    quantized (zeros / the input on the padding), the loss over the unmasked elements (vqp:1317-1325) and the codebook after
-    the masked EMA update (vqp:599-600)."""
+    """`mask` / `lens` calls against the reference's own outputs (oracle/gen_golden.py --mask / --mask-rvq): indices (-1 on the
+    padding), quantized (zeros / the input on the padding), the loss over the unmasked elements (vqp:1317-1325) and the codebooks
+    after the masked EMA update (vqp:599-600) — VectorQuantize, ResidualVQ (rvq:495) and GroupedResidualVQ (rvq:698)."""
     m = vqb()
     g = Golden(name)
     meta = g.meta
-    kw = {k: meta[k] for k in ("use_cosine_sim", "commitment_weight", "return_zeros_for_masked_padding") if k in meta}
-    mod = m.VectorQuantize(dim=meta["dim"], codebook_size=meta["codebook_size"], **kw).to(DEV)
-    cb = mod._codebook
-    st = g.state("s0_pre", 0)
-    with torch.no_grad():
-        cb.embed[0].copy_(torch.from_numpy(st.embed))
-        cb.embed_avg[0].copy_(torch.from_numpy(st.embed_avg))
-        cb.cluster_size[0].copy_(torch.from_numpy(st.cluster_size))
+    if meta["kind"] == "vq":
+        kw = {k: meta[k] for k in ("use_cosine_sim", "commitment_weight", "return_zeros_for_masked_padding") if k in meta}
+        mod = m.VectorQuantize(dim=meta["dim"], codebook_size=meta["codebook_size"], **kw).to(DEV)
+    else:
+        mod = build_module(meta).to(DEV)
+    load_state(mod, g, "s0_pre")
     dt = meta["dtype"]
     vtol = 1e-5 if dt == "fp32" else 8e-3
     for step, mode in enumerate(meta["steps"]):
         mod.train(mode == "train")
-        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(torch.bfloat16 if dt == "bf16" else torch.float32)
+        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(TDT[dt])
         mask = g[f"s{step}_mask"]
         if meta["how"] == "lens":
             q, ind, loss = mod(x, lens=torch.from_numpy(g[f"s{step}_lens"]).to(DEV))
@@ -583,13 +581,15 @@ def test_masked_calls_match_reference(name):
             q, ind, loss = mod(x, mask=torch.from_numpy(mask).to(DEV))
         torch.cuda.synchronize()
         assert q.dtype == x.dtype and q.shape == x.shape and ind.dtype == torch.int64 and loss.dtype == torch.float32
+        assert tuple(ind.shape) == g[f"s{step}_indices"].shape and tuple(loss.shape) == g[f"s{step}_loss"].shape
         assert np.array_equal(ind.cpu().numpy(), g[f"s{step}_indices"]), f"{name} step {step}"
         np.testing.assert_allclose(q.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
         np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"s{step}_loss"], rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
-        ref = g.state(f"s{step}_post", 0)
-        np.testing.assert_allclose(cb.cluster_size[0].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-5)
-        np.testing.assert_allclose(cb.embed_avg[0].cpu().numpy(), ref.embed_avg, rtol=1e-5, atol=1e-5)
-        np.testing.assert_allclose(cb.embed[0].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
+        for i, (cb, j) in enumerate(codebook_slots(mod)):
+            ref = g.state(f"s{step}_post", i)
+            np.testing.assert_allclose(cb.cluster_size[j].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(cb.embed_avg[j].cpu().numpy(), ref.embed_avg, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(cb.embed[j].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
 
 
 # ------------------------------------------------------------------------------------------------ input layouts (vqp:1121-1147)

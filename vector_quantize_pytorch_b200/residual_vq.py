@@ -143,12 +143,14 @@ class _PlanPart:
         arr[self.acc].acc.out = out.data_ptr()
         return all_idx, out, flat
 
-    def finish(self, bound, shape, return_all_codes):
+    def finish(self, bound, shape, return_all_codes, project=True):
         all_idx, out, _ = bound
         rvq = self.rvq
         for b in self.refreshed:
             b._mark_operands_fresh()
-        out = rvq.project_out(out.reshape(shape))  # rvq:610
+        out = out.reshape(shape)
+        if project:
+            out = rvq.project_out(out)  # rvq:610
         ret = (out, all_idx.reshape(*shape[:-1], self.Q), self.losses.clone())
         if return_all_codes:
             ret = (*ret, rvq.get_codes_from_indices(ret[1]))
@@ -266,14 +268,17 @@ class ResidualVQ(nn.Module):
 
     def forward(self, x, mask=None, indices=None, return_all_codes=False, sample_codebook_temp=None,
                 freeze_codebook=False, beam_size=None, rand_quantize_dropout_fixed_seed=None,
-                _stats_sink=None):
-        if mask is not None or indices is not None:
-            _unsupported("ResidualVQ.forward(mask=/indices=)")
+                _stats_sink=None, _projected=False):
+        if indices is not None:
+            _unsupported("ResidualVQ.forward(indices=)")
         if beam_size is not None and beam_size > 1:
             _unsupported("beam search")
         if not x.is_cuda:
             raise RuntimeError("vqb200 has no CPU path: inputs must live on a CUDA (B200, sm_100) device")
-        x = self.project_in(x)
+        if mask is not None:
+            return self._forward_masked(x, mask, return_all_codes, freeze_codebook)
+        if not _projected:   # _projected: the masked path hands in compacted rows that went through project_in already
+            x = self.project_in(x)
         if x.requires_grad and torch.is_grad_enabled():
             # gradients (to the input or to project_in, rvq:406) need the per-stage straight-through / rotation glue of
             # VectorQuantize: take the layered path
@@ -290,7 +295,7 @@ class ResidualVQ(nn.Module):
 
         losses = self._ensure_loss_buf(dev)
         do_update = [training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
-        if self._program_ok(books, do_update):
+        if not _projected and self._program_ok(books, do_update):
             # the whole forward — stages, running sum, deferred EMA updates — as ONE vqb_rvq_forward call / one CUDA graph,
             # from a cached op list in which only the per-call pointers (input, indices, output) are patched
             key = self._part_key(flat, books, do_update)
@@ -357,8 +362,44 @@ class ResidualVQ(nn.Module):
             else:
                 self._finish_update(packed, offs, stat_sizes, do_update, (stage_inputs, shape, peer_ptrs), synced=False)
 
-        quantized_out = self.project_out(quantized_out.reshape(shape))  # rvq:610
+        quantized_out = quantized_out.reshape(shape)
+        if not _projected:
+            quantized_out = self.project_out(quantized_out)  # rvq:610
         ret = (quantized_out, all_idx.reshape(*shape[:-1], Q), losses.clone())
+        if return_all_codes:
+            ret = (*ret, self.get_codes_from_indices(ret[1]))
+        return ret
+
+    def _forward_masked(self, x, mask, return_all_codes, freeze_codebook):
+        """mask (B, N) bool.  The reference hands the mask to every layer (rvq:495): a layer searches every row, but masked rows
+        take no part in its statistics or loss (vqp:599-600, :1317-1325) and come back as zeros / index -1 (vqp:1378-1396), so their
+        residual is never reduced and their running sum stays zero.  That is exactly the forward over the COMPACTED unmasked rows
+        with zeros / -1 scattered around it — which is what runs here (stage-wise path: the compacted row count changes from call
+        to call, a cached program per count would not pay).  project_in / project_out see every row (rvq:406, :610)."""
+        books = self._stage_plan()
+        if any(b.use_cosine_sim for b in books):
+            _unsupported("ResidualVQ.forward(mask=) with use_cosine_sim (the masked loss is taken against the un-normalised input, vqp:1319)")
+        if any(not vq.return_zeros_for_masked_padding for vq in self.layers):
+            _unsupported("ResidualVQ.forward(mask=) with return_zeros_for_masked_padding=False")
+        if self.training and any(b.has_dead_code_replacement for b in books):
+            _unsupported("ResidualVQ.forward(mask=) with dead-code replacement")
+        xp = self.project_in(x)  # rvq:406
+        if xp.requires_grad and torch.is_grad_enabled():
+            _unsupported("ResidualVQ.forward(mask=) on inputs / projections that require grad")
+        assert xp.ndim == 3 and mask.shape == xp.shape[:2]
+        B, N, D = xp.shape
+        Q = self.num_quantizers
+        rows = mask.reshape(-1).nonzero(as_tuple=True)[0]  # host sync (the reference's masked path syncs as well)
+        quantized = torch.zeros((B * N, D), dtype=xp.dtype, device=xp.device)
+        all_idx = torch.full((B * N, Q), -1, dtype=torch.int64, device=xp.device)
+        if rows.numel() > 0:
+            xc = xp.detach().reshape(-1, D)[rows].unsqueeze(0)
+            qc, ic, losses = self.forward(xc, freeze_codebook=freeze_codebook, _projected=True)
+            quantized[rows] = qc[0]
+            all_idx[rows] = ic[0]
+        else:
+            losses = torch.zeros((Q,), dtype=torch.float32, device=xp.device)
+        ret = (self.project_out(quantized.reshape(B, N, D)), all_idx.reshape(B, N, Q), losses)  # rvq:610
         if return_all_codes:
             ret = (*ret, self.get_codes_from_indices(ret[1]))
         return ret
@@ -505,8 +546,8 @@ class GroupedResidualVQ(nn.Module):
         return total <= ops.RvqProgram.MAX_OPS
 
     def forward(self, x, indices=None, return_all_codes=False, sample_codebook_temp=None, freeze_codebook=False, mask=None):
-        if indices is not None or mask is not None:
-            _unsupported("GroupedResidualVQ.forward(indices=/mask=)")
+        if indices is not None:
+            _unsupported("GroupedResidualVQ.forward(indices=)")
         assert x.shape[-1] == self.dim
         chunks = x.chunk(self.groups, dim=-1)  # rvq:690
         if self.training:
@@ -515,7 +556,11 @@ class GroupedResidualVQ(nn.Module):
             seed = torch.randint(0, 10_000, (), device=x.device)
             if distributed.is_available() and distributed.is_initialized() and distributed.get_world_size() > 1:
                 distributed.all_reduce(seed)
-        if self._program_ok(chunks, freeze_codebook):
+        if mask is not None:   # rvq:698: every group receives the mask (ResidualVQ._forward_masked)
+            outs = [rvq(c, mask=mask, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes)
+                    for rvq, c in zip(self.rvqs, chunks)]
+            sink = []
+        elif self._program_ok(chunks, freeze_codebook):
             # every group's stages in ONE vqb_rvq_forward call: the groups are independent chains on parallel lanes; the op
             # list is cached, only the per-call pointers are patched
             flats, keys = [], []
