@@ -309,7 +309,51 @@ def mask_rvq_cases():
         print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def dropout_cases():
+    """quantize_dropout (rvq:423-439, :473-476): in training the layers after a randomly drawn index are skipped (index -1,
+    loss 0).  The seed is passed explicitly (`rand_quantize_dropout_fixed_seed`), one per step, and stored."""
+    ref = load_reference()
+    T, E = "train", "eval"
+    cases = [
+        ("dropout_rvq_separate_fp32", dict(dim=32, num_quantizers=4, codebook_size=64, quantize_dropout=True), (2, 64, 32), "fp32",
+         [T, T, T, E], [3, 11, 5, 0]),
+        ("dropout_rvq_shared_bf16", dict(dim=32, num_quantizers=6, codebook_size=64, shared_codebook=True, quantize_dropout=True,
+                                         quantize_dropout_cutoff_index=1, quantize_dropout_multiple_of=2), (2, 64, 32), "bf16",
+         [T, T, T, E], [7, 2, 9, 0]),
+    ]
+    for name, kw, x_shape, dtype, steps, seeds in cases:
+        torch.manual_seed(1234)
+        gen = torch.Generator().manual_seed(13579)
+        module = ref.ResidualVQ(**kw)
+        randomize_codebooks(module, gen, 1.0, False)
+        tdtype = torch.bfloat16 if dtype == "bf16" else torch.float32
+        store = {}
+        for step, mode in enumerate(steps):
+            x = torch.randn(*x_shape, generator=gen)
+            cb0 = codebooks_of(module)[0].embed[0]
+            x = (cb0[torch.randint(0, cb0.shape[0], x_shape[:-1], generator=gen)] + 0.3 * x).to(tdtype)
+            module.train(mode == "train")
+            if step == 0:
+                snap(module, "s0_pre", store)
+            with torch.no_grad():
+                out = module(x, rand_quantize_dropout_fixed_seed=seeds[step])
+            store[f"s{step}_x"] = f32(x)
+            store[f"s{step}_quantize"] = f32(out[0])
+            store[f"s{step}_indices"] = out[1].cpu().numpy().astype(np.int64)
+            store[f"s{step}_loss"] = f32(out[2])
+            snap(module, f"s{step}_post", store)
+        meta = dict(kw, kind="rvq", name=name, dtype=dtype, steps=list(steps), x_shape=list(x_shape), seeds=seeds,
+                    shared_codebook=bool(kw.get("shared_codebook", False)), torch=torch.__version__,
+                    n_codebooks=len(codebooks_of(module)))
+        store["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+        path = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(path, **store)
+        print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB", [int((store[f's{i}_indices'][0, 0] >= 0).sum()) for i in range(len(steps))])
+
+
 def main():
+    if "--dropout" in sys.argv:
+        return dropout_cases()
     if "--mask-rvq" in sys.argv:
         return mask_rvq_cases()
     if "--layout" in sys.argv:

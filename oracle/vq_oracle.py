@@ -443,8 +443,11 @@ def _bin(a: np.ndarray, dtype: str) -> np.ndarray:
 
 def rvq_forward(x: np.ndarray, dtype: str, states: list, cfg: VQConfig, *, shared_codebook: bool = False,
                 training: bool = True, freeze_codebook: bool = False, all_reduce=None, faithful: bool = False, pick_fn=None,
-                mask: np.ndarray | None = None):
+                mask: np.ndarray | None = None, dropout_index: int | None = None):
     """states: list of Q CodebookState (for shared_codebook all entries are THE SAME object, rvq:302-306).
+
+    dropout_index (training with quantize_dropout, rvq:423-439: `quantize_dropout_index(seed, ...)` below): the layers after it
+    are skipped — their indices come back as -1, their losses as 0 (rvq:473-476).
 
     Returns (quantized_out (..., D) in dtype, indices (..., Q) int64, losses (Q,) fp32, losses_fp32 (Q,)).
     """
@@ -457,6 +460,11 @@ def rvq_forward(x: np.ndarray, dtype: str, states: list, cfg: VQConfig, *, share
     residual = x  # rvq:411
     all_ind, all_loss, all_loss32, all_residuals = [], [], [], []
     for q in range(Q):  # rvq:469
+        if training and dropout_index is not None and q > dropout_index:  # rvq:473-476
+            all_ind.append(np.full(x.shape[:-1], -1, dtype=np.int64))
+            all_loss.append(F32(0.0))
+            all_loss32.append(F32(0.0))
+            continue
         all_residuals.append(residual)  # rvq:489
         quantized, ind, loss, loss32 = vq_forward(residual, dtype, states[q], layer_cfg, training=training,
                                                   freeze_codebook=freeze_codebook, all_reduce=all_reduce,
@@ -480,6 +488,16 @@ def rvq_forward(x: np.ndarray, dtype: str, states: list, cfg: VQConfig, *, share
                          dtype)
     return (quantized_out, np.stack(all_ind, axis=-1), np.array(all_loss, dtype=F32),
             np.array(all_loss32, dtype=F32))
+
+
+def quantize_dropout_index(seed: int, num_quantizers: int, cutoff_index: int = 0, multiple_of: int = 1) -> int:
+    """rvq:434-439: the last layer that still quantizes, drawn from python's `random.Random(seed)`."""
+    import math
+    import random
+    idx = random.Random(seed).randrange(cutoff_index, num_quantizers)
+    if multiple_of != 1:
+        idx = math.ceil((idx + 1) / multiple_of) * multiple_of - 1  # rvq:39-40 round_up_multiple
+    return idx
 
 
 def grouped_rvq_forward(x: np.ndarray, dtype: str, group_states: list, cfg: VQConfig, **kw):

@@ -13,7 +13,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 def golden_names():
     """Small fixtures that store their inputs (the `big*` ones are replayed by tests/test_big_golden.py)."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith(("big", "grad", "simvq", "mask", "layout")))
+                  if not n.startswith(("big", "grad", "simvq", "mask", "layout", "dropout")))
 
 
 def simvq_golden_names():
@@ -29,6 +29,11 @@ def mask_golden_names():
 def layout_golden_names():
     """Input-layout fixtures (oracle/gen_golden.py --layout): feature maps, channel-first, one token per batch element."""
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "layout_*.npz"))))
+
+
+def dropout_golden_names():
+    """quantize_dropout fixtures (oracle/gen_golden.py --dropout): one explicit dropout seed per step in meta["seeds"]."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "dropout_*.npz"))))
 
 
 def grad_golden_names():

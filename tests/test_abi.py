@@ -121,7 +121,7 @@ def test_unsupported_options_raise():
             m.VectorQuantize(dim=64, codebook_size=32, **kw)
     vq = m.VectorQuantize(dim=64, codebook_size=32, kmeans_init=True, kmeans_iters=3)   # supported since round 2
     assert not bool(vq._codebook.initted) and float(vq._codebook.embed.abs().sum()) == 0.0   # vqp:383, :415
-    with pytest.raises(NotImplementedError):
-        m.ResidualVQ(dim=32, num_quantizers=2, codebook_size=16, quantize_dropout=True)
+    rvq = m.ResidualVQ(dim=32, num_quantizers=2, codebook_size=16, quantize_dropout=True)   # supported since round 2
+    assert rvq.quantize_dropout and not m.ResidualVQ(dim=32, num_quantizers=1, codebook_size=16, quantize_dropout=True).quantize_dropout  # rvq:253
     with pytest.raises(NotImplementedError):
         m.ResidualVQ(dim=32, num_quantizers=2, codebook_size=16, beam_size=4)

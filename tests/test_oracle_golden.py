@@ -6,7 +6,7 @@ Bar: indices identical except on rows the reference itself resolves inside fp32 
 import numpy as np
 import pytest
 
-from golden_util import GOLDEN_DIR, Golden, golden_names, near_tie_rows, cpu_pick_fn, simvq_golden_names, mask_golden_names, layout_golden_names
+from golden_util import GOLDEN_DIR, Golden, golden_names, near_tie_rows, cpu_pick_fn, simvq_golden_names, mask_golden_names, layout_golden_names, dropout_golden_names
 from oracle import vq_oracle as O
 
 
@@ -158,3 +158,27 @@ def test_layout_oracle_matches_reference(name):
         np.testing.assert_allclose(loss, g[f"s{step}_loss"], rtol=1e-5 if m["dtype"] == "fp32" else 8e-3, atol=1e-7)
         ref = g.state(f"s{step}_post", 0)
         np.testing.assert_allclose(state.embed, ref.embed, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", dropout_golden_names())
+def test_quantize_dropout_oracle_matches_reference(name):
+    """quantize_dropout (rvq:423-439, :473-476): python's random.Random(seed) picks the last active layer of a training step; the
+    layers after it return index -1 / loss 0 and leave their codebooks alone."""
+    g = Golden(name)
+    m = g.meta
+    states = g.states("s0_pre")
+    Q = m["num_quantizers"]
+    vtol = 1e-5 if m["dtype"] == "fp32" else 8e-3
+    for step, mode in enumerate(m["steps"]):
+        di = O.quantize_dropout_index(m["seeds"][step], Q, m.get("quantize_dropout_cutoff_index", 0), m.get("quantize_dropout_multiple_of", 1))
+        q, ind, loss, _ = O.rvq_forward(g[f"s{step}_x"], m["dtype"], states, g.cfg, shared_codebook=m["shared_codebook"],
+                                        training=mode == "train", dropout_index=di)
+        assert np.array_equal(ind, g[f"s{step}_indices"]), f"{name} step {step}"
+        if mode == "train":
+            assert (ind[..., min(di, Q - 1) + 1:] == -1).all() and (ind[..., :di + 1] >= 0).all()
+        np.testing.assert_allclose(q, g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss, g[f"s{step}_loss"], rtol=1e-5 if m["dtype"] == "fp32" else 8e-3, atol=1e-7)
+        for i, st in enumerate(g.flat_states(states)):
+            ref = g.state(f"s{step}_post", i)
+            np.testing.assert_allclose(st.cluster_size, ref.cluster_size, rtol=1e-5, atol=1e-6)
+            np.testing.assert_allclose(st.embed, ref.embed, rtol=1e-5, atol=1e-5)

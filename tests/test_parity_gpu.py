@@ -13,7 +13,7 @@ import os
 import pytest
 import torch
 
-from golden_util import Golden, golden_names, layout_golden_names, mask_golden_names, near_tie_rows, replayable_on_gpu
+from golden_util import Golden, dropout_golden_names, golden_names, layout_golden_names, mask_golden_names, near_tie_rows, replayable_on_gpu
 from oracle import vq_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -625,4 +625,39 @@ def test_input_layouts_match_reference(name):
             codes = mod.get_codes_from_indices(ind)
             assert codes.shape == q.shape
             np.testing.assert_allclose(codes.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+
+
+# ------------------------------------------------------------------------------------------------ quantize dropout (rvq:423-439, :473-476)
+@pytest.mark.parametrize("name", dropout_golden_names())
+def test_quantize_dropout_matches_reference(name):
+    """ResidualVQ(quantize_dropout=True) with the reference's explicit per-step seeds (oracle/gen_golden.py --dropout): the
+    same layers are skipped (index -1, loss 0, codebook untouched), everything else as usual; coarse indices decode
+    (rvq:333-339)."""
+    m = vqb()
+    g = Golden(name)
+    meta = g.meta
+    kw = {k: meta[k] for k in ("quantize_dropout", "quantize_dropout_cutoff_index", "quantize_dropout_multiple_of") if k in meta}
+    mod = m.ResidualVQ(dim=meta["dim"], num_quantizers=meta["num_quantizers"], codebook_size=meta["codebook_size"],
+                       shared_codebook=meta["shared_codebook"], **kw).to(DEV)
+    load_state(mod, g, "s0_pre")
+    dt = meta["dtype"]
+    vtol = 1e-5 if dt == "fp32" else 8e-3
+    for step, mode in enumerate(meta["steps"]):
+        mod.train(mode == "train")
+        x = torch.from_numpy(g[f"s{step}_x"]).to(DEV).to(TDT[dt])
+        q, ind, loss = mod(x, rand_quantize_dropout_fixed_seed=meta["seeds"][step])
+        torch.cuda.synchronize()
+        assert np.array_equal(ind.cpu().numpy(), g[f"s{step}_indices"]), f"{name} step {step}"
+        np.testing.assert_allclose(q.float().cpu().numpy(), g[f"s{step}_quantize"], rtol=vtol, atol=vtol)
+        np.testing.assert_allclose(loss.detach().cpu().numpy(), g[f"s{step}_loss"], rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
+        for i, (cb, j) in enumerate(codebook_slots(mod)):
+            ref = g.state(f"s{step}_post", i)
+            np.testing.assert_allclose(cb.cluster_size[j].cpu().numpy(), ref.cluster_size, rtol=1e-5, atol=1e-5)
+            np.testing.assert_allclose(cb.embed[j].cpu().numpy(), ref.embed, rtol=1e-5, atol=1e-5)
+    # coarse indices (the first two layers only) decode to the sum of those layers' codes
+    mod.eval()
+    coarse = mod.get_output_from_indices(ind[..., :2])
+    full = ind.clone()
+    full[..., 2:] = -1
+    assert torch.equal(coarse, mod.get_output_from_indices(full))
 

@@ -1,5 +1,5 @@
 """`ResidualVQ` / `GroupedResidualVQ` — drop-ins for residual_vq.py:166-630 and :634-724 of the reference
-on the plain path (no beam search, no quantize-dropout, no implicit neural codebook, no mask).
+(no beam search, no implicit neural codebook; quantize dropout and masks run on the stage-wise path).
 
 The Q-stage recurrence  residual -= q ; quantized_out += q  (rvq:524-525) runs inside the gather
 kernel of every stage (rounded to the input dtype exactly where the reference rounds), indices are
@@ -9,7 +9,9 @@ per forward instead of the reference's 2 per codebook per stage.
 """
 from __future__ import annotations
 
+import math
 import os
+import random
 
 import torch
 import torch.distributed as distributed
@@ -185,8 +187,6 @@ class ResidualVQ(nn.Module):
         assert num_quantizers is not None or isinstance(codebook_size, tuple)  # rvq:192
         if diveq or implicit_neural_codebook:
             _unsupported("diveq / implicit_neural_codebook")
-        if quantize_dropout:
-            _unsupported("quantize_dropout")
         if (beam_size is not None and beam_size > 1) or (eval_beam_size is not None and eval_beam_size > 1):
             _unsupported("beam search")
         if accept_image_fmap:
@@ -215,7 +215,10 @@ class ResidualVQ(nn.Module):
         self.layers = nn.ModuleList([
             VectorQuantize(dim=codebook_dim, codebook_size=k, codebook_dim=codebook_dim, **vq_kwargs) for k in codebook_sizes
         ])  # rvq:249
-        self.quantize_dropout = False
+        self.quantize_dropout = bool(quantize_dropout) and num_quantizers > 1  # rvq:253
+        assert quantize_dropout_cutoff_index >= 0  # rvq:255
+        self.quantize_dropout_cutoff_index = quantize_dropout_cutoff_index
+        self.quantize_dropout_multiple_of = quantize_dropout_multiple_of  # rvq:258
         self.vq_is_ema_updating = self.layers[0].ema_update
         self.quant_grad_frac = 0.
         self.shared_codebook = shared_codebook
@@ -235,9 +238,16 @@ class ResidualVQ(nn.Module):
         books = tuple(layer._codebook.embed[0] for layer in self.layers)
         return torch.stack(books) if self.uniform_codebook_size else books
 
+    def _pad_dropped(self, indices):
+        """rvq:333-339: coarse indices (fewer than num_quantizers columns) are padded with -1 = "layer dropped"."""
+        missing = self.num_quantizers - indices.shape[-1]
+        if missing > 0:
+            assert self.quantize_dropout, "quantize dropout must be on to reconstruct from fewer than num_quantizers indices"  # rvq:338
+            indices = torch.nn.functional.pad(indices, (0, missing), value=-1)
+        return indices
+
     def get_codes_from_indices(self, indices):  # rvq:324-376
-        if indices.shape[-1] < self.num_quantizers:
-            _unsupported("decoding fewer than num_quantizers indices (quantize dropout)")
+        indices = self._pad_dropped(indices)
         if self.uniform_codebook_size:
             q_idx = indices.reshape(-1, self.num_quantizers)
             codes = [ops.decode(self.layers[q]._codebook.embed[0], q_idx[:, q:q + 1].contiguous()) for q in range(self.num_quantizers)]
@@ -247,8 +257,7 @@ class ResidualVQ(nn.Module):
         return torch.stack(codes).reshape(self.num_quantizers, *indices.shape[:-1], self.codebook_dim)
 
     def get_output_from_indices(self, indices):  # rvq:378-382: sum over quantizers in ONE gather kernel
-        if indices.shape[-1] < self.num_quantizers:
-            _unsupported("decoding fewer than num_quantizers indices (quantize dropout)")
+        indices = self._pad_dropped(indices)
         if self.uniform_codebook_size:
             out = ops.decode(self.codebooks.contiguous(), indices)
         else:
@@ -276,13 +285,14 @@ class ResidualVQ(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("vqb200 has no CPU path: inputs must live on a CUDA (B200, sm_100) device")
         if mask is not None:
-            return self._forward_masked(x, mask, return_all_codes, freeze_codebook)
+            return self._forward_masked(x, mask, return_all_codes, freeze_codebook, rand_quantize_dropout_fixed_seed)
         if not _projected:   # _projected: the masked path hands in compacted rows that went through project_in already
             x = self.project_in(x)
         if x.requires_grad and torch.is_grad_enabled():
             # gradients (to the input or to project_in, rvq:406) need the per-stage straight-through / rotation glue of
             # VectorQuantize: take the layered path
-            return self._forward_layered(x, freeze_codebook, return_all_codes)
+            return self._forward_layered(x, freeze_codebook, return_all_codes,
+                                         self._active_layers(rand_quantize_dropout_fixed_seed, x.device))
         shape, dtype = x.shape, x.dtype
         if dtype not in (torch.float32, torch.bfloat16):
             raise TypeError(f"vqb200 supports float32 and bfloat16 inputs, got {dtype}")
@@ -294,8 +304,10 @@ class ResidualVQ(nn.Module):
         books = self._stage_plan()
 
         losses = self._ensure_loss_buf(dev)
-        do_update = [training and not freeze_codebook and (b.ema_update or b.has_dead_code_replacement) for b in books]
-        if not _projected and self._program_ok(books, do_update):
+        n_run = self._active_layers(rand_quantize_dropout_fixed_seed, dev)   # < Q: quantize dropout skips the layers after it
+        do_update = [training and not freeze_codebook and q < n_run and (b.ema_update or b.has_dead_code_replacement)
+                     for q, b in enumerate(books)]
+        if not _projected and n_run == Q and self._program_ok(books, do_update):
             # the whole forward — stages, running sum, deferred EMA updates — as ONE vqb_rvq_forward call / one CUDA graph,
             # from a cached op list in which only the per-call pointers (input, indices, output) are patched
             key = self._part_key(flat, books, do_update)
@@ -312,7 +324,11 @@ class ResidualVQ(nn.Module):
             prog.run()
             return part.finish(bound, shape, return_all_codes)
 
-        all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)
+        if n_run < Q:   # rvq:473-476: the skipped layers report index -1 and loss 0
+            all_idx = torch.full((N, Q), -1, dtype=torch.int64, device=dev)
+            losses.zero_()
+        else:
+            all_idx = torch.empty((N, Q), dtype=torch.int64, device=dev)
         if not training:
             losses.zero_()
         # dead-code expiry samples from the stage inputs after the (deferred) EMA update: keep them all then
@@ -324,7 +340,7 @@ class ResidualVQ(nn.Module):
         # update_codebook ends with expire_codes_, vqp:641, on the one aliased Codebook): such stages cannot be deferred.
         inline = [u and self.shared_codebook and b.has_dead_code_replacement for b, u in zip(books, do_update)]
         stat_sizes = [ops.stats_floats(b.codebook_size, D) if (u and not i) else 0 for b, u, i in zip(books, do_update, inline)]
-        running_sum = torch.zeros_like(flat) if (any(inline) or not self.uniform_codebook_size) else None  # rvq:410
+        running_sum = torch.zeros_like(flat) if (any(inline) or not self.uniform_codebook_size or n_run < Q) else None  # rvq:410
         packed, peer_ptrs = None, None
         if sum(stat_sizes):
             peer = self._peer_reducer(sum(stat_sizes), dev) if any(b.use_ddp for b in books) else None
@@ -335,8 +351,8 @@ class ResidualVQ(nn.Module):
                 packed = torch.empty((sum(stat_sizes),), dtype=torch.float32, device=dev)
         offs = [sum(stat_sizes[:i]) for i in range(Q)]
 
-        for q, book in enumerate(books):  # rvq:469
-            nxt = (bufs[q] if keep_inputs else bufs[q & 1]) if q + 1 < Q else None
+        for q, book in enumerate(books[:n_run]):  # rvq:469
+            nxt = (bufs[q] if keep_inputs else bufs[q & 1]) if q + 1 < n_run else None
             if keep_inputs:
                 stage_inputs.append(residual)
             want_loss = training and self.layers[q].has_commitment_loss
@@ -370,7 +386,25 @@ class ResidualVQ(nn.Module):
             ret = (*ret, self.get_codes_from_indices(ret[1]))
         return ret
 
-    def _forward_masked(self, x, mask, return_all_codes, freeze_codebook):
+    def _active_layers(self, fixed_seed, device) -> int:
+        """Number of leading layers that quantize in this forward.  Training with quantize_dropout (rvq:423-439): python's
+        random.Random(seed).randrange(cutoff, Q) is the last active layer, rounded up to a multiple if asked; without an explicit
+        seed one is drawn like the reference's get_maybe_sync_seed (rvq:96-103: torch.randint on the device, all-reduced, .item())."""
+        Q = self.num_quantizers
+        if not (self.training and self.quantize_dropout):
+            return Q
+        if fixed_seed is None:
+            seed = torch.randint(0, 10_000, (), device=device)
+            if distributed.is_available() and distributed.is_initialized() and distributed.get_world_size() > 1:
+                distributed.all_reduce(seed)
+            fixed_seed = seed.item()
+        index = random.Random(fixed_seed).randrange(self.quantize_dropout_cutoff_index, Q)
+        mult = self.quantize_dropout_multiple_of
+        if mult != 1:
+            index = math.ceil((index + 1) / mult) * mult - 1  # rvq:39-40, :439
+        return min(index + 1, Q)
+
+    def _forward_masked(self, x, mask, return_all_codes, freeze_codebook, dropout_seed=None):
         """mask (B, N) bool.  The reference hands the mask to every layer (rvq:495): a layer searches every row, but masked rows
         take no part in its statistics or loss (vqp:599-600, :1317-1325) and come back as zeros / index -1 (vqp:1378-1396), so their
         residual is never reduced and their running sum stays zero.  That is exactly the forward over the COMPACTED unmasked rows
@@ -394,7 +428,8 @@ class ResidualVQ(nn.Module):
         all_idx = torch.full((B * N, Q), -1, dtype=torch.int64, device=xp.device)
         if rows.numel() > 0:
             xc = xp.detach().reshape(-1, D)[rows].unsqueeze(0)
-            qc, ic, losses = self.forward(xc, freeze_codebook=freeze_codebook, _projected=True)
+            qc, ic, losses = self.forward(xc, freeze_codebook=freeze_codebook, _projected=True,
+                                          rand_quantize_dropout_fixed_seed=dropout_seed)
             quantized[rows] = qc[0]
             all_idx[rows] = ic[0]
         else:
@@ -483,13 +518,17 @@ class ResidualVQ(nn.Module):
                 rows = torch.stack([r[:n0] for r in stage_inputs], dim=1).reshape(-1, stage_inputs[0].shape[-1])
                 shared.expire_codes_(shared.transform_input(rows))
 
-    def _forward_layered(self, x, freeze_codebook, return_all_codes):
+    def _forward_layered(self, x, freeze_codebook, return_all_codes, n_run=None):
         """Differentiable path: the reference's Python loop (rvq:469-568) over our VectorQuantize layers.
-        `x` is already projected (rvq:406)."""
+        `x` is already projected (rvq:406).  n_run < Q: quantize dropout (rvq:473-476)."""
         quantized_out = torch.zeros_like(x)
         residual = x
         all_idx, all_losses = [], []
-        for vq in self.layers:
+        for q, vq in enumerate(self.layers):
+            if n_run is not None and q >= n_run:
+                all_idx.append(torch.full(x.shape[:-1], -1, dtype=torch.int64, device=x.device))
+                all_losses.append(torch.zeros((), dtype=torch.float32, device=x.device))
+                continue
             quantized, ind, loss = vq(residual, freeze_codebook=freeze_codebook)
             residual = residual - quantized.detach()
             quantized_out = quantized_out + quantized
@@ -556,11 +595,14 @@ class GroupedResidualVQ(nn.Module):
             seed = torch.randint(0, 10_000, (), device=x.device)
             if distributed.is_available() and distributed.is_initialized() and distributed.get_world_size() > 1:
                 distributed.all_reduce(seed)
+        dropout_seed = None
+        if self.training and any(rvq.quantize_dropout for rvq in self.rvqs):
+            dropout_seed = int(seed.item())   # rvq:701: the SAME dropout index in every group
         if mask is not None:   # rvq:698: every group receives the mask (ResidualVQ._forward_masked)
-            outs = [rvq(c, mask=mask, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes)
-                    for rvq, c in zip(self.rvqs, chunks)]
+            outs = [rvq(c, mask=mask, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes,
+                        rand_quantize_dropout_fixed_seed=dropout_seed) for rvq, c in zip(self.rvqs, chunks)]
             sink = []
-        elif self._program_ok(chunks, freeze_codebook):
+        elif dropout_seed is None and self._program_ok(chunks, freeze_codebook):
             # every group's stages in ONE vqb_rvq_forward call: the groups are independent chains on parallel lanes; the op
             # list is cached, only the per-call pointers are patched
             flats, keys = [], []
@@ -589,8 +631,8 @@ class GroupedResidualVQ(nn.Module):
             sink = []
         else:
             sink = []
-            outs = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _stats_sink=sink)
-                    for rvq, c in zip(self.rvqs, chunks)]  # rvq:706
+            outs = [rvq(c, freeze_codebook=freeze_codebook, return_all_codes=return_all_codes, _stats_sink=sink,
+                        rand_quantize_dropout_fixed_seed=dropout_seed) for rvq, c in zip(self.rvqs, chunks)]  # rvq:706
         if sink:
             need_sync = any(b.use_ddp for rvq, *_ in sink for b in rvq._stage_plan()) and all(e[5][2] is None for e in sink)
             if need_sync:  # no peer memory: ONE NCCL collective for every codebook of every group
