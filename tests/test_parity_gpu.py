@@ -661,3 +661,30 @@ def test_quantize_dropout_matches_reference(name):
     full[..., 2:] = -1
     assert torch.equal(coarse, mod.get_output_from_indices(full))
 
+
+def test_grouped_quantize_dropout_shares_the_index():
+    """GroupedResidualVQ draws ONE dropout seed per forward and hands it to every group (rvq:701): the same layers are skipped in
+    all groups; the output is the sum of the active layers' codes."""
+    m = vqb()
+    torch.manual_seed(7)
+    g = m.GroupedResidualVQ(dim=64, groups=2, num_quantizers=4, codebook_size=32, quantize_dropout=True).to(DEV)
+    for rvq in g.rvqs:
+        for layer in rvq.layers:
+            _warm_codebook(layer, 32, 32)
+    g.train()
+    seen = set()
+    for _ in range(6):
+        x = torch.randn(2, 50, 64, device=DEV)
+        q, ind, losses = g(x, freeze_codebook=True)
+        assert ind.shape == (2, 2, 50, 4) and losses.shape == (2, 4)
+        active = (ind >= 0).all(dim=1).all(dim=1)          # (G, Q): a layer is active for all rows or for none
+        dropped = (ind == -1).all(dim=1).all(dim=1)
+        assert (active | dropped).all() and torch.equal(active[0], active[1])
+        n = int(active[0].sum())
+        assert active[0, :n].all() and (losses[:, n:] == 0).all()
+        seen.add(n)
+        assert torch.allclose(q, g.get_output_from_indices(ind), atol=1e-5)
+    g.eval()
+    _, ind, _ = g(torch.randn(2, 50, 64, device=DEV))
+    assert (ind >= 0).all()                                  # no dropout in eval mode
+
