@@ -243,6 +243,12 @@ typedef struct vqb_vq_forward_args {
   /* ResidualVQ stages on fp32 rows (Euclidean): a stage can take the bf16 hi / lo split of its input ([2][N][D], written by the
    * previous stage's tail through `planes_out`) instead of running vqb_input_prepare.  NULL = not used. */
   const void* a_planes_in; void* planes_out;
+  /* Variable-length batches (mask / lens, vector_quantize_pytorch.py:1116-1119).  row_mask u8 [N], 0 = padding row: the row is
+   * searched (the tiles stay dense) but gets index -1 in idx32, its q_out / idx64_out are NOT written (the caller pre-fills them:
+   * zeros or the input, and -1, :1378-1396), it adds nothing to the loss (:1317-1325) or to the statistics (:599-600) and is
+   * never re-scored.  n_live i64 [1] (device): the number of unmasked rows, the divisor of the loss (NULL: N).  VectorQuantize
+   * chain only (resid_out / qsum / planes_out must be NULL, stats_mode 1).  NULL = no mask. */
+  const uint8_t* row_mask; const int64_t* n_live;
 } vqb_vq_forward_args;
 size_t vqb_vq_forward_workspace(int64_t N, int D, int K, int dtype, int metric, int update);
 int vqb_vq_forward(const vqb_vq_forward_args* args, void* stream);

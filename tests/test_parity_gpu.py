@@ -688,3 +688,36 @@ def test_grouped_quantize_dropout_shares_the_index():
     _, ind, _ = g(torch.randn(2, 50, 64, device=DEV))
     assert (ind >= 0).all()                                  # no dropout in eval mode
 
+
+@pytest.mark.parametrize("dt", ["bf16", "fp32"])
+def test_in_kernel_mask_equals_compacted_rows(dt):
+    """The row mask inside the search kernel (vqb_vq_forward_args.row_mask) at a many-tile size: a masked training step equals
+    the same step on the compacted unmasked rows — indices, quantized rows, loss, codebook afterwards — and the padding comes
+    back as zeros / -1.  (Tiles mix live and padding rows; flagged rows, the in-kernel histogram and the sort all see the mask.)"""
+    m = vqb()
+    torch.manual_seed(99)
+    B, N, D, K = 4, 3000, 256, 1024
+    a = m.VectorQuantize(dim=D, codebook_size=K).to(DEV)
+    _warm_codebook(a, D, K)
+    b = m.VectorQuantize(dim=D, codebook_size=K).to(DEV)
+    b.load_state_dict(a.state_dict())
+    x = torch.randn(B, N, D, device=DEV).to(TDT[dt])
+    mask = torch.rand(B, N, device=DEV) < 0.7
+    mask[0, :200] = False            # whole tiles of padding
+    mask[1] = True                   # and a fully live sequence
+    a.train(); b.train()
+    for step in range(2):
+        qa, ia, la = a(x, mask=mask)
+        qb, ib, lb = b(x[mask][None])
+        torch.cuda.synchronize()
+        assert torch.equal(ia[mask], ib[0]) and (ia[~mask] == -1).all()
+        assert torch.equal(qa[mask], qb[0]) and (qa[~mask] == 0).all()
+        torch.testing.assert_close(la, lb, rtol=1e-5 if dt == "fp32" else 8e-3, atol=1e-7)
+        for u, v in zip(a.buffers(), b.buffers()):
+            torch.testing.assert_close(u, v, rtol=1e-5, atol=1e-5)
+        x = torch.randn(B, N, D, device=DEV).to(TDT[dt])
+    a.eval(); b.eval()
+    qa, ia, la = a(x, mask=mask)
+    qb, ib, _ = b(x[mask][None])
+    assert torch.equal(ia[mask], ib[0]) and torch.equal(qa[mask], qb[0]) and la.item() == 0.0
+

@@ -31,7 +31,7 @@ class VQForwardArgs(ctypes.Structure):
                 ("decay", _f64), ("eps", _f64), ("stats", _vp), ("margin_rel", _f32), ("workspace", _vp),
                 ("workspace_bytes", _sz), ("ev_search_begin", _vp), ("ev_search_end", _vp),
                 ("peer_stats", _vp), ("peer_flags", _vp), ("peer_epoch", _vp), ("peer_rank", _i32), ("peer_world", _i32),
-                ("peer_slice_offset", _i64), ("a_planes_in", _vp), ("planes_out", _vp)]
+                ("peer_slice_offset", _i64), ("a_planes_in", _vp), ("planes_out", _vp), ("row_mask", _vp), ("n_live", _vp)]
 
 
 class RvqEmaArgs(ctypes.Structure):

@@ -83,6 +83,7 @@ struct AssignParams {
   vqb_flag_entry* flagged;
   int32_t* flag_count;
   float* dbg_best;
+  const uint8_t* row_mask;   // optional [N]: 0 = padding row (vqp:1116-1119): index -1, no tail, no loss, no statistics, never re-scored
   long long* prof;     // optional [gridDim][16] cycle counters (diagnostics)
   FusedOut fo;         // optional fused gather tail (fo.enabled)
   int copy_mode;       // tail = pure row copy q <- codebook row (+ loss from the scores); no x re-read
@@ -508,7 +509,11 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int n = rr.n, i0 = rr.i0, i1 = rr.i1;
         const float best = rr.best;
         const int64_t row = static_cast<int64_t>(tile) * BM + row_in_tile;
-        if (TAIL >= 1 && p.fo.loss_sum && row < p.N && n < 2) {
+        // padding rows of a masked batch (vqp:1116-1119) are searched like any other row — the tile is dense — but take no
+        // part in anything afterwards: index -1, no tail (the caller pre-filled their outputs), no loss (vqp:1317-1325), no
+        // statistics (vqp:599-600: no histogram count, -1 in the provisional indices), never flagged
+        const bool live = row < p.N && (p.row_mask == nullptr || __ldg(p.row_mask + row) != 0);
+        if (TAIL >= 1 && p.fo.loss_sum && live && n < 2) {
           // ||q - x||^2 = ||x||^2 - 2(x.c - 0.5||c||^2)  — the score already holds it (cosine: bias is 0, add ||c||^2).
           // Differs from the reference's bf16 evaluation by << 1e-3 relative; flagged rows get the
           // exact evaluation in vqb_fix_flagged.
@@ -518,11 +523,14 @@ vq_assign_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (p.fo.enabled) {  // hand the certified winners of this tile to the store warps
           mbar_wait(smem_u32(&ctrl->g_empty[t & 1]), ((t >> 1) & 1) ^ 1);
-          ctrl->gidx[t & 1][row_in_tile] = (row < p.N && n < 2) ? i0 : -1;
+          ctrl->gidx[t & 1][row_in_tile] = (live && n < 2) ? i0 : -1;
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&ctrl->g_full[t & 1]));
         }
-        if (row < p.N) {
+        if (row < p.N && !live) {
+          p.idx[row] = -1;
+          if (p.idx_prov) p.idx_prov[row] = -1;
+        } else if (row < p.N) {
           p.idx[row] = i0;
           if (p.idx_prov) p.idx_prov[row] = (n < 2) ? i0 : -1;
           if (p.hist && n < 2) atomicAdd(p.hist + static_cast<size_t>(tile >> p.hist_shift) * p.K + i0, 1);   // RED, fire and forget
@@ -860,7 +868,7 @@ extern "C" int vqb_assign_ex(const void* a_planes, int n_a, int64_t N, int D, co
 int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                        const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, int32_t* idx_prov,
                        int32_t* hist, int hist_shift, vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
-                       const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream) {
+                       const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream, const uint8_t* row_mask) {
   if (!a_planes || !b_planes || !bext || !cmax || !idx || !flagged || !flag_count) return VQB_E_INVALID;
   if (N <= 0 || D <= 0 || K <= 0 || (n_a != 1 && n_a != 2)) return VQB_E_INVALID;
   // Passes (bf16 operands, fp32 accumulation): A = the input rows (n_a = 1) or the bf16 hi / lo planes of an fp32 input
@@ -888,6 +896,7 @@ int vqb::assign_launch(const void* a_planes, int n_a, int64_t N, int D, const vo
   p.num_code_tiles = p.Kpad / p.BN;
   p.margin_rel = margin_rel;
   p.cmax = cmax; p.idx = idx; p.idx_prov = idx_prov; p.hist = hist; p.hist_shift = hist_shift; p.flagged = flagged; p.flag_count = flag_count; p.dbg_best = dbg_best;
+  p.row_mask = row_mask;
   p.prof = g_prof;
   p.dbg_mode = g_dbg_mode;
   p.tagmask = 0xFFFFFFF0u; p.mul1 = 1u; p.mulm1 = 0xFFFFFFFFu;

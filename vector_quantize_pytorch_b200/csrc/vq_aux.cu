@@ -282,7 +282,9 @@ __global__ void gather_kernel(int64_t N, int D, const int32_t* __restrict__ idx,
   }
 }
 
-__global__ void loss_finalize_kernel(const double* loss_sum, int64_t numel, int dtype, float weight, float* loss_out) {
+__global__ void loss_finalize_kernel(const double* loss_sum, int64_t numel, const int64_t* n_live, int D, int dtype, float weight,
+                                     float* loss_out) {
+  if (n_live) numel = max(*n_live, static_cast<int64_t>(1)) * D;   // masked batch: mean over the unmasked elements (vqp:1317-1325)
   float mean = static_cast<float>(*loss_sum / static_cast<double>(numel));
   if (dtype == VQB_DTYPE_BF16) {
     mean = bf16_round(mean);            // F.mse_loss returns a bf16 tensor
@@ -616,11 +618,16 @@ extern "C" int vqb_gather(const void* x_eff, int dtype, int64_t N, int D, const 
   return static_cast<int>(cudaGetLastError());
 }
 
+int vqb::loss_finalize_launch(const double* loss_sum, int64_t numel, const int64_t* n_live, int D, int dtype, float weight,
+                              float* loss_out, void* stream) {
+  if (!loss_sum || !loss_out || numel <= 0) return VQB_E_INVALID;
+  loss_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_sum, numel, n_live, D, dtype, weight, loss_out);
+  return static_cast<int>(cudaGetLastError());
+}
+
 extern "C" int vqb_loss_finalize(const double* loss_sum, int64_t numel, int dtype, float weight, float* loss_out,
                                  void* stream) {
-  if (!loss_sum || !loss_out || numel <= 0) return VQB_E_INVALID;
-  loss_finalize_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(loss_sum, numel, dtype, weight, loss_out);
-  return static_cast<int>(cudaGetLastError());
+  return vqb::loss_finalize_launch(loss_sum, numel, nullptr, 1, dtype, weight, loss_out, stream);
 }
 
 // smem variant of the gather-sum (rounded running sum / decode): the widest power-of-two column slice W of all the codebooks

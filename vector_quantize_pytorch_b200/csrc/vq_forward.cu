@@ -107,7 +107,7 @@ void make_keys(const vqb_vq_forward_args* a, void* stream, uint64_t* sk, uint64_
   auto F = [&](double v) { uint64_t u; memcpy(&u, &v, 8); sk[si++] = u; };
   P(a->x); P(a->cluster_size); P(a->embed_avg); P(a->embed); P(a->planes); P(a->bext); P(a->bias); P(a->cnorm2); P(a->cmax);
   P(a->scratch); P(a->q_out); P(a->idx64_out); P(a->loss_out); P(a->resid_out); P(a->qsum); P(a->idx32); P(a->stats);
-  P(a->workspace); P(a->a_planes_in); P(a->planes_out);
+  P(a->workspace); P(a->a_planes_in); P(a->planes_out); P(a->row_mask); P(a->n_live);
   P(a->peer_epoch);
   for (int r = 0; r < a->peer_world && r < 16; ++r) { P(a->peer_stats ? a->peer_stats[r] : nullptr); P(a->peer_flags ? a->peer_flags[r] : nullptr); }
   I(a->dtype); I(a->metric); I(a->N); I(a->D); I(a->K); I(a->already_normalised); I(a->idx_stride); F(a->loss_weight);
@@ -534,6 +534,10 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
   const bool split_tail = a->qsum && !fused_stats;
   if (a->planes_out && (split_tail || a->dtype != VQB_DTYPE_F32 || !a->resid_out || l2)) return VQB_E_UNSUPPORTED;
   const bool want_tail = !split_tail && (a->q_out || a->idx64_out || a->loss_out || fused_stats);
+  // Masked batch (row_mask): padding rows keep their pre-filled outputs and leave loss and statistics alone (vq_assign.cu,
+  // merge step).  Supported on the VectorQuantize chain: no ResidualVQ recurrence outputs, statistics by the sort.
+  if (a->row_mask && (split_tail || fused_stats || a->resid_out || a->qsum || a->planes_out)) return VQB_E_UNSUPPORTED;
+  if (a->n_live && !a->row_mask) return VQB_E_INVALID;
   vqb_flag_entry* flagged = reinterpret_cast<vqb_flag_entry*>(ws + w.flagged);
   // The EMA sort (histogram -> scans -> scatter -> segmented sums) only needs the indices, and all but ~0.1 % of them
   // are final when the search kernel ends.  So the search also writes a provisional index array (-1 for the rows
@@ -565,7 +569,8 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
   }
   if (a->ev_search_begin) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_begin), s);
   rc = assign_launch(a_planes, n_a, a->N, a->D, a->planes, a->bext, a->cmax, a->K, a->margin_rel, 0, a->idx32, idx_prov,
-                     hist, hist_shift, flagged, flag_count, nullptr, want_tail ? &f : nullptr, a->metric, a->cnorm2, stream);
+                     hist, hist_shift, flagged, flag_count, nullptr, want_tail ? &f : nullptr, a->metric, a->cnorm2, stream,
+                     a->row_mask);
   if (rc) return rc;
   if (a->ev_search_end) cudaEventRecord(static_cast<cudaEvent_t>(a->ev_search_end), s);
   if (side) {  // fork: certified rows -> statistics
@@ -587,7 +592,8 @@ static int vq_forward_enqueue(const vqb_vq_forward_args* a, void* stream, int la
     if (rc) return rc;
   }
   if (a->loss_out) {
-    rc = vqb_loss_finalize(loss_sum, a->N * a->D, a->dtype, a->loss_weight, a->loss_out, stream);
+    rc = loss_finalize_launch(loss_sum, a->N * a->D, a->row_mask ? a->n_live : nullptr, a->D, a->dtype, a->loss_weight, a->loss_out,
+                              stream);
     if (rc) return rc;
   }
   // ---- EMA (vqp:586-617, :576-584)

@@ -76,7 +76,11 @@ __device__ __forceinline__ float warp_sum(float v) {
 int assign_launch(const void* a_planes, int n_a, int64_t N, int D, const void* b_planes, const void* bext,
                   const float* cmax, int K, float margin_rel, int n_passes, int32_t* idx, int32_t* idx_prov,
                   int32_t* hist, int hist_shift, vqb_flag_entry* flagged, int32_t* flag_count, float* dbg_best,
-                  const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream);
+                  const vqb_fused_outputs* fused, int metric, const float* cnorm2, void* stream,
+                  const uint8_t* row_mask = nullptr /* [N], 0 = padding row: index -1, no tail / loss / statistics */);
+// vq_aux.cu: vqb_loss_finalize whose divisor is (*n_live rows) x D when n_live (device, i64[1]) is given — masked batches
+int loss_finalize_launch(const double* loss_sum, int64_t numel, const int64_t* n_live, int D, int dtype, float weight,
+                         float* loss_out, void* stream);
 // vq_ema.cu: add the rows listed in `flagged` (final code = idx[row]) to packed statistics that were built from an
 // index array in which those rows were marked -1
 int stats_add_flagged(const void* x_eff, int dtype, int64_t N, int D, const vqb_flag_entry* flagged,

@@ -189,9 +189,14 @@ def vq_forward_args(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, upd
                     eps: float, q_out=None, idx64_out=None, idx_stride: int = 1, loss_out=None, loss_weight: float = 1.0,
                     resid_out=None, qsum=None, stats=None, margin: float | None = None, already_normalised: bool = False,
                     ws_key=None, stats_accumulate: bool = False, peer=None, peer_ptrs=None, peer_slice_offset: int = 0,
-                    a_planes_in=None, planes_out=None):
+                    a_planes_in=None, planes_out=None, row_mask=None, n_live=None):
     """The argument block of one vqb_vq_forward call (also one VQB_RVQ_STAGE op of vqb_rvq_forward).
+    row_mask (N,) uint8 / n_live (1,) int64 on the device: a masked batch (vqp:1116-1119) — padding rows (0) keep the values
+    q_out / idx64_out were pre-filled with and stay out of the loss and the statistics (include/vqb200.h).
     Returns (args, idx32, stats, n_launches)."""
+    if row_mask is not None:
+        assert row_mask.dtype == torch.uint8 and row_mask.is_contiguous() and row_mask.numel() == x.shape[0] and row_mask.is_cuda
+        assert n_live is None or (n_live.dtype == torch.int64 and n_live.numel() == 1 and n_live.is_cuda)
     _require_cuda(x, state[2])
     assert x.dim() == 2 and x.is_contiguous()
     N, D = x.shape
@@ -213,7 +218,7 @@ def vq_forward_args(x: torch.Tensor, ops: CodebookOperands, state: tuple, *, upd
         qsum=_p(qsum), idx32=_p(idx32), update=int(update), stats_mode=STATS_MODE, stats_accumulate=int(stats_accumulate), do_normalise=int(do_normalise), decay=float(decay),
         eps=float(eps), stats=_p(stats), margin_rel=float(DEFAULT_MARGIN if margin is None else margin),
         workspace=_p(ws), workspace_bytes=nbytes, ev_search_begin=None, ev_search_end=None,
-        a_planes_in=_p(a_planes_in), planes_out=_p(planes_out))
+        a_planes_in=_p(a_planes_in), planes_out=_p(planes_out), row_mask=_p(row_mask), n_live=_p(n_live))
     if update == 3:  # multi-GPU: statistics -> peer barrier -> EMA kernels summing every rank's statistics (vq_peer.cu)
         a.peer_stats = ctypes.cast(peer_ptrs, ctypes.c_void_p)
         a.peer_flags = ctypes.cast(peer.flag_ptrs, ctypes.c_void_p)

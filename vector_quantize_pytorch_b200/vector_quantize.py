@@ -352,9 +352,10 @@ class VectorQuantize(nn.Module):
 
     # ------------------------------------------------------------------ variable-length sequences (vqp:599-600, :1317-1325, :1378-1396)
     def _forward_masked(self, x, mask, freeze_codebook, ema_update, return_loss_breakdown):
-        """mask (B, N) bool.  The kernels run on the compacted unmasked rows: masked positions take no part in the
-        statistics or the loss (the reference zeroes their one-hot rows, vqp:599-600, and averages the loss over the
-        unmasked elements against the ORIGINAL input, vqp:1317-1325) and come back as zeros / index -1."""
+        """mask (B, N) bool.  Masked positions take no part in the statistics or the loss (the reference zeroes their one-hot
+        rows, vqp:599-600, and averages the loss over the unmasked elements against the ORIGINAL input, vqp:1317-1325) and come
+        back as zeros / index -1.  Euclidean codebooks: the search kernel takes the mask (row_mask of vqb_vq_forward).  Cosine
+        codebooks, pending k-means init, dead-code expiry: the kernels run on the compacted unmasked rows."""
         if self.has_projections or self.accept_image_fmap or self.accept_3d_fmap or not self.channel_last or self.heads > 1:
             _unsupported("mask / lens together with projections, feature-map layouts or heads > 1")
         if x.requires_grad and torch.is_grad_enabled():
@@ -368,6 +369,32 @@ class VectorQuantize(nn.Module):
         training = self.training
         B, N, D = x.shape
         flat = x.detach().reshape(-1, D)
+        do_update = training and not freeze_codebook and (ema_update or cbk.has_dead_code_replacement)
+        if (ops.STATS_MODE == 1 and not self.use_cosine_sim and cbk._initted_host and x.dtype in (torch.float32, torch.bfloat16)
+                and not (do_update and cbk.has_dead_code_replacement)):
+            # in-kernel mask: every row is searched (like the reference), the merge step of the search kernel drops the padding
+            # rows — index -1, outputs left as pre-filled here, no loss term, no statistics — and the loss is divided by the
+            # unmasked element count on the device: no host sync, no compaction pass.  (Cosine: the masked loss is taken
+            # against the UN-normalised input, vqp:1319; k-means init / expiry sample from x[mask]: those take the path below.)
+            flat = flat.contiguous()
+            row_mask = mask.reshape(-1).contiguous().view(torch.uint8)
+            n_live = row_mask.sum(dtype=torch.int64).reshape(1)
+            quantize = torch.zeros_like(flat) if self.return_zeros_for_masked_padding else flat.clone()
+            embed_ind = torch.full((B * N,), -1, dtype=torch.int64, device=x.device)
+            want_loss = training and self.has_commitment_loss
+            commit = torch.zeros((), dtype=torch.float32, device=x.device) if want_loss else None
+            cbk.quantize_rows(flat, update=do_update, q_out=quantize, idx64_out=embed_ind, loss_out=commit,
+                              loss_weight=self.commitment_weight, ema_update=ema_update, row_mask=row_mask, n_live=n_live)
+            if want_loss:
+                loss = commit.requires_grad_(torch.is_grad_enabled())
+                commit_loss = commit
+            else:
+                loss = torch.tensor(0., device=x.device, requires_grad=training and torch.is_grad_enabled())
+                commit_loss = self.zero
+            quantize, embed_ind = quantize.reshape(B, N, D), embed_ind.reshape(B, N)
+            if not return_loss_breakdown:
+                return quantize, embed_ind, loss
+            return quantize, embed_ind, loss, LossBreakdown(commit_loss, self.zero, self.zero, self.zero)
         rows = mask.reshape(-1).nonzero(as_tuple=True)[0]  # host sync (the reference's masked path syncs as well)
         quantize = torch.zeros_like(flat) if self.return_zeros_for_masked_padding else flat.clone()
         embed_ind = torch.full((B * N,), -1, dtype=torch.int64, device=x.device)
@@ -377,7 +404,6 @@ class VectorQuantize(nn.Module):
             xc = flat[rows].contiguous()
             qc = torch.empty_like(xc)
             ic = torch.empty((xc.shape[0],), dtype=torch.int64, device=x.device)
-            do_update = training and not freeze_codebook and (ema_update or cbk.has_dead_code_replacement)
             fused = training and self.has_commitment_loss and not self.use_cosine_sim
             commit = torch.empty((), dtype=torch.float32, device=x.device) if fused else None
             cbk.quantize_rows(xc, update=do_update, q_out=qc, idx64_out=ic, loss_out=commit,
