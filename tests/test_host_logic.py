@@ -73,3 +73,45 @@ def test_rvq_op_layout_matches_the_header():
     assert got == [ctypes.sizeof(_C.RvqOp), _C.RvqOp.stage.offset, _C.RvqOp.ema.offset, _C.RvqOp.acc.offset,
                    ctypes.sizeof(_C.VQForwardArgs), _C.RvqOp.bar.offset, _C.RvqOp.emap.offset,
                    _C.RvqOp.emap.offset + _C.RvqEmaPeersArgs.scratch.offset]
+
+
+def test_quantize_dropout_layer_count_follows_the_reference():
+    """ResidualVQ._active_layers (host logic, no GPU needed): python's random.Random(seed).randrange(cutoff, Q) is the last
+    active layer, rounded up to a multiple (rvq:434-439); eval mode and quantize_dropout=False run every layer; Q == 1 switches
+    dropout off (rvq:253)."""
+    import math
+    import random
+    import vector_quantize_pytorch_b200 as m
+    from oracle import vq_oracle as O
+    for Q, cutoff, mult in [(4, 0, 1), (6, 1, 2), (8, 2, 4), (8, 0, 3), (5, 4, 1)]:
+        rvq = m.ResidualVQ(dim=16, num_quantizers=Q, codebook_size=8, quantize_dropout=True, quantize_dropout_cutoff_index=cutoff,
+                           quantize_dropout_multiple_of=mult)
+        rvq.train()
+        seen = set()
+        for seed in range(200):
+            idx = random.Random(seed).randrange(cutoff, Q)            # rvq:436
+            if mult != 1:
+                idx = math.ceil((idx + 1) / mult) * mult - 1          # rvq:439
+            assert idx == O.quantize_dropout_index(seed, Q, cutoff, mult)
+            n = rvq._active_layers(seed, "cpu")
+            assert n == min(idx + 1, Q) and cutoff + 1 <= n <= Q
+            seen.add(n)
+        assert len(seen) > 1 or cutoff == Q - 1
+        rvq.eval()
+        assert rvq._active_layers(3, "cpu") == Q                        # no dropout outside training (rvq:423)
+    assert m.ResidualVQ(dim=16, num_quantizers=3, codebook_size=8).train()._active_layers(3, "cpu") == 3
+    assert not m.ResidualVQ(dim=16, num_quantizers=1, codebook_size=8, quantize_dropout=True).quantize_dropout
+
+
+def test_coarse_indices_are_padded_with_dropped_layers():
+    """rvq:333-339: fewer than num_quantizers index columns decode as if the missing layers had been dropped (-1)."""
+    import torch
+    import vector_quantize_pytorch_b200 as m
+    rvq = m.ResidualVQ(dim=16, num_quantizers=4, codebook_size=8, quantize_dropout=True)
+    ind = torch.randint(0, 8, (2, 5, 2))
+    padded = rvq._pad_dropped(ind)
+    assert padded.shape == (2, 5, 4) and torch.equal(padded[..., :2], ind) and (padded[..., 2:] == -1).all()
+    assert rvq._pad_dropped(padded) is padded
+    import pytest
+    with pytest.raises(AssertionError):
+        m.ResidualVQ(dim=16, num_quantizers=4, codebook_size=8)._pad_dropped(ind)   # rvq:336: only with quantize dropout
